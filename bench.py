@@ -1,0 +1,238 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: 3D Q4 FP64 variable-coefficient Laplace apply, DoFs/s.
+
+A "step" is one LaplaceOperatorGpu::vmult (dst = A*src: fused zero/constraint pass + cell kernel)
+on the uniform cube mesh, the loop of bmop.cu:135-153 (swap(dst,src); vmult(dst,src)).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--refine R] [--degree P] [--dtype f64|f32]
+  python bench.py --impl reference ...   # the reference's CPU path (oracle port, all host threads)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def b_alg(p, dim, s):
+    """Algorithmic bytes per DoF (SURVEY.md 8d / BASELINE.md 3)."""
+    return 2 * s + (s + 4) * ((p + 1) / p) ** dim + s / p ** dim
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_reference_run(args, steps, warmup):
+    """The reference's CPU path (bmop-cpu.cc:138-155) restated: oracle port, OpenMP over colors, all host threads.
+    Bounded sample: the same mesh family at a refinement the host finishes in seconds."""
+    from oracle.oracle import OracleMesh, lib as olib
+    r = min(args.refine, args.cpu_refine)
+    m = OracleMesh(3, args.degree, r)
+    u = np.full(m.n_dofs, 0.1)
+    for _ in range(max(1, warmup)):
+        u2 = m.vmult(u, threaded=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        u2 = m.vmult(u, threaded=True)
+        u, u2 = u2, u
+    dt = time.perf_counter() - t0
+    cores = olib().orc_max_threads()
+    return {"value": m.n_dofs * steps / dt, "unit": "DoFs/s", "cores": cores, "kind": "port",
+            "sample": "%d applies of 3D Q%d FP64 r=%d (%d DoFs), OpenMP over 8 colors" % (steps, args.degree, r, m.n_dofs)}, dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--refine", type=int, default=6, help="global refinements of the cube per GPU (r=6: 16,974,593 DoFs)")
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--dim", type=int, default=3)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--coloring", action="store_true", help="graph-colored scatter instead of FP64 atomics")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-refine", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "3D Q%d %s Laplace apply throughput" % (args.degree, "FP64" if args.dtype == "f64" else "FP32")
+    s = 8 if args.dtype == "f64" else 4
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, args.cpu_steps))
+        cb, sec = cpu_reference_run(args, steps, min(args.warmup, 2))
+        line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "DoFs/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": "bmop-cpu: 3D unit-cube variable-coefficient Laplace apply, FE_Q(%d), uniform mesh; CPU sample %s"
+                                       % (args.degree, cb["sample"])},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import dealii_cuda_b200 as mf
+    if args.gpus > 1 or world > 1:
+        from dealii_cuda_b200 import distributed as mfd
+        return mfd.bench_main(args, metric)
+
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = mf.Context(local_rank, stream)
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    mesh = mf.HyperCubeMesh(ctx, args.dim, args.degree, args.refine)
+    op = mf.LaplaceOperatorGpu(ctx, dtype, use_coloring=args.coloring)
+    op.reinit(mesh)
+    if args.variant:
+        op.set_variant(args.variant)
+    n = mesh.n_dofs
+    # device memory through torch (plumbing); vectors wrapped as GpuVectors
+    ta = torch.full((n,), 0.1, dtype=tdtype, device="cuda")
+    tb = torch.zeros((n,), dtype=tdtype, device="cuda")
+    va, vb = mf.GpuVector.wrap(ctx, ta), mf.GpuVector.wrap(ctx, tb)
+    pa, pb = ta.data_ptr(), tb.data_ptr()
+
+    def apply_steps(k):
+        nonlocal pa, pb
+        for _ in range(k):
+            pa, pb = pb, pa           # dst.swap(src)
+            op.vmult_ptr(pa, pb)      # vmult(dst, src)
+
+    # the raw loop is an un-normalised power iteration; restart from 0.1 every 50 steps so FP32 cannot
+    # overflow -- values do not influence timing (no data-dependent paths)
+    apply_steps(args.warmup)
+    torch.cuda.synchronize()
+    ta.fill_(0.1); tb.fill_(0.1)
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    op.enable_kernel_timing(True)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0.record()
+    apply_steps(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    kernel_ms, kernel_launches = op.kernel_time_ms()
+    op.enable_kernel_timing(False)
+    value = n * args.steps / (ms * 1e-3)
+
+    # end-to-end through the public host-buffer API: pinned host src -> H2D -> vmult -> D2H pinned dst
+    hs = torch.full((n,), 0.1, dtype=tdtype).pin_memory()
+    hd = torch.empty((n,), dtype=tdtype).pin_memory()
+    op.vmult_host(hd.numpy(), hs.numpy())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        op.vmult_host(hd.numpy(), hs.numpy())
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    e2e = {"value": n / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s, "d2h_bytes_per_step": n * s,
+           "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps}
+
+    peak, peak_src = measured_peaks()
+    alg_bytes = b_alg(args.degree, args.dim, s) * n
+    k_avg_ms = kernel_ms / max(1, kernel_launches) * op.cell_launches_per_vmult()
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "laplace cell kernel (variant %d)" % op.active_variant(), "kernel_ms": k_avg_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_dof": b_alg(args.degree, args.dim, s),
+                "whole_vmult_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(args, args.cpu_steps, 2)
+
+    line = {"metric": metric, "value": value, "unit": "DoFs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": "bmop: %dD unit-cube [-1,1]^%d variable-coefficient Laplace apply, FE_Q(%d), refine_global(%d): "
+                                   "%d cells, %d DoFs, %s scatter; bmop.cu loop" % (args.dim, args.dim, args.degree, args.refine,
+                                                                                    mesh.n_cells, n, "colored" if args.coloring else "atomic"),
+                       "l2": "inputs larger than L2 (index + coefficient + 2 vectors = %.0f MB)" %
+                             ((mesh.n_cells * mesh.dofs_per_cell * (4 + s) + 2 * n * s) / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * op.launches_per_vmult(), "roofline": roofline,
+            "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

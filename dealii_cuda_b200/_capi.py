@@ -1,0 +1,137 @@
+"""ctypes binding of libmfgpu.so -- the C ABI declared in include/mfgpu.h.
+
+There is no CPU fallback: if the CUDA library has not been built, importing
+this module raises; if no CUDA device is usable, Context() raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmfgpu.so")
+
+F32, F64 = 0, 1
+SCATTER_ATOMIC, SCATTER_COLOR = 0, 1
+
+
+class MfgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mfgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class BoxDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("log2_cells", C.c_int * 3), ("origin", C.c_double * 3),
+                ("h", C.c_double), ("dirichlet_faces", C.c_uint32)]
+
+
+class MfDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("dtype", C.c_int), ("n_cells", C.c_uint32), ("n_dofs", C.c_uint32),
+                ("loc2glob", C.POINTER(C.c_uint32)), ("geometry", C.c_int), ("inv_jac", C.POINTER(C.c_double)),
+                ("JxW", C.POINTER(C.c_double)), ("quadrature_points", C.POINTER(C.c_double)), ("scatter", C.c_int),
+                ("n_colors", C.c_uint32), ("color_offsets", C.POINTER(C.c_uint32))]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libmfgpu.so is not built (%s). Run `python dealii_cuda_b200/build.py` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32p, dp, sz = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_size_t
+    pp = C.POINTER(C.c_void_p)
+    sig = {
+        "mfg_last_error": (C.c_char_p, []),
+        "mfg_version": (C.c_char_p, []),
+        "mfg_ctx_create": (C.c_int, [C.c_int, vp, pp]),
+        "mfg_ctx_destroy": (C.c_int, [vp]),
+        "mfg_ctx_set_stream": (C.c_int, [vp, vp]),
+        "mfg_ctx_synchronize": (C.c_int, [vp]),
+        "mfg_ctx_device_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz)]),
+        "mfg_vec_create": (C.c_int, [vp, C.c_int, sz, pp]),
+        "mfg_vec_wrap": (C.c_int, [vp, C.c_int, sz, vp, pp]),
+        "mfg_vec_destroy": (C.c_int, [vp]),
+        "mfg_vec_resize": (C.c_int, [vp, sz]),
+        "mfg_vec_size": (sz, [vp]),
+        "mfg_vec_dtype": (C.c_int, [vp]),
+        "mfg_vec_data": (vp, [vp]),
+        "mfg_vec_from_host": (C.c_int, [vp, vp, sz]),
+        "mfg_vec_to_host": (C.c_int, [vp, vp, sz]),
+        "mfg_vec_copy": (C.c_int, [vp, vp]),
+        "mfg_vec_swap": (C.c_int, [vp, vp]),
+        "mfg_vec_fill": (C.c_int, [vp, C.c_double]),
+        "mfg_vec_sadd": (C.c_int, [vp, C.c_double, C.c_double, vp]),
+        "mfg_vec_equ": (C.c_int, [vp, C.c_double, vp]),
+        "mfg_vec_scale": (C.c_int, [vp, vp]),
+        "mfg_vec_divide": (C.c_int, [vp, vp]),
+        "mfg_vec_invert": (C.c_int, [vp]),
+        "mfg_vec_scal": (C.c_int, [vp, C.c_double]),
+        "mfg_vec_dot": (C.c_int, [vp, vp, dp]),
+        "mfg_vec_add_and_dot": (C.c_int, [vp, C.c_double, vp, vp, dp]),
+        "mfg_vec_l2_norm": (C.c_int, [vp, dp]),
+        "mfg_vec_all_zero": (C.c_int, [vp, C.POINTER(C.c_int)]),
+        "mfg_vec_copy_with_indices": (C.c_int, [vp, vp, vp, vp, sz]),
+        "mfg_mesh_create_box": (C.c_int, [vp, C.POINTER(BoxDesc), pp]),
+        "mfg_mesh_hyper_cube": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, pp]),
+        "mfg_mesh_destroy": (C.c_int, [vp]),
+        "mfg_mesh_n_cells": (C.c_uint32, [vp]),
+        "mfg_mesh_n_dofs": (C.c_uint32, [vp]),
+        "mfg_mesh_dofs_per_cell": (C.c_uint32, [vp]),
+        "mfg_mesh_n_constrained": (C.c_uint32, [vp]),
+        "mfg_mesh_loc2glob_device": (vp, [vp]),
+        "mfg_mesh_constrained_device": (vp, [vp]),
+        "mfg_mesh_get_loc2glob": (C.c_int, [vp, u32p]),
+        "mfg_mesh_get_constrained": (C.c_int, [vp, u32p]),
+        "mfg_mesh_get_cell_coords": (C.c_int, [vp, u32p]),
+        "mfg_mesh_lattice_to_dof": (C.c_int, [vp, sz, u32p, u32p]),
+        "mfg_mesh_color_cells": (C.c_int, [vp, u32p, u32p]),
+        "mfg_mf_reinit": (C.c_int, [vp, C.POINTER(MfDesc), pp]),
+        "mfg_mf_reinit_from_mesh": (C.c_int, [vp, vp, C.c_int, C.c_int, pp]),
+        "mfg_mf_destroy": (C.c_int, [vp]),
+        "mfg_mf_n_dofs": (C.c_uint32, [vp]),
+        "mfg_mf_n_cells": (C.c_uint32, [vp]),
+        "mfg_mf_n_colors": (C.c_uint32, [vp]),
+        "mfg_mf_memory_consumption": (sz, [vp]),
+        "mfg_shape_info": (C.c_int, [C.c_int, dp, dp, dp, dp]),
+        "mfg_ch_create": (C.c_int, [vp, C.c_int, u32p, sz, u32p, sz, pp]),
+        "mfg_ch_create_from_mesh": (C.c_int, [vp, C.c_int, vp, pp]),
+        "mfg_ch_destroy": (C.c_int, [vp]),
+        "mfg_ch_n_constrained": (sz, [vp]),
+        "mfg_ch_set_constrained_values": (C.c_int, [vp, vp, C.c_double]),
+        "mfg_ch_save_constrained_values": (C.c_int, [vp, vp]),
+        "mfg_ch_save_constrained_values2": (C.c_int, [vp, vp, vp]),
+        "mfg_ch_load_constrained_values": (C.c_int, [vp, vp]),
+        "mfg_ch_load_and_add_constrained_values": (C.c_int, [vp, vp, vp]),
+        "mfg_ch_copy_edge_values": (C.c_int, [vp, vp, vp]),
+        "mfg_laplace_create": (C.c_int, [vp, vp, C.c_int, C.c_int, pp]),
+        "mfg_laplace_create_from_arrays": (C.c_int, [vp, vp, vp, dp, pp]),
+        "mfg_laplace_set_coefficient": (C.c_int, [vp, dp]),
+        "mfg_laplace_destroy": (C.c_int, [vp]),
+        "mfg_laplace_m": (C.c_uint32, [vp]),
+        "mfg_laplace_set_variant": (C.c_int, [vp, C.c_int]),
+        "mfg_laplace_vmult": (C.c_int, [vp, vp, vp]),
+        "mfg_laplace_vmult_add": (C.c_int, [vp, vp, vp]),
+        "mfg_laplace_vmult_ptr": (C.c_int, [vp, vp, vp]),
+        "mfg_laplace_vmult_add_ptr": (C.c_int, [vp, vp, vp]),
+        "mfg_laplace_vmult_host": (C.c_int, [vp, vp, vp]),
+        "mfg_laplace_compute_diagonal": (C.c_int, [vp]),
+        "mfg_laplace_get_diagonal_inverse": (C.c_int, [vp, pp]),
+        "mfg_laplace_memory_consumption": (sz, [vp]),
+        "mfg_laplace_launches_per_vmult": (C.c_int, [vp]),
+        "mfg_laplace_enable_kernel_timing": (C.c_int, [vp, C.c_int]),
+        "mfg_laplace_kernel_time_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int)]),
+        "mfg_laplace_active_variant": (C.c_int, [vp]),
+        "mfg_laplace_bmop": (C.c_int, [vp, vp, vp, C.c_int, C.c_double, C.POINTER(C.c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)  # AttributeError if a declared symbol is missing
+        f.restype = res
+        f.argtypes = args
+    return L, sorted(sig)
+
+
+lib, DECLARED_SYMBOLS = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise MfgError(rc, lib.mfg_last_error().decode(errors="replace"))

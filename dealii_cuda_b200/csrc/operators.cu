@@ -1,0 +1,473 @@
+// operators.cu -- MatrixFreeGpu / ConstraintHandlerGpu / LaplaceOperatorGpu host logic.
+#include <algorithm>
+#include <numeric>
+#include "kernels_v0.cuh"
+#include "operators.cuh"
+
+namespace mfg {
+
+namespace {
+
+// idx_out[s][i] = l2g[perm ? perm[s] : s][i] | (constrained ? bit31 : 0)
+__global__ void build_kernel_indices(const uint32_t *l2g, const uint32_t *__restrict__ perm,
+                                     const uint8_t *__restrict__ cflag, uint32_t npc, size_t total, uint32_t *out)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint32_t s = (uint32_t)(t / npc), i = (uint32_t)(t % npc);
+  const uint32_t c = perm ? perm[s] : s;
+  uint32_t g = l2g[(size_t)c * npc + i] & ~CONSTRAINED_BIT;
+  if (cflag && cflag[g]) g |= CONSTRAINED_BIT;
+  out[t] = g;
+}
+
+__global__ void flags_from_list(const uint32_t *list, size_t n, uint8_t *flag)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[list[i]] = 1;
+}
+
+__global__ void pack_bits(const uint8_t *flag, size_t n, uint32_t *bits)
+{
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 32 >= n) return;
+  uint32_t v = 0;
+  for (int b = 0; b < 32; ++b) { const size_t i = w * 32 + b; if (i < n && flag[i]) v |= 1u << b; }
+  bits[w] = v;
+}
+
+struct QuadData { double xq[9], wq[9]; };
+
+// cw[s][q] = a(x_q) * (1/h)^2 * h^dim * w_q, a = 1/(0.05 + 2|x|^2)
+// (LocalCoeffOp + Coefficient::value, laplace_operator_gpu.h:191-211, poisson_common.h:146-158)
+template <typename Number>
+__global__ void eval_cw_uniform(MortonMap mm, int dim, int n, uint32_t npc, uint32_t n_cells, const uint32_t *__restrict__ perm,
+                                double ox, double oy, double oz, double h, QuadData qd, Number *__restrict__ cw)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n_cells * npc) return;
+  const uint32_t s = (uint32_t)(t / npc), q = (uint32_t)(t % npc);
+  const uint32_t c = perm ? perm[s] : s;
+  uint32_t x[3]; mm.decode(c, x);
+  const int qi[3] = {(int)(q % n), (int)((q / n) % n), (int)(q / (n * n))};
+  const double o[3] = {ox, oy, oz};
+  double r2 = 0, w = 1;
+  for (int d = 0; d < dim; ++d)
+    {
+      const double X = o[d] + h * ((double)x[d] + qd.xq[qi[d]]);
+      r2 += X * X; w *= h * qd.wq[qi[d]];
+    }
+  const double a = 1.0 / (0.05 + 2.0 * r2);
+  cw[t] = (Number)(a * w / (h * h));
+}
+
+struct DiagTables { double val[81], grad[81]; };
+
+// compute_diagonal (laplace_operator_gpu.h:355-421): diag_i = sum_q cw_q sum_d (dphi_i/dxi_d (q))^2.
+// The reference applies the cell operator to every local unit vector
+// (O(n^(2dim+1)) per cell); the same number is obtained here in closed form.
+template <typename Number>
+__global__ void diagonal_kernel(const uint32_t *__restrict__ idx, const Number *__restrict__ cw, int dim, int n, uint32_t npc,
+                                uint32_t n_cells, DiagTables tb, Number *__restrict__ diag)
+{
+  const uint32_t cell = blockIdx.x;
+  if (cell >= n_cells) return;
+  for (uint32_t i = threadIdx.x; i < npc; i += blockDim.x)
+    {
+      const uint32_t g = idx[(size_t)cell * npc + i];
+      if (g & CONSTRAINED_BIT) continue;
+      const int ii[3] = {(int)(i % n), (int)((i / n) % n), (int)(i / (n * n))};
+      double acc = 0;
+      for (uint32_t q = 0; q < npc; ++q)
+        {
+          const int qi[3] = {(int)(q % n), (int)((q / n) % n), (int)(q / (n * n))};
+          double v[3], g2[3];
+          for (int d = 0; d < dim; ++d)
+            {
+              const double a = tb.val[ii[d] * n + qi[d]], b = tb.grad[ii[d] * n + qi[d]];
+              v[d] = a * a; g2[d] = b * b;
+            }
+          double s;
+          if (dim == 2) s = g2[0] * v[1] + v[0] * g2[1];
+          else s = g2[0] * v[1] * v[2] + v[0] * g2[1] * v[2] + v[0] * v[1] * g2[2];
+          acc += s * (double)cw[(size_t)cell * npc + q];
+        }
+      atomicAdd(diag + g, (Number)acc);
+    }
+}
+
+template <typename Number> __global__ void k_set(Number *v, const uint32_t *list, size_t n, Number val)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[list[i]] = val;
+}
+// save_constrained_dofs_kernel (constraint_handler_gpu.cu:233-244)
+template <typename Number> __global__ void k_save(Number *in, Number *tmp_in, const uint32_t *list, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t c = list[i]; tmp_in[i] = in[c]; in[c] = 0; }
+}
+// (constraint_handler_gpu.cu:248-262)
+template <typename Number> __global__ void k_save2(const Number *out, Number *in, Number *tmp_out, Number *tmp_in, const uint32_t *list, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t c = list[i]; tmp_out[i] = out[c]; tmp_in[i] = in[c]; in[c] = 0; }
+}
+// (constraint_handler_gpu.cu:264-274)
+template <typename Number> __global__ void k_load(Number *in, const Number *tmp_in, const uint32_t *list, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) in[list[i]] = tmp_in[i];
+}
+// (constraint_handler_gpu.cu:277-289)
+template <typename Number> __global__ void k_load_add(Number *out, Number *in, const Number *tmp_out, const Number *tmp_in, const uint32_t *list, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t c = list[i]; out[c] = tmp_out[i] + tmp_in[i]; in[c] = tmp_in[i]; }
+}
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// coloring
+// ---------------------------------------------------------------------------
+// On the structured box every cell conflicts only with its 3^dim-1 neighbours,
+// so the 2^dim parity classes are a valid (and minimal) coloring.  The
+// reference calls deal.II's GraphColoring::make_graph_coloring (coloring.cc:20-33);
+// any valid coloring yields the same operator up to summation order.
+void mesh_parity_colors(const mfg_mesh *m, std::vector<uint32_t> &color_of_cell, uint32_t &n_colors)
+{
+  std::vector<uint32_t> xyz((size_t)m->n_cells * 3);
+  mesh_cell_coords(m, xyz.data());
+  color_of_cell.resize(m->n_cells);
+  uint32_t used[8] = {0};
+  for (uint32_t c = 0; c < m->n_cells; ++c)
+    {
+      uint32_t col = 0;
+      for (int d = 0; d < m->dim; ++d) col |= (xyz[3 * (size_t)c + d] & 1u) << d;
+      color_of_cell[c] = col; used[col] = 1;
+    }
+  // compress to the colors actually used (e.g. a single cell -> one color)
+  uint32_t remap[8], k = 0;
+  for (int i = 0; i < 8; ++i) remap[i] = used[i] ? k++ : 0;
+  for (auto &c : color_of_cell) c = remap[c];
+  n_colors = k;
+}
+
+// ---------------------------------------------------------------------------
+// MatrixFreeGpu
+// ---------------------------------------------------------------------------
+mfg_mf *mf_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter)
+{
+  std::unique_ptr<mfg_mf> mf(new mfg_mf);
+  mf->ctx = ctx; mf->dim = mesh->dim; mf->p = mesh->p; mf->n = mesh->n; mf->npc = mesh->npc;
+  mf->n_cells = mesh->n_cells; mf->n_dofs = mesh->n_dofs; mf->dt = dt; mf->scatter = scatter; mf->fe = mesh->fe; mf->mesh = mesh;
+  cudaStream_t s = ctx->stream;
+  if (scatter == MFG_SCATTER_COLOR)
+    {
+      std::vector<uint32_t> col; uint32_t ncol = 0;
+      mesh_parity_colors(mesh, col, ncol);
+      std::vector<uint32_t> perm(mesh->n_cells);
+      std::iota(perm.begin(), perm.end(), 0u);
+      std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return col[a] < col[b]; });
+      mf->color_offsets.assign(ncol + 1, 0);
+      for (uint32_t c = 0; c < mesh->n_cells; ++c) mf->color_offsets[col[c] + 1]++;
+      for (uint32_t k = 0; k < ncol; ++k) mf->color_offsets[k + 1] += mf->color_offsets[k];
+      mf->cell_perm.upload(perm.data(), perm.size(), s);
+    }
+  else mf->color_offsets = {0u, mesh->n_cells};
+  const size_t total = (size_t)mesh->n_cells * mesh->npc;
+  mf->idx.alloc(total);
+  build_kernel_indices<<<nblk(total), 256, 0, s>>>(mesh->l2g.p, mf->cell_perm.p, mesh->cflag.p, mesh->npc, total, mf->idx.p);
+  MFG_CUDA_LAST();
+  return mf.release();
+}
+
+mfg_mf *mf_from_desc(mfg_ctx *ctx, const mfg_mf_desc &d)
+{
+  MFG_REQUIRE(d.dim == 2 || d.dim == 3, "dim must be 2 or 3");
+  MFG_REQUIRE(d.degree >= 1 && d.degree <= 8, "degree must be in 1..8");
+  MFG_REQUIRE(d.loc2glob != nullptr && d.inv_jac != nullptr, "loc2glob and inv_jac are required");
+  if (d.geometry != MFG_GEOM_UNIFORM) throw Error(MFG_ERR_UNSUPPORTED, "only MFG_GEOM_UNIFORM is implemented");
+  MFG_REQUIRE(d.n_dofs < CONSTRAINED_BIT, "n_dofs must be < 2^31");
+  std::unique_ptr<mfg_mf> mf(new mfg_mf);
+  mf->ctx = ctx; mf->dim = d.dim; mf->p = d.degree; mf->n = d.degree + 1; mf->npc = ipow(mf->n, mf->dim);
+  mf->n_cells = d.n_cells; mf->n_dofs = d.n_dofs; mf->dt = d.dtype; mf->scatter = d.scatter; mf->fe = make_fe_data(d.degree);
+  if (d.scatter == MFG_SCATTER_COLOR)
+    {
+      MFG_REQUIRE(d.n_colors >= 1 && d.color_offsets != nullptr, "coloring needs n_colors and color_offsets");
+      mf->color_offsets.assign(d.color_offsets, d.color_offsets + d.n_colors + 1);
+      MFG_REQUIRE(mf->color_offsets.front() == 0 && mf->color_offsets.back() == d.n_cells, "color_offsets must span all cells");
+    }
+  else mf->color_offsets = {0u, d.n_cells};
+  const size_t total = (size_t)d.n_cells * mf->npc;
+  for (size_t i = 0; i < total; ++i) MFG_REQUIRE(d.loc2glob[i] < d.n_dofs, "loc2glob entry out of range");
+  mf->idx.upload(d.loc2glob, total, ctx->stream);
+  // merged geometry factor inv_jac^2 * JxW_q  (fee_gpu.cuh:228,270: grad = J0*g ; submit = grad*J0*jxw)
+  mf->geom_host.resize(total);
+  for (uint32_t c = 0; c < d.n_cells; ++c)
+    for (uint32_t q = 0; q < mf->npc; ++q)
+      {
+        double jxw;
+        if (d.JxW) jxw = d.JxW[(size_t)c * mf->npc + q];
+        else
+          {
+            jxw = 1.0;
+            uint32_t qq = q;
+            for (int k = 0; k < mf->dim; ++k) { jxw *= mf->fe.qwts[qq % mf->n] / d.inv_jac[c]; qq /= mf->n; }
+          }
+        mf->geom_host[(size_t)c * mf->npc + q] = d.inv_jac[c] * d.inv_jac[c] * jxw;
+      }
+  if (d.quadrature_points) mf->qpoints_host.assign(d.quadrature_points, d.quadrature_points + total * mf->dim);
+  return mf.release();
+}
+
+// ---------------------------------------------------------------------------
+// ConstraintHandlerGpu
+// ---------------------------------------------------------------------------
+mfg_ch *ch_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *constrained_host, size_t nc, const uint32_t *edge_host, size_t ne)
+{
+  std::unique_ptr<mfg_ch> ch(new mfg_ch);
+  ch->ctx = ctx; ch->dt = dt;
+  ch->constrained.upload(constrained_host, nc, ctx->stream);
+  ch->edge.upload(edge_host, ne, ctx->stream);
+  const size_t es = dt == MFG_F64 ? 8 : 4;
+  ch->tmp_src.alloc(nc * es); ch->tmp_dst.alloc(nc * es);
+  return ch.release();
+}
+
+mfg_ch *ch_from_mesh(mfg_ctx *ctx, mfg_dtype dt, const mfg_mesh *mesh)
+{
+  std::unique_ptr<mfg_ch> ch(new mfg_ch);
+  ch->ctx = ctx; ch->dt = dt;
+  ch->constrained.alloc(mesh->n_constrained);
+  if (mesh->n_constrained)
+    MFG_CUDA(cudaMemcpyAsync(ch->constrained.p, mesh->constrained.p, mesh->n_constrained * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  const size_t es = dt == MFG_F64 ? 8 : 4;
+  ch->tmp_src.alloc(mesh->n_constrained * es); ch->tmp_dst.alloc(mesh->n_constrained * es);
+  return ch.release();
+}
+
+#define CH_DISPATCH(ch, CALL)                               \
+  do {                                                      \
+    if ((ch)->dt == MFG_F64) { typedef double T; CALL; }    \
+    else { typedef float T; CALL; }                         \
+    MFG_CUDA_LAST();                                        \
+  } while (0)
+
+static void ch_check(const mfg_ch *ch, const mfg_vec *v) { MFG_REQUIRE(v->dt == ch->dt, "vector dtype differs from constraint handler dtype"); }
+
+void ch_set(mfg_ch *ch, mfg_vec *v, double val)
+{
+  ch_check(ch, v); const size_t n = ch->n(); if (!n) return;
+  CH_DISPATCH(ch, (k_set<T><<<nblk(n, 128), 128, 0, ch->ctx->stream>>>((T *)v->p, ch->constrained.p, n, (T)val)));
+}
+void ch_save(mfg_ch *ch, mfg_vec *v)
+{
+  ch_check(ch, v); const size_t n = ch->n(); if (!n) return;
+  CH_DISPATCH(ch, (k_save<T><<<nblk(n, 128), 128, 0, ch->ctx->stream>>>((T *)v->p, (T *)ch->tmp_src.p, ch->constrained.p, n)));
+}
+void ch_save2(mfg_ch *ch, const mfg_vec *v1, mfg_vec *v2)
+{
+  ch_check(ch, v1); ch_check(ch, v2); const size_t n = ch->n(); if (!n) return;
+  CH_DISPATCH(ch, (k_save2<T><<<nblk(n, 128), 128, 0, ch->ctx->stream>>>((const T *)v1->p, (T *)v2->p, (T *)ch->tmp_dst.p, (T *)ch->tmp_src.p, ch->constrained.p, n)));
+}
+void ch_load(mfg_ch *ch, mfg_vec *v)
+{
+  ch_check(ch, v); const size_t n = ch->n(); if (!n) return;
+  CH_DISPATCH(ch, (k_load<T><<<nblk(n, 128), 128, 0, ch->ctx->stream>>>((T *)v->p, (const T *)ch->tmp_src.p, ch->constrained.p, n)));
+}
+void ch_load_and_add(mfg_ch *ch, mfg_vec *v1, mfg_vec *v2)
+{
+  ch_check(ch, v1); ch_check(ch, v2); const size_t n = ch->n(); if (!n) return;
+  CH_DISPATCH(ch, (k_load_add<T><<<nblk(n, 128), 128, 0, ch->ctx->stream>>>((T *)v1->p, (T *)v2->p, (const T *)ch->tmp_dst.p, (const T *)ch->tmp_src.p, ch->constrained.p, n)));
+}
+
+// ---------------------------------------------------------------------------
+// LaplaceOperatorGpu
+// ---------------------------------------------------------------------------
+static void laplace_finish_setup(mfg_laplace *op, const uint8_t *cflag_dev)
+{
+  // bitmask of constrained DoFs for the fused `dst = 0 / dst[c] = src[c]` pass
+  const size_t nd = op->mf->n_dofs;
+  op->cbits.alloc((nd + 31) / 32);
+  pack_bits<<<nblk((nd + 31) / 32), 256, 0, op->ctx->stream>>>(cflag_dev, nd, op->cbits.p);
+  MFG_CUDA_LAST();
+}
+
+mfg_laplace *laplace_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter)
+{
+  std::unique_ptr<mfg_laplace> op(new mfg_laplace);
+  op->ctx = ctx;
+  op->mf = mf_from_mesh(ctx, mesh, dt, scatter); op->owns_mf = true;
+  op->ch = ch_from_mesh(ctx, dt, mesh); op->owns_ch = true;
+  laplace_finish_setup(op.get(), mesh->cflag.p);
+  // evaluate_coefficient (laplace_operator_gpu.h:204-211) fused with the geometry factors
+  const size_t total = (size_t)mesh->n_cells * mesh->npc;
+  const size_t es = dt == MFG_F64 ? 8 : 4;
+  op->cw.alloc(total * es);
+  QuadData qd;
+  for (int i = 0; i < mesh->n; ++i) { qd.xq[i] = mesh->fe.qpts[i]; qd.wq[i] = mesh->fe.qwts[i]; }
+  MortonMap mm; mm.dim = mesh->dim; for (int d = 0; d < 3; ++d) mm.lg[d] = mesh->lg[d];
+  if (dt == MFG_F64)
+    eval_cw_uniform<double><<<nblk(total), 256, 0, ctx->stream>>>(mm, mesh->dim, mesh->n, mesh->npc, mesh->n_cells, op->mf->cell_perm.p,
+                                                                  mesh->origin[0], mesh->origin[1], mesh->origin[2], mesh->h, qd, (double *)op->cw.p);
+  else
+    eval_cw_uniform<float><<<nblk(total), 256, 0, ctx->stream>>>(mm, mesh->dim, mesh->n, mesh->npc, mesh->n_cells, op->mf->cell_perm.p,
+                                                                 mesh->origin[0], mesh->origin[1], mesh->origin[2], mesh->h, qd, (float *)op->cw.p);
+  MFG_CUDA_LAST();
+  MFG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return op.release();
+}
+
+mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const double *coef_host)
+{
+  MFG_REQUIRE(mf && ch && coef_host, "mf, ch and coefficient are required");
+  MFG_REQUIRE(mf->dt == ch->dt, "mf and ch dtypes differ");
+  MFG_REQUIRE(!mf->geom_host.empty() || mf->mesh, "mf has no geometry");
+  std::unique_ptr<mfg_laplace> op(new mfg_laplace);
+  op->ctx = ctx; op->mf = mf; op->ch = ch;
+  // mark constrained DoFs in the kernel index array (in place)
+  DevBuf<uint8_t> flag(mf->n_dofs);
+  MFG_CUDA(cudaMemsetAsync(flag.p, 0, mf->n_dofs, ctx->stream));
+  if (ch->n()) { flags_from_list<<<nblk(ch->n()), 256, 0, ctx->stream>>>(ch->constrained.p, ch->n(), flag.p); MFG_CUDA_LAST(); }
+  const size_t total = (size_t)mf->n_cells * mf->npc;
+  build_kernel_indices<<<nblk(total), 256, 0, ctx->stream>>>(mf->idx.p, nullptr, flag.p, mf->npc, total, mf->idx.p);
+  MFG_CUDA_LAST();
+  laplace_finish_setup(op.get(), flag.p);
+  op->cw.alloc(total * (mf->dt == MFG_F64 ? 8 : 4));
+  laplace_set_coefficient_host(op.get(), coef_host);
+  MFG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return op.release();
+}
+
+// coefficient values a(x_q), [n_cells][npc], ORIGINAL cell order -> merged weights in kernel cell order
+void laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host)
+{
+  const mfg_mf *mf = op->mf;
+  const size_t total = (size_t)mf->n_cells * mf->npc;
+  std::vector<uint32_t> perm;
+  if (mf->cell_perm.n) { perm.resize(mf->n_cells); mf->cell_perm.download(perm.data(), op->ctx->stream); }
+  std::vector<double> geom_q;  // uniform mesh: same factors for every cell
+  if (mf->geom_host.empty())
+    {
+      geom_q.resize(mf->npc);
+      const double h = mf->mesh->h;
+      for (uint32_t q = 0; q < mf->npc; ++q)
+        {
+          double w = 1.0; uint32_t qq = q;
+          for (int k = 0; k < mf->dim; ++k) { w *= h * mf->fe.qwts[qq % mf->n]; qq /= mf->n; }
+          geom_q[q] = w / (h * h);
+        }
+    }
+  std::vector<double> merged(total);
+  for (uint32_t s = 0; s < mf->n_cells; ++s)
+    {
+      const uint32_t c = perm.empty() ? s : perm[s];
+      for (uint32_t q = 0; q < mf->npc; ++q)
+        merged[(size_t)s * mf->npc + q] = coef_host[(size_t)c * mf->npc + q] * (geom_q.empty() ? mf->geom_host[(size_t)c * mf->npc + q] : geom_q[q]);
+    }
+  if (mf->dt == MFG_F64)
+    MFG_CUDA(cudaMemcpyAsync(op->cw.p, merged.data(), total * 8, cudaMemcpyHostToDevice, op->ctx->stream));
+  else
+    {
+      std::vector<float> mf32(merged.begin(), merged.end());
+      MFG_CUDA(cudaMemcpyAsync(op->cw.p, mf32.data(), total * 4, cudaMemcpyHostToDevice, op->ctx->stream));
+      MFG_CUDA(cudaStreamSynchronize(op->ctx->stream));
+    }
+  MFG_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  op->diagonal_is_available = false;
+}
+
+int laplace_launches_per_vmult(const mfg_laplace *op) { return 1 + (int)op->mf->n_colors(); }
+
+template <typename Number>
+static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add)
+{
+  const mfg_mf *mf = op->mf;
+  cudaStream_t  s  = op->ctx->stream;
+  // vmult: dst = 0 (laplace_operator_gpu.h:221) fused with dst[c] = src[c];
+  // vmult_add: dst[c] += src[c]  (load_and_add_constrained_values, :302)
+  if (!add)
+    {
+      const unsigned nb = (unsigned)std::min<size_t>((mf->n_dofs + 1023) / 1024, (size_t)op->ctx->sm_count * 16);
+      vmult_prepare<Number><<<std::max(1u, nb), 256, 0, s>>>(dst, src, op->cbits.p, mf->n_dofs);
+      MFG_CUDA_LAST();
+    }
+  else if (op->ch->n())
+    {
+      constrained_add<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n());
+      MFG_CUDA_LAST();
+    }
+  // cell_loop (matrix_free_gpu.h:369-380): one launch per color
+  const bool atomic = mf->scatter == MFG_SCATTER_ATOMIC;
+  for (uint32_t c = 0; c + 1 < mf->color_offsets.size(); ++c)
+    {
+      if (op->timing)
+        {
+          if (op->ev_used + 2 > op->ev.size())
+            for (int k = 0; k < 2; ++k) { cudaEvent_t e; MFG_CUDA(cudaEventCreate(&e)); op->ev.push_back(e); }
+          MFG_CUDA(cudaEventRecord(op->ev[op->ev_used], s));
+        }
+      if (mf->dim == 2)
+        launch_laplace_v0_dim<2, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->color_offsets[c],
+                                         mf->color_offsets[c + 1], mf->fe.val.data(), mf->fe.colloc.data(), s);
+      else
+        launch_laplace_v0_dim<3, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->color_offsets[c],
+                                         mf->color_offsets[c + 1], mf->fe.val.data(), mf->fe.colloc.data(), s);
+      if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
+    }
+}
+
+int laplace_active_variant(const mfg_laplace *op) { return op->variant == 0 ? 1 : op->variant; }
+
+void laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches)
+{
+  MFG_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  double tot = 0;
+  for (size_t i = 0; i + 1 < op->ev_used; i += 2)
+    {
+      float ms = 0;
+      MFG_CUDA(cudaEventElapsedTime(&ms, op->ev[i], op->ev[i + 1]));
+      tot += ms;
+    }
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = (int)(op->ev_used / 2);
+  op->ev_used = 0;
+}
+
+void laplace_vmult(mfg_laplace *op, void *dst, const void *src, bool add)
+{
+  MFG_REQUIRE(dst != src, "vmult: dst and src must not alias");
+  if (op->mf->dt == MFG_F64) vmult_impl<double>(op, (double *)dst, (const double *)src, add);
+  else vmult_impl<float>(op, (float *)dst, (const float *)src, add);
+}
+
+void laplace_compute_diagonal(mfg_laplace *op)
+{
+  const mfg_mf *mf = op->mf;
+  cudaStream_t  s  = op->ctx->stream;
+  if (!op->inv_diag)
+    {
+      op->inv_diag.reset(new mfg_vec);
+      op->inv_diag->ctx = op->ctx; op->inv_diag->dt = mf->dt; op->inv_diag->n = op->inv_diag->cap = mf->n_dofs;
+      MFG_CUDA(cudaMalloc(&op->inv_diag->p, (size_t)mf->n_dofs * op->inv_diag->esize()));
+    }
+  vec_fill(op->inv_diag.get(), 0.0);
+  DiagTables tb;
+  for (int i = 0; i < mf->n * mf->n; ++i) { tb.val[i] = mf->fe.val[i]; tb.grad[i] = mf->fe.grad[i]; }
+  const int threads = (int)std::min<uint32_t>(256, ((mf->npc + 31) / 32) * 32);
+  if (mf->dt == MFG_F64)
+    diagonal_kernel<double><<<mf->n_cells, threads, 0, s>>>(mf->idx.p, (const double *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (double *)op->inv_diag->p);
+  else
+    diagonal_kernel<float><<<mf->n_cells, threads, 0, s>>>(mf->idx.p, (const float *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (float *)op->inv_diag->p);
+  MFG_CUDA_LAST();
+  // constraint_handler.set_constrained_values(inv_diag, 1.0); inv_diag.invert()  (:416-418)
+  ch_set(op->ch, op->inv_diag.get(), 1.0);
+  vec_invert(op->inv_diag.get());
+  op->diagonal_is_available = true;
+}
+
+}  // namespace mfg

@@ -1,0 +1,81 @@
+// operators.cuh -- host objects behind the C ABI handles:
+//   mfg_mf      <-> MatrixFreeGpu<dim,Number>          (matrix_free_gpu.h:81-229)
+//   mfg_ch      <-> ConstraintHandlerGpu<Number>       (constraint_handler_gpu.h:13-59)
+//   mfg_laplace <-> LaplaceOperatorGpu<dim,p,Number>   (laplace_operator_gpu.h:35-96)
+#pragma once
+#include <memory>
+#include "common.cuh"
+#include "fe_data.h"
+#include "mesh.cuh"
+#include "vector.cuh"
+
+struct mfg_mf
+{
+  mfg_ctx    *ctx = nullptr;
+  int         dim = 0, p = 0, n = 0;
+  uint32_t    npc = 0, n_cells = 0, n_dofs = 0;
+  mfg_dtype   dt = MFG_F64;
+  mfg_scatter scatter = MFG_SCATTER_ATOMIC;
+  std::vector<uint32_t> color_offsets;  // [n_colors+1] over the (color-sorted) cell order
+  mfg::DevBuf<uint32_t> idx;            // [n_cells][npc] lexicographic; bit 31 = constrained DoF
+  mfg::DevBuf<uint32_t> cell_perm;      // sorted position -> original cell (empty: identity)
+  mfg::FEData1D         fe;
+  // geometry: either a uniform mesh (origin/h/Morton map) or host arrays from the explicit description
+  const mfg_mesh       *mesh = nullptr;         // not owned
+  std::vector<double>   geom_host;              // [n_cells][npc]: inv_jac^2 * JxW_q, original cell order
+  std::vector<double>   qpoints_host;           // optional [n_cells][npc][dim]
+  uint32_t              n_colors() const { return (uint32_t)color_offsets.size() - 1; }
+};
+
+struct mfg_ch
+{
+  mfg_ctx  *ctx = nullptr;
+  mfg_dtype dt = MFG_F64;
+  mfg::DevBuf<uint32_t> constrained, edge;
+  mfg::DevBuf<uint8_t>  tmp_src, tmp_dst;  // constrained_values_src/dst (constraint_handler_gpu.h:51-52)
+  size_t                n() const { return constrained.n; }
+};
+
+struct mfg_laplace
+{
+  mfg_ctx *ctx = nullptr;
+  mfg_mf  *mf = nullptr;
+  mfg_ch  *ch = nullptr;
+  bool     owns_mf = false, owns_ch = false;
+  mfg::DevBuf<uint8_t>  cw;     // [n_cells][npc] merged weights, operator dtype, color-sorted cell order
+  mfg::DevBuf<uint32_t> cbits;  // bit i = DoF i constrained
+  std::unique_ptr<mfg_vec> inv_diag;
+  bool     diagonal_is_available = false;
+  int      variant = 0;
+  mfg::DevBuf<uint8_t> host_stage_src, host_stage_dst;  // device staging for vmult_host
+  // optional per-launch timing of the cell kernel (bench.py roofline figure)
+  bool                     timing = false;
+  std::vector<cudaEvent_t> ev;        // pairs (start, stop)
+  size_t                   ev_used = 0;
+};
+
+namespace mfg {
+mfg_mesh *build_box_mesh(mfg_ctx *ctx, const mfg_box_desc &d);
+void      mesh_lattice_to_dof(const mfg_mesh *m, size_t npts, const uint32_t *xyz_host, uint32_t *out_host);
+void      mesh_cell_coords(const mfg_mesh *m, uint32_t *out_host);
+void      mesh_parity_colors(const mfg_mesh *m, std::vector<uint32_t> &color_of_cell, uint32_t &n_colors);
+
+mfg_mf *mf_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter);
+mfg_mf *mf_from_desc(mfg_ctx *ctx, const mfg_mf_desc &d);
+mfg_ch *ch_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *constrained_host, size_t nc, const uint32_t *edge_host, size_t ne);
+mfg_ch *ch_from_mesh(mfg_ctx *ctx, mfg_dtype dt, const mfg_mesh *mesh);
+void    ch_set(mfg_ch *ch, mfg_vec *v, double val);
+void    ch_save(mfg_ch *ch, mfg_vec *v);
+void    ch_save2(mfg_ch *ch, const mfg_vec *v1, mfg_vec *v2);
+void    ch_load(mfg_ch *ch, mfg_vec *v);
+void    ch_load_and_add(mfg_ch *ch, mfg_vec *v1, mfg_vec *v2);
+
+mfg_laplace *laplace_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter);
+mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const double *coef_host);
+void         laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host);
+void         laplace_vmult(mfg_laplace *op, void *dst, const void *src, bool add);
+void         laplace_compute_diagonal(mfg_laplace *op);
+int          laplace_launches_per_vmult(const mfg_laplace *op);
+int          laplace_active_variant(const mfg_laplace *op);
+void         laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches);
+}  // namespace mfg

@@ -1,0 +1,214 @@
+/*
+ * mfgpu.h -- C ABI of the B200-native matrix-free engine (libmfgpu.so).
+ *
+ * The reference (kalj/dealii-cuda) has no FFI boundary: its operator API is a
+ * set of C++ templates on top of deal.II.  This header is the boundary a
+ * maintainer binds instead; every entry point names the reference interface it
+ * replaces (file:line relative to the reference tree).  The header-only C++
+ * facade in include/dealii_cuda_b200/ re-creates the reference's class names
+ * (GpuVector, MatrixFreeGpu, ConstraintHandlerGpu, LaplaceOperatorGpu, ...) on
+ * top of these calls.
+ *
+ * Conventions: opaque handles; every call returns 0 on success or a negative
+ * mfg_status; mfg_last_error() returns a thread-local message (the reference
+ * throws dealii::ExcMessage from CUDA_CHECK_SUCCESS, cuda_utils.cuh:15-23).
+ * All work is enqueued on the context's CUDA stream; only calls documented as
+ * "blocking" synchronise.  There is NO CPU fallback: if no CUDA device is
+ * usable, mfg_ctx_create fails.
+ */
+#ifndef MFGPU_H
+#define MFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mfg_status
+{
+  MFG_OK             = 0,
+  MFG_ERR_INVALID    = -1, /* bad argument / unsupported configuration */
+  MFG_ERR_CUDA       = -2, /* CUDA runtime error (message has file:line) */
+  MFG_ERR_NOMEM      = -3,
+  MFG_ERR_UNSUPPORTED = -4
+} mfg_status;
+
+typedef enum mfg_dtype { MFG_F32 = 0, MFG_F64 = 1 } mfg_dtype;
+
+/* scatter strategy of the cell loop (reference: -DMATRIX_FREE_COLOR vs atomics,
+ * laplace_operator_gpu.h:132-136, fee_gpu.cuh:358-361) */
+typedef enum mfg_scatter { MFG_SCATTER_ATOMIC = 0, MFG_SCATTER_COLOR = 1 } mfg_scatter;
+
+typedef struct mfg_ctx     mfg_ctx;
+typedef struct mfg_vec     mfg_vec;     /* GpuVector<Number>            gpu_vec.h:22-176 */
+typedef struct mfg_mesh    mfg_mesh;    /* Triangulation+DoFHandler+ConstraintMatrix substitute */
+typedef struct mfg_mf      mfg_mf;      /* MatrixFreeGpu<dim,Number>    matrix_free_gpu.h:81-229 */
+typedef struct mfg_ch      mfg_ch;      /* ConstraintHandlerGpu<Number> constraint_handler_gpu.h:13-59 */
+typedef struct mfg_laplace mfg_laplace; /* LaplaceOperatorGpu<dim,p,Number> laplace_operator_gpu.h:35-96 */
+
+const char *mfg_last_error(void);
+const char *mfg_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL
+ * for the legacy default stream (what the reference uses everywhere). */
+int mfg_ctx_create(int device, void *stream, mfg_ctx **out);
+int mfg_ctx_destroy(mfg_ctx *ctx);
+int mfg_ctx_set_stream(mfg_ctx *ctx, void *stream);
+int mfg_ctx_synchronize(mfg_ctx *ctx); /* blocking; timer() in timing.cu:10-17 */
+int mfg_ctx_device_info(mfg_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
+
+/* ---- GpuVector ---------------------------------------------------------- */
+/* gpu_vec.h / gpu_vec.cu.  n elements of dtype; create zero-fills like
+ * GpuVector(unsigned) (gpu_vec.cu:33-37); resize does not (gpu_vec.cu:185-196). */
+int mfg_vec_create(mfg_ctx *ctx, mfg_dtype dt, size_t n, mfg_vec **out);
+int mfg_vec_wrap(mfg_ctx *ctx, mfg_dtype dt, size_t n, void *device_ptr, mfg_vec **out); /* non-owning view */
+int mfg_vec_destroy(mfg_vec *v);
+int mfg_vec_resize(mfg_vec *v, size_t n);
+size_t mfg_vec_size(const mfg_vec *v);
+mfg_dtype mfg_vec_dtype(const mfg_vec *v);
+void *mfg_vec_data(mfg_vec *v);                                   /* getData()/getDataRO() */
+int mfg_vec_from_host(mfg_vec *v, const void *host, size_t n);    /* fromHost, blocking */
+int mfg_vec_to_host(const mfg_vec *v, void *host, size_t n);      /* copyToHost, blocking */
+int mfg_vec_copy(mfg_vec *dst, const mfg_vec *src);               /* operator=(GpuVector), converts f32<->f64 */
+int mfg_vec_swap(mfg_vec *a, mfg_vec *b);                         /* swap, gpu_vec.h:164-172 */
+int mfg_vec_fill(mfg_vec *v, double a);                           /* operator=(Number)  gpu_vec.cu:373-381 */
+int mfg_vec_sadd(mfg_vec *v, double s, double a, const mfg_vec *x);  /* v = s*v + a*x   gpu_vec.cu:306-313 */
+int mfg_vec_equ(mfg_vec *v, double a, const mfg_vec *x);          /* v = a*x            gpu_vec.cu:345-351 */
+int mfg_vec_scale(mfg_vec *v, const mfg_vec *x);                  /* v *= x (pointwise) gpu_vec.cu:317-322 */
+int mfg_vec_divide(mfg_vec *v, const mfg_vec *x);                 /* v /= x (pointwise) gpu_vec.cu:325-331 */
+int mfg_vec_invert(mfg_vec *v);                                   /* v = 1/v            gpu_vec.cu:333-340 */
+int mfg_vec_scal(mfg_vec *v, double a);                           /* v *= a             gpu_vec.cu:356-362 */
+int mfg_vec_dot(const mfg_vec *a, const mfg_vec *b, double *out); /* operator*, blocking gpu_vec.cu:541-558 */
+int mfg_vec_add_and_dot(mfg_vec *v, double a, const mfg_vec *x, const mfg_vec *w, double *out); /* v+=a*x; return v.w  gpu_vec.cu:567-617 */
+int mfg_vec_l2_norm(const mfg_vec *v, double *out);               /* gpu_vec.cu:366-369 */
+int mfg_vec_all_zero(const mfg_vec *v, int *out);                 /* gpu_vec.cu:511-527 */
+/* dst[dst_idx[i]] = src[src_idx[i]]  (device index arrays) gpu_vec.cu:624-644 */
+int mfg_vec_copy_with_indices(mfg_vec *dst, const mfg_vec *src, const uint32_t *dst_idx, const uint32_t *src_idx, size_t n);
+
+/* ---- mesh / DoF substrate ------------------------------------------------ */
+/* What the reference obtains from deal.II (GridGenerator::hyper_cube +
+ * refine_global, DoFHandler::distribute_dofs, interpolate_boundary_values;
+ * bmop.cu:111-132, poisson_common.h:58-72, bmop_common.h:108-120), built on
+ * the device.  Cells are ordered along the Morton curve (deal.II's order after
+ * global refinement), DoFs are numbered first-touch in hierarchic order
+ * (vertices, lines, quads, hex) exactly like DoFHandler::distribute_dofs. */
+typedef struct mfg_box_desc
+{
+  int      dim;            /* 2 or 3 */
+  int      degree;         /* FE_Q degree 1..8 */
+  int      log2_cells[3];  /* cells per direction = 2^log2_cells[d] */
+  double   origin[3];      /* lower corner */
+  double   h;              /* cell edge length */
+  uint32_t dirichlet_faces;/* bit f set: face f (x0,x1,y0,y1,z0,z1) carries homogeneous Dirichlet data */
+} mfg_box_desc;
+
+int mfg_mesh_create_box(mfg_ctx *ctx, const mfg_box_desc *desc, mfg_mesh **out);
+/* hyper_cube(left,right)^dim refined n_refine times, Dirichlet on the whole boundary */
+int mfg_mesh_hyper_cube(mfg_ctx *ctx, int dim, int degree, int n_refine, double left, double right, mfg_mesh **out);
+int mfg_mesh_destroy(mfg_mesh *m);
+uint32_t mfg_mesh_n_cells(const mfg_mesh *m);
+uint32_t mfg_mesh_n_dofs(const mfg_mesh *m);
+uint32_t mfg_mesh_dofs_per_cell(const mfg_mesh *m);
+uint32_t mfg_mesh_n_constrained(const mfg_mesh *m);
+/* device pointers (valid until mfg_mesh_destroy) */
+const uint32_t *mfg_mesh_loc2glob_device(const mfg_mesh *m);     /* [n_cells][(p+1)^dim] lexicographic */
+const uint32_t *mfg_mesh_constrained_device(const mfg_mesh *m);  /* ascending */
+/* blocking copies to host */
+int mfg_mesh_get_loc2glob(const mfg_mesh *m, uint32_t *host);
+int mfg_mesh_get_constrained(const mfg_mesh *m, uint32_t *host);
+int mfg_mesh_get_cell_coords(const mfg_mesh *m, uint32_t *host /* [n_cells][3] */);
+/* global DoF index of lattice points (x,y,z in 0..p*N_d), host arrays, blocking */
+int mfg_mesh_lattice_to_dof(const mfg_mesh *m, size_t n, const uint32_t *lattice_xyz, uint32_t *dof);
+/* graph coloring of the cells (coloring.cc:20-33): color_of_cell[n_cells] to host; returns n_colors in *n_colors */
+int mfg_mesh_color_cells(const mfg_mesh *m, uint32_t *color_of_cell, uint32_t *n_colors);
+
+/* ---- MatrixFreeGpu ------------------------------------------------------- */
+/* Explicit-array description: what ReinitHelper extracts from deal.II
+ * (matrix_free_gpu.cu:283-339) -- this is the call a deal.II-based caller makes. */
+typedef enum mfg_geometry
+{
+  MFG_GEOM_UNIFORM = 0, /* -DMATRIX_FREE_UNIFORM_MESH: scalar J^-1[0][0] per cell (matrix_free_gpu.cu:332-334) */
+  MFG_GEOM_GENERAL = 1  /* full J^-1 per quadrature point (not yet supported) */
+} mfg_geometry;
+
+typedef struct mfg_mf_desc
+{
+  int             dim, degree;
+  mfg_dtype       dtype;
+  uint32_t        n_cells, n_dofs;
+  const uint32_t *loc2glob;        /* host, [n_cells][(p+1)^dim], lexicographic, unpadded */
+  mfg_geometry    geometry;
+  const double   *inv_jac;         /* host, UNIFORM: [n_cells] */
+  const double   *JxW;             /* host, [n_cells][(p+1)^dim] or NULL: then JxW = inv_jac^-dim * w_q */
+  const double   *quadrature_points; /* host, [n_cells][(p+1)^dim][dim] (for evaluate_on_cells) or NULL */
+  mfg_scatter     scatter;
+  uint32_t        n_colors;        /* COLOR: cells must be sorted by color */
+  const uint32_t *color_offsets;   /* COLOR: [n_colors+1] */
+} mfg_mf_desc;
+
+int mfg_mf_reinit(mfg_ctx *ctx, const mfg_mf_desc *desc, mfg_mf **out);              /* MatrixFreeGpu::reinit matrix_free_gpu.cu:448-563 */
+int mfg_mf_reinit_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter, mfg_mf **out);
+int mfg_mf_destroy(mfg_mf *mf);                                                       /* MatrixFreeGpu::free matrix_free_gpu.cu:566-596 */
+uint32_t mfg_mf_n_dofs(const mfg_mf *mf);
+uint32_t mfg_mf_n_cells(const mfg_mf *mf);
+uint32_t mfg_mf_n_colors(const mfg_mf *mf);
+size_t mfg_mf_memory_consumption(const mfg_mf *mf);                                   /* matrix_free_gpu.h:437-459 */
+/* shape tables handed to the kernels: [i*n+q] = phi_i(x_q), phi_i'(x_q) (matrix_free_gpu.cu:502-513) */
+int mfg_shape_info(int degree, double *shape_values, double *shape_gradients, double *q_points, double *q_weights);
+
+/* ---- ConstraintHandlerGpu ------------------------------------------------ */
+int mfg_ch_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *constrained_host, size_t n_constrained,
+                  const uint32_t *edge_host, size_t n_edge, mfg_ch **out);          /* reinit constraint_handler_gpu.cu:69-123 */
+int mfg_ch_create_from_mesh(mfg_ctx *ctx, mfg_dtype dt, const mfg_mesh *mesh, mfg_ch **out);
+int mfg_ch_destroy(mfg_ch *ch);
+size_t mfg_ch_n_constrained(const mfg_ch *ch);
+int mfg_ch_set_constrained_values(mfg_ch *ch, mfg_vec *v, double val);               /* :127-137 */
+int mfg_ch_save_constrained_values(mfg_ch *ch, mfg_vec *v);                          /* :140-150 */
+int mfg_ch_save_constrained_values2(mfg_ch *ch, const mfg_vec *v1, mfg_vec *v2);     /* :153-166 */
+int mfg_ch_load_constrained_values(mfg_ch *ch, mfg_vec *v);                          /* :168-178 */
+int mfg_ch_load_and_add_constrained_values(mfg_ch *ch, mfg_vec *v1, mfg_vec *v2);    /* :181-194 */
+int mfg_ch_copy_edge_values(mfg_ch *ch, mfg_vec *dst, const mfg_vec *src);           /* :196-200 */
+
+/* ---- LaplaceOperatorGpu --------------------------------------------------- */
+/* reinit(dof_handler, constraints) laplace_operator_gpu.h:120-151.  The
+ * coefficient 1/(0.05+2|x|^2) (poisson_common.h:146-158) is evaluated on the
+ * device at the Gauss points (evaluate_coefficient, :204-211).  */
+int mfg_laplace_create(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter, mfg_laplace **out);
+/* explicit arrays: mf (from mfg_mf_reinit), constraint handler, and coefficient
+ * values at quadrature points [n_cells][(p+1)^dim] (host, double). The operator
+ * takes ownership of neither mf nor ch. */
+int mfg_laplace_create_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const double *coefficient_host, mfg_laplace **out);
+/* replace the coefficient: a(x_q) at quadrature points, host, [n_cells][(p+1)^dim], cells in mesh / descriptor order */
+int mfg_laplace_set_coefficient(mfg_laplace *op, const double *coefficient_host);
+int mfg_laplace_destroy(mfg_laplace *op);                                            /* clear() :110-117 */
+uint32_t mfg_laplace_m(const mfg_laplace *op);                                       /* m()/n() :52-53 */
+/* kernel variant: 0 = auto, otherwise a variant id; for A/B measurements */
+int mfg_laplace_set_variant(mfg_laplace *op, int variant);
+int mfg_laplace_vmult(mfg_laplace *op, mfg_vec *dst, const mfg_vec *src);            /* :216-223 (Tvmult identical) */
+int mfg_laplace_vmult_add(mfg_laplace *op, mfg_vec *dst, const mfg_vec *src);        /* :286-303 */
+/* raw device pointers (dtype of the operator), for callers that own their memory */
+int mfg_laplace_vmult_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev);
+int mfg_laplace_vmult_add_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev);
+/* host buffers: H2D copy of src, vmult, D2H copy of dst; blocking */
+int mfg_laplace_vmult_host(mfg_laplace *op, void *dst_host, const void *src_host);
+int mfg_laplace_compute_diagonal(mfg_laplace *op);                                   /* :405-421 */
+int mfg_laplace_get_diagonal_inverse(mfg_laplace *op, mfg_vec **out);                /* :423-429, borrowed */
+size_t mfg_laplace_memory_consumption(const mfg_laplace *op);                        /* :434-445 */
+/* number of kernel launches one vmult enqueues (for bench.py's gpu_launches) */
+int mfg_laplace_launches_per_vmult(const mfg_laplace *op);
+/* per-kernel device timing for the roofline figure: when enabled every cell-kernel launch is bracketed by
+ * CUDA events on the context stream; kernel_time_ms (blocking) returns and resets the accumulated time. */
+int mfg_laplace_enable_kernel_timing(mfg_laplace *op, int on);
+int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launches);
+int mfg_laplace_active_variant(const mfg_laplace *op);
+/* bmop loop (bmop.cu:135-153): dst=init; k times {swap; vmult}; result left in *dst.
+ * Returns device milliseconds measured with CUDA events on the context stream. */
+int mfg_laplace_bmop(mfg_laplace *op, mfg_vec *dst, mfg_vec *src, int k, double init, float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFGPU_H */

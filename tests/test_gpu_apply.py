@@ -1,0 +1,300 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(ctypes binding of include/mfgpu.h), against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): DoF maps / constraint lists bit-exact; operator
+output within 1e-12 relative (FP64) or 1e-5 (FP32)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.oracle import OracleMesh, sm64  # noqa: E402  (checker only)
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def max_rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+MESH_CASES = [(2, 1, 1), (2, 2, 1), (2, 4, 2), (2, 3, 3), (2, 8, 2), (2, 5, 0), (3, 1, 1), (3, 1, 3), (3, 2, 2), (3, 3, 2),
+              (3, 4, 1), (3, 4, 2), (3, 4, 3), (3, 5, 1), (3, 6, 1), (3, 7, 1), (3, 8, 1), (3, 4, 0)]
+
+
+@pytest.mark.parametrize("dim,p,r", MESH_CASES)
+def test_dof_map_and_constraints_bit_exact(ctx, dim, p, r):
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(dim, p, r)
+    m = mf.HyperCubeMesh(ctx, dim, p, r)
+    assert (m.n_cells, m.n_dofs, m.n_constrained) == (o.n_cells, o.n_dofs, o.n_constrained)
+    assert np.array_equal(m.loc2glob(), o.loc2glob)
+    assert np.array_equal(m.constrained_dofs(), o.constrained)
+    assert np.array_equal(m.cell_coords(), o.cell_coords)
+    # lattice lookup agrees with the oracle's DoF -> lattice table
+    lat = o.dof_lattice
+    assert np.array_equal(m.lattice_to_dof(lat), np.arange(o.n_dofs, dtype=np.uint32))
+
+
+def test_shape_info_matches_oracle():
+    import dealii_cuda_b200 as mf
+    from oracle.oracle import shape_1d
+    for p in range(1, 9):
+        val, grad, xq, wq = mf.shape_info(p)
+        oval, ograd, _, oxq, owq = shape_1d(p)
+        assert np.allclose(val, oval, rtol=0, atol=1e-15)
+        assert np.allclose(grad, ograd, rtol=0, atol=2e-13)
+        assert np.allclose(xq, oxq, rtol=0, atol=1e-16) and np.allclose(wq, owq, rtol=0, atol=1e-16)
+
+
+APPLY_CASES = [(2, p, 3) for p in range(1, 9)] + [(3, p, 2) for p in range(1, 9)] + [(3, 4, 3), (3, 4, 0), (2, 4, 0), (3, 1, 4), (2, 1, 6)]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("coloring", [False, True])
+@pytest.mark.parametrize("dim,p,r", APPLY_CASES)
+def test_vmult_matches_oracle(ctx, dim, p, r, coloring, dtype):
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(dim, p, r)
+    m = mf.HyperCubeMesh(ctx, dim, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, dtype, use_coloring=coloring)
+    op.reinit(m)
+    assert op.m() == o.n_dofs
+    u = sm64(1, o.n_dofs)
+    src = mf.GpuVector.from_numpy(ctx, u.astype(dtype))
+    dst = mf.GpuVector(ctx, o.n_dofs, dtype)
+    dst.fill(123.0)  # vmult must overwrite
+    op.vmult(dst, src)
+    got = dst.toVector()
+    want = o.vmult(u.astype(dtype).astype(np.float64))
+    assert rel_err(got, want) <= TOL[dtype]
+    assert max_rel_err(got, want) <= 4 * TOL[dtype]
+    # constrained rows are the identity, bit-exact; src is left untouched bit-exactly
+    con = o.constrained
+    assert np.array_equal(got[con], u.astype(dtype)[con])
+    assert np.array_equal(src.toVector(), u.astype(dtype))
+
+
+def test_golden_fixtures(ctx):
+    import dealii_cuda_b200 as mf
+    for c in json.load(open(os.path.join(GOLD, "apply_cases.json"))):
+        g = np.load(os.path.join(GOLD, c["file"]))
+        m = mf.HyperCubeMesh(ctx, c["dim"], c["p"], c["r"], c["left"], c["right"])
+        assert np.array_equal(m.loc2glob(), g["loc2glob"])
+        assert np.array_equal(m.constrained_dofs(), g["constrained"])
+        op = mf.LaplaceOperatorGpu(ctx, np.float64)
+        op.reinit(m)
+        src = mf.GpuVector.from_numpy(ctx, sm64(c["seed"], m.n_dofs))
+        dst = mf.GpuVector(ctx, m.n_dofs)
+        op.vmult(dst, src)
+        assert rel_err(dst.toVector(), g["Au"]) <= 1e-12
+        # bmop loop, 3 applications from dst = 0.1
+        a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs)
+        op.bmop(a, b, 3, 0.1)
+        assert rel_err(a.toVector(), g["bmop3"]) <= 1e-12
+        op.compute_diagonal()
+        assert rel_err(op.get_diagonal_inverse().toVector(), g["inv_diag"]) <= 1e-12
+
+
+@pytest.mark.parametrize("dim,p,r", [(3, 4, 2), (2, 4, 3)])
+def test_bmop_100_applications(ctx, dim, p, r):
+    """bmop.cu:135-153: the raw loop grows like lambda_max^100 -> relative comparison."""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(dim, p, r)
+    want = o.bmop(100)
+    m = mf.HyperCubeMesh(ctx, dim, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(m)
+    a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs)
+    ms = op.bmop(a, b, 100, 0.1)
+    assert ms > 0
+    got = a.toVector()
+    assert np.all(np.isfinite(got))
+    assert rel_err(got, want) <= 1e-11  # 100 applications accumulate ~sqrt(100) roundoff
+    assert max_rel_err(got, want) <= 1e-11
+
+
+def test_bmop_fp32_renormalised(ctx):
+    """FP32 overflows in the raw 100-loop: compare a per-step renormalised loop, k = 15."""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, 4, 2)
+    m = mf.HyperCubeMesh(ctx, 3, 4, 2)
+    op = mf.LaplaceOperatorGpu(ctx, np.float32)
+    op.reinit(m)
+    u = np.full(o.n_dofs, 0.1)
+    d, s = mf.GpuVector(ctx, o.n_dofs, np.float32), mf.GpuVector(ctx, o.n_dofs, np.float32)
+    d.fill(0.1)
+    for _ in range(15):
+        d.swap(s)
+        op.vmult(d, s)
+        d *= 1.0 / d.l2_norm()
+        u = o.vmult(u); u /= np.linalg.norm(u)
+    assert rel_err(d.toVector(), u) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_vmult_add_and_constrained_rows(ctx, dtype):
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, 3, 2)
+    m = mf.HyperCubeMesh(ctx, 3, 3, 2)
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(m)
+    u, d0 = sm64(5, o.n_dofs).astype(dtype), sm64(6, o.n_dofs).astype(dtype)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector.from_numpy(ctx, d0)
+    op.vmult_add(dst, src)
+    got = dst.toVector()
+    want = o.vmult_add(d0.astype(np.float64), u.astype(np.float64))
+    assert rel_err(got, want) <= TOL[dtype]
+    con = o.constrained
+    assert np.array_equal(got[con], (d0[con] + u[con]).astype(dtype))
+
+
+def test_inverse_diagonal(ctx):
+    import dealii_cuda_b200 as mf
+    for dim, p, r in [(2, 4, 2), (3, 2, 2), (3, 4, 1), (3, 7, 1)]:
+        o = OracleMesh(dim, p, r)
+        m = mf.HyperCubeMesh(ctx, dim, p, r)
+        op = mf.LaplaceOperatorGpu(ctx, np.float64)
+        op.reinit(m)
+        with pytest.raises(mf.MfgError):
+            op.get_diagonal_inverse()  # Assert(diagonal_is_available)
+        op.compute_diagonal()
+        assert rel_err(op.get_diagonal_inverse().toVector(), o.inverse_diagonal()) <= 1e-12
+
+
+def test_explicit_array_reinit_matches_mesh_path(ctx):
+    """mfg_mf_reinit (what a deal.II based caller uses): loc2glob / inv_jac / coefficient as host arrays."""
+    import dealii_cuda_b200 as mf
+    for dim, p, r, coloring in [(3, 4, 2, False), (2, 3, 3, False), (3, 2, 2, True)]:
+        o = OracleMesh(dim, p, r)
+        l2g, coef = o.loc2glob.copy(), o.coefficient.copy()
+        arrays = dict(dim=dim, degree=p, n_dofs=o.n_dofs, loc2glob=l2g, inv_jac=np.full(o.n_cells, (1 << r) / 2.0))
+        if coloring:
+            cc = o.cell_coords
+            col = (cc[:, 0] & 1) + 2 * (cc[:, 1] & 1) + 4 * (cc[:, 2] & 1)
+            order = np.argsort(col, kind="stable")
+            arrays["loc2glob"], coef = l2g[order], coef[order]
+            arrays["color_offsets"] = np.concatenate(([0], np.cumsum(np.bincount(col, minlength=1 << dim)))).astype(np.uint32)
+        data = mf.MatrixFreeGpu(ctx, np.float64)
+        data.reinit(arrays, use_coloring=coloring)
+        assert data.n_dofs == o.n_dofs and data.n_cells_tot == o.n_cells
+        ch = mf.ConstraintHandlerGpu(ctx, np.float64)
+        ch.reinit(o.constrained, o.n_dofs)
+        op = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=coloring)
+        op.reinit(data, ch, coefficient=coef)
+        u = sm64(9, o.n_dofs)
+        src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs)
+        op.vmult(dst, src)
+        assert rel_err(dst.toVector(), o.vmult(u)) <= 1e-12
+
+
+def test_vmult_host_and_ptr_entry_points(ctx):
+    import torch
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, 4, 2)
+    m = mf.HyperCubeMesh(ctx, 3, 4, 2)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(m)
+    u = sm64(4, o.n_dofs)
+    want = o.vmult(u)
+    out = np.empty_like(u)
+    op.vmult_host(out, u)
+    assert rel_err(out, want) <= 1e-12
+    ts = torch.from_numpy(u).cuda(); td = torch.empty_like(ts)
+    torch.cuda.synchronize()
+    op.vmult_ptr(td.data_ptr(), ts.data_ptr())
+    ctx.synchronize()
+    assert rel_err(td.cpu().numpy(), want) <= 1e-12
+    # wrapped torch tensors as GpuVectors
+    vs, vd = mf.GpuVector.wrap(ctx, ts), mf.GpuVector.wrap(ctx, td)
+    td.zero_(); torch.cuda.synchronize()
+    op.vmult(vd, vs); ctx.synchronize()
+    assert rel_err(td.cpu().numpy(), want) <= 1e-12
+
+
+def test_error_behaviour(ctx):
+    import dealii_cuda_b200 as mf
+    with pytest.raises(mf.MfgError):
+        mf.HyperCubeMesh(ctx, 3, 9, 1)  # degree > 8
+    with pytest.raises(mf.MfgError):
+        mf.HyperCubeMesh(ctx, 4, 2, 1)
+    m = mf.HyperCubeMesh(ctx, 3, 2, 1)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(m)
+    a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs + 1)
+    with pytest.raises(mf.MfgError):
+        op.vmult(a, b)  # size mismatch
+    with pytest.raises(mf.MfgError):
+        op.vmult(a, a)  # aliasing
+    c = mf.GpuVector(ctx, m.n_dofs, np.float32)
+    with pytest.raises(mf.MfgError):
+        op.vmult(a, c)  # dtype mismatch
+
+
+# ---- full-size cases: size-independent properties + direct comparison with the threaded oracle ----
+
+@pytest.mark.parametrize("coloring", [False, True])
+def test_full_size_r5_against_threaded_oracle(ctx, coloring):
+    """BASELINE configs[0]: 3D Q4 r=5, 2,146,689 DoFs."""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, 4, 5)
+    assert o.n_dofs == 2146689 and o.n_constrained == 98306
+    m = mf.HyperCubeMesh(ctx, 3, 4, 5)
+    assert np.array_equal(m.loc2glob(), o.loc2glob)
+    assert np.array_equal(m.constrained_dofs(), o.constrained)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=coloring)
+    op.reinit(m)
+    u = sm64(1, o.n_dofs)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs)
+    op.vmult(dst, src)
+    want = o.vmult(u, threaded=True)
+    assert rel_err(dst.toVector(), want) <= 1e-12
+
+
+def test_full_size_r6_properties(ctx):
+    """1-GPU roofline point: 3D Q4 r=6, 16,974,593 DoFs.  Symmetry, linearity, constrained-row identity,
+    atomic == colored, A*1 = 0 on rows away from the boundary for a constant coefficient."""
+    import dealii_cuda_b200 as mf
+    m = mf.HyperCubeMesh(ctx, 3, 4, 6)
+    assert m.n_dofs == 16974593 and m.n_cells == 262144 and m.n_constrained == 257 ** 3 - 255 ** 3
+    n = m.n_dofs
+    opa = mf.LaplaceOperatorGpu(ctx, np.float64); opa.reinit(m)
+    opc = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=True); opc.reinit(m)
+    u, v = sm64(1, n), sm64(2, n)
+    gu, gv = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector.from_numpy(ctx, v)
+    Au, Av, Auc, w = (mf.GpuVector(ctx, n) for _ in range(4))
+    opa.vmult(Au, gu); opa.vmult(Av, gv); opc.vmult(Auc, gu)
+    # symmetry
+    vAu, uAv = gv.dot(Au), gu.dot(Av)
+    assert abs(vAu - uAv) <= 1e-11 * abs(vAu)
+    # atomics vs coloring: same operator up to summation order
+    d = Au.toVector() - Auc.toVector()
+    assert np.linalg.norm(d) <= 1e-13 * Au.l2_norm()
+    # linearity: A(2u - 3v) = 2Au - 3Av
+    w.equ(2.0, gu); w.add(-3.0, gv)
+    Aw = mf.GpuVector(ctx, n); opa.vmult(Aw, w)
+    Aw.add(-2.0, Au); Aw.add(3.0, Av)
+    assert Aw.l2_norm() <= 1e-12 * Au.l2_norm()
+    # constrained rows: identity, bit-exact
+    con = m.constrained_dofs()
+    assert np.array_equal(Au.toVector()[con], u[con])
+    # constant coefficient: A*1 vanishes on all rows whose cells touch no constrained DoF
+    opa.set_coefficient(np.ones((m.n_cells, m.dofs_per_cell)))
+    one = mf.GpuVector(ctx, n); one.fill(1.0)
+    opa.vmult(Au, one)
+    r = Au.toVector()
+    l2g = m.loc2glob()
+    cflag = np.zeros(n, dtype=bool); cflag[con] = True
+    touched = np.zeros(n, dtype=bool)
+    bcells = cflag[l2g].any(axis=1)
+    touched[l2g[bcells].ravel()] = True
+    assert np.abs(r[~touched]).max() <= 1e-12
