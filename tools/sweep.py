@@ -42,7 +42,10 @@ if __name__ == "__main__":
     ctx = mf.Context(0, torch.cuda.current_stream().cuda_stream)
     cases = []
     if args.quick:
-        cases = [(3, 4, 5, np.float64, False), (3, 4, 6, np.float64, False), (3, 4, 6, np.float64, True), (3, 4, 6, np.float32, False)]
+        cases = [(3, 4, 5, np.float64, False, 1), (3, 4, 5, np.float64, False, 2), (3, 4, 6, np.float64, False, 1), (3, 4, 6, np.float64, False, 2),
+                 (3, 4, 6, np.float64, False, 3), (3, 4, 6, np.float64, True, 1), (3, 4, 6, np.float32, False, 1), (3, 4, 6, np.float32, False, 2),
+                 (3, 3, 6, np.float64, False, 1), (3, 3, 6, np.float64, False, 2), (3, 2, 7, np.float64, False, 1), (3, 2, 7, np.float64, False, 2),
+                 (3, 1, 7, np.float64, False, 1), (3, 1, 7, np.float64, False, 2), (3, 4, 7, np.float64, False, 2)]
     else:
         # ~16M+ DoFs per case where memory allows
         r3 = {1: 8, 2: 7, 3: 6, 4: 6, 5: 6, 6: 5, 7: 5, 8: 5}
@@ -55,6 +58,6 @@ if __name__ == "__main__":
         cases += [(3, 4, 5, np.float64, False), (3, 4, 5, np.float64, True), (3, 4, 6, np.float64, True), (3, 4, 7, np.float64, False)]
     for c in cases:
         try:
-            print(json.dumps(run(ctx, *c, steps=args.steps)), flush=True)
+            print(json.dumps(run(ctx, *c[:5], steps=args.steps, variant=(c[5] if len(c) > 5 else 0))), flush=True)
         except Exception as e:  # keep sweeping
             print(json.dumps(dict(case=str(c), error=str(e))), flush=True)
