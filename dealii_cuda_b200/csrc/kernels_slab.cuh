@@ -11,9 +11,12 @@
 //   * a warp owns floor(32/n) cells and never synchronises with other warps (__syncwarp only);
 //   * every transpose uses its own padded address function (tools/slab_layout_search.py) that is
 //     bank-conflict free for both the writing and the reading layout;
-//   * the merged coefficient block of a group (contiguous in global memory) is copied to shared memory
-//     with cp.async one group ahead, so it costs no registers and its latency is off the critical path;
-//   * a single transpose buffer per warp (phases separated by __syncwarp) keeps 12 warps per SM resident.
+//   * software pipeline with cp.async (the kernel is register-limited to 10-12 warps per SM, so latency
+//     is hidden inside each warp, not by occupancy): the DoF values of the NEXT group are gathered
+//     asynchronously (8-byte cp.async, zero-fill for constrained DoFs) behind the back half of the current
+//     group; the merged coefficient block of a group (contiguous in global memory, L2-prefetched one group
+//     ahead) is copied to shared memory with 16-byte cp.async behind the B phase; both share one buffer;
+//   * a single transpose buffer per warp (phases separated by __syncwarp).
 // Layouts (thread a of a cell, registers r):
 //   L  lexicographic staging order, entry e = 32 q + lane   (coalesced gather / scatter)
 //   A  S_xy: a = k, r = i + n j       B  S_yz: a = i, r = j + n k       C  S_xz: a = j, r = i + n k
@@ -62,9 +65,9 @@ template <int n, typename Number, int MINB_ = 0> struct SlabCfg
   static constexpr int     Q   = (GE + 31) / 32;  // staging instructions per lane
   static constexpr SlabStr LB = slab_str_LB<n, WB>(), AB = slab_str_AB<n, WB>(), AC = slab_str_AC<n, WB>();
   static constexpr int     BUF = ((cmax3(LB.SC, AB.SC, AC.SC) * CW + 3) / 4) * 4;  // elements of the transpose buffer
-  static constexpr int     WBUF = ((GE + 3) / 4) * 4;                               // elements of the coefficient buffer
-  static constexpr int     WPB = MINB_ == 2 ? 5 : 4;  // warps per block (variant 3: 2 blocks x 5 warps, up to 204 registers)
-  static constexpr size_t  SMEM = (size_t)WPB * (BUF + WBUF) * sizeof(Number);
+  static constexpr int     XBUF = (((LB.SC * CW > GE ? LB.SC * CW : GE) + 3) / 4) * 4;    // elements of the staging / coefficient buffer
+  static constexpr int     WPB = 4;  // warps per block (the register file is per SM sub-partition: 3 warps each -> 168 registers, 2 -> 255)
+  static constexpr size_t  SMEM = (size_t)WPB * (BUF + XBUF) * sizeof(Number);
   static constexpr int     MINB = MINB_ ? MINB_ : (n <= 4 ? 4 : 3);
   // cp.async chunk for the coefficient block of one group (GE*WB bytes, contiguous in global memory)
   static constexpr int     CHUNK = (GE * WB) % 16 == 0 ? 16 : 8;
@@ -86,6 +89,11 @@ template <int BYTES> __device__ __forceinline__ void cp_async(void *smem_dst, co
 {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(gsrc), "n"(BYTES) : "memory");
+}
+template <int BYTES> __device__ __forceinline__ void cp_async_zfill(void *smem_dst, const void *gsrc, int src_bytes)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(sa), "l"(gsrc), "n"(BYTES), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -118,78 +126,99 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
   constexpr SlabStr LB = Cfg::LB, AB = Cfg::AB, AC = Cfg::AC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  Number   *buf  = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * (Cfg::BUF + Cfg::WBUF);
-  Number   *bufW = buf + Cfg::BUF;  // merged coefficient of the current group, dense [c][i + n j + n^2 k]
+  Number   *buf  = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * (Cfg::BUF + Cfg::XBUF);
+  // X is time-shared: gathered DoF values of the NEXT group (staging layout LB) from the end of the
+  // quadrature phase until the B loads, then the merged coefficient block of the CURRENT group
+  // (dense [c][i + n j + n^2 k]) until the end of the quadrature phase.
+  Number   *X    = buf + Cfg::BUF;
   const int  c = lane / n, a = lane % n;
   const bool active = lane < NA;
   const uint32_t total_warps = gridDim.x * Cfg::WPB;
   const uint32_t g0 = blockIdx.x * Cfg::WPB + warp;
+  if (g0 >= n_groups) return;
 
-  // asynchronous copy of one group's coefficient block (cw is padded to whole groups)
-  auto prefetch_w = [&](uint32_t g) {
-    const char *gsrc = reinterpret_cast<const char *>(cw + (size_t)g * GE);
-    char       *sdst = reinterpret_cast<char *>(bufW);
-#pragma unroll
-    for (int ch = lane; ch < Cfg::NCHUNK; ch += 32) cp_async<Cfg::CHUNK>(sdst + ch * Cfg::CHUNK, gsrc + ch * Cfg::CHUNK);
-    cp_async_commit();
-  };
-  if (g0 < n_groups) prefetch_w(g0);
-
-  for (uint32_t g = g0; g < n_groups; g += total_warps)
-    {
-      const size_t   ebase = (size_t)g * GE;
-      const uint32_t cell0 = g * CW;
-      const bool     full  = cell0 + CW <= n_cells;
-      // ---- read_dof_values: coalesced gather in lexicographic order, staged to shared memory ----
+  // index row entries of group g owned by this lane (CONSTRAINED_BIT for padding / cells beyond the mesh)
+  auto load_ids = [&](uint32_t g, uint32_t (&ids)[Q]) {
+    const size_t   ebase = (size_t)g * GE;
+    const uint32_t cell0 = g * CW;
+    if (cell0 + CW <= n_cells)
       {
-        Number vals[Q];
-        if (full)
-          {
-#pragma unroll
-            for (int q = 0; q < Q; ++q)
-              {
-                const int e = 32 * q + lane;
-                uint32_t  id = CONSTRAINED_BIT;
-                if (q < Q - 1 || e < GE) id = __ldg(idx + ebase + e);
-                vals[q] = (id & CONSTRAINED_BIT) ? Number(0) : __ldg(src + id);
-              }
-          }
-        else
-          {
-#pragma unroll
-            for (int q = 0; q < Q; ++q)
-              {
-                const int  e  = 32 * q + lane;
-                const bool ok = e < GE && cell0 + e / NPC < n_cells;
-                const uint32_t id = ok ? __ldg(idx + ebase + e) : CONSTRAINED_BIT;
-                vals[q] = (id & CONSTRAINED_BIT) ? Number(0) : __ldg(src + id);
-              }
-          }
 #pragma unroll
         for (int q = 0; q < Q; ++q)
           {
             const int e = 32 * q + lane;
-            if (q < Q - 1 || e < GE) buf[slab_stage_addr<n>(LB, e)] = vals[q];
+            ids[q] = (q < Q - 1 || e < GE) ? __ldg(idx + ebase + e) : CONSTRAINED_BIT;
           }
       }
-      __syncwarp();
+    else
+      {
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+          {
+            const int e = 32 * q + lane;
+            ids[q] = (e < GE && cell0 + e / NPC < n_cells) ? __ldg(idx + ebase + e) : CONSTRAINED_BIT;
+          }
+      }
+  };
+  // read_dof_values, asynchronous: src[ids] -> X in staging layout; constrained entries are zero-filled
+  auto issue_gather = [&](const uint32_t (&ids)[Q]) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+      {
+        const int e = 32 * q + lane;
+        if (q < Q - 1 || e < GE)
+          {
+            const bool con = ids[q] & CONSTRAINED_BIT;
+            cp_async_zfill<sizeof(Number)>(X + slab_stage_addr<n>(LB, e), src + (con ? 0u : ids[q]), con ? 0 : (int)sizeof(Number));
+          }
+      }
+    cp_async_commit();
+  };
+  auto issue_w = [&](uint32_t g) {
+    const char *gsrc = reinterpret_cast<const char *>(cw + (size_t)g * GE);
+    char       *sdst = reinterpret_cast<char *>(X);
+#pragma unroll
+    for (int ch = lane; ch < Cfg::NCHUNK; ch += 32) cp_async<Cfg::CHUNK>(sdst + ch * Cfg::CHUNK, gsrc + ch * Cfg::CHUNK);
+    cp_async_commit();
+  };
+  auto prefetch_l2 = [&](uint32_t g) {  // index rows and coefficient block of a later group
+    const char *pi = reinterpret_cast<const char *>(idx + (size_t)g * GE);
+    const char *pw = reinterpret_cast<const char *>(cw + (size_t)g * GE);
+    for (int l = lane; l < (GE * 4 + 127) / 128; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + 128 * l));
+    for (int l = lane; l < (GE * Cfg::WB + 127) / 128; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + 128 * l));
+  };
+
+  {
+    uint32_t ids[Q];
+    load_ids(g0, ids);
+    issue_gather(ids);
+  }
+  const int bLB = slab_addr(LB, c, a, 0, 0), bAB_B = slab_addr(AB, c, a, 0, 0);
+  const int bAB_A = slab_addr(AB, c, 0, 0, a), bAC_A = slab_addr(AC, c, 0, 0, a), bAC_C = slab_addr(AC, c, 0, a, 0);
+
+  for (uint32_t g = g0; g < n_groups; g += total_warps)
+    {
+      const uint32_t gn       = g + total_warps;
+      const bool     has_next = gn < n_groups;
       Number G[NS], R[NS];
+      cp_async_wait_all();
+      __syncwarp();  // gathered values of this group are in X
       // ---- B = S_yz (a = i): N_y, N_z ----
-      const int bLB = slab_addr(LB, c, a, 0, 0), bAB_B = slab_addr(AB, c, a, 0, 0);
-      const int bAB_A = slab_addr(AB, c, 0, 0, a), bAC_A = slab_addr(AC, c, 0, 0, a), bAC_C = slab_addr(AC, c, 0, a, 0);
       if (active)
         {
 #pragma unroll
           for (int k = 0; k < n; ++k)
 #pragma unroll
-            for (int j = 0; j < n; ++j) G[j + n * k] = buf[bLB + LB.RJ * j + LB.RK * k];
+            for (int j = 0; j < n; ++j) G[j + n * k] = X[bLB + LB.RJ * j + LB.RK * k];
         }
       else
         {
 #pragma unroll
           for (int m = 0; m < NS; ++m) G[m] = 0;
         }
-      __syncwarp();  // all lanes hold their slab: the buffer may be overwritten
+      __syncwarp();  // X consumed
+      issue_w(g);    // coefficient block of this group (L2-prefetched one group ago) -> X
+      if (has_next) prefetch_l2(gn);
       slab_apply<n, 1, n, false>(sh.N, G);
       slab_apply<n, n, 1, false>(sh.N, G);
       if (active)
@@ -208,9 +237,9 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
 #pragma unroll
             for (int i = 0; i < n; ++i) G[i + n * j] = buf[bAB_A + i + AB.RJ * j];
         }
-      cp_async_wait_all();  // this lane's part of the coefficient block has landed ...
-      __syncwarp();         // ... and so has everybody else's; buf (AB) has been consumed
       slab_apply<n, 1, n, false>(sh.N, G);  // G = u at the quadrature points
+      cp_async_wait_all();  // this lane's part of the coefficient block has landed ...
+      __syncwarp();         // ... and everybody else's; buf (AB) has been consumed
       if (active)
         {
 #pragma unroll
@@ -219,7 +248,7 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
             for (int i = 0; i < n; ++i) buf[bAC_A + i + AC.RJ * j] = G[i + n * j];
         }
       {
-        const Number *wA = bufW + NPC * c + NS * a;  // W(c; i, j, k = a) at wA[i + n j]
+        const Number *wA = X + NPC * c + NS * a;  // W(c; i, j, k = a) at wA[i + n j]
         // x lines
 #pragma unroll
         for (int j = 0; j < n; ++j)
@@ -259,7 +288,7 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
       // ---- C = S_xz (a = j): quadrature phase z, streamed line by line; result replaces G in buf ----
       if (active)
         {
-          const Number *wC = bufW + NPC * c + n * a;  // W(c; i, j = a, k) at wC[i + n^2 k]
+          const Number *wC = X + NPC * c + n * a;  // W(c; i, j = a, k) at wC[i + n^2 k]
 #pragma unroll
           for (int i = 0; i < n; ++i)
             {
@@ -274,9 +303,10 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
               for (int k = 0; k < n; ++k) buf[bAC_C + i + AC.RK * k] = t[k];
             }
         }
-      __syncwarp();
-      // the coefficient buffer is free again: fetch the next group's block behind the rest of this group
-      if (g + total_warps < n_groups) prefetch_w(g + total_warps);
+      __syncwarp();  // X is free again
+      // index rows of the next group (L2 hits): in flight during the A phase below
+      uint32_t ids[Q];
+      if (has_next) load_ids(gn, ids);
       // ---- A: sum the three directions, N_x^T, N_y^T ----
       if (active)
         {
@@ -295,6 +325,8 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
 #pragma unroll
             for (int i = 0; i < n; ++i) buf[bAB_A + i + AB.RJ * j] = R[i + n * j];
         }
+      // asynchronous gather of the next group's DoF values behind the rest of this group
+      if (has_next) issue_gather(ids);
       __syncwarp();
       // ---- B: N_z^T ----
       if (active)
@@ -315,32 +347,36 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
         }
       __syncwarp();
       // ---- distribute_local_to_global: lexicographic order, red.add ----
-      if (full)
-        {
+      {
+        const size_t   ebase = (size_t)g * GE;
+        const uint32_t cell0 = g * CW;
+        if (cell0 + CW <= n_cells)
+          {
 #pragma unroll
-          for (int q = 0; q < Q; ++q)
-            {
-              const int e = 32 * q + lane;
-              if (q < Q - 1 || e < GE)
-                {
-                  const uint32_t id = __ldg(idx + ebase + e);
-                  if (!(id & CONSTRAINED_BIT)) red_add(dst + id, buf[slab_stage_addr<n>(LB, e)]);
-                }
-            }
-        }
-      else
-        {
+            for (int q = 0; q < Q; ++q)
+              {
+                const int e = 32 * q + lane;
+                if (q < Q - 1 || e < GE)
+                  {
+                    const uint32_t id = __ldg(idx + ebase + e);
+                    if (!(id & CONSTRAINED_BIT)) red_add(dst + id, buf[slab_stage_addr<n>(LB, e)]);
+                  }
+              }
+          }
+        else
+          {
 #pragma unroll
-          for (int q = 0; q < Q; ++q)
-            {
-              const int e = 32 * q + lane;
-              if (e < GE && cell0 + e / NPC < n_cells)
-                {
-                  const uint32_t id = __ldg(idx + ebase + e);
-                  if (!(id & CONSTRAINED_BIT)) red_add(dst + id, buf[slab_stage_addr<n>(LB, e)]);
-                }
-            }
-        }
+            for (int q = 0; q < Q; ++q)
+              {
+                const int e = 32 * q + lane;
+                if (e < GE && cell0 + e / NPC < n_cells)
+                  {
+                    const uint32_t id = __ldg(idx + ebase + e);
+                    if (!(id & CONSTRAINED_BIT)) red_add(dst + id, buf[slab_stage_addr<n>(LB, e)]);
+                  }
+              }
+          }
+      }
       __syncwarp();
     }
   cp_async_wait_all();

@@ -63,14 +63,13 @@ template <int dim, int n, int r> __device__ __forceinline__ int lay(int t, int e
 template <int n, bool TR, typename Number>
 __device__ __forceinline__ void apply1d(const Number *__restrict__ M, const Number (&in)[n], Number (&out)[n])
 {
+  // outer-product order: the n accumulators advance together, so consecutive FMAs are independent
 #pragma unroll
-  for (int a = 0; a < n; ++a)
-    {
-      Number s = (TR ? M[a * n + 0] : M[0 * n + a]) * in[0];
+  for (int a = 0; a < n; ++a) out[a] = (TR ? M[a * n + 0] : M[0 * n + a]) * in[0];
 #pragma unroll
-      for (int b = 1; b < n; ++b) s += (TR ? M[a * n + b] : M[b * n + a]) * in[b];
-      out[a] = s;
-    }
+  for (int b = 1; b < n; ++b)
+#pragma unroll
+    for (int a = 0; a < n; ++a) out[a] = fma((TR ? M[a * n + b] : M[b * n + a]), in[b], out[a]);
 }
 
 template <int dim, int n, int r, typename Number>

@@ -423,7 +423,10 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
             for (int k = 0; k < 2; ++k) { cudaEvent_t e; MFG_CUDA(cudaEventCreate(&e)); op->ev.push_back(e); }
           MFG_CUDA(cudaEventRecord(op->ev[op->ev_used], s));
         }
-      launch_laplace_slab<Number>(mf->p, op->variant == 3 ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->n_cells, mf->fe.val.data(),
+      // variant 3 = 2 blocks x 4 warps per SM with up to 255 registers (no spills); measured faster than 3 x 4 x 168
+      // for degree 4 in FP64 (profiles/r01_*), which is therefore what "auto" picks there
+      const bool two_blocks = op->variant == 3 || (op->variant == 0 && mf->p == 4 && mf->dt == MFG_F64);
+      launch_laplace_slab<Number>(mf->p, two_blocks ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->n_cells, mf->fe.val.data(),
                                   mf->fe.colloc.data(), op->ctx->sm_count, s);
       if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
       return;
