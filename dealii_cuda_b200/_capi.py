@@ -120,6 +120,11 @@ def _load():
         "mfg_laplace_enable_kernel_timing": (C.c_int, [vp, C.c_int]),
         "mfg_laplace_kernel_time_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int)]),
         "mfg_laplace_active_variant": (C.c_int, [vp]),
+        "mfg_exchange_create": (C.c_int, [vp, C.c_int, u32p, sz, u32p, sz, u32p, C.POINTER(C.c_int32), sz, pp]),
+        "mfg_exchange_destroy": (C.c_int, [vp]),
+        "mfg_exchange_pack": (C.c_int, [vp, vp, vp]),
+        "mfg_exchange_accumulate": (C.c_int, [vp, vp, vp]),
+        "mfg_vec_dot_masked": (C.c_int, [vp, vp, vp, dp]),
         "mfg_laplace_bmop": (C.c_int, [vp, vp, vp, C.c_int, C.c_double, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():

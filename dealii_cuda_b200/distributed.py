@@ -1,0 +1,185 @@
+"""Multi-GPU Laplace operator: one process per GPU (torch.distributed, NCCL), box partition of the mesh,
+interface-DoF exchange after the local cell loop.  See partition.py for the layout."""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import (Context, GpuVector, HyperCubeMesh, LaplaceOperatorGpu, _capi, check, lib)
+from .partition import box_for_rank, build_exchange_plan, global_n_dofs
+
+
+class InterfaceExchange:
+    """mfg_exchange + send/recv buffers + the collective."""
+
+    def __init__(self, ctx, plan, dtype, group=None):
+        import torch
+        self.ctx, self.plan, self.group = ctx, plan, group
+        code = _capi.F64 if np.dtype(dtype) == np.float64 else _capi.F32
+        h = C.c_void_p()
+        u32 = C.POINTER(C.c_uint32)
+        check(lib.mfg_exchange_create(ctx.h, code, plan.pack_idx.ctypes.data_as(u32), plan.n_send, plan.shared_dofs.ctypes.data_as(u32),
+                                      plan.shared_dofs.size, plan.offsets.ctypes.data_as(u32),
+                                      plan.slots.ctypes.data_as(C.POINTER(C.c_int32)), plan.slots.size, C.byref(h)))
+        self.h = h
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        self.send = torch.empty(max(1, plan.n_send), dtype=tdt, device="cuda")
+        self.recv = torch.empty(max(1, plan.n_send), dtype=tdt, device="cuda")
+        self.owned_mask = torch.from_numpy(plan.owned_mask).cuda()
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.mfg_exchange_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def add_interface_contributions(self, vec_ptr):
+        """compress(add) + update_ghost_values in one step: every replica of an interface DoF ends with the
+        sum of all partial sums, added in ascending rank order."""
+        import torch.distributed as dist
+        if self.plan.world == 1 or self.plan.n_send == 0:
+            return
+        check(lib.mfg_exchange_pack(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.send.data_ptr())))
+        n = self.plan.n_send
+        dist.all_to_all_single(self.recv[:n], self.send[:n], self.plan.splits, self.plan.splits, group=self.group)
+        check(lib.mfg_exchange_accumulate(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.recv.data_ptr())))
+
+
+class DistributedLaplaceOperator:
+    """LaplaceOperatorGpu over a box partition: vmult = local cell loop + interface exchange."""
+
+    def __init__(self, ctx, rank, world, dim, degree, r, dtype=np.float64, left=-1.0, right=1.0, variant=0, group=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        box, self.me, self.grid = box_for_rank(rank, world, dim, r, left, right)
+        self.mesh = HyperCubeMesh(ctx, dim, degree, box=box)
+        self.op = LaplaceOperatorGpu(ctx, dtype)
+        self.op.reinit(self.mesh)
+        if variant:
+            self.op.set_variant(variant)
+        self.plan = build_exchange_plan(rank, world, dim, degree, r, self.mesh.lattice_to_dof, self.mesh.n_dofs)
+        self.exchange = InterfaceExchange(ctx, self.plan, dtype, group)
+        self.n_local = self.mesh.n_dofs
+        self.n_global = global_n_dofs(world, dim, degree, r)
+
+    def vmult_ptr(self, dst_ptr, src_ptr):
+        self.op.vmult_ptr(dst_ptr, src_ptr)
+        self.exchange.add_interface_contributions(dst_ptr)
+
+    def vmult(self, dst, src):
+        self.vmult_ptr(dst.getData(), src.getData())
+
+    def dot(self, a, b):
+        """Global dot product: owned DoFs locally (deterministic two-pass reduction), then all_reduce."""
+        import torch
+        import torch.distributed as dist
+        out = C.c_double()
+        check(lib.mfg_vec_dot_masked(a.h, b.h, C.c_void_p(self.exchange.owned_mask.data_ptr()), C.byref(out)))
+        if self.world == 1:
+            return out.value
+        t = torch.tensor([out.value], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, group=self.exchange.group)
+        return float(t.item())
+
+
+def bench_main(args, metric):
+    """bench.py --gpus N (N > 1): weak scaling, one 2^r cube of cells per GPU."""
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, b_alg, measured_peaks, cpu_reference_run
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = Context(local_rank, stream)
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    s = 8 if args.dtype == "f64" else 4
+    dop = DistributedLaplaceOperator(ctx, rank, world, args.dim, args.degree, args.refine, dtype, variant=args.variant)
+    n = dop.n_local
+    ta = torch.full((n,), 0.1, dtype=tdtype, device="cuda")
+    tb = torch.zeros((n,), dtype=tdtype, device="cuda")
+    pa, pb = ta.data_ptr(), tb.data_ptr()
+
+    def apply_steps(k):
+        nonlocal pa, pb
+        for _ in range(k):
+            pa, pb = pb, pa
+            dop.vmult_ptr(pa, pb)
+
+    apply_steps(args.warmup)
+    torch.cuda.synchronize()
+    ta.fill_(0.1); tb.fill_(0.1)
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dop.op.enable_kernel_timing(True)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    apply_steps(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_local = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms, kernel_launches = dop.op.kernel_time_ms()
+    dop.op.enable_kernel_timing(False)
+    t = torch.tensor([ms_local, kernel_ms / max(1, kernel_launches)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, k_avg_ms = float(t[0]), float(t[1])
+
+    # end to end: pinned host src -> H2D -> vmult (+exchange) -> D2H
+    hs = torch.full((n,), 0.1, dtype=tdtype).pin_memory()
+    hd = torch.empty((n,), dtype=tdtype).pin_memory()
+
+    def e2e_step():
+        ta.copy_(hs, non_blocking=True)
+        dop.vmult_ptr(tb.data_ptr(), ta.data_ptr())
+        hd.copy_(tb, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    dist.barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+
+    if rank == 0:
+        ng = dop.n_global
+        peak, peak_src = measured_peaks()
+        alg_bytes = b_alg(args.degree, args.dim, s) * n
+        achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+        line = {"metric": metric, "value": ng * args.steps / (ms * 1e-3), "unit": "DoFs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": "bmop: 3D variable-coefficient Laplace apply, FE_Q(%d), one refine_global(%d) cube of %d cells per GPU, "
+                                       "%s grid of cubes, %d global DoFs (%d per GPU incl. interface replicas), atomic scatter, "
+                                       "NCCL all_to_all interface exchange" % (args.degree, args.refine, dop.mesh.n_cells,
+                                                                               "x".join(map(str, dop.grid)), ng, n),
+                           "l2": "inputs larger than L2"},
+                "clocks": clocks,
+                "e2e": {"value": ng / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
+                        "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
+                "gpu_launches": args.steps * (dop.op.launches_per_vmult() + 2) * world,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "laplace cell kernel (variant %d), per GPU, max over ranks" % dop.op.active_variant(),
+                             "kernel_ms": k_avg_ms, "peak_source": peak_src},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -208,6 +208,26 @@ int mfg_laplace_active_variant(const mfg_laplace *op);
  * Returns device milliseconds measured with CUDA events on the context stream. */
 int mfg_laplace_bmop(mfg_laplace *op, mfg_vec *dst, mfg_vec *src, int k, double init, float *elapsed_ms);
 
+/* ---- multi-GPU: interface-DoF exchange (new capability; the reference is single-GPU) -----------
+ * The mesh is partitioned into boxes of cells, one per GPU.  Every rank stores all DoFs its cells touch;
+ * DoFs on partition interfaces are replicated and kept consistent.  After the local cell loop the partial
+ * sums of the interface DoFs are exchanged and added in ascending rank order on every replica
+ * (bit-identical replicas).  The transport is the caller's (NCCL all_to_all / P2P copies); this object owns
+ * the index lists and the pack / ordered-accumulate kernels.
+ *   pack_idx[n_send]            local DoF of every send-buffer entry (send buffer = concatenation over
+ *                               destination ranks in ascending rank order)
+ *   shared_dofs[n_shared]       local DoFs that receive contributions
+ *   offsets[n_shared+1], slots  CSR: contributions of shared DoF u in ascending rank order; slot >= 0 is an
+ *                               index into the receive buffer, slot == -1 is this rank's own partial sum */
+typedef struct mfg_exchange mfg_exchange;
+int mfg_exchange_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *pack_idx_host, size_t n_send, const uint32_t *shared_dofs_host,
+                        size_t n_shared, const uint32_t *offsets_host, const int32_t *slots_host, size_t n_slots, mfg_exchange **out);
+int mfg_exchange_destroy(mfg_exchange *ex);
+int mfg_exchange_pack(mfg_exchange *ex, const void *vec_dev, void *send_dev);           /* send[k] = vec[pack_idx[k]] */
+int mfg_exchange_accumulate(mfg_exchange *ex, void *vec_dev, const void *recv_dev);     /* ordered sum into vec */
+/* owned-DoF dot product support: mask[i] = 1 if this rank owns DoF i (lowest rank touching it) */
+int mfg_vec_dot_masked(const mfg_vec *a, const mfg_vec *b, const uint8_t *owned_mask_dev, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,7 +45,11 @@
 typedef struct orc_mesh
 {
   int      dim, p, n, r;
-  uint32_t N;       /* cells per direction = 2^r */
+  uint32_t N;       /* cells per direction = 2^r (cube meshes) */
+  int      lg[3];   /* log2 cells per direction (box meshes) */
+  uint32_t nc[3];
+  double   origin[3];
+  uint32_t dirichlet_faces;
   double   left, right, h;
   uint32_t n_cells, n_dofs, npc; /* npc = n^dim */
   uint32_t *l2g;    /* [n_cells][npc], lexicographic local order (x fastest) */
@@ -233,26 +237,35 @@ void orc_destroy(orc_mesh *m)
   free(m->coef); free(m->lex2hier); free(m->color_cells); free(m);
 }
 
-/* hyper_cube(left,right)^dim, refine_global(r), FE_Q(p), Dirichlet on the whole
- * boundary (bmop.cu:111-132), coefficient at Gauss(p+1) points. */
-orc_mesh *orc_create(int dim, int p, int r, double left, double right)
+/* Box of 2^lg[d] cells per direction with edge h and lower corner origin, FE_Q(p), homogeneous Dirichlet data
+ * on the faces selected by dirichlet_faces (bit 2d: lower face of direction d, bit 2d+1: upper face).
+ * hyper_cube(left,right)^dim + refine_global(r) (bmop.cu:111-132) is the special case lg = (r,r,r), all faces.
+ * Cells are ordered along the (generalised) Morton curve, x least significant. */
+orc_mesh *orc_create_box(int dim, int p, const int *lg, const double *origin, double h, uint32_t dirichlet_faces)
 {
-  if (dim < 2 || dim > 3 || p < 1 || p > 8 || r < 0 || r > 10) return NULL;
+  if (dim < 2 || dim > 3 || p < 1 || p > 8) return NULL;
   orc_mesh *m = (orc_mesh *)calloc(1, sizeof(orc_mesh));
-  m->dim = dim; m->p = p; m->n = p + 1; m->r = r; m->N = 1u << r;
-  m->left = left; m->right = right; m->h = (right - left) / m->N;
-  const uint32_t n = m->n, N = m->N, npc = ipow_u(n, dim);
-  m->npc = npc; m->n_cells = ipow_u(N, dim);
+  m->dim = dim; m->p = p; m->n = p + 1; m->h = h; m->dirichlet_faces = dirichlet_faces;
+  m->n_cells = 1;
+  for (int d = 0; d < 3; ++d)
+    {
+      m->lg[d] = d < dim ? lg[d] : 0; m->nc[d] = 1u << m->lg[d]; m->origin[d] = d < dim ? origin[d] : 0.0;
+      m->n_cells *= m->nc[d];
+    }
+  m->r = m->lg[0]; m->N = m->nc[0]; m->left = m->origin[0]; m->right = m->origin[0] + h * m->nc[0];
+  const uint32_t n = m->n, npc = ipow_u(n, dim);
+  m->npc = npc;
   orc_shape_1d(p, m->sv, m->sg, m->xn, m->xq, m->wq);
 
-  /* cells in deal.II order after global refinement: children of cell k are
-   * 2^dim*k .. , child index = x + 2y + 4z  => Morton order, x = LSB */
+  /* deal.II order after global refinement: children of cell k are 2^dim*k.., child index = x + 2y + 4z
+   * => Morton order, x = LSB; directions with fewer cells run out of bits first */
   m->cxyz = (uint32_t *)calloc((size_t)m->n_cells * 3, sizeof(uint32_t));
   for (uint32_t c = 0; c < m->n_cells; ++c)
     {
-      uint32_t x[3] = {0, 0, 0};
-      for (int b = 0; b < r; ++b)
-        for (int d = 0; d < dim; ++d) x[d] |= ((c >> (dim * b + d)) & 1u) << b;
+      uint32_t x[3] = {0, 0, 0}; int pos = 0;
+      for (int b = 0; b < 11; ++b)
+        for (int d = 0; d < dim; ++d)
+          if (b < m->lg[d]) { x[d] |= ((c >> pos) & 1u) << b; ++pos; }
       for (int d = 0; d < 3; ++d) m->cxyz[3 * (size_t)c + d] = x[d];
     }
 
@@ -262,8 +275,8 @@ orc_mesh *orc_create(int dim, int p, int r, double left, double right)
   orc_hier_to_lex(dim, p, h2l);
   m->lex2hier = (uint32_t *)malloc(npc * sizeof(uint32_t));
   for (uint32_t hI = 0; hI < npc; ++hI) m->lex2hier[h2l[hI]] = hI;
-  const uint32_t M = p * N + 1; /* lattice points per direction */
-  const size_t nlat = (dim == 2) ? (size_t)M * M : (size_t)M * M * M;
+  const uint32_t M[3] = {p * m->nc[0] + 1, p * m->nc[1] + 1, dim == 3 ? p * m->nc[2] + 1 : 1};
+  const size_t nlat = (size_t)M[0] * M[1] * M[2];
   uint32_t *lat = (uint32_t *)malloc(nlat * sizeof(uint32_t));
   memset(lat, 0xff, nlat * sizeof(uint32_t));
   m->l2g = (uint32_t *)malloc((size_t)m->n_cells * npc * sizeof(uint32_t));
@@ -275,7 +288,7 @@ orc_mesh *orc_create(int dim, int p, int r, double left, double right)
         {
           const uint32_t li = h2l[hI];
           const uint32_t i = li % n, j = (li / n) % n, k = (dim == 3) ? li / (n * n) : 0;
-          const size_t   a = (size_t)(cx[0] * p + i) + (size_t)M * ((cx[1] * p + j) + (size_t)M * (dim == 3 ? cx[2] * p + k : 0));
+          const size_t   a = (size_t)(cx[0] * p + i) + (size_t)M[0] * ((cx[1] * p + j) + (size_t)M[1] * (dim == 3 ? cx[2] * p + k : 0));
           if (lat[a] == 0xffffffffu) lat[a] = next++;
           m->l2g[(size_t)c * npc + li] = lat[a];
         }
@@ -285,16 +298,20 @@ orc_mesh *orc_create(int dim, int p, int r, double left, double right)
 
   m->dof_lattice = (uint32_t *)malloc((size_t)m->n_dofs * 3 * sizeof(uint32_t));
   m->is_constrained = (uint8_t *)calloc(m->n_dofs, 1);
-  const uint32_t Mz = (dim == 3) ? M : 1;
-  for (uint32_t z = 0; z < Mz; ++z)
-    for (uint32_t y = 0; y < M; ++y)
-      for (uint32_t x = 0; x < M; ++x)
+  for (uint32_t z = 0; z < M[2]; ++z)
+    for (uint32_t y = 0; y < M[1]; ++y)
+      for (uint32_t x = 0; x < M[0]; ++x)
         {
-          const uint32_t g = lat[(size_t)x + (size_t)M * (y + (size_t)M * z)];
+          const uint32_t g = lat[(size_t)x + (size_t)M[0] * (y + (size_t)M[1] * z)];
           m->dof_lattice[3 * (size_t)g + 0] = x; m->dof_lattice[3 * (size_t)g + 1] = y; m->dof_lattice[3 * (size_t)g + 2] = z;
-          /* interpolate_boundary_values(dof_handler,0,ZeroFunction): every DoF on the boundary */
-          int onb = (x == 0 || x == M - 1 || y == 0 || y == M - 1);
-          if (dim == 3) onb = onb || z == 0 || z == M - 1;
+          /* interpolate_boundary_values(dof_handler,0,ZeroFunction): every DoF on a Dirichlet face */
+          const uint32_t X[3] = {x, y, z};
+          int onb = 0;
+          for (int d = 0; d < dim; ++d)
+            {
+              if (X[d] == 0 && ((dirichlet_faces >> (2 * d)) & 1u)) onb = 1;
+              if (X[d] == M[d] - 1 && ((dirichlet_faces >> (2 * d + 1)) & 1u)) onb = 1;
+            }
           m->is_constrained[g] = (uint8_t)onb;
         }
   free(lat);
@@ -316,7 +333,7 @@ orc_mesh *orc_create(int dim, int p, int r, double left, double right)
         {
           const uint32_t qi[3] = {q % n, (q / n) % n, (dim == 3) ? q / (n * n) : 0};
           double x[3];
-          for (int d = 0; d < dim; ++d) x[d] = m->left + m->h * (cx[d] + m->xq[qi[d]]);
+          for (int d = 0; d < dim; ++d) x[d] = m->origin[d] + m->h * (cx[d] + m->xq[qi[d]]);
           m->coef[(size_t)c * npc + q] = coefficient_value(x, dim);
         }
     }
@@ -339,6 +356,18 @@ orc_mesh *orc_create(int dim, int p, int r, double left, double right)
         m->color_cells[pos[(cx[0] & 1) + 2 * (cx[1] & 1) + 4 * (cx[2] & 1)]++] = c;
       }
   }
+  return m;
+}
+
+/* hyper_cube(left,right)^dim, refine_global(r), FE_Q(p), Dirichlet on the whole
+ * boundary (bmop.cu:111-132), coefficient at Gauss(p+1) points. */
+orc_mesh *orc_create(int dim, int p, int r, double left, double right)
+{
+  if (r < 0 || r > 10) return NULL;
+  const int    lg[3] = {r, r, r};
+  const double origin[3] = {left, left, left};
+  orc_mesh *m = orc_create_box(dim, p, lg, origin, (right - left) / (double)(1u << r), 0x3f);
+  if (m) { m->left = left; m->right = right; }
   return m;
 }
 
@@ -454,6 +483,21 @@ void orc_vmult_add(const orc_mesh *m, double *dst, const double *src)
       for (uint32_t i = 0; i < npc; ++i) if (!m->is_constrained[row[i]]) dst[row[i]] += v[i];
     }
   for (uint32_t g = 0; g < m->n_dofs; ++g) if (m->is_constrained[g]) dst[g] += src[g];
+}
+
+/* cell loop over the cells [cell_begin, cell_end) only, no constrained-row identity: the partial sums one
+ * partition of the mesh contributes (used by the multi-GPU partition tests) */
+void orc_cell_loop_range(const orc_mesh *m, double *dst, const double *src, uint32_t cell_begin, uint32_t cell_end)
+{
+  const uint32_t npc = m->npc;
+  double u[ORC_MAXN * ORC_MAXN * ORC_MAXN], v[ORC_MAXN * ORC_MAXN * ORC_MAXN];
+  for (uint32_t c = cell_begin; c < cell_end && c < m->n_cells; ++c)
+    {
+      const uint32_t *row = &m->l2g[(size_t)c * npc];
+      for (uint32_t i = 0; i < npc; ++i) u[i] = m->is_constrained[row[i]] ? 0.0 : src[row[i]];
+      cell_apply(m, c, u, v);
+      for (uint32_t i = 0; i < npc; ++i) if (!m->is_constrained[row[i]]) dst[row[i]] += v[i];
+    }
 }
 
 /* vmult: dst = 0; vmult_add  (laplace_operator_gpu.h:216-223) */

@@ -33,6 +33,9 @@ def lib():
         L = C.CDLL(_SO)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.orc_create_box.restype = C.c_void_p
+        L.orc_create_box.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_double, C.c_uint32]
+        L.orc_cell_loop_range.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32, C.c_uint32]
         L.orc_destroy.argtypes = [C.c_void_p]
         for f in ("orc_n_cells", "orc_n_dofs", "orc_dofs_per_cell", "orc_n_constrained"):
             getattr(L, f).restype = C.c_uint32
@@ -95,9 +98,15 @@ def hier_to_lex(dim, p):
 class OracleMesh:
     """hyper_cube(left,right)^dim + refine_global(r) + FE_Q(p) + Dirichlet boundary."""
 
-    def __init__(self, dim, p, r, left=-1.0, right=1.0):
+    def __init__(self, dim, p, r=None, left=-1.0, right=1.0, box=None):
         self.L = lib()
-        self.h = self.L.orc_create(dim, p, r, left, right)
+        if box is None:
+            self.h = self.L.orc_create(dim, p, r, left, right)
+        else:  # box = dict(log2_cells, origin, h, dirichlet_faces) like mfg_box_desc
+            lg = (C.c_int * 3)(*[int(x) for x in (list(box["log2_cells"]) + [0, 0, 0])[:3]])
+            org = (C.c_double * 3)(*[float(x) for x in (list(box["origin"]) + [0.0, 0.0, 0.0])[:3]])
+            self.h = self.L.orc_create_box(dim, p, lg, org, float(box["h"]), int(box.get("dirichlet_faces", 0x3f)))
+            r = int(box["log2_cells"][0])
         if not self.h:
             raise ValueError("orc_create failed")
         self.dim, self.p, self.r, self.left, self.right = dim, p, r, left, right
@@ -157,6 +166,13 @@ class OracleMesh:
         src = np.ascontiguousarray(src, dtype=np.float64)
         dst = np.empty_like(src)
         (self.L.orc_vmult_omp if threaded else self.L.orc_vmult)(self.h, _dp(dst), _dp(src))
+        return dst
+
+    def cell_loop_range(self, src, cell_begin, cell_end):
+        """partial sums of the cells [cell_begin, cell_end) (no constrained-row identity)"""
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        dst = np.zeros_like(src)
+        self.L.orc_cell_loop_range(self.h, _dp(dst), _dp(src), int(cell_begin), int(cell_end))
         return dst
 
     def vmult_add(self, dst, src):
