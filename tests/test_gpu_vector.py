@@ -38,7 +38,7 @@ def test_blas1(ctx, n, dtype, tol):
     # deep copy, type conversion, swap
     w = mf.GpuVector(ctx, 0, np.float64 if dtype == np.float32 else np.float32)
     w.assign(va)
-    assert w.size() == n and np.allclose(w.toVector(), a, rtol=1e-6)
+    assert w.size() == n and np.allclose(w.toVector(), a, rtol=1e-5, atol=1e-6)
     x, y = mf.GpuVector.from_numpy(ctx, a), mf.GpuVector.from_numpy(ctx, b)
     px, py = x.getData(), y.getData()
     x.swap(y)
