@@ -234,13 +234,30 @@ laplace_cell_v0(const uint32_t *__restrict__ idx, const Number *__restrict__ cw,
 template <typename Number>
 __global__ void vmult_prepare(Number *__restrict__ dst, const Number *__restrict__ src, const uint32_t *__restrict__ cbits, size_t n)
 {
+  // one 16-byte store per thread and iteration; a 32-bit mask word covers 32 DoFs
+  constexpr int V = 16 / (int)sizeof(Number);
+  struct alignas(16) Vec { Number v[V]; };
+  const size_t nvec   = n / V;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  for (size_t iv = (size_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride)
     {
-      const uint32_t word = cbits[i >> 5];
-      Number val = 0;
-      if ((word >> (i & 31)) & 1u) val = src[i];
-      dst[i] = val;
+      const size_t   i    = iv * V;
+      const uint32_t bits = (cbits[i >> 5] >> (i & 31)) & ((1u << V) - 1u);
+      Vec out;
+#pragma unroll
+      for (int k = 0; k < V; ++k) out.v[k] = Number(0);
+      if (bits)
+        {
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            if ((bits >> k) & 1u) out.v[k] = src[i + k];
+        }
+      *reinterpret_cast<Vec *>(dst + i) = out;
+    }
+  if (blockIdx.x == 0 && threadIdx.x < n - nvec * V)
+    {
+      const size_t i = nvec * V + threadIdx.x;
+      dst[i] = ((cbits[i >> 5] >> (i & 31)) & 1u) ? src[i] : Number(0);
     }
 }
 

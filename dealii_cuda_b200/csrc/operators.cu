@@ -406,7 +406,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
   // vmult_add: dst[c] += src[c]  (load_and_add_constrained_values, :302)
   if (!add)
     {
-      const unsigned nb = (unsigned)std::min<size_t>((mf->n_dofs + 1023) / 1024, (size_t)op->ctx->sm_count * 16);
+      const unsigned nb = (unsigned)std::min<size_t>((mf->n_dofs + 2047) / 2048, (size_t)op->ctx->sm_count * 8);
       vmult_prepare<Number><<<std::max(1u, nb), 256, 0, s>>>(dst, src, op->cbits.p, mf->n_dofs);
       MFG_CUDA_LAST();
     }

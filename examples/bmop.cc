@@ -1,0 +1,56 @@
+// bmop.cc -- the reference's benchmark driver (bmop.cu:66-230) on the C++ facade: host code is plain C++
+// (g++), all device work happens inside libmfgpu.so.   usage: bmop <max_refinement> [min_refinement]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include "../include/dealii_cuda_b200/matrix_free_gpu.h"
+
+using namespace dealii_cuda_b200;
+
+#ifndef DEGREE_FE
+#define DEGREE_FE 4
+#endif
+#ifndef DIMENSION
+#define DIMENSION 3
+#endif
+#ifdef BMOP_USE_FLOATS
+typedef float number;
+#else
+typedef double number;
+#endif
+#define N_ITERATIONS 100
+
+template <int dim, int fe_degree> void run(int n_ref)
+{
+  HyperCubeMesh<dim> mesh(fe_degree, n_ref);  // bmop_setup_mesh + setup_system (bmop.cu:111-132)
+  LaplaceOperatorGpu<dim, fe_degree, number> system_matrix;
+  system_matrix.reinit(mesh);
+  GpuVector<number> src(system_matrix.n()), dst(system_matrix.n());
+  check(mfg_ctx_synchronize(default_context()));
+  const auto t0 = std::chrono::steady_clock::now();
+  dst = number(0.1);  // IC (bmop.cu:140)
+  for (int i = 0; i < N_ITERATIONS; ++i)
+    {
+      dst.swap(src);
+      system_matrix.vmult(dst, src);
+    }
+  check(mfg_ctx_synchronize(default_context()));
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::printf("%d\t%d\t%u\t%g\n", dim, fe_degree, mesh.n_dofs(), sec / N_ITERATIONS);
+}
+
+int main(int argc, char **argv)
+{
+  try
+    {
+      const int max_refinement = argc > 1 ? std::atoi(argv[1]) : 1;
+      const int min_refinement = argc > 2 ? std::atoi(argv[2]) : 0;
+      for (int r = min_refinement; r <= max_refinement; ++r) run<DIMENSION, DEGREE_FE>(r);
+    }
+  catch (std::exception &exc)
+    {
+      std::fprintf(stderr, "Exception on processing:\n%s\nAborting!\n", exc.what());
+      return 1;
+    }
+  return 0;
+}

@@ -1,0 +1,151 @@
+// matrix_free_gpu.h -- C++ facade: HyperCubeMesh (stands in for Triangulation + DoFHandler + ConstraintMatrix),
+// ConstraintHandlerGpu<Number> (constraint_handler_gpu.h:13-59), MatrixFreeGpu<dim,Number>
+// (matrix_free_gpu.h:81-229) and LaplaceOperatorGpu<dim,fe_degree,Number> (laplace_operator_gpu.h:35-96).
+#pragma once
+#include <memory>
+#include "gpu_vec.h"
+
+namespace dealii_cuda_b200 {
+
+// GridGenerator::hyper_cube(left,right) + refine_global(n_refine) + FE_Q(fe_degree) + distribute_dofs +
+// interpolate_boundary_values(0, ZeroFunction)   (bmop.cu:111-132, poisson_common.h:58-72)
+template <int dim> class HyperCubeMesh
+{
+public:
+  HyperCubeMesh(unsigned int fe_degree, unsigned int n_refine, double left = -1., double right = 1.)
+  {
+    check(mfg_mesh_hyper_cube(default_context(), dim, (int)fe_degree, (int)n_refine, left, right, &m_));
+  }
+  ~HyperCubeMesh() { if (m_) mfg_mesh_destroy(m_); }
+  HyperCubeMesh(const HyperCubeMesh &) = delete;
+  unsigned int n_dofs() const { return mfg_mesh_n_dofs(m_); }
+  unsigned int n_active_cells() const { return mfg_mesh_n_cells(m_); }
+  unsigned int n_constraints() const { return mfg_mesh_n_constrained(m_); }
+  std::vector<unsigned int> get_loc2glob() const
+  {
+    std::vector<unsigned int> h((size_t)mfg_mesh_n_cells(m_) * mfg_mesh_dofs_per_cell(m_));
+    check(mfg_mesh_get_loc2glob(m_, h.data()));
+    return h;
+  }
+  std::vector<unsigned int> constrained_dofs() const
+  {
+    std::vector<unsigned int> h(mfg_mesh_n_constrained(m_));
+    check(mfg_mesh_get_constrained(m_, h.data()));
+    return h;
+  }
+  mfg_mesh *handle() const { return m_; }
+
+private:
+  mfg_mesh *m_ = nullptr;
+};
+
+template <typename Number> class ConstraintHandlerGpu
+{
+public:
+  ~ConstraintHandlerGpu() { if (ch_) mfg_ch_destroy(ch_); }
+  // reinit(ConstraintMatrix, n_dofs): ascending list of constrained DoFs (constraint_handler_gpu.cu:69-95)
+  void reinit(const std::vector<unsigned int> &constrained, unsigned int /*n_dofs*/,
+              const std::vector<unsigned int> &edge = std::vector<unsigned int>())
+  {
+    if (ch_) mfg_ch_destroy(ch_);
+    ch_ = nullptr;
+    check(mfg_ch_create(default_context(), dtype_of<Number>(), constrained.data(), constrained.size(), edge.data(), edge.size(), &ch_));
+  }
+  template <int dim> void reinit(const HyperCubeMesh<dim> &mesh)
+  {
+    if (ch_) mfg_ch_destroy(ch_);
+    ch_ = nullptr;
+    check(mfg_ch_create_from_mesh(default_context(), dtype_of<Number>(), mesh.handle(), &ch_));
+  }
+  void set_constrained_values(GpuVector<Number> &v, Number val) const { check(mfg_ch_set_constrained_values(ch_, v.handle(), (double)val)); }
+  void save_constrained_values(GpuVector<Number> &v) { check(mfg_ch_save_constrained_values(ch_, v.handle())); }
+  void save_constrained_values(const GpuVector<Number> &v1, GpuVector<Number> &v2) { check(mfg_ch_save_constrained_values2(ch_, v1.handle(), v2.handle())); }
+  void load_constrained_values(GpuVector<Number> &v) const { check(mfg_ch_load_constrained_values(ch_, v.handle())); }
+  void load_and_add_constrained_values(GpuVector<Number> &v1, GpuVector<Number> &v2) const { check(mfg_ch_load_and_add_constrained_values(ch_, v1.handle(), v2.handle())); }
+  void copy_edge_values(GpuVector<Number> &dst, const GpuVector<Number> &src) const { check(mfg_ch_copy_edge_values(ch_, dst.handle(), src.handle())); }
+  mfg_ch *handle() const { return ch_; }
+
+private:
+  mfg_ch *ch_ = nullptr;
+};
+
+template <int dim, typename Number> class MatrixFreeGpu
+{
+public:
+  enum ParallelizationScheme { scheme_par_in_elem, scheme_par_over_elems };
+  struct AdditionalData
+  {
+    AdditionalData(ParallelizationScheme s = scheme_par_in_elem, bool use_coloring = false) : parallelization_scheme(s), use_coloring(use_coloring) {}
+    ParallelizationScheme parallelization_scheme;
+    bool                  use_coloring;
+  };
+  unsigned int n_cells_tot = 0, n_dofs = 0, fe_degree = 0, dofs_per_cell = 0, qpts_per_cell = 0, num_colors = 0;
+  bool         use_coloring = false;
+
+  ~MatrixFreeGpu() { free(); }
+  // reinit(dof_handler, constraints, quad, additional_data)  (matrix_free_gpu.cu:448-563)
+  void reinit(const HyperCubeMesh<dim> &mesh, const AdditionalData ad = AdditionalData())
+  {
+    free();
+    check(mfg_mf_reinit_from_mesh(default_context(), mesh.handle(), dtype_of<Number>(), ad.use_coloring ? MFG_SCATTER_COLOR : MFG_SCATTER_ATOMIC, &mf_));
+    fill_counters(ad.use_coloring);
+  }
+  // explicit arrays, as ReinitHelper extracts them from deal.II (matrix_free_gpu.cu:283-339)
+  void reinit(const mfg_mf_desc &desc)
+  {
+    free();
+    check(mfg_mf_reinit(default_context(), &desc, &mf_));
+    fe_degree = desc.degree;
+    fill_counters(desc.scatter == MFG_SCATTER_COLOR);
+  }
+  void        free() { if (mf_) mfg_mf_destroy(mf_); mf_ = nullptr; }
+  std::size_t memory_consumption() const { return mfg_mf_memory_consumption(mf_); }
+  mfg_mf     *handle() const { return mf_; }
+
+private:
+  void fill_counters(bool coloring)
+  {
+    n_cells_tot = mfg_mf_n_cells(mf_); n_dofs = mfg_mf_n_dofs(mf_); num_colors = mfg_mf_n_colors(mf_); use_coloring = coloring;
+  }
+  mfg_mf *mf_ = nullptr;
+};
+
+template <int dim, int fe_degree, typename Number> class LaplaceOperatorGpu
+{
+public:
+  typedef Number            value_type;
+  typedef GpuVector<Number> VectorType;
+
+  explicit LaplaceOperatorGpu(bool use_coloring = false) : use_coloring_(use_coloring) {}
+  ~LaplaceOperatorGpu() { clear(); }
+  void clear() { if (op_) mfg_laplace_destroy(op_); op_ = nullptr; }
+  // reinit(dof_handler, constraints)  (laplace_operator_gpu.h:120-151)
+  void reinit(const HyperCubeMesh<dim> &mesh)
+  {
+    clear();
+    check(mfg_laplace_create(default_context(), mesh.handle(), dtype_of<Number>(), use_coloring_ ? MFG_SCATTER_COLOR : MFG_SCATTER_ATOMIC, &op_));
+  }
+  // explicit arrays: MatrixFreeGpu built from mfg_mf_desc, constraint handler, coefficient at the quadrature points
+  void reinit(const MatrixFreeGpu<dim, Number> &data, const ConstraintHandlerGpu<Number> &ch, const std::vector<double> &coefficient)
+  {
+    clear();
+    check(mfg_laplace_create_from_arrays(default_context(), data.handle(), ch.handle(), coefficient.data(), &op_));
+  }
+  unsigned int m() const { return mfg_laplace_m(op_); }
+  unsigned int n() const { return mfg_laplace_m(op_); }
+  void vmult(VectorType &dst, const VectorType &src) const { check(mfg_laplace_vmult(op_, dst.handle(), src.handle())); }
+  void Tvmult(VectorType &dst, const VectorType &src) const { vmult(dst, src); }
+  void vmult_add(VectorType &dst, const VectorType &src) const { check(mfg_laplace_vmult_add(op_, dst.handle(), src.handle())); }
+  void Tvmult_add(VectorType &dst, const VectorType &src) const { vmult_add(dst, src); }
+  void compute_diagonal() { check(mfg_laplace_compute_diagonal(op_)); }
+  // borrowed handle to the inverse diagonal (DiagonalMatrix<VectorType>::get_vector in the reference)
+  mfg_vec *get_diagonal_inverse() const { mfg_vec *v = nullptr; check(mfg_laplace_get_diagonal_inverse(op_, &v)); return v; }
+  std::size_t  memory_consumption() const { return mfg_laplace_memory_consumption(op_); }
+  mfg_laplace *handle() const { return op_; }
+
+private:
+  bool         use_coloring_;
+  mfg_laplace *op_ = nullptr;
+};
+
+}  // namespace dealii_cuda_b200

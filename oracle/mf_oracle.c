@@ -660,6 +660,130 @@ void orc_vmult_omp(const orc_mesh *m, double *dst, const double *src)
   }
 }
 
+/* ------------------------------------------------------------------------ */
+/* timed CPU baseline: what deal.II's MatrixFree/FEEvaluation does on the    */
+/* host (laplace_operator_cpu.cc:125-143): sum factorisation in the          */
+/* collocation form, 8 cells per SIMD batch (VectorizedArray<double> on      */
+/* AVX-512), OpenMP over conflict-free colors (partition_color, :51-52).     */
+/* Same bilinear form as orc_vmult, different summation order.               */
+/* ------------------------------------------------------------------------ */
+#define ORC_LANES 8
+typedef double lane_t[ORC_LANES] __attribute__((aligned(64)));
+
+static inline __attribute__((always_inline)) void
+batch_contract(const int n, const int dim, const int dir, const int tr, const double *M, lane_t *in, lane_t *out)
+{
+  const int nz = dim == 3 ? n : 1;
+  int stride = 1; for (int d = 0; d < dir; ++d) stride *= n;
+  for (int z = 0; z < nz; ++z)
+    for (int y = 0; y < n; ++y)
+      for (int x = 0; x < n; ++x)
+        {
+          const int c[3] = {x, y, z};
+          if (c[dir] != 0) continue;
+          const int base = x + n * (y + n * z);
+          for (int q = 0; q < n; ++q)
+            {
+              double acc[ORC_LANES];
+              const double m0 = tr ? M[q * n + 0] : M[0 * n + q];
+              for (int l = 0; l < ORC_LANES; ++l) acc[l] = m0 * in[base][l];
+              for (int k = 1; k < n; ++k)
+                {
+                  const double mk = tr ? M[q * n + k] : M[k * n + q];
+                  for (int l = 0; l < ORC_LANES; ++l) acc[l] += mk * in[base + k * stride][l];
+                }
+              for (int l = 0; l < ORC_LANES; ++l) out[base + q * stride][l] = acc[l];
+            }
+        }
+}
+
+static inline __attribute__((always_inline)) void
+batch_apply(const orc_mesh *m, const int n, const int dim, const double *Dc, const double *wfac, const uint32_t *cells, const int nb,
+            const double *src, double *dst)
+{
+  const int npc = dim == 3 ? n * n * n : n * n;
+  lane_t u[ORC_MAXN * ORC_MAXN * ORC_MAXN], t[ORC_MAXN * ORC_MAXN * ORC_MAXN], g[ORC_MAXN * ORC_MAXN * ORC_MAXN], R[ORC_MAXN * ORC_MAXN * ORC_MAXN];
+  for (int e = 0; e < npc; ++e)
+    for (int l = 0; l < ORC_LANES; ++l)
+      {
+        double v = 0.0;
+        if (l < nb) { const uint32_t gi = m->l2g[(size_t)cells[l] * npc + e]; v = m->is_constrained[gi] ? 0.0 : src[gi]; }
+        u[e][l] = v;
+      }
+  /* values at the quadrature points */
+  batch_contract(n, dim, 0, 0, m->sv, u, t);
+  batch_contract(n, dim, 1, 0, m->sv, t, u);
+  if (dim == 3) { batch_contract(n, dim, 2, 0, m->sv, u, t); } else { for (int e = 0; e < npc; ++e) for (int l = 0; l < ORC_LANES; ++l) t[e][l] = u[e][l]; }
+  /* R = sum_d D_d^T ( a * JxW * J^-2 .* D_d G ) */
+  for (int e = 0; e < npc; ++e) for (int l = 0; l < ORC_LANES; ++l) R[e][l] = 0.0;
+  for (int d = 0; d < dim; ++d)
+    {
+      batch_contract(n, dim, d, 0, Dc, t, g);
+      for (int e = 0; e < npc; ++e)
+        for (int l = 0; l < ORC_LANES; ++l)
+          g[e][l] *= (l < nb ? m->coef[(size_t)cells[l] * npc + e] : 0.0) * wfac[e];
+      batch_contract(n, dim, d, 1, Dc, g, u);
+      for (int e = 0; e < npc; ++e) for (int l = 0; l < ORC_LANES; ++l) R[e][l] += u[e][l];
+    }
+  batch_contract(n, dim, 0, 1, m->sv, R, u);
+  batch_contract(n, dim, 1, 1, m->sv, u, t);
+  if (dim == 3) batch_contract(n, dim, 2, 1, m->sv, t, u);
+  lane_t *res = dim == 3 ? u : t;
+  for (int l = 0; l < nb; ++l)
+    for (int e = 0; e < npc; ++e)
+      {
+        const uint32_t gi = m->l2g[(size_t)cells[l] * npc + e];
+        if (!m->is_constrained[gi]) dst[gi] += res[e][l];
+      }
+}
+
+/* AVX-512 clone where the host has it (the reference's VectorizedArray<double> width), x86-64-v3 otherwise */
+__attribute__((target_clones("avx512f", "default")))
+static void batch_apply_dispatch(const orc_mesh *m, const double *Dc, const double *wfac, const uint32_t *cells, int nb, const double *src, double *dst)
+{
+  if (m->dim == 3)
+    switch (m->n) { case 2: batch_apply(m, 2, 3, Dc, wfac, cells, nb, src, dst); break; case 3: batch_apply(m, 3, 3, Dc, wfac, cells, nb, src, dst); break;
+      case 4: batch_apply(m, 4, 3, Dc, wfac, cells, nb, src, dst); break; case 5: batch_apply(m, 5, 3, Dc, wfac, cells, nb, src, dst); break;
+      case 6: batch_apply(m, 6, 3, Dc, wfac, cells, nb, src, dst); break; case 7: batch_apply(m, 7, 3, Dc, wfac, cells, nb, src, dst); break;
+      case 8: batch_apply(m, 8, 3, Dc, wfac, cells, nb, src, dst); break; default: batch_apply(m, 9, 3, Dc, wfac, cells, nb, src, dst); break; }
+  else
+    switch (m->n) { case 2: batch_apply(m, 2, 2, Dc, wfac, cells, nb, src, dst); break; case 3: batch_apply(m, 3, 2, Dc, wfac, cells, nb, src, dst); break;
+      case 4: batch_apply(m, 4, 2, Dc, wfac, cells, nb, src, dst); break; case 5: batch_apply(m, 5, 2, Dc, wfac, cells, nb, src, dst); break;
+      case 6: batch_apply(m, 6, 2, Dc, wfac, cells, nb, src, dst); break; case 7: batch_apply(m, 7, 2, Dc, wfac, cells, nb, src, dst); break;
+      case 8: batch_apply(m, 8, 2, Dc, wfac, cells, nb, src, dst); break; default: batch_apply(m, 9, 2, Dc, wfac, cells, nb, src, dst); break; }
+}
+
+void orc_vmult_fast(const orc_mesh *m, double *dst, const double *src)
+{
+  const int n = m->n, dim = m->dim; const uint32_t npc = m->npc; const int ncol = 1 << dim;
+  double Dc[ORC_MAXN * ORC_MAXN], dummy[ORC_MAXN * ORC_MAXN], wfac[ORC_MAXN * ORC_MAXN * ORC_MAXN];
+  lagrange_eval(n, m->xq, n, m->xq, dummy, Dc); /* collocation derivative: Lagrange basis through the Gauss points */
+  double hd = 1.0; for (int d = 0; d < dim; ++d) hd *= m->h;
+  for (uint32_t q = 0; q < npc; ++q)
+    {
+      const int qi[3] = {(int)(q % n), (int)((q / n) % n), dim == 3 ? (int)(q / (n * n)) : 0};
+      double w = hd / (m->h * m->h); for (int d = 0; d < dim; ++d) w *= m->wq[qi[d]];
+      wfac[q] = w;
+    }
+#pragma omp parallel
+  {
+#pragma omp for schedule(static)
+    for (uint32_t g = 0; g < m->n_dofs; ++g) dst[g] = m->is_constrained[g] ? src[g] : 0.0;
+    for (int col = 0; col < ncol; ++col)
+      {
+        const uint32_t c0 = m->color_off[col], c1 = m->color_off[col + 1];
+        const uint32_t nbatch = (c1 - c0 + ORC_LANES - 1) / ORC_LANES;
+#pragma omp for schedule(static)
+        for (uint32_t b = 0; b < nbatch; ++b)
+          {
+            const uint32_t first = c0 + b * ORC_LANES;
+            const int nb = (int)((c1 - first) < ORC_LANES ? (c1 - first) : ORC_LANES);
+            batch_apply_dispatch(m, Dc, wfac, &m->color_cells[first], nb, src, dst);
+          }
+      }
+  }
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -48,6 +48,7 @@ def lib():
         L.orc_vmult.argtypes = [C.c_void_p, dp, dp]
         L.orc_vmult_add.argtypes = [C.c_void_p, dp, dp]
         L.orc_vmult_omp.argtypes = [C.c_void_p, dp, dp]
+        L.orc_vmult_fast.argtypes = [C.c_void_p, dp, dp]
         L.orc_bmop.argtypes = [C.c_void_p, C.c_int, C.c_double, dp]
         L.orc_inverse_diagonal.argtypes = [C.c_void_p, dp]
         L.orc_assemble_dense.argtypes = [C.c_void_p, dp]
@@ -162,10 +163,13 @@ class OracleMesh:
     def clear_constraints(self):
         self.L.orc_clear_constraints(self.h)
 
-    def vmult(self, src, threaded=False):
+    def vmult(self, src, threaded=False, fast=False):
+        """scalar reference restatement; threaded=True: same arithmetic, OpenMP over colors; fast=True: the timed
+        CPU baseline (collocation form, 8-cell SIMD batches, OpenMP) -- same operator, different summation order"""
         src = np.ascontiguousarray(src, dtype=np.float64)
         dst = np.empty_like(src)
-        (self.L.orc_vmult_omp if threaded else self.L.orc_vmult)(self.h, _dp(dst), _dp(src))
+        f = self.L.orc_vmult_fast if fast else (self.L.orc_vmult_omp if threaded else self.L.orc_vmult)
+        f(self.h, _dp(dst), _dp(src))
         return dst
 
     def cell_loop_range(self, src, cell_begin, cell_end):

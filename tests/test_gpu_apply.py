@@ -272,6 +272,18 @@ def test_vmult_host_and_ptr_entry_points(ctx):
     assert rel_err(td.cpu().numpy(), want) <= 1e-12
 
 
+def test_cpp_facade_bmop_example():
+    """examples/bmop.cc: the reference's bmop.cu driver on the header-only C++ facade (host code built with g++)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "examples"), "-s"])
+    out = subprocess.run([os.path.join(root, "examples", "_build", "bmop"), "3", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert [r[:3] for r in rows] == [["3", "4", "4913"], ["3", "4", "35937"]]  # dim, degree, n_dofs as bmop.cu:152 prints them
+    assert all(float(r[3]) > 0 for r in rows)
+
+
 def test_error_behaviour(ctx):
     import dealii_cuda_b200 as mf
     with pytest.raises(mf.MfgError):

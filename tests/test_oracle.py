@@ -182,6 +182,16 @@ def test_threaded_baseline_matches_scalar():
     assert np.linalg.norm(a - b) <= 1e-14 * np.linalg.norm(a)
 
 
+@pytest.mark.parametrize("dim,p,r", [(3, 4, 2), (2, 5, 2), (3, 1, 3), (3, 8, 1), (2, 2, 4)])
+def test_simd_cpu_baseline_matches_scalar(dim, p, r):
+    """the timed CPU baseline (collocation form, 8-cell batches) is the same operator as the scalar restatement"""
+    m = OracleMesh(dim, p, r)
+    u = sm64(2, m.n_dofs)
+    a, b = m.vmult(u), m.vmult(u, fast=True)
+    assert np.linalg.norm(a - b) <= 1e-13 * np.linalg.norm(a)
+    assert np.array_equal(a[m.constrained], b[m.constrained])
+
+
 def test_golden_vectors_match_oracle():
     """tests/golden/*.npz were generated by tests/golden/make_golden.py from this oracle;
     they pin the oracle against accidental change and are what the -m gpu tests compare to."""
