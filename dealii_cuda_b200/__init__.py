@@ -286,6 +286,14 @@ class HyperCubeMesh:
         return out, nc.value
 
 
+def hanging_node_weights(degree):
+    """W[k][i] = phi_i(xi_k/2) (setup_constraint_weights, hanging_nodes.cuh:580-598)."""
+    n = degree + 1
+    w = np.empty((n, n))
+    check(lib.mfg_hanging_node_weights(degree, _dp(w)))
+    return w
+
+
 def shape_info(degree):
     """ShapeInfo::shape_values / shape_gradients [i*n+q], Gauss points and weights on [0,1]."""
     n = degree + 1
@@ -377,6 +385,10 @@ class MatrixFreeGpu:
                 off = np.ascontiguousarray(a["color_offsets"], dtype=np.uint32)
                 d.n_colors, d.color_offsets = off.size - 1, _u32p(off)
                 keep.append(off)
+            if a.get("constraint_mask") is not None:
+                cm = np.ascontiguousarray(a["constraint_mask"], dtype=np.uint32)
+                d.constraint_mask = _u32p(cm)
+                keep.append(cm)
             check(lib.mfg_mf_reinit(self.ctx.h, C.byref(d), C.byref(h)))
         self.h = h
         self.n_dofs = lib.mfg_mf_n_dofs(h)

@@ -28,7 +28,7 @@ class MfDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("dtype", C.c_int), ("n_cells", C.c_uint32), ("n_dofs", C.c_uint32),
                 ("loc2glob", C.POINTER(C.c_uint32)), ("geometry", C.c_int), ("inv_jac", C.POINTER(C.c_double)),
                 ("JxW", C.POINTER(C.c_double)), ("quadrature_points", C.POINTER(C.c_double)), ("scatter", C.c_int),
-                ("n_colors", C.c_uint32), ("color_offsets", C.POINTER(C.c_uint32))]
+                ("n_colors", C.c_uint32), ("color_offsets", C.POINTER(C.c_uint32)), ("constraint_mask", C.POINTER(C.c_uint32))]
 
 
 def _load():
@@ -92,6 +92,7 @@ def _load():
         "mfg_mf_n_colors": (C.c_uint32, [vp]),
         "mfg_mf_memory_consumption": (sz, [vp]),
         "mfg_shape_info": (C.c_int, [C.c_int, dp, dp, dp, dp]),
+        "mfg_hanging_node_weights": (C.c_int, [C.c_int, dp]),
         "mfg_ch_create": (C.c_int, [vp, C.c_int, u32p, sz, u32p, sz, pp]),
         "mfg_ch_create_from_mesh": (C.c_int, [vp, C.c_int, vp, pp]),
         "mfg_ch_destroy": (C.c_int, [vp]),

@@ -236,6 +236,15 @@ int mfg_shape_info(int degree, double *shape_values, double *shape_gradients, do
   });
 }
 
+int mfg_hanging_node_weights(int degree, double *weights)
+{
+  return guarded([&] {
+    MFG_REQUIRE(degree >= 1 && degree <= 8 && weights, "degree must be in 1..8 and weights non-null");
+    const FEData1D fe = make_fe_data(degree);
+    std::copy(fe.hanging.begin(), fe.hanging.end(), weights);
+  });
+}
+
 // ---- ConstraintHandlerGpu ---------------------------------------------------------
 int mfg_ch_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *constrained_host, size_t n_constrained, const uint32_t *edge_host, size_t n_edge, mfg_ch **out)
 {

@@ -17,6 +17,7 @@ struct FEData1D
   std::vector<double> val;        // val[i*n+q]  = phi_i(x_q)
   std::vector<double> grad;       // grad[i*n+q] = phi_i'(x_q)   (reference-cell derivative)
   std::vector<double> colloc;     // colloc[a*n+q] = l_a'(x_q), l_a = Lagrange basis through the Gauss points
+  std::vector<double> hanging;    // hanging[k*n+i] = phi_i(xi_k/2): subface interpolation, first child (hanging_nodes.cuh:580-598)
 };
 
 namespace detail {
@@ -104,7 +105,7 @@ inline FEData1D make_fe_data(int degree)
   for (int i = 0; i < n; ++i) { xn01[i] = (xl[i] + 1) / 2; xq01[i] = (xg[i] + 1) / 2; }
   fe.nodes.resize(n); fe.qpts.resize(n); fe.qwts.resize(n);
   for (int i = 0; i < n; ++i) { fe.nodes[i] = (double)xn01[i]; fe.qpts[i] = (double)xq01[i]; fe.qwts[i] = (double)(wg[i] / 2); }
-  fe.val.resize(n * n); fe.grad.resize(n * n); fe.colloc.resize(n * n);
+  fe.val.resize(n * n); fe.grad.resize(n * n); fe.colloc.resize(n * n); fe.hanging.resize(n * n);
   const std::vector<ld> wn = detail::bary_weights(xn01), wq = detail::bary_weights(xq01);
   for (int i = 0; i < n; ++i)
     for (int q = 0; q < n; ++q)
@@ -114,6 +115,8 @@ inline FEData1D make_fe_data(int degree)
         fe.val[i * n + q] = (double)v; fe.grad[i * n + q] = (double)d;
         detail::lagrange_at(xq01, wq, i, xq01[q], v, d);
         fe.colloc[i * n + q] = (double)d;
+        detail::lagrange_at(xn01, wn, i, xn01[q] / 2, v, d);  // q plays the role of the fine node k
+        fe.hanging[q * n + i] = (double)v;
       }
   return fe;
 }

@@ -111,11 +111,83 @@ __device__ __forceinline__ void qphase(const Number *__restrict__ D, const Numbe
   for (int e = 0; e < n; ++e) R[e] = FIRST ? t[e] : R[e] + t[e];
 }
 
-template <int dim, int n, typename Number, bool ATOMIC>
+template <typename Number, int n> struct HangingMat
+{
+  Number W[n * n];  // W[k*n+i] = phi_i(xi_k/2), first child; second child by index reversal (hanging_nodes.cuh:665-682)
+};
+
+// resolve_hanging_nodes_shmem<dim,fe_degree,transpose> (hanging_nodes.cuh:617-778) for the column layout:
+// the cell tensor is staged in shared memory, one sweep per direction (x, y[, z]) ping-ponging between two
+// buffers; every point on a constrained face / edge is replaced by the 1-D interpolation along the sweep
+// direction.  `u` enters and leaves in the gather/scatter layout (register axis dim-1).  Executed by every
+// thread of the block (uniform barriers); cells with mask 0 just copy.
+template <int dim, int n, bool TR, typename Number>
+__device__ __forceinline__ void hn_resolve(Number (&u)[n], Number *b0, Number *b1, const int t, const unsigned mask,
+                                           const bool in_blk, const Number *__restrict__ W)
+{
+  constexpr int RL = dim - 1, p = n - 1;
+  if (in_blk) st_lay<dim, n, RL>(b0, t, u);
+  __syncthreads();
+  Number *in = b0, *out = b1;
+#pragma unroll
+  for (int d = 0; d < dim; ++d)
+    {
+      if (in_blk)
+        {
+#pragma unroll
+          for (int e = 0; e < n; ++e)
+            {
+              int c[3];
+              if (dim == 3) { c[0] = t % n; c[1] = t / n; c[2] = e; }
+              else { c[0] = t; c[1] = e; c[2] = 0; }
+              bool flag;
+              if (dim == 2)
+                {
+                  const int a = 1 - d;
+                  const bool on = (mask & (1u << a)) ? (c[a] == 0) : (c[a] == p);
+                  flag = (mask & (8u << a)) && on;
+                }
+              else
+                {
+                  const int f1 = (d + 1) % 3, f2 = (d + 2) % 3;
+                  const bool on1 = (mask & (1u << f1)) ? (c[f1] == 0) : (c[f1] == p);
+                  const bool on2 = (mask & (1u << f2)) ? (c[f2] == 0) : (c[f2] == p);
+                  // edge bit by the direction the edge runs along: x -> EDGE_YZ (1<<7), y -> EDGE_ZX (1<<8), z -> EDGE_XY (1<<6)
+                  const unsigned ebit = d == 0 ? (1u << 7) : d == 1 ? (1u << 8) : (1u << 6);
+                  flag = ((mask & (8u << f1)) && on1) || ((mask & (8u << f2)) && on2) || ((mask & ebit) && on1 && on2);
+                }
+              const int stride = d == 0 ? 1 : d == 1 ? n : n * n;
+              const int here   = c[0] + n * (c[1] + n * c[2]);
+              Number val = in[here];
+              if (flag)
+                {
+                  const int  k     = c[d];
+                  const int  base  = here - k * stride;
+                  const bool first = mask & (1u << d);
+                  Number acc = 0;
+                  for (int i = 0; i < n; ++i)
+                    {
+                      const Number w = first ? (TR ? W[i * n + k] : W[k * n + i]) : (TR ? W[(p - i) * n + p - k] : W[(p - k) * n + p - i]);
+                      acc += w * in[base + i * stride];
+                    }
+                  val = acc;
+                }
+              out[here] = val;
+            }
+        }
+      __syncthreads();
+      Number *tmp = in; in = out; out = tmp;
+    }
+  if (in_blk) ld_lay<dim, n, RL>(in, t, u);
+  __syncthreads();  // the staging buffers are reused by the caller
+}
+
+template <int dim, int n, typename Number, bool ATOMIC, bool HN>
 __global__ void __launch_bounds__(v0_block_threads(dim, n))
 laplace_cell_v0(const uint32_t *__restrict__ idx, const Number *__restrict__ cw, const Number *__restrict__ src,
                 Number *__restrict__ dst, const uint32_t cell_begin, const uint32_t cell_end,
-                const __grid_constant__ ShapeMats<Number, n> sh)
+                const __grid_constant__ ShapeMats<Number, n> sh, const uint32_t *__restrict__ hn_mask,
+                const __grid_constant__ HangingMat<Number, n> hm)
 {
   constexpr int TPC = v0_threads_per_cell(dim, n);
   constexpr int CPB = v0_cells_per_block(dim, n);
@@ -153,6 +225,13 @@ laplace_cell_v0(const uint32_t *__restrict__ idx, const Number *__restrict__ cw,
       for (int e = 0; e < n; ++e) { id[e] = CONSTRAINED_BIT; w[e] = 0; u[e] = 0; }
     }
   if (in_blk) st_lay<dim, n, RL>(bufW, t, w);
+  unsigned mask = 0;
+  if (HN)
+    {
+      // hanging nodes: interpolate the coarse-face values gathered through the rewritten map (fee_gpu.cuh:333-335)
+      if (active) mask = hn_mask[cell];
+      hn_resolve<dim, n, false>(u, bufA, bufB, t, mask, in_blk, hm.W);
+    }
 
   // ---- interpolate to Gauss points: N along dim-1, ..., 0 -------------------
   apply1d<n, false>(sh.N, u, v);
@@ -219,6 +298,11 @@ laplace_cell_v0(const uint32_t *__restrict__ idx, const Number *__restrict__ cw,
     }
 
   // ---- distribute_local_to_global (fee_gpu.cuh:346-365) ---------------------
+  if (HN)
+    {
+      __syncthreads();  // everybody has read the result before the buffers are recycled
+      hn_resolve<dim, n, true>(v, dim == 3 ? bufB : bufA, dim == 3 ? bufA : bufB, t, mask, in_blk, hm.W);
+    }
 #pragma unroll
   for (int e = 0; e < n; ++e)
     if (!(id[e] & CONSTRAINED_BIT))
@@ -272,6 +356,7 @@ __global__ void constrained_add(Number *__restrict__ dst, const Number *__restri
 // host-side launcher, explicitly instantiated per (dim, dtype) in kernels_v0_inst.cu
 template <int dim, typename Number>
 void launch_laplace_v0_dim(int degree, bool atomic, const uint32_t *idx, const Number *cw, const Number *src, Number *dst,
-                           uint32_t cell_begin, uint32_t cell_end, const double *N, const double *D, cudaStream_t stream);
+                           uint32_t cell_begin, uint32_t cell_end, const double *N, const double *D, cudaStream_t stream,
+                           const uint32_t *hn_mask = nullptr, const double *hn_weights = nullptr);
 
 }  // namespace mfg

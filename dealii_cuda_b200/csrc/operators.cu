@@ -61,21 +61,24 @@ __global__ void eval_cw_uniform(MortonMap mm, int dim, int n, uint32_t npc, uint
   cw[t] = (Number)(a * w / (h * h));
 }
 
-struct DiagTables { double val[81], grad[81]; };
+struct DiagTables { double val[81], grad[81], hang[81]; };
 
 // compute_diagonal (laplace_operator_gpu.h:355-421): diag_i = sum_q cw_q sum_d (dphi_i/dxi_d (q))^2.
-// The reference applies the cell operator to every local unit vector
-// (O(n^(2dim+1)) per cell); the same number is obtained here in closed form.
+// The reference applies the cell operator to every local unit vector (O(n^(2dim+1)) per cell); the same number is
+// obtained here in closed form.  Like the reference's DiagonalLocalOperator, cells with hanging nodes pass their
+// local diagonal through the TRANSPOSED hanging-node interpolation before it is scattered (:397-399).
 template <typename Number>
 __global__ void diagonal_kernel(const uint32_t *__restrict__ idx, const Number *__restrict__ cw, int dim, int n, uint32_t npc,
-                                uint32_t n_cells, DiagTables tb, Number *__restrict__ diag)
+                                uint32_t n_cells, DiagTables tb, Number *__restrict__ diag, const uint32_t *__restrict__ hn_mask)
 {
+  extern __shared__ double dsm[];  // 2 * npc
+  double *a = dsm, *b = dsm + npc;
   const uint32_t cell = blockIdx.x;
   if (cell >= n_cells) return;
+  const unsigned mask = hn_mask ? hn_mask[cell] : 0u;
+  const int p = n - 1;
   for (uint32_t i = threadIdx.x; i < npc; i += blockDim.x)
     {
-      const uint32_t g = idx[(size_t)cell * npc + i];
-      if (g & CONSTRAINED_BIT) continue;
       const int ii[3] = {(int)(i % n), (int)((i / n) % n), (int)(i / (n * n))};
       double acc = 0;
       for (uint32_t q = 0; q < npc; ++q)
@@ -84,15 +87,56 @@ __global__ void diagonal_kernel(const uint32_t *__restrict__ idx, const Number *
           double v[3], g2[3];
           for (int d = 0; d < dim; ++d)
             {
-              const double a = tb.val[ii[d] * n + qi[d]], b = tb.grad[ii[d] * n + qi[d]];
-              v[d] = a * a; g2[d] = b * b;
+              const double x = tb.val[ii[d] * n + qi[d]], y = tb.grad[ii[d] * n + qi[d]];
+              v[d] = x * x; g2[d] = y * y;
             }
           double s;
           if (dim == 2) s = g2[0] * v[1] + v[0] * g2[1];
           else s = g2[0] * v[1] * v[2] + v[0] * g2[1] * v[2] + v[0] * v[1] * g2[2];
           acc += s * (double)cw[(size_t)cell * npc + q];
         }
-      atomicAdd(diag + g, (Number)acc);
+      a[i] = acc;
+    }
+  __syncthreads();
+  if (mask)
+    for (int d = 0; d < dim; ++d)
+      {
+        for (uint32_t i = threadIdx.x; i < npc; i += blockDim.x)
+          {
+            const int c[3] = {(int)(i % n), (int)((i / n) % n), (int)(i / (n * n))};
+            bool flag;
+            if (dim == 2)
+              {
+                const int o = 1 - d;
+                const bool on = (mask & (1u << o)) ? (c[o] == 0) : (c[o] == p);
+                flag = (mask & (8u << o)) && on;
+              }
+            else
+              {
+                const int f1 = (d + 1) % 3, f2 = (d + 2) % 3;
+                const bool on1 = (mask & (1u << f1)) ? (c[f1] == 0) : (c[f1] == p);
+                const bool on2 = (mask & (1u << f2)) ? (c[f2] == 0) : (c[f2] == p);
+                const unsigned ebit = d == 0 ? (1u << 7) : d == 1 ? (1u << 8) : (1u << 6);
+                flag = ((mask & (8u << f1)) && on1) || ((mask & (8u << f2)) && on2) || ((mask & ebit) && on1 && on2);
+              }
+            double val = a[i];
+            if (flag)
+              {
+                const int stride = d == 0 ? 1 : d == 1 ? n : n * n, k = c[d], base = (int)i - k * stride;
+                const bool first = mask & (1u << d);
+                double acc = 0;
+                for (int j = 0; j < n; ++j) acc += (first ? tb.hang[j * n + k] : tb.hang[(p - j) * n + p - k]) * a[base + j * stride];
+                val = acc;
+              }
+            b[i] = val;
+          }
+        __syncthreads();
+        double *t = a; a = b; b = t;
+      }
+  for (uint32_t i = threadIdx.x; i < npc; i += blockDim.x)
+    {
+      const uint32_t g = idx[(size_t)cell * npc + i];
+      if (!(g & CONSTRAINED_BIT)) atomicAdd(diag + g, (Number)a[i]);
     }
 }
 
@@ -204,7 +248,30 @@ mfg_mf *mf_from_desc(mfg_ctx *ctx, const mfg_mf_desc &d)
   else mf->color_offsets = {0u, d.n_cells};
   const size_t total = (size_t)d.n_cells * mf->npc;
   for (size_t i = 0; i < total; ++i) MFG_REQUIRE(d.loc2glob[i] < d.n_dofs, "loc2glob entry out of range");
-  mf->idx.upload(d.loc2glob, total, ctx->stream);
+  if (d.constraint_mask)
+    {
+      // hanging nodes: cells without constraints first (they take the fast kernels), constrained cells last
+      MFG_REQUIRE(d.scatter == MFG_SCATTER_ATOMIC, "hanging nodes need the atomic scatter");
+      std::vector<uint32_t> perm(d.n_cells);
+      std::iota(perm.begin(), perm.end(), 0u);
+      std::stable_partition(perm.begin(), perm.end(), [&](uint32_t c) { return d.constraint_mask[c] == 0; });
+      uint32_t n_plain = 0;
+      for (uint32_t c = 0; c < d.n_cells; ++c) n_plain += d.constraint_mask[c] == 0;
+      std::vector<uint32_t> l2g_perm(total), mask_perm(d.n_cells);
+      for (uint32_t s = 0; s < d.n_cells; ++s)
+        {
+          std::copy(d.loc2glob + (size_t)perm[s] * mf->npc, d.loc2glob + (size_t)(perm[s] + 1) * mf->npc, l2g_perm.begin() + (size_t)s * mf->npc);
+          mask_perm[s] = d.constraint_mask[perm[s]];
+          MFG_REQUIRE(mask_perm[s] < 512u, "constraint mask has more than 9 bits");
+        }
+      mf->n_plain = n_plain;
+      mf->color_offsets = {0u, n_plain};
+      mf->idx.upload(l2g_perm.data(), total, ctx->stream);
+      mf->hn_mask.upload(mask_perm.data(), d.n_cells, ctx->stream);
+      mf->cell_perm.upload(perm.data(), d.n_cells, ctx->stream);
+    }
+  else
+    mf->idx.upload(d.loc2glob, total, ctx->stream);
   // merged geometry factor inv_jac^2 * JxW_q  (fee_gpu.cuh:228,270: grad = J0*g ; submit = grad*J0*jxw)
   mf->geom_host.resize(total);
   for (uint32_t c = 0; c < d.n_cells; ++c)
@@ -383,7 +450,7 @@ void laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host)
   op->diagonal_is_available = false;
 }
 
-int laplace_launches_per_vmult(const mfg_laplace *op) { return 1 + (int)op->mf->n_colors(); }
+int laplace_launches_per_vmult(const mfg_laplace *op) { return 1 + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0); }
 
 // kernel variants: 1 = column kernel (kernels_v0.cuh, every dim/degree/dtype/scatter),
 //                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter). 0 = auto.
@@ -415,39 +482,53 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       constrained_add<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n());
       MFG_CUDA_LAST();
     }
+  const bool     hanging = mf->hn_mask.n != 0;
+  const uint32_t n_plain = hanging ? mf->n_plain : mf->n_cells;
+  auto time_begin = [&]() {
+    if (!op->timing) return;
+    if (op->ev_used + 2 > op->ev.size())
+      for (int k = 0; k < 2; ++k) { cudaEvent_t e; MFG_CUDA(cudaEventCreate(&e)); op->ev.push_back(e); }
+    MFG_CUDA(cudaEventRecord(op->ev[op->ev_used], s));
+  };
+  auto time_end = [&]() {
+    if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
+  };
+  const bool atomic = mf->scatter == MFG_SCATTER_ATOMIC;
+  auto launch_v0 = [&](uint32_t c0, uint32_t c1, const uint32_t *mask) {
+    if (mf->dim == 2)
+      launch_laplace_v0_dim<2, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, c0, c1, mf->fe.val.data(),
+                                       mf->fe.colloc.data(), s, mask, mf->fe.hanging.data());
+    else
+      launch_laplace_v0_dim<3, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, c0, c1, mf->fe.val.data(),
+                                       mf->fe.colloc.data(), s, mask, mf->fe.hanging.data());
+  };
   if (laplace_active_variant(op) == 2)
     {
-      if (op->timing)
-        {
-          if (op->ev_used + 2 > op->ev.size())
-            for (int k = 0; k < 2; ++k) { cudaEvent_t e; MFG_CUDA(cudaEventCreate(&e)); op->ev.push_back(e); }
-          MFG_CUDA(cudaEventRecord(op->ev[op->ev_used], s));
-        }
       // variant 3 = 2 blocks x 4 warps per SM with up to 255 registers (no spills); measured faster than 3 x 4 x 168
       // for degree 4 in FP64 (profiles/r01_*), which is therefore what "auto" picks there
       const bool two_blocks = op->variant == 3 || (op->variant == 0 && mf->p == 4 && mf->dt == MFG_F64);
-      launch_laplace_slab<Number>(mf->p, two_blocks ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->n_cells, mf->fe.val.data(),
+      time_begin();
+      launch_laplace_slab<Number>(mf->p, two_blocks ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, n_plain, mf->fe.val.data(),
                                   mf->fe.colloc.data(), op->ctx->sm_count, s);
-      if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
-      return;
+      time_end();
     }
-  // cell_loop (matrix_free_gpu.h:369-380): one launch per color
-  const bool atomic = mf->scatter == MFG_SCATTER_ATOMIC;
-  for (uint32_t c = 0; c + 1 < mf->color_offsets.size(); ++c)
+  else
     {
-      if (op->timing)
+      // cell_loop (matrix_free_gpu.h:369-380): one launch per color
+      for (uint32_t c = 0; c + 1 < mf->color_offsets.size(); ++c)
         {
-          if (op->ev_used + 2 > op->ev.size())
-            for (int k = 0; k < 2; ++k) { cudaEvent_t e; MFG_CUDA(cudaEventCreate(&e)); op->ev.push_back(e); }
-          MFG_CUDA(cudaEventRecord(op->ev[op->ev_used], s));
+          time_begin();
+          launch_v0(mf->color_offsets[c], mf->color_offsets[c + 1], nullptr);
+          time_end();
         }
-      if (mf->dim == 2)
-        launch_laplace_v0_dim<2, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->color_offsets[c],
-                                         mf->color_offsets[c + 1], mf->fe.val.data(), mf->fe.colloc.data(), s);
-      else
-        launch_laplace_v0_dim<3, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->color_offsets[c],
-                                         mf->color_offsets[c + 1], mf->fe.val.data(), mf->fe.colloc.data(), s);
-      if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
+    }
+  // cells with hanging-node constraints (sorted to the end): column kernel with the interpolation fused into
+  // gather and scatter (resolve_hanging_nodes_shmem, fee_gpu.cuh:333-335, 349-351)
+  if (hanging && n_plain < mf->n_cells)
+    {
+      time_begin();
+      launch_v0(n_plain, mf->n_cells, mf->hn_mask.p);
+      time_end();
     }
 }
 
@@ -485,12 +566,14 @@ void laplace_compute_diagonal(mfg_laplace *op)
     }
   vec_fill(op->inv_diag.get(), 0.0);
   DiagTables tb;
-  for (int i = 0; i < mf->n * mf->n; ++i) { tb.val[i] = mf->fe.val[i]; tb.grad[i] = mf->fe.grad[i]; }
+  for (int i = 0; i < mf->n * mf->n; ++i) { tb.val[i] = mf->fe.val[i]; tb.grad[i] = mf->fe.grad[i]; tb.hang[i] = mf->fe.hanging[i]; }
+  const size_t dsm = 2 * (size_t)mf->npc * sizeof(double);
+  const uint32_t *hmask = mf->hn_mask.n ? mf->hn_mask.p : nullptr;
   const int threads = (int)std::min<uint32_t>(256, ((mf->npc + 31) / 32) * 32);
   if (mf->dt == MFG_F64)
-    diagonal_kernel<double><<<mf->n_cells, threads, 0, s>>>(mf->idx.p, (const double *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (double *)op->inv_diag->p);
+    diagonal_kernel<double><<<mf->n_cells, threads, dsm, s>>>(mf->idx.p, (const double *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (double *)op->inv_diag->p, hmask);
   else
-    diagonal_kernel<float><<<mf->n_cells, threads, 0, s>>>(mf->idx.p, (const float *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (float *)op->inv_diag->p);
+    diagonal_kernel<float><<<mf->n_cells, threads, dsm, s>>>(mf->idx.p, (const float *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (float *)op->inv_diag->p, hmask);
   MFG_CUDA_LAST();
   // constraint_handler.set_constrained_values(inv_diag, 1.0); inv_diag.invert()  (:416-418)
   ch_set(op->ch, op->inv_diag.get(), 1.0);

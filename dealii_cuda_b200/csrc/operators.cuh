@@ -19,6 +19,9 @@ struct mfg_mf
   std::vector<uint32_t> color_offsets;  // [n_colors+1] over the (color-sorted) cell order
   mfg::DevBuf<uint32_t> idx;            // [n_cells][npc] lexicographic; bit 31 = constrained DoF
   mfg::DevBuf<uint32_t> cell_perm;      // sorted position -> original cell (empty: identity)
+  // hanging nodes: cells [0, n_plain) have mask 0, cells [n_plain, n_cells) carry hn_mask[cell]
+  uint32_t              n_plain = 0;
+  mfg::DevBuf<uint32_t> hn_mask;        // [n_cells] in kernel cell order (empty: no hanging nodes)
   mfg::FEData1D         fe;
   // geometry: either a uniform mesh (origin/h/Morton map) or host arrays from the explicit description
   const mfg_mesh       *mesh = nullptr;         // not owned

@@ -147,6 +147,10 @@ typedef struct mfg_mf_desc
   mfg_scatter     scatter;
   uint32_t        n_colors;        /* COLOR: cells must be sorted by color */
   const uint32_t *color_offsets;   /* COLOR: [n_colors+1] */
+  /* hanging nodes (-DMATRIX_FREE_HANGING_NODES): per-cell 9-bit mask of HangingNodes::setup_constraints
+   * (hanging_nodes.cuh:38-50, 209-454); loc2glob must already carry the coarse neighbour's DoFs on the
+   * constrained faces / edges.  NULL: no hanging nodes.  Atomic scatter only. */
+  const uint32_t *constraint_mask; /* host, [n_cells] or NULL */
 } mfg_mf_desc;
 
 int mfg_mf_reinit(mfg_ctx *ctx, const mfg_mf_desc *desc, mfg_mf **out);              /* MatrixFreeGpu::reinit matrix_free_gpu.cu:448-563 */
@@ -158,6 +162,8 @@ uint32_t mfg_mf_n_colors(const mfg_mf *mf);
 size_t mfg_mf_memory_consumption(const mfg_mf *mf);                                   /* matrix_free_gpu.h:437-459 */
 /* shape tables handed to the kernels: [i*n+q] = phi_i(x_q), phi_i'(x_q) (matrix_free_gpu.cu:502-513) */
 int mfg_shape_info(int degree, double *shape_values, double *shape_gradients, double *q_points, double *q_weights);
+/* 1-D hanging-node interpolation weights W[k*n+i] = phi_i(xi_k/2) (setup_constraint_weights, hanging_nodes.cuh:580-598) */
+int mfg_hanging_node_weights(int degree, double *weights);
 
 /* ---- ConstraintHandlerGpu ------------------------------------------------ */
 int mfg_ch_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *constrained_host, size_t n_constrained,
