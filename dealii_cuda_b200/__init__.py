@@ -22,7 +22,7 @@ from . import _capi
 from ._capi import F32, F64, SCATTER_ATOMIC, SCATTER_COLOR, MfgError, check, lib
 
 __all__ = ["Context", "GpuVector", "HyperCubeMesh", "MatrixFreeGpu", "ConstraintHandlerGpu", "LaplaceOperatorGpu",
-           "shape_info", "F32", "F64", "SCATTER_ATOMIC", "SCATTER_COLOR", "MfgError"]
+           "shape_info", "solver_cg", "hanging_node_weights", "F32", "F64", "SCATTER_ATOMIC", "SCATTER_COLOR", "MfgError"]
 
 _NP = {F32: np.float32, F64: np.float64}
 
@@ -300,6 +300,18 @@ def shape_info(degree):
     val, grad, xq, wq = np.empty((n, n)), np.empty((n, n)), np.empty(n), np.empty(n)
     check(lib.mfg_shape_info(degree, _dp(val), _dp(grad), _dp(xq), _dp(wq)))
     return val, grad, xq, wq
+
+
+def solver_cg(op, x, b, abs_tol, max_iter=10000, use_jacobi=True, history=False):
+    """SolverCG<GpuVector>::solve(op, x, b, preconditioner) as the reference runs it (poisson.cu:247-260).
+    Returns (iterations, last residual[, residual history])."""
+    it, res = C.c_int(), C.c_double()
+    hist = np.zeros(max_iter + 1) if history else None
+    check(lib.mfg_solver_cg(op.h, x.h, b.h, float(abs_tol), int(max_iter), 1 if use_jacobi else 0, C.byref(it), C.byref(res),
+                            _dp(hist) if history else None))
+    if history:
+        return it.value, res.value, hist[:it.value + 1]
+    return it.value, res.value
 
 
 class ConstraintHandlerGpu:

@@ -214,6 +214,14 @@ int mfg_laplace_active_variant(const mfg_laplace *op);
  * Returns device milliseconds measured with CUDA events on the context stream. */
 int mfg_laplace_bmop(mfg_laplace *op, mfg_vec *dst, mfg_vec *src, int k, double init, float *elapsed_ms);
 
+/* ---- solver ----------------------------------------------------------------------------------------------
+ * Conjugate gradients with the control flow of deal.II's SolverCG as instantiated on GpuVector by the reference
+ * (poisson.cu:233-260): stops when |r| <= abs_tol (the reference uses 1e-12*|b|) or after max_iter iterations.
+ * use_jacobi: precondition with the operator's inverse diagonal (PreconditionChebyshev's default degree 0 is a
+ * scaled Jacobi step).  residual_history (optional) receives |r| after every iteration: max_iter+1 entries. */
+int mfg_solver_cg(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter, int use_jacobi, int *iters,
+                  double *last_residual, double *residual_history);
+
 /* ---- multi-GPU: interface-DoF exchange (new capability; the reference is single-GPU) -----------
  * The mesh is partitioned into boxes of cells, one per GPU.  Every rank stores all DoFs its cells touch;
  * DoFs on partition interfaces are replicated and kept consistent.  After the local cell loop the partial
