@@ -39,6 +39,11 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the cell kernel from the committed `ncu --set full`
+# captures (profiles/r01_*_ncu.txt), keyed by (dim, degree, dtype, refine, kernel variant); None if not profiled
+PROFILED_TRAFFIC = {(3, 4, "f64", 6, 2): 789.6e6, (3, 4, "f64", 6, 1): 789.3e6}
+
+
 class ClockSampler:
     """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -123,6 +128,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cg", action="store_true", help="skip the CG solve-time measurement (second part of BASELINE's metric)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,11 +214,30 @@ def main():
     e2e = {"value": n / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s, "d2h_bytes_per_step": n * s,
            "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps}
 
+    # CG solve time on the same operator (BASELINE metric "CG time"; poisson.cu:233-260 control flow, Jacobi
+    # preconditioner, |r| <= 1e-12 |b|, right-hand side b = A u for a seeded random u)
+    cg = None
+    if not args.no_cg:
+        ue = mf.GpuVector.wrap(ctx, torch.rand((n,), dtype=tdtype, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
+        vb_, vx_ = mf.GpuVector(ctx, n, dtype), mf.GpuVector(ctx, n, dtype)
+        op.vmult(vb_, ue)
+        op.compute_diagonal()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        its, res = mf.solver_cg(op, vx_, vb_, (1e-12 if args.dtype == "f64" else 1e-5) * vb_.l2_norm(), 10000)
+        ctx.synchronize()
+        cg_s = time.perf_counter() - t0
+        vx_.add(-1.0, ue)
+        cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "rel_error": vx_.l2_norm() / ue.l2_norm(),
+              "n_dofs": n, "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|"}
+        del ue, vb_, vx_
+
     peak, peak_src = measured_peaks()
     alg_bytes = b_alg(args.degree, args.dim, s) * n
     k_avg_ms = kernel_ms / max(1, kernel_launches) * op.cell_launches_per_vmult()
     achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": PROFILED_TRAFFIC.get((args.dim, args.degree, args.dtype, args.refine, op.active_variant())),
                 "kernel": "laplace cell kernel (variant %d)" % op.active_variant(), "kernel_ms": k_avg_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_dof": b_alg(args.degree, args.dim, s),
                 "whole_vmult_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
@@ -229,7 +254,7 @@ def main():
                        "l2": "inputs larger than L2 (index + coefficient + 2 vectors = %.0f MB)" %
                              ((mesh.n_cells * mesh.dofs_per_cell * (4 + s) + 2 * n * s) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * op.launches_per_vmult(), "roofline": roofline,
-            "cpu_baseline": cpu_baseline}
+            "cpu_baseline": cpu_baseline, "cg_solve": cg}
     print(json.dumps(line))
     return 0
 

@@ -52,8 +52,10 @@ def test_cg_matches_numpy_restatement(ctx, dim, p, r, jacobi):
     x, vb = mf.GpuVector(ctx, o.n_dofs), mf.GpuVector.from_numpy(ctx, b)
     it, res, hist = mf.solver_cg(op, x, vb, tol, 2000, use_jacobi=jacobi, history=True)
     assert abs(it - itr) <= 1, (it, itr)
-    k = int(0.8 * min(it, itr))
-    assert np.allclose(hist[:k], hr[:k], rtol=1e-6)
+    # CG iterates are roundoff-sensitive once orthogonality degrades: the first iterations are compared tightly, the
+    # whole run through the iteration count, the final residual and the solution
+    k = min(15, it, itr)
+    assert np.allclose(hist[:k], hr[:k], rtol=1e-9)
     got = x.toVector()
     assert np.linalg.norm(got - u_exact) <= 1e-8 * np.linalg.norm(u_exact)
     assert np.linalg.norm(got - xr) <= 1e-8 * np.linalg.norm(xr)
