@@ -487,6 +487,13 @@ class LaplaceOperatorGpu:
         """dst, src: contiguous numpy arrays (or pinned torch CPU tensors via .numpy())."""
         check(lib.mfg_laplace_vmult_host(self.h, dst.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p)))
 
+    def vmult_host_async(self, dst, src, slot):
+        """pipelined variant: returns immediately; alternate slot 0/1 with separate pinned buffers, then host_sync()"""
+        check(lib.mfg_laplace_vmult_host_async(self.h, dst.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), int(slot)))
+
+    def host_sync(self):
+        check(lib.mfg_laplace_host_sync(self.h))
+
     def compute_diagonal(self):
         check(lib.mfg_laplace_compute_diagonal(self.h))
 

@@ -114,6 +114,8 @@ def _load():
         "mfg_laplace_vmult_ptr": (C.c_int, [vp, vp, vp]),
         "mfg_laplace_vmult_add_ptr": (C.c_int, [vp, vp, vp]),
         "mfg_laplace_vmult_host": (C.c_int, [vp, vp, vp]),
+        "mfg_laplace_vmult_host_async": (C.c_int, [vp, vp, vp, C.c_int]),
+        "mfg_laplace_host_sync": (C.c_int, [vp]),
         "mfg_laplace_compute_diagonal": (C.c_int, [vp]),
         "mfg_laplace_get_diagonal_inverse": (C.c_int, [vp, pp]),
         "mfg_laplace_memory_consumption": (sz, [vp]),

@@ -288,6 +288,8 @@ int mfg_laplace_destroy(mfg_laplace *op)
     if (!op) return;
     if (op->inv_diag && op->inv_diag->p) cudaFree(op->inv_diag->p);
     for (cudaEvent_t e : op->ev) cudaEventDestroy(e);
+    for (auto &sl : op->slots) { if (sl.h2d) { cudaEventDestroy(sl.h2d); cudaEventDestroy(sl.done); cudaEventDestroy(sl.d2h); } }
+    if (op->h2d_stream) { cudaStreamDestroy(op->h2d_stream); cudaStreamDestroy(op->d2h_stream); }
     if (op->owns_mf) delete op->mf;
     if (op->owns_ch) delete op->ch;
     delete op;
@@ -317,6 +319,52 @@ int mfg_laplace_vmult_host(mfg_laplace *op, void *dst_host, const void *src_host
     laplace_vmult(op, op->host_stage_dst.p, op->host_stage_src.p, false);
     MFG_CUDA(cudaMemcpyAsync(dst_host, op->host_stage_dst.p, bytes, cudaMemcpyDeviceToHost, s));
     MFG_CUDA(cudaStreamSynchronize(s));
+  });
+}
+int mfg_laplace_vmult_host_async(mfg_laplace *op, void *dst_host, const void *src_host, int slot)
+{
+  return guarded([&] {
+    MFG_REQUIRE(op && dst_host && src_host, "null argument");
+    MFG_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+    const size_t bytes = (size_t)op->mf->n_dofs * (op->mf->dt == MFG_F64 ? 8 : 4);
+    if (!op->h2d_stream)
+      {
+        MFG_CUDA(cudaStreamCreateWithFlags(&op->h2d_stream, cudaStreamNonBlocking));
+        MFG_CUDA(cudaStreamCreateWithFlags(&op->d2h_stream, cudaStreamNonBlocking));
+      }
+    mfg_laplace::HostSlot &sl = op->slots[slot];
+    if (sl.src.n != bytes)
+      {
+        sl.src.alloc(bytes); sl.dst.alloc(bytes);
+        if (!sl.h2d)
+          {
+            MFG_CUDA(cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+            MFG_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+            MFG_CUDA(cudaEventCreateWithFlags(&sl.d2h, cudaEventDisableTiming));
+          }
+        sl.used = false;
+      }
+    cudaStream_t cs = op->ctx->stream;
+    // the slot's staging buffers are free once its previous apply has been computed (src) and copied out (dst)
+    if (sl.used) MFG_CUDA(cudaStreamWaitEvent(op->h2d_stream, sl.done, 0));
+    MFG_CUDA(cudaMemcpyAsync(sl.src.p, src_host, bytes, cudaMemcpyHostToDevice, op->h2d_stream));
+    MFG_CUDA(cudaEventRecord(sl.h2d, op->h2d_stream));
+    MFG_CUDA(cudaStreamWaitEvent(cs, sl.h2d, 0));
+    if (sl.used) MFG_CUDA(cudaStreamWaitEvent(cs, sl.d2h, 0));
+    laplace_vmult(op, sl.dst.p, sl.src.p, false);
+    MFG_CUDA(cudaEventRecord(sl.done, cs));
+    MFG_CUDA(cudaStreamWaitEvent(op->d2h_stream, sl.done, 0));
+    MFG_CUDA(cudaMemcpyAsync(dst_host, sl.dst.p, bytes, cudaMemcpyDeviceToHost, op->d2h_stream));
+    MFG_CUDA(cudaEventRecord(sl.d2h, op->d2h_stream));
+    sl.used = true;
+  });
+}
+int mfg_laplace_host_sync(mfg_laplace *op)
+{
+  return guarded([&] {
+    MFG_REQUIRE(op, "null operator");
+    if (op->h2d_stream) { MFG_CUDA(cudaStreamSynchronize(op->h2d_stream)); MFG_CUDA(cudaStreamSynchronize(op->d2h_stream)); }
+    MFG_CUDA(cudaStreamSynchronize(op->ctx->stream));
   });
 }
 int mfg_laplace_compute_diagonal(mfg_laplace *op) { return guarded([&] { MFG_REQUIRE(op, "null operator"); laplace_compute_diagonal(op); }); }

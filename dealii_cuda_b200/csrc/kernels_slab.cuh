@@ -66,9 +66,12 @@ template <int n, typename Number, int MINB_ = 0> struct SlabCfg
   static constexpr SlabStr LB = slab_str_LB<n, WB>(), AB = slab_str_AB<n, WB>(), AC = slab_str_AC<n, WB>();
   static constexpr int     BUF = ((cmax3(LB.SC, AB.SC, AC.SC) * CW + 3) / 4) * 4;  // elements of the transpose buffer
   static constexpr int     XBUF = (((LB.SC * CW > GE ? LB.SC * CW : GE) + 3) / 4) * 4;    // elements of the staging / coefficient buffer
-  static constexpr int     WPB = 4;  // warps per block (the register file is per SM sub-partition: 3 warps each -> 168 registers, 2 -> 255)
+  // warps per block.  The register file is per SM sub-partition: 2 warps each -> 255 registers, 3 -> 168, 4 -> 128.
+  // MINB_ == 15 selects the low-register variant: 3 blocks x 5 warps = 15 warps per SM at 128 registers.
+  static constexpr bool    LOWREG = MINB_ == 15;
+  static constexpr int     WPB = LOWREG ? 5 : 4;
   static constexpr size_t  SMEM = (size_t)WPB * (BUF + XBUF) * sizeof(Number);
-  static constexpr int     MINB = MINB_ ? MINB_ : (n <= 4 ? 4 : 3);
+  static constexpr int     MINB = LOWREG ? 3 : MINB_ ? MINB_ : (n <= 4 ? 4 : 3);
   // cp.async chunk for the coefficient block of one group (GE*WB bytes, contiguous in global memory)
   static constexpr int     CHUNK = (GE * WB) % 16 == 0 ? 16 : 8;
   static constexpr int     NCHUNK = GE * WB / CHUNK;
@@ -124,6 +127,7 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
   using Cfg = SlabCfg<n, Number, MINB_>;
   constexpr int CW = Cfg::CW, NA = Cfg::NA, NPC = Cfg::NPC, NS = Cfg::NS, GE = Cfg::GE, Q = Cfg::Q;
   constexpr SlabStr LB = Cfg::LB, AB = Cfg::AB, AC = Cfg::AC;
+  constexpr bool LOWREG = Cfg::LOWREG;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Number   *buf  = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * (Cfg::BUF + Cfg::XBUF);
@@ -161,11 +165,11 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
       }
   };
   // read_dof_values, asynchronous: src[ids] -> X in staging layout; constrained entries are zero-filled
-  auto issue_gather = [&](const uint32_t (&ids)[Q]) {
+  auto issue_gather = [&](const uint32_t (&ids)[Q], const int lane_o) {
 #pragma unroll
     for (int q = 0; q < Q; ++q)
       {
-        const int e = 32 * q + lane;
+        const int e = 32 * q + lane_o;
         if (q < Q - 1 || e < GE)
           {
             const bool con = ids[q] & CONSTRAINED_BIT;
@@ -191,13 +195,14 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
   {
     uint32_t ids[Q];
     load_ids(g0, ids);
-    issue_gather(ids);
+    issue_gather(ids, lane);
   }
   const int bLB = slab_addr(LB, c, a, 0, 0), bAB_B = slab_addr(AB, c, a, 0, 0);
   const int bAB_A = slab_addr(AB, c, 0, 0, a), bAC_A = slab_addr(AC, c, 0, 0, a), bAC_C = slab_addr(AC, c, 0, a, 0);
 
   for (uint32_t g = g0; g < n_groups; g += total_warps)
     {
+      const int lane_o = lane;
       const uint32_t gn       = g + total_warps;
       const bool     has_next = gn < n_groups;
       Number G[NS], R[NS];
@@ -249,13 +254,29 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
         }
       {
         const Number *wA = X + NPC * c + NS * a;  // W(c; i, j, k = a) at wA[i + n j]
-        // x lines
+        // x lines  (LOWREG: operands re-read from this thread's own entries in buf, see below)
 #pragma unroll
         for (int j = 0; j < n; ++j)
           {
             Number in[n], gq[n], t[n];
+            if (LOWREG)
+              {
+                if (active)
+                  {
 #pragma unroll
-            for (int i = 0; i < n; ++i) in[i] = G[i + n * j];
+                    for (int i = 0; i < n; ++i) in[i] = buf[bAC_A + i + AC.RJ * j];
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int i = 0; i < n; ++i) in[i] = 0;
+                  }
+              }
+            else
+              {
+#pragma unroll
+                for (int i = 0; i < n; ++i) in[i] = G[i + n * j];
+              }
             apply1d<n, false>(sh.D, in, gq);
             if (active)
               {
@@ -266,13 +287,30 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
 #pragma unroll
             for (int i = 0; i < n; ++i) R[i + n * j] = t[i];
           }
-        // y lines
+        // y lines.  LOWREG: re-read G from this thread's own entries in buf (written just above) so that G's registers
+        // are dead after the x lines -- one slab less in the register peak (128 registers, 15 warps per SM)
 #pragma unroll
         for (int i = 0; i < n; ++i)
           {
             Number in[n], gq[n], t[n];
+            if (LOWREG)
+              {
+                if (active)
+                  {
 #pragma unroll
-            for (int j = 0; j < n; ++j) in[j] = G[i + n * j];
+                    for (int j = 0; j < n; ++j) in[j] = buf[bAC_A + i + AC.RJ * j];
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int j = 0; j < n; ++j) in[j] = 0;
+                  }
+              }
+            else
+              {
+#pragma unroll
+                for (int j = 0; j < n; ++j) in[j] = G[i + n * j];
+              }
             apply1d<n, false>(sh.D, in, gq);
             if (active)
               {
@@ -326,7 +364,7 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
             for (int i = 0; i < n; ++i) buf[bAB_A + i + AB.RJ * j] = R[i + n * j];
         }
       // asynchronous gather of the next group's DoF values behind the rest of this group
-      if (has_next) issue_gather(ids);
+      if (has_next) issue_gather(ids, lane_o);
       __syncwarp();
       // ---- B: N_z^T ----
       if (active)
@@ -355,7 +393,7 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
 #pragma unroll
             for (int q = 0; q < Q; ++q)
               {
-                const int e = 32 * q + lane;
+                const int e = 32 * q + lane_o;
                 if (q < Q - 1 || e < GE)
                   {
                     const uint32_t id = __ldg(idx + ebase + e);
@@ -368,7 +406,7 @@ laplace_cell_slab(const uint32_t *__restrict__ idx, const Number *__restrict__ c
 #pragma unroll
             for (int q = 0; q < Q; ++q)
               {
-                const int e = 32 * q + lane;
+                const int e = 32 * q + lane_o;
                 if (e < GE && cell0 + e / NPC < n_cells)
                   {
                     const uint32_t id = __ldg(idx + ebase + e);

@@ -323,6 +323,7 @@ __global__ void vmult_prepare(Number *__restrict__ dst, const Number *__restrict
   struct alignas(16) Vec { Number v[V]; };
   const size_t nvec   = n / V;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 4
   for (size_t iv = (size_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride)
     {
       const size_t   i    = iv * V;

@@ -458,7 +458,7 @@ int laplace_active_variant(const mfg_laplace *op)
 {
   const mfg_mf *mf = op->mf;
   const bool slab_ok = slab_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
-  if (op->variant >= 2 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
+  if (op->variant >= 2 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3/4 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
   if (op->variant == 1) return 1;
   if (op->variant >= 2) return 2;
   return slab_ok ? 2 : 1;
@@ -508,7 +508,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       // for degree 4 in FP64 (profiles/r01_*), which is therefore what "auto" picks there
       const bool two_blocks = op->variant == 3 || (op->variant == 0 && mf->p == 4 && mf->dt == MFG_F64);
       time_begin();
-      launch_laplace_slab<Number>(mf->p, two_blocks ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, n_plain, mf->fe.val.data(),
+      launch_laplace_slab<Number>(mf->p, op->variant == 4 ? 15 : two_blocks ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, n_plain, mf->fe.val.data(),
                                   mf->fe.colloc.data(), op->ctx->sm_count, s);
       time_end();
     }

@@ -51,6 +51,10 @@ struct mfg_laplace
   bool     diagonal_is_available = false;
   int      variant = 0;
   mfg::DevBuf<uint8_t> host_stage_src, host_stage_dst;  // device staging for vmult_host
+  // pipelined host API (mfg_laplace_vmult_host_async): 2 slots x {src,dst} staging, copy streams, events
+  struct HostSlot { mfg::DevBuf<uint8_t> src, dst; cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr; bool used = false; };
+  HostSlot     slots[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // optional per-launch timing of the cell kernel (bench.py roofline figure)
   bool                     timing = false;
   std::vector<cudaEvent_t> ev;        // pairs (start, stop)

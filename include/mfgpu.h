@@ -200,6 +200,11 @@ int mfg_laplace_vmult_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev);
 int mfg_laplace_vmult_add_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev);
 /* host buffers: H2D copy of src, vmult, D2H copy of dst; blocking */
 int mfg_laplace_vmult_host(mfg_laplace *op, void *dst_host, const void *src_host);
+/* pipelined host-buffer apply: two slots (0/1), each with its own device staging; H2D, vmult and D2H of
+ * consecutive calls overlap on three streams (PCIe is full duplex).  Host buffers should be pinned and must stay
+ * valid until mfg_laplace_host_sync.  Non-blocking. */
+int mfg_laplace_vmult_host_async(mfg_laplace *op, void *dst_host, const void *src_host, int slot);
+int mfg_laplace_host_sync(mfg_laplace *op);   /* blocking: all pipelined applies have landed in their dst_host */
 int mfg_laplace_compute_diagonal(mfg_laplace *op);                                   /* :405-421 */
 int mfg_laplace_get_diagonal_inverse(mfg_laplace *op, mfg_vec **out);                /* :423-429, borrowed */
 size_t mfg_laplace_memory_consumption(const mfg_laplace *op);                        /* :434-445 */

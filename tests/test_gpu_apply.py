@@ -260,6 +260,15 @@ def test_vmult_host_and_ptr_entry_points(ctx):
     out = np.empty_like(u)
     op.vmult_host(out, u)
     assert rel_err(out, want) <= 1e-12
+    # pipelined host API: two slots in flight, different inputs
+    u2 = sm64(5, o.n_dofs)
+    hs = [torch.from_numpy(u).pin_memory(), torch.from_numpy(u2).pin_memory()]
+    hd = [torch.empty(o.n_dofs, dtype=torch.float64).pin_memory() for _ in range(2)]
+    for rep in range(3):
+        for k in range(2):
+            op.vmult_host_async(hd[k].numpy(), hs[k].numpy(), k)
+    op.host_sync()
+    assert rel_err(hd[0].numpy(), want) <= 1e-12 and rel_err(hd[1].numpy(), o.vmult(u2)) <= 1e-12
     ts = torch.from_numpy(u).cuda(); td = torch.empty_like(ts)
     torch.cuda.synchronize()
     op.vmult_ptr(td.data_ptr(), ts.data_ptr())
