@@ -509,7 +509,7 @@ class LaplaceOperatorGpu:
         return lib.mfg_laplace_launches_per_vmult(self.h)
 
     def cell_launches_per_vmult(self):
-        return self.launches_per_vmult() - 1
+        return lib.mfg_laplace_cell_launches_per_vmult(self.h)
 
     def active_variant(self):
         return lib.mfg_laplace_active_variant(self.h)

@@ -120,6 +120,7 @@ def _load():
         "mfg_laplace_get_diagonal_inverse": (C.c_int, [vp, pp]),
         "mfg_laplace_memory_consumption": (sz, [vp]),
         "mfg_laplace_launches_per_vmult": (C.c_int, [vp]),
+        "mfg_laplace_cell_launches_per_vmult": (C.c_int, [vp]),
         "mfg_laplace_enable_kernel_timing": (C.c_int, [vp, C.c_int]),
         "mfg_laplace_kernel_time_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int)]),
         "mfg_laplace_active_variant": (C.c_int, [vp]),

@@ -393,6 +393,7 @@ int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launche
 }
 int mfg_laplace_active_variant(const mfg_laplace *op) { return op ? laplace_active_variant(op) : 0; }
 int mfg_laplace_launches_per_vmult(const mfg_laplace *op) { return op ? laplace_launches_per_vmult(op) : 0; }
+int mfg_laplace_cell_launches_per_vmult(const mfg_laplace *op) { return op ? (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0) : 0; }
 int mfg_laplace_bmop(mfg_laplace *op, mfg_vec *dst, mfg_vec *src, int k, double init, float *elapsed_ms)
 {
   return guarded([&] {

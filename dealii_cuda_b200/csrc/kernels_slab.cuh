@@ -68,10 +68,10 @@ template <int n, typename Number, int MINB_ = 0> struct SlabCfg
   static constexpr int     XBUF = (((LB.SC * CW > GE ? LB.SC * CW : GE) + 3) / 4) * 4;    // elements of the staging / coefficient buffer
   // warps per block.  The register file is per SM sub-partition: 2 warps each -> 255 registers, 3 -> 168, 4 -> 128.
   // MINB_ == 15 selects the low-register variant: 3 blocks x 5 warps = 15 warps per SM at 128 registers.
-  static constexpr bool    LOWREG = MINB_ == 15;
-  static constexpr int     WPB = LOWREG ? 5 : 4;
+  static constexpr bool    LOWREG = MINB_ == 15 || MINB_ == 12;  // 12: low-register code at 3 blocks x 4 warps (168 registers)
+  static constexpr int     WPB = MINB_ == 15 ? 5 : 4;
   static constexpr size_t  SMEM = (size_t)WPB * (BUF + XBUF) * sizeof(Number);
-  static constexpr int     MINB = LOWREG ? 3 : MINB_ ? MINB_ : (n <= 4 ? 4 : 3);
+  static constexpr int     MINB = (MINB_ == 15 || MINB_ == 12) ? 3 : MINB_ ? MINB_ : (n <= 4 ? 4 : 3);
   // cp.async chunk for the coefficient block of one group (GE*WB bytes, contiguous in global memory)
   static constexpr int     CHUNK = (GE * WB) % 16 == 0 ? 16 : 8;
   static constexpr int     NCHUNK = GE * WB / CHUNK;

@@ -48,6 +48,7 @@ void launch_laplace_slab<inst_number>(int degree, int min_blocks, const uint32_t
       case 4:
         if (min_blocks == 2) launch_n<5, inst_number, 2>(idx, cw, src, dst, n_cells, N, D, sm_count, stream);
         else if (min_blocks == 15) launch_n<5, inst_number, 15>(idx, cw, src, dst, n_cells, N, D, sm_count, stream);
+        else if (min_blocks == 12) launch_n<5, inst_number, 12>(idx, cw, src, dst, n_cells, N, D, sm_count, stream);
         else launch_n<5, inst_number, 0>(idx, cw, src, dst, n_cells, N, D, sm_count, stream);
         break;
       default: throw Error(MFG_ERR_UNSUPPORTED, "slab kernel: degree must be in 1..4");

@@ -346,6 +346,14 @@ __global__ void vmult_prepare(Number *__restrict__ dst, const Number *__restrict
     }
 }
 
+// dst[c] = src[c] over the constrained list (vmult after a memset of dst)
+template <typename Number>
+__global__ void constrained_copy(Number *__restrict__ dst, const Number *__restrict__ src, const uint32_t *__restrict__ list, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint32_t c = list[i]; dst[c] = src[c]; }
+}
+
 // dst[c] += src[c] over the constrained list (vmult_add)
 template <typename Number>
 __global__ void constrained_add(Number *__restrict__ dst, const Number *__restrict__ src, const uint32_t *__restrict__ list, size_t n)

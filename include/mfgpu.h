@@ -210,6 +210,7 @@ int mfg_laplace_get_diagonal_inverse(mfg_laplace *op, mfg_vec **out);           
 size_t mfg_laplace_memory_consumption(const mfg_laplace *op);                        /* :434-445 */
 /* number of kernel launches one vmult enqueues (for bench.py's gpu_launches) */
 int mfg_laplace_launches_per_vmult(const mfg_laplace *op);
+int mfg_laplace_cell_launches_per_vmult(const mfg_laplace *op); /* cell-kernel launches among them */
 /* per-kernel device timing for the roofline figure: when enabled every cell-kernel launch is bracketed by
  * CUDA events on the context stream; kernel_time_ms (blocking) returns and resets the accumulated time. */
 int mfg_laplace_enable_kernel_timing(mfg_laplace *op, int on);

@@ -43,7 +43,7 @@ if __name__ == "__main__":
     cases = []
     if args.quick:
         cases = [(3, 4, 5, np.float64, False, 1), (3, 4, 5, np.float64, False, 2), (3, 4, 6, np.float64, False, 1), (3, 4, 6, np.float64, False, 2),
-                 (3, 4, 6, np.float64, False, 3), (3, 4, 6, np.float64, False, 4), (3, 4, 6, np.float64, True, 1), (3, 4, 6, np.float32, False, 3), (3, 4, 6, np.float32, False, 4), (3, 4, 6, np.float32, False, 1), (3, 4, 6, np.float32, False, 2),
+                 (3, 4, 6, np.float64, False, 3), (3, 4, 6, np.float64, False, 4), (3, 4, 6, np.float64, False, 5), (3, 4, 6, np.float64, True, 1), (3, 4, 6, np.float32, False, 5), (3, 4, 6, np.float32, False, 3), (3, 4, 6, np.float32, False, 4), (3, 4, 6, np.float32, False, 1), (3, 4, 6, np.float32, False, 2),
                  (3, 3, 6, np.float64, False, 1), (3, 3, 6, np.float64, False, 2), (3, 2, 7, np.float64, False, 1), (3, 2, 7, np.float64, False, 2),
                  (3, 1, 7, np.float64, False, 1), (3, 1, 7, np.float64, False, 2), (3, 4, 7, np.float64, False, 2)]
     else:
