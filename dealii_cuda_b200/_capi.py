@@ -124,6 +124,10 @@ def _load():
         "mfg_laplace_enable_kernel_timing": (C.c_int, [vp, C.c_int]),
         "mfg_laplace_kernel_time_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int)]),
         "mfg_laplace_active_variant": (C.c_int, [vp]),
+        "mfg_mgt_build": (C.c_int, [vp, vp, vp, C.c_int, pp]),
+        "mfg_mgt_destroy": (C.c_int, [vp]),
+        "mfg_mgt_prolongate": (C.c_int, [vp, vp, vp]),
+        "mfg_mgt_restrict_and_add": (C.c_int, [vp, vp, vp]),
         "mfg_solver_cg": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), dp, dp]),
         "mfg_exchange_create": (C.c_int, [vp, C.c_int, u32p, sz, u32p, sz, u32p, C.POINTER(C.c_int32), sz, pp]),
         "mfg_exchange_destroy": (C.c_int, [vp]),

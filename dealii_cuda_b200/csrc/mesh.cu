@@ -12,6 +12,7 @@
 //     directions d where it has a lower neighbour: prod_d (p + [c_d == 0]) DoFs;
 //   * inside the cell they are numbered in hierarchic order (vertices, lines,
 //     quads, hex) -- a table of 2^dim variants indexed by the boundary flags.
+#include <memory>
 #include <cub/cub.cuh>
 #include "mesh.cuh"
 
@@ -235,6 +236,13 @@ void mesh_lattice_to_dof(const mfg_mesh *m, size_t npts, const uint32_t *xyz_hos
   lattice_lookup<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(params_of(m), m->cell_first.p, m->rank_table.p, npts, xyz.p, out.p);
   MFG_CUDA_LAST();
   out.download(out_host, s);
+}
+
+void mesh_lattice_to_dof_device(const mfg_mesh *m, size_t npts, const uint32_t *xyz_dev, uint32_t *out_dev)
+{
+  if (!npts) return;
+  lattice_lookup<<<(unsigned)((npts + 255) / 256), 256, 0, m->ctx->stream>>>(params_of(m), m->cell_first.p, m->rank_table.p, npts, xyz_dev, out_dev);
+  MFG_CUDA_LAST();
 }
 
 void mesh_cell_coords(const mfg_mesh *m, uint32_t *out_host)

@@ -220,6 +220,18 @@ int mfg_laplace_active_variant(const mfg_laplace *op);
  * Returns device milliseconds measured with CUDA events on the context stream. */
 int mfg_laplace_bmop(mfg_laplace *op, mfg_vec *dst, mfg_vec *src, int k, double init, float *elapsed_ms);
 
+/* ---- MGTransferMatrixFreeGpu (matrix_free_gpu/mg_transfer_matrix_free_gpu.h:64-307) ----------------------------
+ * One object per level pair of a globally refined mesh hierarchy (fine = global refinement of coarse).
+ * prolongate: dst_fine = P src_coarse, coarse Dirichlet DoFs read as 0 (.cu:592-622).
+ * restrict_and_add: dst_coarse += P^T src_fine on non-Dirichlet coarse DoFs (.cu:626-654).
+ * copy_to_mg / copy_from_mg (.cu:688-757) are plain copies on globally refined meshes (the finest level IS the
+ * active mesh with the same numbering): mfg_vec_copy. */
+typedef struct mfg_mgt mfg_mgt;
+int mfg_mgt_build(mfg_ctx *ctx, const mfg_mesh *coarse, const mfg_mesh *fine, mfg_dtype dt, mfg_mgt **out);
+int mfg_mgt_destroy(mfg_mgt *t);
+int mfg_mgt_prolongate(mfg_mgt *t, mfg_vec *dst_fine, const mfg_vec *src_coarse);
+int mfg_mgt_restrict_and_add(mfg_mgt *t, mfg_vec *dst_coarse, const mfg_vec *src_fine);
+
 /* ---- solver ----------------------------------------------------------------------------------------------
  * Conjugate gradients with the control flow of deal.II's SolverCG as instantiated on GpuVector by the reference
  * (poisson.cu:233-260): stops when |r| <= abs_tol (the reference uses 1e-12*|b|) or after max_iter iterations.
