@@ -21,7 +21,7 @@ import numpy as np
 from . import _capi
 from ._capi import F32, F64, SCATTER_ATOMIC, SCATTER_COLOR, MfgError, check, lib
 
-__all__ = ["Context", "multigrid", "GpuVector", "HyperCubeMesh", "MatrixFreeGpu", "ConstraintHandlerGpu", "LaplaceOperatorGpu",
+__all__ = ["Context", "GpuVector", "HyperCubeMesh", "MatrixFreeGpu", "ConstraintHandlerGpu", "LaplaceOperatorGpu",
            "shape_info", "solver_cg", "hanging_node_weights", "F32", "F64", "SCATTER_ATOMIC", "SCATTER_COLOR", "MfgError"]
 
 _NP = {F32: np.float32, F64: np.float64}
