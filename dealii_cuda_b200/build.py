@@ -25,6 +25,7 @@ for dim in (2, 3):
         UNITS.append(("kernels_v0_inst.cu", f"_d{dim}_f{f64}", [f"-DMFG_INST_DIM={dim}", f"-DMFG_INST_F64={f64}"]))
 for f64 in (0, 1):
     UNITS.append(("kernels_slab_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
+    UNITS.append(("kernels_slab2_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
 
 
 def _headers():

@@ -1,0 +1,424 @@
+// kernels_slab2.cuh -- second-generation slab Laplace cell kernel for 3D, n = p+1 <= 6.
+//
+// Same operator as kernels_v0.cuh / kernels_slab.cuh (the reference's apply_kernel_shmem<LocalOperator>,
+// matrix_free_gpu.h:318-341 + fee_gpu.cuh:197-365 + tensor_ops.cuh:179-261).  Built from the ncu profile of the
+// first slab kernel (profiles/r01_slab_kernel_8warps_q4_f64_r6_ncu.txt): 224 L1-data-pipe wavefronts per cell
+// (172 shared + 52 global) at 65 % of the pipe, FP64 pipe 41 %.  Changes:
+//   * the kernel's own copies of the index map and of the merged coefficient are stored in the order the threads
+//     consume them (built once at setup, operators.cu):
+//       idxP [group][slot j + n k][32 lanes]     one fully coalesced 128-byte row per gather / scatter instruction,
+//                                                every lane reads the DoF indices of its OWN slab -> the gathered
+//                                                values land in registers, no staging round trip through shared memory;
+//       cwP  [group][shared-memory image]        one bulk-async copy (TMA, cp.async.bulk + mbarrier) per group puts the
+//                                                coefficient block into shared memory without touching registers or
+//                                                the LSU store path; the image is conflict free for BOTH layouts that
+//                                                read it;
+//   * 4 transposes per cell tensor entry instead of 7 shared-memory round trips:
+//       A (owns y,z) --T1--> B (owns x,y) --T2: u_q and the x,y part of the result--> C (owns x,z) --T3--> A
+//   * even-odd decomposition of every 1-D contraction (the Gauss / Gauss-Lobatto points are symmetric about the cell
+//     centre, so the interpolation matrix is centro-symmetric and the collocation derivative centro-antisymmetric):
+//     21 resp. 20 FP64 operations per line of 5 instead of 25;
+//   * results are scattered straight from registers with red.global.add.
+// Thread layouts (a warp = CW = 32/n cells, lane <-> (cell c, index x), see slab2_lane):
+//   A: x = i, registers (j,k)     B: x = k, registers (i,j)     C: x = j, registers (i,k)
+// Sequence per group of cells:
+//   gather -> A: N_y N_z -> B: N_x, quadrature phases x and y -> C: quadrature phase z, sum, N_x^T N_z^T
+//          -> A: N_y^T -> red.add
+#pragma once
+#include "kernels_v0.cuh"
+
+namespace mfg {
+
+struct Slab2Lay { int SL, SH, SI, SJ, SK; };
+
+// Lane map ("half split"): a warp group holds CW = 32/n cells, cell c = cl + HC*ch with HC = CW/2; the cells with ch = 0
+// live in lanes 0..15, the others in lanes 16..31, lane = 16 ch + n cl + x.  A 64-bit gather / scatter instruction is
+// processed per half warp, and this way each half touches the DoFs of HC cells only (tools/gather_line_model.py).
+// For odd CW (n = 6) there is no split: lane = n c + x.
+// Strides found by tools/slab2_layout_search.py: element (c,i,j,k) of a group at SL*cl + SH*ch + SI*i + SJ*j + SK*k.
+// AB: conflict free for lanes (c,i) and (c,k); BC: lanes (c,k) and (c,j); CA: lanes (c,j) and (c,i).
+// F = elements per buffer, a multiple of 16 bytes; the coefficient image uses the BC layout.
+template <int n, int WB> struct Slab2Tab;
+#define MFG_SLAB2_TAB(n_, WB_, AB_, BC_, CA_, F_)                                                  \
+  template <> struct Slab2Tab<n_, WB_>                                                             \
+  {                                                                                                \
+    static constexpr Slab2Lay AB() { return Slab2Lay AB_; }                                        \
+    static constexpr Slab2Lay BC() { return Slab2Lay BC_; }                                        \
+    static constexpr Slab2Lay CA() { return Slab2Lay CA_; }                                        \
+    static constexpr int F = F_;                                                                   \
+  }
+#define MFG_L(...) {__VA_ARGS__}
+MFG_SLAB2_TAB(2, 8, MFG_L(2, 16, 1, 32, 65), MFG_L(2, 16, 32, 1, 65), MFG_L(2, 16, 1, 65, 32), 130);
+MFG_SLAB2_TAB(3, 8, MFG_L(3, 45, 1, 90, 15), MFG_L(9, 135, 1, 3, 45), MFG_L(3, 45, 1, 15, 90), 270);
+MFG_SLAB2_TAB(4, 8, MFG_L(4, 16, 1, 32, 129), MFG_L(4, 16, 32, 1, 129), MFG_L(4, 16, 1, 129, 32), 516);
+MFG_SLAB2_TAB(5, 8, MFG_L(5, 75, 1, 150, 15), MFG_L(25, 375, 1, 5, 75), MFG_L(5, 75, 1, 15, 150), 750);
+MFG_SLAB2_TAB(6, 8, MFG_L(6, 0, 1, 30, 185), MFG_L(6, 0, 30, 1, 185), MFG_L(6, 0, 1, 185, 30), 1106);
+MFG_SLAB2_TAB(2, 4, MFG_L(4, 1, 2, 32, 66), MFG_L(4, 1, 32, 2, 66), MFG_L(4, 1, 2, 66, 32), 132);
+MFG_SLAB2_TAB(3, 4, MFG_L(1, 15, 5, 30, 91), MFG_L(1, 15, 30, 5, 91), MFG_L(1, 15, 5, 91, 30), 272);
+MFG_SLAB2_TAB(4, 4, MFG_L(4, 16, 1, 32, 129), MFG_L(4, 16, 32, 1, 129), MFG_L(4, 16, 1, 129, 32), 516);
+MFG_SLAB2_TAB(5, 4, MFG_L(10, 1, 2, 150, 30), MFG_L(50, 1, 2, 10, 150), MFG_L(10, 1, 2, 30, 150), 752);
+MFG_SLAB2_TAB(6, 4, MFG_L(1, 0, 5, 30, 187), MFG_L(1, 0, 30, 5, 187), MFG_L(1, 0, 5, 187, 30), 1116);
+#undef MFG_L
+#undef MFG_SLAB2_TAB
+
+// lane <-> (cell in group, index x); idle lanes get cell = -1
+struct Slab2Lane { int c, cl, ch, x; };
+template <int n> __host__ __device__ inline Slab2Lane slab2_lane(int lane)
+{
+  constexpr int  CW = 32 / n, HC = CW % 2 == 0 ? CW / 2 : CW;
+  constexpr bool SPLIT = CW % 2 == 0;
+  const int      ch = SPLIT ? lane / 16 : 0, l16 = SPLIT ? lane % 16 : lane;
+  if (l16 >= HC * n) return Slab2Lane{-1, 0, ch, 0};
+  return Slab2Lane{HC * ch + l16 / n, l16 / n, ch, l16 % n};
+}
+
+// Even-odd tables of one 1-D matrix M (out[q] = sum_k M[k][q] in[k]) with M[n-1-k][n-1-q] = +-M[k][q]:
+//   Ce[k][q] = (M[k][q] + M[n-1-k][q]) / 2   (k < n/2),   Ce[n/2][q] = M[n/2][q]  (n odd: the middle input)
+//   Co[k][q] = (M[k][q] - M[n-1-k][q]) / 2   (k < n/2)
+// rows have length m = (n+1)/2
+template <typename Number, int n> struct EoTab
+{
+  static constexpr int h = n / 2, m = (n + 1) / 2;
+  Number Ce[(h + 1) * m];
+  Number Co[h * m];
+};
+template <typename Number, int n> struct EoMats { EoTab<Number, n> N, NT, D, DT; };
+
+// out = M^T-contraction of one line.  ANTI = false: centro-symmetric M (interpolation), true: centro-antisymmetric
+// (collocation derivative)
+template <int n, bool ANTI, typename Number>
+__device__ __forceinline__ void eo_apply(const EoTab<Number, n> &T, const Number (&in)[n], Number (&out)[n])
+{
+  constexpr int  h = n / 2, m = (n + 1) / 2;
+  constexpr bool odd = n & 1;
+  constexpr int  qe = ANTI ? h : m;  // outputs fed by the even part of the input (+ the middle input)
+  constexpr int  qo = ANTI ? m : h;  // outputs fed by the odd part
+  Number e[h], o[h], P[m], R[m];
+#pragma unroll
+  for (int k = 0; k < h; ++k) { e[k] = in[k] + in[n - 1 - k]; o[k] = in[k] - in[n - 1 - k]; }
+#pragma unroll
+  for (int q = 0; q < qe; ++q) P[q] = T.Ce[q] * e[0];
+#pragma unroll
+  for (int k = 1; k < h; ++k)
+#pragma unroll
+    for (int q = 0; q < qe; ++q) P[q] = fma(T.Ce[k * m + q], e[k], P[q]);
+  if (odd)
+    {
+#pragma unroll
+      for (int q = 0; q < qe; ++q) P[q] = fma(T.Ce[h * m + q], in[h], P[q]);
+    }
+#pragma unroll
+  for (int q = 0; q < qo; ++q) R[q] = T.Co[q] * o[0];
+#pragma unroll
+  for (int k = 1; k < h; ++k)
+#pragma unroll
+    for (int q = 0; q < qo; ++q) R[q] = fma(T.Co[k * m + q], o[k], R[q]);
+#pragma unroll
+  for (int q = 0; q < h; ++q)
+    {
+      out[q]         = ANTI ? R[q] + P[q] : P[q] + R[q];
+      out[n - 1 - q] = ANTI ? R[q] - P[q] : P[q] - R[q];
+    }
+  if (odd) out[h] = ANTI ? R[h] : P[h];
+}
+
+// contraction of every line of a slab held in registers: contracted index has register stride S, lines stride T
+template <int n, int S, int T, bool ANTI, typename Number>
+__device__ __forceinline__ void slab2_apply(const EoTab<Number, n> &M, Number (&v)[n * n])
+{
+#pragma unroll
+  for (int l = 0; l < n; ++l)
+    {
+      Number in[n], out[n];
+#pragma unroll
+      for (int e = 0; e < n; ++e) in[e] = v[l * T + e * S];
+      eo_apply<n, ANTI>(M, in, out);
+#pragma unroll
+      for (int e = 0; e < n; ++e) v[l * T + e * S] = out[e];
+    }
+}
+
+// CFG: 0 = 3 blocks x 4 warps per SM (168 registers), 2 transpose buffers per warp
+//      1 = 2 blocks x 4 warps (255 registers), 2 buffers
+//      2 = 4 blocks x 4 warps (128 registers), 1 buffer
+//      3 = 3 blocks x 4 warps (168 registers), 1 buffer (more L1 left for the gather)
+template <int n, typename Number, int CFG> struct Slab2Cfg
+{
+  static constexpr int WB  = (int)sizeof(Number);
+  using Tab = Slab2Tab<n, WB>;
+  static constexpr int CW  = 32 / n;   // cells per warp group
+  static constexpr int NPC = n * n * n;
+  static constexpr int NS  = n * n;
+  static constexpr int WPB = 4;
+  static constexpr int OCC  = CFG % 4;
+  static constexpr bool TEX = (CFG / 4) % 2;  // gather src through the texture pipe (tex1Dfetch) instead of the LSU pipe
+  // software pipeline: 0 = none; 1 = the index rows of the next group are loaded during the C phase of the current one
+  // and the rows needed by the scatter are re-read before N_y^T; 2 = in addition the gather of the next group is issued
+  // before the scatter of the current one
+  static constexpr int PF   = CFG / 8;
+  static constexpr int MINB = OCC == 1 ? 2 : OCC == 2 ? 4 : 3;
+  static constexpr int NBUF = (OCC == 2 || OCC == 3) ? 1 : 2;
+  static constexpr int F   = Tab::F;
+  static constexpr int CWF = Tab::F;  // the coefficient image has the BC layout
+  static constexpr int PER_WARP = CWF + NBUF * F;    // elements
+  static constexpr size_t SMEM = 16 * WPB /* mbarriers */ + (size_t)WPB * PER_WARP * sizeof(Number);
+  static constexpr uint32_t CW_BYTES = CWF * WB;
+  static_assert(CW_BYTES % 16 == 0 && (F * WB) % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// one bulk-async copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+
+template <typename Number> __device__ __forceinline__ Number tex_fetch(cudaTextureObject_t tex, uint32_t i);
+template <> __device__ __forceinline__ double tex_fetch<double>(cudaTextureObject_t tex, uint32_t i)
+{
+  const int2 t = tex1Dfetch<int2>(tex, (int)i);
+  return __hiloint2double(t.y, t.x);
+}
+template <> __device__ __forceinline__ float tex_fetch<float>(cudaTextureObject_t tex, uint32_t i) { return tex1Dfetch<float>(tex, (int)i); }
+
+template <int n, typename Number, int CFG>
+__global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n, Number, CFG>::MINB)
+laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
+                   Number *__restrict__ dst, const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em,
+                   const cudaTextureObject_t tex)
+{
+  using Cfg = Slab2Cfg<n, Number, CFG>;
+  using Tab = typename Cfg::Tab;
+  constexpr int NS = Cfg::NS;
+  constexpr Slab2Lay AB = Tab::AB(), BC = Tab::BC(), CA = Tab::CA();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw) + 2 * warp;
+  Number   *W   = reinterpret_cast<Number *>(smem_raw + 16 * Cfg::WPB) + (size_t)warp * Cfg::PER_WARP;  // coefficient image
+  Number   *P   = W + Cfg::CWF;
+  Number   *Q   = Cfg::NBUF == 2 ? P + Cfg::F : P;
+  const Slab2Lane lm = slab2_lane<n>(lane);
+  const bool active = lm.c >= 0;
+  // idle lanes shadow the first lane of their own half warp for loads (broadcast, no conflict) and never store
+  const int cl = lm.cl, ch = lm.ch, x = lm.x;
+  const uint32_t total_warps = gridDim.x * Cfg::WPB;
+  const uint32_t g0 = blockIdx.x * Cfg::WPB + warp;
+  if (g0 >= n_groups) return;
+
+  if (lane == 0)
+    {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  __syncwarp();
+  if (lane == 0) bulk_load(W, cwP + (size_t)g0 * Cfg::CWF, Cfg::CW_BYTES, bar);
+  unsigned phase = 0;
+
+  // per-lane base addresses: layout XY written in X, read in Y
+  const int cAB = AB.SL * cl + AB.SH * ch, cBC = BC.SL * cl + BC.SH * ch, cCA = CA.SL * cl + CA.SH * ch;
+  const int bABw = cAB + AB.SI * x, bABr = cAB + AB.SK * x;  // A: x = i ; B: x = k
+  const int bBCw = cBC + BC.SK * x, bBCr = cBC + BC.SJ * x;  // B: x = k ; C: x = j
+  const int bCAw = cCA + CA.SJ * x, bCAr = cCA + CA.SI * x;  // C: x = j ; A: x = i
+
+  auto load_ids = [&](uint32_t g, uint32_t (&id)[NS]) {
+    const uint32_t *row = idxP + (size_t)g * NS * 32 + lane;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) id[s] = __ldg(row + 32 * s);
+  };
+  // read_dof_values (fee_gpu.cuh:323-338): every lane gathers its own slab, u[j + n k]
+  auto gather = [&](const uint32_t (&id)[NS], Number (&u)[NS]) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      {
+        if (Cfg::TEX) u[s] = (id[s] & CONSTRAINED_BIT) ? Number(0) : tex_fetch<Number>(tex, id[s]);
+        else u[s] = (id[s] & CONSTRAINED_BIT) ? Number(0) : __ldg(src + id[s]);
+      }
+  };
+  uint32_t id[NS];   // PF >= 1: index rows of the group whose gather comes next
+  Number   un[NS];   // PF == 2: gathered values of the next group
+  if (Cfg::PF >= 1) load_ids(g0, id);
+  if (Cfg::PF == 2) gather(id, un);
+
+  for (uint32_t g = g0; g < n_groups; g += total_warps)
+    {
+      const uint32_t  gn   = g + total_warps;
+      const uint32_t *irow = idxP + (size_t)g * NS * 32 + lane;
+      Number u[NS], r[NS];
+      if (Cfg::PF == 0) load_ids(g, id);
+      if (Cfg::PF == 2)
+        {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) u[s] = un[s];
+        }
+      else gather(id, u);
+      if (gn < n_groups && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
+      // ---- A: N_y, N_z ----
+      slab2_apply<n, 1, n, false>(em.N, u);
+      slab2_apply<n, n, 1, false>(em.N, u);
+      if (active)
+        {
+#pragma unroll
+          for (int k = 0; k < n; ++k)
+#pragma unroll
+            for (int j = 0; j < n; ++j) P[bABw + AB.SJ * j + AB.SK * k] = u[j + n * k];
+        }
+      __syncwarp();
+      // ---- B: N_x -> u at the quadrature points, u[i + n j] ----
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+#pragma unroll
+        for (int i = 0; i < n; ++i) u[i + n * j] = P[bABr + AB.SI * i + AB.SJ * j];
+      __syncwarp();  // P consumed
+      slab2_apply<n, 1, n, false>(em.N, u);
+      if (active)
+        {
+#pragma unroll
+          for (int j = 0; j < n; ++j)
+#pragma unroll
+            for (int i = 0; i < n; ++i) Q[bBCw + BC.SI * i + BC.SJ * j] = u[i + n * j];
+        }
+      if (Cfg::NBUF == 1) __syncwarp();
+      mbar_wait(bar, phase);  // coefficient image of this group has landed
+      phase ^= 1;
+      // quadrature phases x and y: r = D_x^T (w .* D_x u) + D_y^T (w .* D_y u)
+#pragma unroll
+      for (int j = 0; j < n; ++j)
+        {
+          Number in[n], gq[n], t[n];
+#pragma unroll
+          for (int i = 0; i < n; ++i) in[i] = u[i + n * j];
+          eo_apply<n, true>(em.D, in, gq);
+#pragma unroll
+          for (int i = 0; i < n; ++i) gq[i] *= W[bBCw + BC.SI * i + BC.SJ * j];
+          eo_apply<n, true>(em.DT, gq, t);
+#pragma unroll
+          for (int i = 0; i < n; ++i) r[i + n * j] = t[i];
+        }
+#pragma unroll
+      for (int i = 0; i < n; ++i)
+        {
+          Number in[n], gq[n], t[n];
+#pragma unroll
+          for (int j = 0; j < n; ++j) in[j] = u[i + n * j];
+          eo_apply<n, true>(em.D, in, gq);
+#pragma unroll
+          for (int j = 0; j < n; ++j) gq[j] *= W[bBCw + BC.SI * i + BC.SJ * j];
+          eo_apply<n, true>(em.DT, gq, t);
+#pragma unroll
+          for (int j = 0; j < n; ++j) r[i + n * j] += t[j];
+        }
+      if (Cfg::NBUF == 2)
+        {
+          if (active)
+            {
+#pragma unroll
+              for (int j = 0; j < n; ++j)
+#pragma unroll
+                for (int i = 0; i < n; ++i) P[bBCw + BC.SI * i + BC.SJ * j] = r[i + n * j];
+            }
+          __syncwarp();
+        }
+      // ---- C: quadrature phase z on u[i + n k] ----
+#pragma unroll
+      for (int k = 0; k < n; ++k)
+#pragma unroll
+        for (int i = 0; i < n; ++i) u[i + n * k] = Q[bBCr + BC.SI * i + BC.SK * k];
+      if (Cfg::PF >= 1)
+        {
+          if (gn < n_groups) load_ids(gn, id);
+          else
+            {
+#pragma unroll
+              for (int s = 0; s < NS; ++s) id[s] = CONSTRAINED_BIT;
+            }
+        }
+      if (Cfg::NBUF == 1)
+        {
+          __syncwarp();  // u consumed by every lane: the buffer now carries r
+          if (active)
+            {
+#pragma unroll
+              for (int j = 0; j < n; ++j)
+#pragma unroll
+                for (int i = 0; i < n; ++i) P[bBCw + BC.SI * i + BC.SJ * j] = r[i + n * j];
+            }
+          __syncwarp();
+        }
+#pragma unroll
+      for (int i = 0; i < n; ++i)
+        {
+          Number in[n], gq[n], t[n];
+#pragma unroll
+          for (int k = 0; k < n; ++k) in[k] = u[i + n * k];
+          eo_apply<n, true>(em.D, in, gq);
+#pragma unroll
+          for (int k = 0; k < n; ++k) gq[k] *= W[bBCr + BC.SI * i + BC.SK * k];
+          eo_apply<n, true>(em.DT, gq, t);
+#pragma unroll
+          for (int k = 0; k < n; ++k) u[i + n * k] = t[k] + P[bBCr + BC.SI * i + BC.SK * k];
+        }
+      __syncwarp();  // P, Q and the coefficient image are consumed
+      if (gn < n_groups && lane == 0) bulk_load(W, cwP + (size_t)gn * Cfg::CWF, Cfg::CW_BYTES, bar);
+      // ---- C: N_x^T, N_z^T ----
+      slab2_apply<n, 1, n, false>(em.NT, u);
+      slab2_apply<n, n, 1, false>(em.NT, u);
+      if (active)
+        {
+#pragma unroll
+          for (int k = 0; k < n; ++k)
+#pragma unroll
+            for (int i = 0; i < n; ++i) Q[bCAw + CA.SI * i + CA.SK * k] = u[i + n * k];
+        }
+      __syncwarp();
+      // ---- A: N_y^T ----
+#pragma unroll
+      for (int k = 0; k < n; ++k)
+#pragma unroll
+        for (int j = 0; j < n; ++j) u[j + n * k] = Q[bCAr + CA.SJ * j + CA.SK * k];
+      if (Cfg::NBUF == 1) __syncwarp();  // the next group's first store goes to the same memory
+      uint32_t idc[NS];  // index rows of this group for the scatter
+      if (Cfg::PF >= 1)
+        {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) idc[s] = __ldg(irow + 32 * s);
+        }
+      slab2_apply<n, 1, n, false>(em.NT, u);
+      if (Cfg::PF == 2 && gn < n_groups) gather(id, un);
+      // ---- distribute_local_to_global (fee_gpu.cuh:346-365): red.add straight from registers ----
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        {
+          const uint32_t ii = Cfg::PF >= 1 ? idc[s] : __ldg(irow + 32 * s);
+          if (!(ii & CONSTRAINED_BIT)) red_add(dst + ii, u[s]);
+        }
+    }
+}
+
+template <typename Number>
+void launch_laplace_slab2(int degree, int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups,
+                          const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0);
+// layout of the kernel's private arrays (for the builders in operators.cu)
+struct Slab2Geom { int n, cw, hc, cwf; Slab2Lay bc; };
+bool      slab2_supported(int dim, int degree, mfg_dtype dt);
+Slab2Geom slab2_geom(int degree, mfg_dtype dt);
+
+}  // namespace mfg

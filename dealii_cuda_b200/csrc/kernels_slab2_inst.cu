@@ -1,0 +1,128 @@
+// kernels_slab2_inst.cu -- instantiation + dispatch of the slab2 kernel (one TU per dtype).
+#include <cmath>
+#include "kernels_slab2.cuh"
+
+#ifndef MFG_INST_F64
+#error "compile with -DMFG_INST_F64=0|1"
+#endif
+
+namespace mfg {
+
+#if MFG_INST_F64
+typedef double inst_number;
+#else
+typedef float inst_number;
+#endif
+
+// even-odd tables of M (TR: of its transpose); sign = +1 centro-symmetric, -1 centro-antisymmetric
+template <typename Number, int n> static void make_eo(const double *M, bool TR, int sign, EoTab<Number, n> &T)
+{
+  constexpr int h = n / 2, m = (n + 1) / 2;
+  auto at = [&](int k, int q) { return TR ? M[q * n + k] : M[k * n + q]; };
+  double scale = 0;
+  for (int i = 0; i < n * n; ++i) scale = std::max(scale, std::fabs(M[i]));
+  for (int k = 0; k < n; ++k)
+    for (int q = 0; q < n; ++q)
+      if (std::fabs(at(k, q) - sign * at(n - 1 - k, n - 1 - q)) > 1e-12 * scale)
+        throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: 1-D shape matrices are not centro-(anti)symmetric");
+  for (int i = 0; i < (h + 1) * m; ++i) T.Ce[i] = 0;
+  for (int i = 0; i < h * m; ++i) T.Co[i] = 0;
+  for (int k = 0; k < h; ++k)
+    for (int q = 0; q < m; ++q)
+      {
+        T.Ce[k * m + q] = (Number)(0.5 * (at(k, q) + at(n - 1 - k, q)));
+        T.Co[k * m + q] = (Number)(0.5 * (at(k, q) - at(n - 1 - k, q)));
+      }
+  if (n & 1)
+    for (int q = 0; q < m; ++q) T.Ce[h * m + q] = (Number)at(h, q);
+}
+
+template <int n, typename Number, int CFG>
+static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
+                     const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex)
+{
+  using Cfg = Slab2Cfg<n, Number, CFG>;
+  if (n_groups == 0) return;
+  EoMats<Number, n> em;
+  make_eo<Number, n>(N, false, +1, em.N);
+  make_eo<Number, n>(N, true, +1, em.NT);
+  make_eo<Number, n>(D, false, -1, em.D);
+  make_eo<Number, n>(D, true, -1, em.DT);
+  auto       kern          = laplace_cell_slab2<n, Number, CFG>;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0)
+    {
+      MFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+      MFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, Cfg::WPB * 32, Cfg::SMEM));
+      if (blocks_per_sm < 1) throw Error(MFG_ERR_CUDA, "slab2 kernel does not fit on an SM");
+    }
+  const uint32_t want = (n_groups + Cfg::WPB - 1) / Cfg::WPB;
+  const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sm_count * blocks_per_sm));
+  kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, tex);
+  MFG_CUDA_LAST();
+}
+
+template <int n, typename Number>
+static void launch_cfg(int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
+                       const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex)
+{
+  switch (cfg)
+    {
+      case 1: launch_n<n, Number, 1>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 3: launch_n<n, Number, 3>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 4: launch_n<n, Number, 4>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 7: launch_n<n, Number, 7>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 9: launch_n<n, Number, 9>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 11: launch_n<n, Number, 11>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 13: launch_n<n, Number, 13>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 15: launch_n<n, Number, 15>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 17: launch_n<n, Number, 17>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 19: launch_n<n, Number, 19>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 21: launch_n<n, Number, 21>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 23: launch_n<n, Number, 23>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 0: launch_n<n, Number, 0>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 2: launch_n<n, Number, 2>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      default: throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: unknown configuration");
+    }
+}
+
+template <>
+void launch_laplace_slab2<inst_number>(int degree, int cfg, const uint32_t *idxP, const inst_number *cwP, const inst_number *src, inst_number *dst,
+                                       uint32_t n_groups, const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex)
+{
+  switch (degree)
+    {
+      case 1: launch_cfg<2, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 2: launch_cfg<3, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 3: launch_cfg<4, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 4: launch_cfg<5, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      case 5: launch_cfg<6, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      default: throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: degree must be in 1..5");
+    }
+}
+
+#if MFG_INST_F64
+bool slab2_supported(int dim, int degree, mfg_dtype) { return dim == 3 && degree >= 1 && degree <= 5; }
+
+template <int n, int WB> static Slab2Geom geom_of()
+{
+  using Tab = Slab2Tab<n, WB>;
+  constexpr int CW = 32 / n;
+  return Slab2Geom{n, CW, CW % 2 == 0 ? CW / 2 : CW, Tab::F, Tab::BC()};
+}
+Slab2Geom slab2_geom(int degree, mfg_dtype dt)
+{
+  const bool f64 = dt == MFG_F64;
+  switch (degree)
+    {
+      case 1: return f64 ? geom_of<2, 8>() : geom_of<2, 4>();
+      case 2: return f64 ? geom_of<3, 8>() : geom_of<3, 4>();
+      case 3: return f64 ? geom_of<4, 8>() : geom_of<4, 4>();
+      case 4: return f64 ? geom_of<5, 8>() : geom_of<5, 4>();
+      case 5: return f64 ? geom_of<6, 8>() : geom_of<6, 4>();
+      default: throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: degree must be in 1..5");
+    }
+}
+#endif
+
+}  // namespace mfg

@@ -3,6 +3,7 @@
 #include <numeric>
 #include <cstdlib>
 #include "kernels_slab.cuh"
+#include "kernels_slab2.cuh"
 #include "operators.cuh"
 
 namespace mfg {
@@ -35,6 +36,42 @@ __global__ void pack_bits(const uint8_t *flag, size_t n, uint32_t *bits)
   uint32_t v = 0;
   for (int b = 0; b < 32; ++b) { const size_t i = w * 32 + b; if (i < n && flag[i]) v |= 1u << b; }
   bits[w] = v;
+}
+
+// slab2 kernel: idxP[g][s = j + n k][lane <-> (c, i)] = idx[g*CW + c][i + n j + n^2 k]  (bit 31 set for idle lanes and
+// for cells beyond the mesh)
+__global__ void build_slab2_indices(const uint32_t *__restrict__ idx, uint32_t n_cells, uint32_t n_groups, int n, Slab2Geom gm,
+                                    uint32_t *__restrict__ out)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int    ns = n * n;
+  if (t >= (size_t)n_groups * ns * 32) return;
+  const int      lane = (int)(t % 32), s = (int)((t / 32) % ns);
+  const uint32_t g = (uint32_t)(t / (32 * (size_t)ns));
+  // lane map of the kernel (slab2_lane): lane = 16 ch + n cl + i with c = cl + hc ch (no split when cw is odd)
+  const bool split = gm.cw % 2 == 0;
+  const int  ch = split ? lane / 16 : 0, l16 = split ? lane % 16 : lane;
+  uint32_t v = CONSTRAINED_BIT;
+  if (l16 < gm.hc * n)
+    {
+      const int      c = gm.hc * ch + l16 / n, i = l16 % n;
+      const uint32_t cell = g * gm.cw + c;
+      if (cell < n_cells) v = idx[(size_t)cell * n * ns + i + n * s];
+    }
+  out[t] = v;
+}
+
+// slab2 kernel: coefficient image of a group, element (c,i,j,k) at SC c + SI i + SJ j + SK k (padding stays zero)
+template <typename Number>
+__global__ void build_slab2_weights(const Number *__restrict__ cw, uint32_t n_cells, int n, Slab2Geom gm, Number *__restrict__ out)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int    npc = n * n * n;
+  if (t >= (size_t)n_cells * npc) return;
+  const uint32_t cell = (uint32_t)(t / npc);
+  const int      q = (int)(t % npc), i = q % n, j = (q / n) % n, k = q / (n * n);
+  const uint32_t g = cell / gm.cw, c = cell % gm.cw;
+  out[(size_t)g * gm.cwf + gm.bc.SL * (c % gm.hc) + gm.bc.SH * (c / gm.hc) + gm.bc.SI * i + gm.bc.SJ * j + gm.bc.SK * k] = cw[t];
 }
 
 struct QuadData { double xq[9], wq[9]; };
@@ -449,19 +486,82 @@ void laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host)
     }
   MFG_CUDA(cudaStreamSynchronize(op->ctx->stream));
   op->diagonal_is_available = false;
+  op->cwP_valid = false;
+}
+
+// texture object over a source vector (cached per pointer; a handful of vectors alternate in solvers and in bmop)
+static cudaTextureObject_t laplace_src_texture(mfg_laplace *op, const void *src)
+{
+  const mfg_mf *mf = op->mf;
+  for (auto &t : op->src_tex)
+    if (t.p == src && t.n == mf->n_dofs) return t.tex;
+  if (op->src_tex.size() >= 16)
+    {
+      for (auto &t : op->src_tex) cudaDestroyTextureObject(t.tex);
+      op->src_tex.clear();
+    }
+  cudaResourceDesc rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeLinear;
+  rd.res.linear.devPtr = const_cast<void *>(src);
+  rd.res.linear.desc = mf->dt == MFG_F64 ? cudaCreateChannelDesc<int2>() : cudaCreateChannelDesc<float>();
+  rd.res.linear.sizeInBytes = (size_t)mf->n_dofs * (mf->dt == MFG_F64 ? 8 : 4);
+  cudaTextureDesc td;
+  std::memset(&td, 0, sizeof(td));
+  td.readMode = cudaReadModeElementType;
+  cudaTextureObject_t tex = 0;
+  MFG_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  op->src_tex.push_back({src, mf->n_dofs, tex});
+  return tex;
+}
+
+// (re)build the slab2 kernel's private arrays from idx / cw
+static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
+{
+  const mfg_mf   *mf = op->mf;
+  const Slab2Geom gm = slab2_geom(mf->p, mf->dt);
+  const uint32_t  n_groups = (n_plain + gm.cw - 1) / gm.cw;
+  cudaStream_t    s = op->ctx->stream;
+  const int       ns = mf->n * mf->n;
+  if (op->idxP.n != (size_t)n_groups * ns * 32 || op->slab2_groups != n_groups)
+    {
+      op->idxP.alloc((size_t)n_groups * ns * 32);
+      if (n_groups) build_slab2_indices<<<nblk(op->idxP.n), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm, op->idxP.p);
+      MFG_CUDA_LAST();
+      op->slab2_groups = n_groups;
+      op->cwP_valid = false;
+    }
+  if (!op->cwP_valid)
+    {
+      const size_t es = mf->dt == MFG_F64 ? 8 : 4;
+      if (op->cwP.n != (size_t)n_groups * gm.cwf * es) op->cwP.alloc((size_t)n_groups * gm.cwf * es);
+      if (n_groups)
+        {
+          MFG_CUDA(cudaMemsetAsync(op->cwP.p, 0, op->cwP.bytes(), s));
+          const size_t total = (size_t)n_plain * mf->npc;
+          if (mf->dt == MFG_F64) build_slab2_weights<double><<<nblk(total), 256, 0, s>>>((const double *)op->cw.p, n_plain, mf->n, gm, (double *)op->cwP.p);
+          else build_slab2_weights<float><<<nblk(total), 256, 0, s>>>((const float *)op->cw.p, n_plain, mf->n, gm, (float *)op->cwP.p);
+          MFG_CUDA_LAST();
+        }
+      op->cwP_valid = true;
+    }
 }
 
 // kernels of this library one vmult enqueues (the cudaMemsetAsync of dst is not counted)
 int laplace_launches_per_vmult(const mfg_laplace *op) { return (op->ch->n() ? 1 : 0) + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0); }
 
 // kernel variants: 1 = column kernel (kernels_v0.cuh, every dim/degree/dtype/scatter),
-//                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter). 0 = auto.
+//                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter),
+//                  6 = slab2 kernel (kernels_slab2.cuh: 3D, degree <= 5, atomic scatter). 0 = auto.
 int laplace_active_variant(const mfg_laplace *op)
 {
   const mfg_mf *mf = op->mf;
   const bool slab_ok = slab_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
-  if (op->variant >= 2 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3/4 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
+  const bool slab2_ok = slab2_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
+  if (op->variant >= 6 && !slab2_ok) throw Error(MFG_ERR_UNSUPPORTED, "variants 6..9 (slab2 kernel) need dim 3, degree <= 5, atomic scatter");
+  if (op->variant >= 2 && op->variant < 6 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3/4 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
   if (op->variant == 1) return 1;
+  if (op->variant >= 6) return 6;
   if (op->variant >= 2) return 2;
   return slab_ok ? 2 : 1;
 }
@@ -515,7 +615,17 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       launch_laplace_v0_dim<3, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, c0, c1, mf->fe.val.data(),
                                        mf->fe.colloc.data(), s, mask, mf->fe.hanging.data());
   };
-  if (laplace_active_variant(op) == 2)
+  if (laplace_active_variant(op) == 6)
+    {
+      laplace_prepare_slab2(op, n_plain);
+      const int cfg = op->variant >= 6 ? op->variant - 6 : 0;
+      const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
+      time_begin();
+      launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, op->slab2_groups,
+                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex);
+      time_end();
+    }
+  else if (laplace_active_variant(op) == 2)
     {
       // variant 3 = 2 blocks x 4 warps per SM with up to 255 registers (no spills); measured faster than 3 x 4 x 168
       // for degree 4 in FP64 (profiles/r01_*), which is therefore what "auto" picks there

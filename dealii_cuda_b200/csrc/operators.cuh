@@ -50,6 +50,15 @@ struct mfg_laplace
   std::unique_ptr<mfg_vec> inv_diag;
   bool     diagonal_is_available = false;
   int      variant = 0;
+  // slab2 kernel (kernels_slab2.cuh): the index map and the merged weights in the order its threads consume them,
+  // built on first use from idx / cw
+  mfg::DevBuf<uint32_t> idxP;   // [n_groups][n^2 slots][32 lanes]
+  mfg::DevBuf<uint8_t>  cwP;    // [n_groups][shared-memory image]
+  uint32_t              slab2_groups = 0;
+  bool                  cwP_valid = false;
+  // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer
+  struct SrcTex { const void *p; size_t n; cudaTextureObject_t tex; };
+  std::vector<SrcTex>   src_tex;
   mfg::DevBuf<uint8_t> host_stage_src, host_stage_dst;  // device staging for vmult_host
   // pipelined host API (mfg_laplace_vmult_host_async): 2 slots x {src,dst} staging, copy streams, events
   struct HostSlot { mfg::DevBuf<uint8_t> src, dst; cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr; bool used = false; };

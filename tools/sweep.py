@@ -38,10 +38,15 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--custom", default="", help="semicolon-separated dim,p,r,f64|f32,variant cases (A/B runs)")
     args = ap.parse_args()
     ctx = mf.Context(0, torch.cuda.current_stream().cuda_stream)
     cases = []
-    if args.quick:
+    if args.custom:
+        for c in args.custom.split(";"):
+            d, p, r, dt, v = c.split(",")
+            cases.append((int(d), int(p), int(r), np.float64 if dt == "f64" else np.float32, False, int(v)))
+    elif args.quick:
         cases = [(3, 4, 5, np.float64, False, 1), (3, 4, 5, np.float64, False, 2), (3, 4, 6, np.float64, False, 1), (3, 4, 6, np.float64, False, 2),
                  (3, 4, 6, np.float64, False, 3), (3, 4, 6, np.float64, False, 4), (3, 4, 6, np.float64, False, 5), (3, 4, 6, np.float64, True, 1), (3, 4, 6, np.float32, False, 5), (3, 4, 6, np.float32, False, 3), (3, 4, 6, np.float32, False, 4), (3, 4, 6, np.float32, False, 1), (3, 4, 6, np.float32, False, 2),
                  (3, 3, 6, np.float64, False, 1), (3, 3, 6, np.float64, False, 2), (3, 2, 7, np.float64, False, 1), (3, 2, 7, np.float64, False, 2),
