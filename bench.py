@@ -41,7 +41,7 @@ def measured_peaks():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the cell kernel from the committed `ncu --set full`
 # captures (profiles/r01_*_ncu.txt), keyed by (dim, degree, dtype, refine, kernel variant); None if not profiled
-PROFILED_TRAFFIC = {(3, 4, "f64", 6, 2): 789.6e6, (3, 4, "f64", 6, 1): 789.3e6}
+PROFILED_TRAFFIC = {(3, 4, "f64", 6, 6): 800.9e6, (3, 4, "f64", 6, 2): 789.6e6, (3, 4, "f64", 6, 1): 789.3e6}
 
 
 class ClockSampler:

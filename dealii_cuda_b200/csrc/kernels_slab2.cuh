@@ -86,9 +86,15 @@ template <typename Number, int n> struct EoMats { EoTab<Number, n> N, NT, D, DT;
 
 // out = M^T-contraction of one line.  ANTI = false: centro-symmetric M (interpolation), true: centro-antisymmetric
 // (collocation derivative)
-template <int n, bool ANTI, typename Number>
+template <int n, bool ANTI, typename Number, bool NOP = false>
 __device__ __forceinline__ void eo_apply(const EoTab<Number, n> &T, const Number (&in)[n], Number (&out)[n])
 {
+  if (NOP)
+    {
+#pragma unroll
+      for (int q = 0; q < n; ++q) out[q] = in[q];
+      return;
+    }
   constexpr int  h = n / 2, m = (n + 1) / 2;
   constexpr bool odd = n & 1;
   constexpr int  qe = ANTI ? h : m;  // outputs fed by the even part of the input (+ the middle input)
@@ -123,16 +129,17 @@ __device__ __forceinline__ void eo_apply(const EoTab<Number, n> &T, const Number
 }
 
 // contraction of every line of a slab held in registers: contracted index has register stride S, lines stride T
-template <int n, int S, int T, bool ANTI, typename Number>
+template <int n, int S, int T, bool ANTI, typename Number, bool NOP = false>
 __device__ __forceinline__ void slab2_apply(const EoTab<Number, n> &M, Number (&v)[n * n])
 {
+  if (NOP) return;
 #pragma unroll
   for (int l = 0; l < n; ++l)
     {
       Number in[n], out[n];
 #pragma unroll
       for (int e = 0; e < n; ++e) in[e] = v[l * T + e * S];
-      eo_apply<n, ANTI>(M, in, out);
+      eo_apply<n, ANTI, Number, NOP>(M, in, out);
 #pragma unroll
       for (int e = 0; e < n; ++e) v[l * T + e * S] = out[e];
     }
@@ -155,7 +162,9 @@ template <int n, typename Number, int CFG> struct Slab2Cfg
   // software pipeline: 0 = none; 1 = the index rows of the next group are loaded during the C phase of the current one
   // and the rows needed by the scatter are re-read before N_y^T; 2 = in addition the gather of the next group is issued
   // before the scatter of the current one
-  static constexpr int PF   = CFG / 8;
+  static constexpr int PF   = (CFG % 32) / 8;
+  // measurement-only ablations (tools/ablate.py; results are wrong): 1 = no src gather, 2 = no scatter, 4 = no contractions
+  static constexpr int ABL  = CFG / 32;
   static constexpr int MINB = OCC == 1 ? 2 : OCC == 2 ? 4 : 3;
   static constexpr int NBUF = (OCC == 2 || OCC == 3) ? 1 : 2;
   static constexpr int F   = Tab::F;
@@ -200,6 +209,10 @@ template <> __device__ __forceinline__ double tex_fetch<double>(cudaTextureObjec
 }
 template <> __device__ __forceinline__ float tex_fetch<float>(cudaTextureObject_t tex, uint32_t i) { return tex1Dfetch<float>(tex, (int)i); }
 
+#ifdef MFG_SLAB2_ABLATE
+__constant__ int g_slab2_delay[2];  // experiment: start-up stagger {ns per step, mode}
+#endif
+
 template <int n, typename Number, int CFG>
 __global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n, Number, CFG>::MINB)
 laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
@@ -209,6 +222,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
   using Cfg = Slab2Cfg<n, Number, CFG>;
   using Tab = typename Cfg::Tab;
   constexpr int NS = Cfg::NS;
+  constexpr bool NOPC = (Cfg::ABL & 4) != 0;
   constexpr Slab2Lay AB = Tab::AB(), BC = Tab::BC(), CA = Tab::CA();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -223,6 +237,14 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
   const uint32_t total_warps = gridDim.x * Cfg::WPB;
   const uint32_t g0 = blockIdx.x * Cfg::WPB + warp;
   if (g0 >= n_groups) return;
+#ifdef MFG_SLAB2_ABLATE
+  if (g_slab2_delay[0] > 0)
+    {
+      const int mode = g_slab2_delay[1];
+      const unsigned k = mode == 0 ? (blockIdx.x / 148) % Cfg::MINB : mode == 1 ? warp % 2 : mode == 2 ? (blockIdx.x % Cfg::MINB) : warp;
+      for (unsigned t = 0; t < k; ++t) __nanosleep(g_slab2_delay[0]);
+    }
+#endif
 
   if (lane == 0)
     {
@@ -249,7 +271,8 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       {
-        if (Cfg::TEX) u[s] = (id[s] & CONSTRAINED_BIT) ? Number(0) : tex_fetch<Number>(tex, id[s]);
+        if (Cfg::ABL & 1) u[s] = Number(id[s] & 0xffu);
+        else if (Cfg::TEX) u[s] = (id[s] & CONSTRAINED_BIT) ? Number(0) : tex_fetch<Number>(tex, id[s]);
         else u[s] = (id[s] & CONSTRAINED_BIT) ? Number(0) : __ldg(src + id[s]);
       }
   };
@@ -272,8 +295,8 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
       else gather(id, u);
       if (gn < n_groups && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
       // ---- A: N_y, N_z ----
-      slab2_apply<n, 1, n, false>(em.N, u);
-      slab2_apply<n, n, 1, false>(em.N, u);
+      slab2_apply<n, 1, n, false, Number, NOPC>(em.N, u);
+      slab2_apply<n, n, 1, false, Number, NOPC>(em.N, u);
       if (active)
         {
 #pragma unroll
@@ -288,7 +311,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
 #pragma unroll
         for (int i = 0; i < n; ++i) u[i + n * j] = P[bABr + AB.SI * i + AB.SJ * j];
       __syncwarp();  // P consumed
-      slab2_apply<n, 1, n, false>(em.N, u);
+      slab2_apply<n, 1, n, false, Number, NOPC>(em.N, u);
       if (active)
         {
 #pragma unroll
@@ -306,10 +329,10 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
           Number in[n], gq[n], t[n];
 #pragma unroll
           for (int i = 0; i < n; ++i) in[i] = u[i + n * j];
-          eo_apply<n, true>(em.D, in, gq);
+          eo_apply<n, true, Number, NOPC>(em.D, in, gq);
 #pragma unroll
           for (int i = 0; i < n; ++i) gq[i] *= W[bBCw + BC.SI * i + BC.SJ * j];
-          eo_apply<n, true>(em.DT, gq, t);
+          eo_apply<n, true, Number, NOPC>(em.DT, gq, t);
 #pragma unroll
           for (int i = 0; i < n; ++i) r[i + n * j] = t[i];
         }
@@ -319,10 +342,10 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
           Number in[n], gq[n], t[n];
 #pragma unroll
           for (int j = 0; j < n; ++j) in[j] = u[i + n * j];
-          eo_apply<n, true>(em.D, in, gq);
+          eo_apply<n, true, Number, NOPC>(em.D, in, gq);
 #pragma unroll
           for (int j = 0; j < n; ++j) gq[j] *= W[bBCw + BC.SI * i + BC.SJ * j];
-          eo_apply<n, true>(em.DT, gq, t);
+          eo_apply<n, true, Number, NOPC>(em.DT, gq, t);
 #pragma unroll
           for (int j = 0; j < n; ++j) r[i + n * j] += t[j];
         }
@@ -369,18 +392,18 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
           Number in[n], gq[n], t[n];
 #pragma unroll
           for (int k = 0; k < n; ++k) in[k] = u[i + n * k];
-          eo_apply<n, true>(em.D, in, gq);
+          eo_apply<n, true, Number, NOPC>(em.D, in, gq);
 #pragma unroll
           for (int k = 0; k < n; ++k) gq[k] *= W[bBCr + BC.SI * i + BC.SK * k];
-          eo_apply<n, true>(em.DT, gq, t);
+          eo_apply<n, true, Number, NOPC>(em.DT, gq, t);
 #pragma unroll
           for (int k = 0; k < n; ++k) u[i + n * k] = t[k] + P[bBCr + BC.SI * i + BC.SK * k];
         }
       __syncwarp();  // P, Q and the coefficient image are consumed
       if (gn < n_groups && lane == 0) bulk_load(W, cwP + (size_t)gn * Cfg::CWF, Cfg::CW_BYTES, bar);
       // ---- C: N_x^T, N_z^T ----
-      slab2_apply<n, 1, n, false>(em.NT, u);
-      slab2_apply<n, n, 1, false>(em.NT, u);
+      slab2_apply<n, 1, n, false, Number, NOPC>(em.NT, u);
+      slab2_apply<n, n, 1, false, Number, NOPC>(em.NT, u);
       if (active)
         {
 #pragma unroll
@@ -401,14 +424,18 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
 #pragma unroll
           for (int s = 0; s < NS; ++s) idc[s] = __ldg(irow + 32 * s);
         }
-      slab2_apply<n, 1, n, false>(em.NT, u);
+      slab2_apply<n, 1, n, false, Number, NOPC>(em.NT, u);
       if (Cfg::PF == 2 && gn < n_groups) gather(id, un);
       // ---- distribute_local_to_global (fee_gpu.cuh:346-365): red.add straight from registers ----
 #pragma unroll
       for (int s = 0; s < NS; ++s)
         {
           const uint32_t ii = Cfg::PF >= 1 ? idc[s] : __ldg(irow + 32 * s);
-          if (!(ii & CONSTRAINED_BIT)) red_add(dst + ii, u[s]);
+          if (Cfg::ABL & 2)
+            {
+              if (u[s] == Number(12345.678)) red_add(dst + ii, u[s]);
+            }
+          else if (!(ii & CONSTRAINED_BIT)) red_add(dst + ii, u[s]);
         }
     }
 }

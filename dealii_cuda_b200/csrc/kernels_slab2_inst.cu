@@ -1,5 +1,6 @@
 // kernels_slab2_inst.cu -- instantiation + dispatch of the slab2 kernel (one TU per dtype).
 #include <cmath>
+#include <cstdlib>
 #include "kernels_slab2.cuh"
 
 #ifndef MFG_INST_F64
@@ -56,6 +57,12 @@ static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src,
       MFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, Cfg::WPB * 32, Cfg::SMEM));
       if (blocks_per_sm < 1) throw Error(MFG_ERR_CUDA, "slab2 kernel does not fit on an SM");
     }
+#ifdef MFG_SLAB2_ABLATE
+  {
+    int d[2] = {getenv("MFG_SLAB2_DELAY") ? atoi(getenv("MFG_SLAB2_DELAY")) : 0, getenv("MFG_SLAB2_DELAY_MODE") ? atoi(getenv("MFG_SLAB2_DELAY_MODE")) : 0};
+    MFG_CUDA(cudaMemcpyToSymbolAsync(g_slab2_delay, d, sizeof(d), 0, cudaMemcpyHostToDevice, stream));
+  }
+#endif
   const uint32_t want = (n_groups + Cfg::WPB - 1) / Cfg::WPB;
   const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sm_count * blocks_per_sm));
   kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, tex);
@@ -82,6 +89,11 @@ static void launch_cfg(int cfg, const uint32_t *idxP, const Number *cwP, const N
       case 23: launch_n<n, Number, 23>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
       case 0: launch_n<n, Number, 0>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
       case 2: launch_n<n, Number, 2>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+#ifdef MFG_SLAB2_ABLATE
+#define MFG_ABL(a) case 7 + 32 * a: if constexpr (n == 5) launch_n<n, Number, 7 + 32 * a>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex); break;
+      MFG_ABL(1) MFG_ABL(2) MFG_ABL(3) MFG_ABL(4) MFG_ABL(5) MFG_ABL(6) MFG_ABL(7)
+#undef MFG_ABL
+#endif
       default: throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: unknown configuration");
     }
 }

@@ -563,6 +563,8 @@ int laplace_active_variant(const mfg_laplace *op)
   if (op->variant == 1) return 1;
   if (op->variant >= 6) return 6;
   if (op->variant >= 2) return 2;
+  // auto: measured on B200 (profiles/r01_sweep_slab2.jsonl): slab2 wins for degree 1, 3, 4, 5, the first slab kernel for degree 2
+  if (slab2_ok && mf->p != 2) return 6;
   return slab_ok ? 2 : 1;
 }
 
@@ -618,7 +620,8 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
   if (laplace_active_variant(op) == 6)
     {
       laplace_prepare_slab2(op, n_plain);
-      const int cfg = op->variant >= 6 ? op->variant - 6 : 0;
+      // auto = configuration 3 (3 blocks x 4 warps, 168 registers, one transpose buffer per warp, LSU gather)
+      const int cfg = op->variant >= 6 ? op->variant - 6 : 3;
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
       time_begin();
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, op->slab2_groups,

@@ -137,11 +137,11 @@ def test_slab2_variants_match_oracle(ctx, p, r, variant, dtype):
 
 def test_slab_variant_rejected_where_unsupported(ctx):
     import dealii_cuda_b200 as mf
-    for dim, p, coloring in [(2, 4, False), (3, 5, False), (3, 4, True)]:
+    for dim, p, coloring, auto in [(2, 4, False, 1), (3, 5, False, 6), (3, 4, True, 1), (3, 6, False, 1)]:
         m = mf.HyperCubeMesh(ctx, dim, p, 1)
         op = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=coloring)
         op.reinit(m)
-        assert op.active_variant() == 1
+        assert op.active_variant() == auto  # auto: slab2 for 3D degree 1, 3, 4, 5 with atomics, slab for degree 2
         op.set_variant(2)
         a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs)
         with pytest.raises(mf.MfgError):

@@ -30,7 +30,7 @@ def run(ctx, dim, p, r, dtype, coloring, steps, variant=0):
     peak, _ = measured_peaks()
     gdofs = n / (best * 1e-3) / 1e9
     frac = gdofs * b_alg(p, dim, s) / peak
-    return dict(dim=dim, p=p, r=r, dtype=np.dtype(dtype).name, coloring=coloring, variant=op.active_variant(), n_dofs=n, ms=best,
+    return dict(dim=dim, p=p, r=r, dtype=np.dtype(dtype).name, coloring=coloring, variant=op.active_variant(), requested=variant, n_dofs=n, ms=best,
                 gdofs=gdofs, roofline_frac=frac)
 
 
