@@ -18,7 +18,11 @@
 //   * even-odd decomposition of every 1-D contraction (the Gauss / Gauss-Lobatto points are symmetric about the cell
 //     centre, so the interpolation matrix is centro-symmetric and the collocation derivative centro-antisymmetric):
 //     21 resp. 20 FP64 operations per line of 5 instead of 25;
-//   * results are scattered straight from registers with red.global.add.
+//   * results are scattered straight from registers with red.global.add;
+//   * cells of a group that share a face (x-, y-, z-neighbours inside the group, detected at setup by comparing the
+//     index rows, operators.cu build_slab2_merge) sum their face contributions with warp shuffles first and only one
+//     of them issues the red: the scatter is bound by the L1 -> L2 request rate (one 32-byte sector per cycle,
+//     profiles/r01_slab2_ablation.jsonl), and this removes 27 % of the sectors of a 6-cell group.
 // Thread layouts (a warp = CW = 32/n cells, lane <-> (cell c, index x), see slab2_lane):
 //   A: x = i, registers (j,k)     B: x = k, registers (i,j)     C: x = j, registers (i,k)
 // Sequence per group of cells:
@@ -30,6 +34,10 @@
 namespace mfg {
 
 struct Slab2Lay { int SL, SH, SI, SJ, SK; };
+
+// merge mask of a group: bit (10 d + c) = cell c of the group hands the contributions of its upper face in direction d
+// to cell c + 2^d of the same group (whose lower face has the same DoF indices) and does not scatter them itself
+constexpr int SLAB2_MERGE_MAX_CW = 10;
 
 // Lane map ("half split"): a warp group holds CW = 32/n cells, cell c = cl + HC*ch with HC = CW/2; the cells with ch = 0
 // live in lanes 0..15, the others in lanes 16..31, lane = 16 ch + n cl + x.  A 64-bit gather / scatter instruction is
@@ -70,6 +78,15 @@ template <int n> __host__ __device__ inline Slab2Lane slab2_lane(int lane)
   const int      ch = SPLIT ? lane / 16 : 0, l16 = SPLIT ? lane % 16 : lane;
   if (l16 >= HC * n) return Slab2Lane{-1, 0, ch, 0};
   return Slab2Lane{HC * ch + l16 / n, l16 / n, ch, l16 % n};
+}
+
+// inverse of slab2_lane (any c, clamped into the warp: the result is only used where the merge mask says so)
+template <int n> __host__ __device__ inline int slab2_lane_of(int c, int x)
+{
+  constexpr int  CW = 32 / n, HC = CW % 2 == 0 ? CW / 2 : CW;
+  constexpr bool SPLIT = CW % 2 == 0;
+  if (c < 0) c = 0;
+  return (SPLIT ? 16 * (c / HC) + n * (c % HC) : n * c) + x;
 }
 
 // Even-odd tables of one 1-D matrix M (out[q] = sum_k M[k][q] in[k]) with M[n-1-k][n-1-q] = +-M[k][q]:
@@ -217,7 +234,7 @@ template <int n, typename Number, int CFG>
 __global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n, Number, CFG>::MINB)
 laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
                    Number *__restrict__ dst, const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em,
-                   const cudaTextureObject_t tex)
+                   const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   using Tab = typename Cfg::Tab;
@@ -425,6 +442,53 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
           for (int s = 0; s < NS; ++s) idc[s] = __ldg(irow + 32 * s);
         }
       slab2_apply<n, 1, n, false, Number, NOPC>(em.NT, u);
+      // ---- face merge inside the group: x (lanes i = n-1 -> i = 0 of cell c+1), y (slots j = n-1 -> j = 0 of cell c+2),
+      //      z (slots k = n-1 -> k = 0 of cell c+4); a handed-over value is zeroed so that a later merge does not move it twice
+      bool xs = false, ys = false, zs = false;  // this lane hands over its i = n-1 entries / its j = n-1 slots / its k = n-1 slots
+      if (Cfg::CW <= SLAB2_MERGE_MAX_CW)
+        {
+          const uint32_t mm = __ldg(mergeP + g);
+          if (mm != 0)
+            {
+              const int c = lm.c;
+              xs = active && x == n - 1 && ((mm >> c) & 1u);
+              ys = active && ((mm >> (10 + c)) & 1u);
+              zs = active && ((mm >> (20 + c)) & 1u);
+              const bool xd = active && x == 0 && c >= 1 && ((mm >> (c - 1)) & 1u);
+              const bool yd = active && c >= 2 && ((mm >> (10 + c - 2)) & 1u);
+              const bool zd = active && c >= 4 && ((mm >> (20 + c - 4)) & 1u);
+              const int  lx = slab2_lane_of<n>(c - 1, n - 1), ly = slab2_lane_of<n>(c - 2, x), lz = slab2_lane_of<n>(c - 4, x);
+              if (mm & 0x3ffu)
+                {
+#pragma unroll
+                  for (int s = 0; s < NS; ++s)
+                    {
+                      const Number t = __shfl_sync(0xffffffffu, u[s], lx);
+                      u[s] = xd ? u[s] + t : (xs ? Number(0) : u[s]);
+                    }
+                }
+              if (mm & (0x3ffu << 10))
+                {
+#pragma unroll
+                  for (int k = 0; k < n; ++k)
+                    {
+                      const Number t = __shfl_sync(0xffffffffu, u[(n - 1) + n * k], ly);
+                      if (yd) u[n * k] += t;
+                      if (ys) u[(n - 1) + n * k] = Number(0);
+                    }
+                }
+              if (mm & (0x3ffu << 20))
+                {
+#pragma unroll
+                  for (int j = 0; j < n; ++j)
+                    {
+                      const Number t = __shfl_sync(0xffffffffu, u[j + n * (n - 1)], lz);
+                      if (zd) u[j] += t;
+                      if (zs) u[j + n * (n - 1)] = Number(0);
+                    }
+                }
+            }
+        }
       if (Cfg::PF == 2 && gn < n_groups) gather(id, un);
       // ---- distribute_local_to_global (fee_gpu.cuh:346-365): red.add straight from registers ----
 #pragma unroll
@@ -435,14 +499,19 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
             {
               if (u[s] == Number(12345.678)) red_add(dst + ii, u[s]);
             }
-          else if (!(ii & CONSTRAINED_BIT)) red_add(dst + ii, u[s]);
+          else
+            {
+              const bool handed_over = xs || (s % n == n - 1 && ys) || (s / n == n - 1 && zs);
+              if (!(ii & CONSTRAINED_BIT) && !handed_over) red_add(dst + ii, u[s]);
+            }
         }
     }
 }
 
 template <typename Number>
 void launch_laplace_slab2(int degree, int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups,
-                          const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0);
+                          const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0,
+                          const uint32_t *mergeP = nullptr);
 // layout of the kernel's private arrays (for the builders in operators.cu)
 struct Slab2Geom { int n, cw, hc, cwf; Slab2Lay bc; };
 bool      slab2_supported(int dim, int degree, mfg_dtype dt);

@@ -61,6 +61,40 @@ __global__ void build_slab2_indices(const uint32_t *__restrict__ idx, uint32_t n
   out[t] = v;
 }
 
+// slab2 kernel: face-merge mask of every group (kernels_slab2.cuh): bit (10 d + c) is set when the upper face of cell c in
+// direction d and the lower face of cell c + 2^d of the same group carry identical index entries.  A merge whose receiving
+// entries would themselves be handed over by an earlier direction without the sender doing the same is dropped, so that
+// no contribution can be lost whatever the cell order of the mesh is.
+__global__ void build_slab2_merge(const uint32_t *__restrict__ idx, uint32_t n_cells, uint32_t n_groups, int n, int cw, int dirs,
+                                  uint32_t *__restrict__ out)
+{
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const int npc = n * n * n;
+  uint32_t  m = 0;
+  if (cw <= SLAB2_MERGE_MAX_CW)
+    for (int d = 0; d < 3; ++d)
+      {
+        if (!((dirs >> d) & 1)) continue;
+        const int step = 1 << d, sd = d == 0 ? 1 : d == 1 ? n : n * n;  // stride of the direction inside a cell tensor
+        for (int c = 0; c + step < cw; ++c)
+          {
+            const uint32_t a = g * cw + c, b = a + step;
+            if (b >= n_cells) continue;
+            bool same = true;
+            for (int q = 0; q < npc && same; ++q)
+              if ((q / sd) % n == n - 1) same = idx[(size_t)a * npc + q] == idx[(size_t)b * npc + q - (n - 1) * sd];
+            if (same) m |= 1u << (10 * d + c);
+          }
+      }
+  auto bit = [&](int d, int c) { return c < SLAB2_MERGE_MAX_CW && ((m >> (10 * d + c)) & 1u); };
+  for (int c = 0; c + 2 < cw && cw <= SLAB2_MERGE_MAX_CW; ++c)
+    if (bit(1, c) && bit(0, c + 2) && !bit(0, c)) m &= ~(1u << (10 + c));
+  for (int c = 0; c + 4 < cw && cw <= SLAB2_MERGE_MAX_CW; ++c)
+    if (bit(2, c) && ((bit(0, c + 4) && !bit(0, c)) || (bit(1, c + 4) && !bit(1, c)))) m &= ~(1u << (20 + c));
+  out[g] = m;
+}
+
 // slab2 kernel: coefficient image of a group, element (c,i,j,k) at SC c + SI i + SJ j + SK k (padding stays zero)
 template <typename Number>
 __global__ void build_slab2_weights(const Number *__restrict__ cw, uint32_t n_cells, int n, Slab2Geom gm, Number *__restrict__ out)
@@ -528,6 +562,13 @@ static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
       op->idxP.alloc((size_t)n_groups * ns * 32);
       if (n_groups) build_slab2_indices<<<nblk(op->idxP.n), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm, op->idxP.p);
       MFG_CUDA_LAST();
+      // MFG_SLAB2_MERGE: bit mask of the directions (1 x, 2 y, 4 z) whose in-group face merge is enabled.  Measured on
+      // B200 at 3D Q4 r=6 (profiles/r01_slab2_merge.txt): 22 % fewer red sectors, but the shuffles cost as many L1 data-pipe
+      // wavefronts as the removed sectors in FP64 (+4 % time), while FP32 gains 3.6 % -> on for FP32, off for FP64
+      const int dirs = getenv("MFG_SLAB2_MERGE") ? atoi(getenv("MFG_SLAB2_MERGE")) : (mf->dt == MFG_F64 ? 0 : 7);
+      op->mergeP.alloc(n_groups);
+      if (n_groups) build_slab2_merge<<<nblk(n_groups), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm.cw, dirs, op->mergeP.p);
+      MFG_CUDA_LAST();
       op->slab2_groups = n_groups;
       op->cwP_valid = false;
     }
@@ -625,7 +666,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
       time_begin();
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, op->slab2_groups,
-                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex);
+                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p);
       time_end();
     }
   else if (laplace_active_variant(op) == 2)

@@ -54,6 +54,7 @@ struct mfg_laplace
   // built on first use from idx / cw
   mfg::DevBuf<uint32_t> idxP;   // [n_groups][n^2 slots][32 lanes]
   mfg::DevBuf<uint8_t>  cwP;    // [n_groups][shared-memory image]
+  mfg::DevBuf<uint32_t> mergeP; // [n_groups] face-merge mask
   uint32_t              slab2_groups = 0;
   bool                  cwP_valid = false;
   // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer

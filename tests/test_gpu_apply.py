@@ -135,6 +135,23 @@ def test_slab2_variants_match_oracle(ctx, p, r, variant, dtype):
     assert rel_err(dst.toVector(), o.vmult_add(d0.astype(np.float64), u.astype(np.float64))) <= TOL[dtype]
 
 
+@pytest.mark.parametrize("dirs", [1, 2, 4, 7])
+@pytest.mark.parametrize("p,r", [(4, 2), (4, 3), (3, 3), (2, 3), (5, 2)])
+def test_slab2_face_merge_f64(ctx, p, r, dirs, monkeypatch):
+    """in-group face merge of the slab2 scatter (default on for FP32 only): every direction subset, FP64."""
+    import dealii_cuda_b200 as mf
+    monkeypatch.setenv("MFG_SLAB2_MERGE", str(dirs))
+    o = OracleMesh(3, p, r)
+    m = mf.HyperCubeMesh(ctx, 3, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(m)
+    op.set_variant(9)
+    u = sm64(11, o.n_dofs)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs)
+    op.vmult(dst, src)
+    assert rel_err(dst.toVector(), o.vmult(u)) <= TOL[np.float64]
+
+
 def test_slab_variant_rejected_where_unsupported(ctx):
     import dealii_cuda_b200 as mf
     for dim, p, coloring, auto in [(2, 4, False, 1), (3, 5, False, 6), (3, 4, True, 1), (3, 6, False, 1)]:
