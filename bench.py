@@ -233,6 +233,8 @@ def main():
         vb_, vx_ = mf.GpuVector(ctx, n, dtype), mf.GpuVector(ctx, n, dtype)
         op.vmult(vb_, ue)
         op.compute_diagonal()
+        mf.solver_cg(op, vx_, vb_, 0.0, 3)  # warm-up: loads the solver kernels (lazy module loading), like the warm-up applies
+        vx_.fill(0.0)
         ctx.synchronize()
         t0 = time.perf_counter()
         its, res = mf.solver_cg(op, vx_, vb_, (1e-12 if args.dtype == "f64" else 1e-5) * vb_.l2_norm(), 10000)

@@ -31,7 +31,7 @@ int mfg_ctx_create(int device, void *stream, mfg_ctx **out)
     MFG_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount; ctx->cc_major = prop.major; ctx->cc_minor = prop.minor; ctx->l2_bytes = (size_t)prop.l2CacheSize;
     MFG_CUDA(cudaMalloc(&ctx->red_dev, RED_SCRATCH_DOUBLES * sizeof(double)));
-    MFG_CUDA(cudaMallocHost(&ctx->red_host, 8 * sizeof(double)));
+    MFG_CUDA(cudaMallocHost(&ctx->red_host, RED_HOST_DOUBLES * sizeof(double)));
     *out = ctx.release();
   });
 }

@@ -88,5 +88,5 @@ struct mfg_ctx
   size_t       l2_bytes = 0;
   // device scratch for reductions (the reference cudaMallocs per call, gpu_vec.cu:543-557)
   double      *red_dev  = nullptr;   // [8]
-  double      *red_host = nullptr;   // pinned [8]
+  double      *red_host = nullptr;   // pinned [RED_HOST_DOUBLES]
 };

@@ -60,6 +60,7 @@ struct mfg_laplace
   // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer
   struct SrcTex { const void *p; size_t n; cudaTextureObject_t tex; };
   std::vector<SrcTex>   src_tex;
+  mfg::DevBuf<uint8_t> solver_work;  // mfg_solver_cg: residual, direction, A*direction, device-resident scalars (reused across solves)
   mfg::DevBuf<uint8_t> host_stage_src, host_stage_dst;  // device staging for vmult_host
   // pipelined host API (mfg_laplace_vmult_host_async): 2 slots x {src,dst} staging, copy streams, events
   struct HostSlot { mfg::DevBuf<uint8_t> src, dst; cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr; bool used = false; };

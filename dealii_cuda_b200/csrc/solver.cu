@@ -1,9 +1,13 @@
 // solver.cu -- conjugate gradients on GpuVectors with the Laplace operator: the control flow of deal.II's
 // SolverCG<GpuVector> as the reference instantiates it (poisson.cu:233-260), with the
-// BLAS-1 of every iteration fused into two reduction kernels instead of the reference's five
+// BLAS-1 of every iteration fused into three kernels (12 vector passes) instead of the reference's five
 // (operator*, add, add_and_dot, DiagonalMatrix::vmult -> scale, sadd; gpu_vec.cu:306-617), each of which
-// cudaMallocs and blocks on a D2H copy there.  Preconditioner: the inverse diagonal (PreconditionChebyshev with
+// cudaMallocs and blocks on a D2H copy there; here alpha, beta and the residual stay on the device and the host
+// never waits inside the loop.  Preconditioner: the inverse diagonal (PreconditionChebyshev with
 // its default degree 0 is a scaled Jacobi step; the scaling does not change the CG iterates).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "operators.cuh"
 
 namespace mfg {
@@ -31,66 +35,116 @@ __device__ inline void block_sum2(double &a, double &b)
     }
 }
 
-// x += alpha d ; g += alpha h ; z = Minv .* g (or z = g) ; partial[2b] = g.g, partial[2b+1] = g.z
-template <typename T>
-__global__ void cg_update(T *__restrict__ x, T *__restrict__ g, T *__restrict__ z, const T *__restrict__ d, const T *__restrict__ h,
-                          const T *__restrict__ minv, T alpha, size_t n, double *__restrict__ partial)
+// Device-resident state of one solve: the scalars never travel to the host inside the loop.  Every kernel of an
+// iteration reads what it needs from here, the last block of a reduction kernel (ticket counter) finishes the sum in
+// a fixed order and updates it.  Once `converged_at` is set, the kernels of later iterations return at once, so the
+// host may enqueue a few iterations ahead of what it has seen of the residual without changing the result.
+struct CgState
 {
+  double gh;            // g . h of the current iterate (h = Minv g)
+  double alpha, beta;
+  double res;           // |g|
+  double tol;
+  int    converged_at;  // iteration at which |g| <= tol was met, -1 before
+  unsigned ticket;
+};
+
+__device__ inline bool last_block_done(unsigned *ticket)
+{
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  return last;
+}
+// sum of the per-block partials in block order by the calling (last) block; result valid in thread 0
+__device__ inline void sum_partials2(const volatile double *partial, double &a, double &b)
+{
+  a = 0; b = 0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+  __syncthreads();
+  block_sum2(a, b);
+}
+
+// alpha = g.h / d.h
+template <typename T>
+__global__ void cg_dot(const T *__restrict__ d, const T *__restrict__ h, size_t n, double *__restrict__ partial, CgState *st)
+{
+  if (st->converged_at >= 0) return;
+  double s0 = 0, s1 = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride)  // four independent loads per vector in flight
+    {
+      const T d0 = d[i], d1 = d[i + stride], d2 = d[i + 2 * stride], d3 = d[i + 3 * stride];
+      const T h0 = h[i], h1 = h[i + stride], h2 = h[i + 2 * stride], h3 = h[i + 3 * stride];
+      s0 += (double)d0 * (double)h0 + (double)d1 * (double)h1;
+      s1 += (double)d2 * (double)h2 + (double)d3 * (double)h3;
+    }
+  for (; i < n; i += stride) s0 += (double)d[i] * (double)h[i];
+  s0 += s1; s1 = 0;
+  block_sum2(s0, s1);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = 0; }
+  if (last_block_done(&st->ticket))
+    {
+      sum_partials2(partial, s0, s1);
+      if (threadIdx.x == 0) { st->alpha = st->gh / s0; st->ticket = 0; }
+    }
+}
+// g += alpha h ; z = Minv .* g (z overwrites h) ; |g|, g.z ; convergence test ; beta = g.z / gh_old
+// (first = true: alpha = 0, h holds nothing yet: only z and the sums, the start of the iteration)
+template <typename T>
+__global__ void cg_residual(T *__restrict__ g, T *__restrict__ h, const T *__restrict__ minv, size_t n, double *__restrict__ partial, CgState *st,
+                            int it, double *__restrict__ history)
+{
+  if (st->converged_at >= 0) return;
+  const bool first = it == 0;
+  const T alpha = first ? T(0) : (T)st->alpha;
   double gg = 0, gz = 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-      x[i] += alpha * d[i];
-      const T gi = g[i] + alpha * h[i];
-      g[i] = gi;
+      const T gi = first ? g[i] : g[i] + alpha * h[i];
+      if (!first) g[i] = gi;
       const T zi = minv ? minv[i] * gi : gi;
-      z[i] = zi;
+      h[i] = zi;
       gg += (double)gi * (double)gi;
       gz += (double)gi * (double)zi;
     }
   block_sum2(gg, gz);
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = gg; partial[2 * blockIdx.x + 1] = gz; }
+  if (last_block_done(&st->ticket))
+    {
+      sum_partials2(partial, gg, gz);
+      if (threadIdx.x == 0)
+        {
+          const double res = sqrt(gg);
+          st->res = res;
+          if (history) history[it] = res;
+          if (res <= st->tol) st->converged_at = it;
+          st->beta = first ? 0.0 : gz / st->gh;
+          st->gh = gz;
+          st->ticket = 0;
+        }
+    }
 }
-// d = beta d - z ; (fused with nothing else: the next operation is the operator apply)
-template <typename T> __global__ void cg_direction(T *__restrict__ d, const T *__restrict__ z, T beta, size_t n)
+// x += alpha d (also in the iteration that converged, as SolverCG updates the solution before the check) ;
+// d = beta d - z ; h = 0 is left to the operator
+template <typename T> __global__ void cg_advance(T *__restrict__ x, T *__restrict__ d, const T *__restrict__ z, size_t n, const CgState *st, int it)
 {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = beta * d[i] - z[i];
-}
-// partial[2b] = a.b, partial[2b+1] = c.c
-template <typename T>
-__global__ void dot2(const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ c, size_t n, double *__restrict__ partial)
-{
-  double s0 = 0, s1 = 0;
+  const int c = st->converged_at;
+  if (c >= 0 && c < it) return;
+  const bool first = it == 0, done = c == it;
+  const T alpha = (T)st->alpha, beta = (T)st->beta;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-      s0 += (double)a[i] * (double)b[i];
-      if (c) s1 += (double)c[i] * (double)c[i];
+      const T di = first ? T(0) : d[i];
+      if (!first) x[i] += alpha * di;
+      if (!done) d[i] = beta * di - z[i];
     }
-  block_sum2(s0, s1);
-  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = s1; }
 }
-__global__ void finish2(const double *partial, int nb, double *out)
-{
-  double a = 0, b = 0;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
-  block_sum2(a, b);
-  if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
-}
-
-template <typename T> struct Cg
-{
-  mfg_laplace *op; mfg_ctx *ctx; size_t n; int nb;
-  void reduce2(double &a, double &b)
-  {
-    finish2<<<1, TH, 0, ctx->stream>>>(ctx->red_dev + 8, nb, ctx->red_dev);
-    MFG_CUDA_LAST();
-    MFG_CUDA(cudaMemcpyAsync(ctx->red_host, ctx->red_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    MFG_CUDA(cudaStreamSynchronize(ctx->stream));
-    a = ctx->red_host[0]; b = ctx->red_host[1];
-  }
-};
 
 template <typename T>
 void cg_solve(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double tol, int max_iter, bool jacobi, int *iters, double *last_res,
@@ -99,60 +153,78 @@ void cg_solve(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double tol, int max
   mfg_ctx *ctx = op->ctx;
   const size_t n = op->mf->n_dofs;
   cudaStream_t s = ctx->stream;
-  Cg<T> cg{op, ctx, n, (int)std::max<size_t>(1, std::min<size_t>((RED_SCRATCH_DOUBLES - 8) / 2, (n + TH * 8 - 1) / (TH * 8)))};
-  const int nb = cg.nb;
-  DevBuf<T> g(n), d(n), h(n);
-  MFG_CUDA(cudaMemsetAsync(d.p, 0, n * sizeof(T), s));
-  MFG_CUDA(cudaMemsetAsync(h.p, 0, n * sizeof(T), s));
+  const int nb = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((RED_SCRATCH_DOUBLES - 8) / 2, (size_t)ctx->sm_count * 8), (n + TH * 8 - 1) / (TH * 8)));
+  // work vectors live in the operator and are reused by later solves: cudaMalloc / cudaFree of vectors this size cost
+  // tens of milliseconds per solve once the process holds large pinned host buffers (measured)
+  const size_t wbytes = ((3 * n * sizeof(T) + 63) / 64) * 64 + 256;
+  if (op->solver_work.n != wbytes) op->solver_work.alloc(wbytes);
+  struct View { T *p; } g{(T *)op->solver_work.p}, d{g.p + n}, h{d.p + n};
+  struct SView { CgState *p; } st{reinterpret_cast<CgState *>(op->solver_work.p + ((3 * n * sizeof(T) + 63) / 64) * 64)};
+  DevBuf<double> hist(history ? (size_t)max_iter + 1 : 0);
   const T *minv = nullptr;
   if (jacobi)
     {
       if (!op->diagonal_is_available) laplace_compute_diagonal(op);
       minv = (const T *)op->inv_diag->p;
     }
-  mfg_vec vg, vd, vh;
-  vg.ctx = vd.ctx = vh.ctx = ctx; vg.dt = vd.dt = vh.dt = x->dt; vg.n = vd.n = vh.n = n; vg.owns = vd.owns = vh.owns = false;
-  vg.p = g.p; vd.p = d.p; vh.p = h.p;
+  mfg_vec vg;
+  vg.ctx = ctx; vg.dt = x->dt; vg.n = n; vg.owns = false; vg.p = g.p;
   // g = A x - b   (g = -b if x is zero)
   if (vec_all_zero(x)) vec_equ(&vg, -1.0, b);
   else { laplace_vmult(op, g.p, x->p, false); vec_sadd(&vg, 1.0, -1.0, b); }
-  // h = Minv g (or g) ; d = -h ; gh = g.h ; res = |g|
-  double gg, gh;
-  cg_update<T><<<nb, TH, 0, s>>>((T *)x->p, g.p, h.p, d.p, h.p, minv, T(0), n, ctx->red_dev + 8);  // alpha = 0: only z and the sums
+  CgState init;
+  init.gh = 0; init.alpha = 0; init.beta = 0; init.res = 0; init.tol = tol; init.converged_at = -1; init.ticket = 0;
+  MFG_CUDA(cudaMemcpyAsync(st.p, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+  double *partial = ctx->red_dev + 8;
+  // pinned mirror of the state, refreshed after every iteration; the host looks at the copy of iteration it - LAG
+  // (already complete in practice) and stops enqueueing once it shows convergence
+  constexpr int LAG = 3;
+  static_assert((LAG + 1) * sizeof(CgState) <= RED_HOST_DOUBLES * sizeof(double), "pinned scratch too small");
+  CgState *mirror = reinterpret_cast<CgState *>(ctx->red_host);
+  cudaEvent_t ev[LAG + 1];
+  for (auto &e : ev) MFG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  auto snapshot = [&](int it) {
+    MFG_CUDA(cudaMemcpyAsync(mirror + it % (LAG + 1), st.p, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+    MFG_CUDA(cudaEventRecord(ev[it % (LAG + 1)], s));
+  };
+  // iteration 0: h = Minv g, |g|, g.h ; d = -h
+  cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, 0, hist.p);
   MFG_CUDA_LAST();
-  cg.reduce2(gg, gh);
-  double res = std::sqrt(gg);
-  int it = 0;
-  if (history) history[0] = res;
-  if (res > tol)
+  cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, 0);
+  MFG_CUDA_LAST();
+  snapshot(0);
+  const bool dbg = getenv("MFG_CG_DEBUG") != nullptr;
+  double t_wait = 0, t_vmult = 0, t_rest = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  for (int it = 1; it <= max_iter; ++it)
     {
-      vec_equ(&vd, -1.0, &vh);
-      for (it = 1; it <= max_iter; ++it)
+      const double ta = dbg ? now() : 0;
+      if (it > LAG)
         {
-          laplace_vmult(op, h.p, d.p, false);                               // h = A d
-          dot2<T><<<nb, TH, 0, s>>>(d.p, h.p, (const T *)nullptr, n, ctx->red_dev + 8);
-          MFG_CUDA_LAST();
-          double dh, dummy;
-          cg.reduce2(dh, dummy);
-          const double alpha = gh / dh;
-          // x += alpha d ; g += alpha h ; h = Minv g ; |g|^2 ; g.h
-          cg_update<T><<<nb, TH, 0, s>>>((T *)x->p, g.p, h.p, d.p, h.p, minv, (T)alpha, n, ctx->red_dev + 8);
-          MFG_CUDA_LAST();
-          double gh_new;
-          cg.reduce2(gg, gh_new);
-          res = std::sqrt(gg);
-          if (history) history[it] = res;
-          if (res <= tol) break;
-          const double beta = gh_new / gh;
-          gh = gh_new;
-          cg_direction<T><<<nb, TH, 0, s>>>(d.p, h.p, (T)beta, n);          // d = beta d - h
-          MFG_CUDA_LAST();
+          MFG_CUDA(cudaEventSynchronize(ev[(it - LAG) % (LAG + 1)]));
+          if (mirror[(it - LAG) % (LAG + 1)].converged_at >= 0) break;
         }
-      if (it > max_iter) it = max_iter;
+      const double tb = dbg ? now() : 0;
+      laplace_vmult(op, h.p, d.p, false);                                   // h = A d
+      const double tc = dbg ? now() : 0;
+      cg_dot<T><<<nb, TH, 0, s>>>(d.p, h.p, n, partial, st.p);             // alpha
+      MFG_CUDA_LAST();
+      cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, it, hist.p);
+      MFG_CUDA_LAST();
+      cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, it);
+      MFG_CUDA_LAST();
+      snapshot(it);
+      if (dbg) { const double td = now(); t_wait += tb - ta; t_vmult += tc - tb; t_rest += td - tc; }
     }
+  if (dbg) fprintf(stderr, "cg host time: wait %.3f ms, vmult enqueue %.3f ms, other enqueue %.3f ms\n", 1e3 * t_wait, 1e3 * t_vmult, 1e3 * t_rest);
+  CgState fin;
+  MFG_CUDA(cudaMemcpyAsync(&fin, st.p, sizeof(fin), cudaMemcpyDeviceToHost, s));
   MFG_CUDA(cudaStreamSynchronize(s));
+  const int it = fin.converged_at >= 0 ? fin.converged_at : max_iter;
+  if (history) MFG_CUDA(cudaMemcpy(history, hist.p, ((size_t)it + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  for (auto &e : ev) cudaEventDestroy(e);
   if (iters) *iters = it;
-  if (last_res) *last_res = res;
+  if (last_res) *last_res = fin.res;
 }
 
 }  // namespace

@@ -16,6 +16,7 @@ struct mfg_vec
 
 namespace mfg {
 constexpr int RED_SCRATCH_DOUBLES = 8 + 1024;
+constexpr int RED_HOST_DOUBLES = 64;  // pinned host scratch of a context (reduction results, solver state mirror)
 void   vec_fill(mfg_vec *v, double a);
 void   vec_scal(mfg_vec *v, double a);
 void   vec_invert(mfg_vec *v);
