@@ -483,6 +483,18 @@ class LaplaceOperatorGpu:
     def vmult_ptr(self, dst_ptr, src_ptr):
         check(lib.mfg_laplace_vmult_ptr(self.h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr)))
 
+    def set_interface_dofs(self, dofs):
+        """Multi-GPU: DoFs whose partial sums are exchanged after the cell loop; returns the number of cell groups that
+        contribute to them (0: the active kernel has no work list, part 0 then does the whole apply)."""
+        d = np.ascontiguousarray(dofs, dtype=np.uint32)
+        k = C.c_uint32()
+        check(lib.mfg_laplace_set_interface_dofs(self.h, d.ctypes.data_as(C.POINTER(C.c_uint32)), d.size, C.byref(k)))
+        return k.value
+
+    def vmult_part_ptr(self, dst_ptr, src_ptr, part):
+        """part 0: zero/constraint pass + interface cell groups, part 1: the other groups, -1: everything."""
+        check(lib.mfg_laplace_vmult_part_ptr(self.h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(part)))
+
     def vmult_host(self, dst, src):
         """dst, src: contiguous numpy arrays (or pinned torch CPU tensors via .numpy())."""
         check(lib.mfg_laplace_vmult_host(self.h, dst.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p)))

@@ -104,18 +104,24 @@ int mfg_exchange_pack(mfg_exchange *ex, const void *vec_dev, void *send_dev)
     MFG_CUDA_LAST();
   });
 }
+static void accumulate_on(mfg_exchange *ex, void *vec_dev, const void *recv_dev, cudaStream_t st)
+{
+  MFG_REQUIRE(ex && vec_dev, "null argument");
+  const size_t n = ex->shared_dofs.n; if (!n) return;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  if (ex->dt == MFG_F64)
+    k_accumulate<double><<<nb, 256, 0, st>>>((double *)vec_dev, (const double *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
+  else
+    k_accumulate<float><<<nb, 256, 0, st>>>((float *)vec_dev, (const float *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
+  MFG_CUDA_LAST();
+}
 int mfg_exchange_accumulate(mfg_exchange *ex, void *vec_dev, const void *recv_dev)
 {
-  return guarded([&] {
-    MFG_REQUIRE(ex && vec_dev, "null argument");
-    const size_t n = ex->shared_dofs.n; if (!n) return;
-    const unsigned nb = (unsigned)((n + 255) / 256);
-    if (ex->dt == MFG_F64)
-      k_accumulate<double><<<nb, 256, 0, ex->ctx->stream>>>((double *)vec_dev, (const double *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
-    else
-      k_accumulate<float><<<nb, 256, 0, ex->ctx->stream>>>((float *)vec_dev, (const float *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
-    MFG_CUDA_LAST();
-  });
+  return guarded([&] { MFG_REQUIRE(ex, "null argument"); accumulate_on(ex, vec_dev, recv_dev, ex->ctx->stream); });
+}
+int mfg_exchange_accumulate_stream(mfg_exchange *ex, void *vec_dev, const void *recv_dev, void *cuda_stream)
+{
+  return guarded([&] { accumulate_on(ex, vec_dev, recv_dev, (cudaStream_t)cuda_stream); });
 }
 int mfg_vec_dot_masked(const mfg_vec *a, const mfg_vec *b, const uint8_t *owned_mask_dev, double *out)
 {

@@ -234,7 +234,7 @@ template <int n, typename Number, int CFG>
 __global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n, Number, CFG>::MINB)
 laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
                    Number *__restrict__ dst, const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em,
-                   const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP)
+                   const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP, const uint32_t *__restrict__ glist)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   using Tab = typename Cfg::Tab;
@@ -252,8 +252,11 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
   // idle lanes shadow the first lane of their own half warp for loads (broadcast, no conflict) and never store
   const int cl = lm.cl, ch = lm.ch, x = lm.x;
   const uint32_t total_warps = gridDim.x * Cfg::WPB;
-  const uint32_t g0 = blockIdx.x * Cfg::WPB + warp;
-  if (g0 >= n_groups) return;
+  // work list: groups glist[0 .. n_groups) (multi-GPU: interface groups first, interior groups while the exchange
+  // runs) or simply 0 .. n_groups
+  const uint32_t k0 = blockIdx.x * Cfg::WPB + warp;
+  if (k0 >= n_groups) return;
+  const uint32_t g0 = glist ? __ldg(glist + k0) : k0;
 #ifdef MFG_SLAB2_ABLATE
   if (g_slab2_delay[0] > 0)
     {
@@ -298,9 +301,11 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
   if (Cfg::PF >= 1) load_ids(g0, id);
   if (Cfg::PF == 2) gather(id, un);
 
-  for (uint32_t g = g0; g < n_groups; g += total_warps)
+  uint32_t g = g0;
+  for (uint32_t k = k0; k < n_groups; k += total_warps)
     {
-      const uint32_t  gn   = g + total_warps;
+      const bool      more = k + total_warps < n_groups;
+      const uint32_t  gn   = more ? (glist ? __ldg(glist + k + total_warps) : k + total_warps) : 0;
       const uint32_t *irow = idxP + (size_t)g * NS * 32 + lane;
       Number u[NS], r[NS];
       if (Cfg::PF == 0) load_ids(g, id);
@@ -310,7 +315,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
           for (int s = 0; s < NS; ++s) u[s] = un[s];
         }
       else gather(id, u);
-      if (gn < n_groups && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
+      if (more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
       // ---- A: N_y, N_z ----
       slab2_apply<n, 1, n, false, Number, NOPC>(em.N, u);
       slab2_apply<n, n, 1, false, Number, NOPC>(em.N, u);
@@ -384,7 +389,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
         for (int i = 0; i < n; ++i) u[i + n * k] = Q[bBCr + BC.SI * i + BC.SK * k];
       if (Cfg::PF >= 1)
         {
-          if (gn < n_groups) load_ids(gn, id);
+          if (more) load_ids(gn, id);
           else
             {
 #pragma unroll
@@ -417,7 +422,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
           for (int k = 0; k < n; ++k) u[i + n * k] = t[k] + P[bBCr + BC.SI * i + BC.SK * k];
         }
       __syncwarp();  // P, Q and the coefficient image are consumed
-      if (gn < n_groups && lane == 0) bulk_load(W, cwP + (size_t)gn * Cfg::CWF, Cfg::CW_BYTES, bar);
+      if (more && lane == 0) bulk_load(W, cwP + (size_t)gn * Cfg::CWF, Cfg::CW_BYTES, bar);
       // ---- C: N_x^T, N_z^T ----
       slab2_apply<n, 1, n, false, Number, NOPC>(em.NT, u);
       slab2_apply<n, n, 1, false, Number, NOPC>(em.NT, u);
@@ -489,7 +494,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
                 }
             }
         }
-      if (Cfg::PF == 2 && gn < n_groups) gather(id, un);
+      if (Cfg::PF == 2 && more) gather(id, un);
       // ---- distribute_local_to_global (fee_gpu.cuh:346-365): red.add straight from registers ----
 #pragma unroll
       for (int s = 0; s < NS; ++s)
@@ -505,13 +510,14 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
               if (!(ii & CONSTRAINED_BIT) && !handed_over) red_add(dst + ii, u[s]);
             }
         }
+      g = gn;
     }
 }
 
 template <typename Number>
 void launch_laplace_slab2(int degree, int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups,
                           const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0,
-                          const uint32_t *mergeP = nullptr);
+                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr);
 // layout of the kernel's private arrays (for the builders in operators.cu)
 struct Slab2Geom { int n, cw, hc, cwf; Slab2Lay bc; };
 bool      slab2_supported(int dim, int degree, mfg_dtype dt);

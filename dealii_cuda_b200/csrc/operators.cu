@@ -609,11 +609,17 @@ int laplace_active_variant(const mfg_laplace *op)
   return slab_ok ? 2 : 1;
 }
 
+// part: -1 = the whole apply; 0 = zero/constraint pass + the cell groups that touch interface DoFs (multi-GPU: what
+// the exchange waits for); 1 = the remaining groups.  Without an interface partition part 0 does everything.
 template <typename Number>
-static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add)
+static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add, int part = -1)
 {
   const mfg_mf *mf = op->mf;
   cudaStream_t  s  = op->ctx->stream;
+  const bool split = part >= 0 && op->glist.n != 0 && laplace_active_variant(op) == 6;
+  if (part == 1 && !split) return;
+  if (part != 1)
+    {
   // vmult: dst = 0 (laplace_operator_gpu.h:221) fused with dst[c] = src[c];
   // vmult_add: dst[c] += src[c]  (load_and_add_constrained_values, :302)
   if (!add)
@@ -637,6 +643,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
     {
       constrained_add<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n());
       MFG_CUDA_LAST();
+    }
     }
   const bool     hanging = mf->hn_mask.n != 0;
   const uint32_t n_plain = hanging ? mf->n_plain : mf->n_cells;
@@ -664,9 +671,11 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       // auto = configuration 3 (3 blocks x 4 warps, 168 registers, one transpose buffer per warp, LSU gather)
       const int cfg = op->variant >= 6 ? op->variant - 6 : 3;
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
+      const uint32_t *gl = split ? op->glist.p + (part == 1 ? op->n_iface_groups : 0) : nullptr;
+      const uint32_t  ng = !split ? op->slab2_groups : part == 1 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
       time_begin();
-      launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, op->slab2_groups,
-                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p);
+      launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
+                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl);
       time_end();
     }
   else if (laplace_active_variant(op) == 2)
@@ -691,7 +700,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
     }
   // cells with hanging-node constraints (sorted to the end): column kernel with the interpolation fused into
   // gather and scatter (resolve_hanging_nodes_shmem, fee_gpu.cuh:333-335, 349-351)
-  if (hanging && n_plain < mf->n_cells)
+  if (hanging && n_plain < mf->n_cells && part != 1)
     {
       time_begin();
       launch_v0(n_plain, mf->n_cells, mf->hn_mask.p);
@@ -714,11 +723,57 @@ void laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches)
   op->ev_used = 0;
 }
 
-void laplace_vmult(mfg_laplace *op, void *dst, const void *src, bool add)
+void laplace_vmult(mfg_laplace *op, void *dst, const void *src, bool add, int part)
 {
   MFG_REQUIRE(dst != src, "vmult: dst and src must not alias");
-  if (op->mf->dt == MFG_F64) vmult_impl<double>(op, (double *)dst, (const double *)src, add);
-  else vmult_impl<float>(op, (float *)dst, (const float *)src, add);
+  MFG_REQUIRE(part >= -1 && part <= 1, "vmult: part must be -1, 0 or 1");
+  if (op->mf->dt == MFG_F64) vmult_impl<double>(op, (double *)dst, (const double *)src, add, part);
+  else vmult_impl<float>(op, (float *)dst, (const float *)src, add, part);
+}
+
+// slab2 work list: 1 where a group holds an unconstrained entry of a flagged DoF
+__global__ void mark_interface_groups(const uint32_t *__restrict__ idxP, size_t n_entries, int per_group, const uint8_t *__restrict__ flag,
+                                      uint8_t *__restrict__ gflag)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_entries) return;
+  const uint32_t id = idxP[t];
+  if (!(id & CONSTRAINED_BIT) && flag[id]) gflag[t / per_group] = 1;
+}
+
+// Multi-GPU: the DoFs whose partial sums are exchanged after the cell loop.  Splits the cell groups of the
+// slab2 kernel into those that contribute to such a DoF (launched first) and the rest (launched while the exchange
+// runs); returns the number of groups in the first set, 0 if the active kernel has no work list.
+uint32_t laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, size_t n)
+{
+  const mfg_mf *mf = op->mf;
+  op->glist.release();
+  op->n_iface_groups = 0;
+  if (laplace_active_variant(op) != 6 || n == 0) return 0;
+  cudaStream_t   s = op->ctx->stream;
+  const uint32_t n_plain = mf->hn_mask.n ? mf->n_plain : mf->n_cells;
+  laplace_prepare_slab2(op, n_plain);
+  const uint32_t ng = op->slab2_groups;
+  if (ng == 0) return 0;
+  for (size_t i = 0; i < n; ++i) MFG_REQUIRE(dofs_host[i] < mf->n_dofs, "interface DoF index out of range");
+  DevBuf<uint32_t> list; list.upload(dofs_host, n, s);
+  DevBuf<uint8_t> flag(mf->n_dofs), gflag(ng);
+  MFG_CUDA(cudaMemsetAsync(flag.p, 0, mf->n_dofs, s));
+  MFG_CUDA(cudaMemsetAsync(gflag.p, 0, ng, s));
+  flags_from_list<<<nblk(n), 256, 0, s>>>(list.p, n, flag.p);
+  MFG_CUDA_LAST();
+  const int per_group = mf->n * mf->n * 32;
+  mark_interface_groups<<<nblk(op->idxP.n), 256, 0, s>>>(op->idxP.p, op->idxP.n, per_group, flag.p, gflag.p);
+  MFG_CUDA_LAST();
+  std::vector<uint8_t> gf(ng);
+  gflag.download(gf.data(), s);
+  std::vector<uint32_t> order;
+  order.reserve(ng);
+  for (uint32_t g = 0; g < ng; ++g) if (gf[g]) order.push_back(g);
+  op->n_iface_groups = (uint32_t)order.size();
+  for (uint32_t g = 0; g < ng; ++g) if (!gf[g]) order.push_back(g);
+  op->glist.upload(order.data(), ng, s);
+  return op->n_iface_groups;
 }
 
 void laplace_compute_diagonal(mfg_laplace *op)

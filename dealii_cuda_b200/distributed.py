@@ -28,6 +28,9 @@ class InterfaceExchange:
         self.send = torch.empty(max(1, plan.n_send), dtype=tdt, device="cuda")
         self.recv = torch.empty(max(1, plan.n_send), dtype=tdt, device="cuda")
         self.owned_mask = torch.from_numpy(plan.owned_mask).cuda()
+        # second stream for the exchange when it is overlapped with the interior cells
+        self.side = torch.cuda.Stream() if plan.world > 1 and plan.n_send else None
+        self.ev_packed, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
 
     def __del__(self):
         try:
@@ -49,10 +52,33 @@ class InterfaceExchange:
         check(lib.mfg_exchange_accumulate(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.recv.data_ptr())))
 
 
+    def start(self, vec_ptr):
+        """After the interface cell groups: pack on the main stream, all_to_all + ordered accumulate on the side stream."""
+        import torch
+        import torch.distributed as dist
+        if self.side is None:
+            return
+        check(lib.mfg_exchange_pack(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.send.data_ptr())))
+        self.ev_packed.record()
+        n = self.plan.n_send
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_packed)
+            dist.all_to_all_single(self.recv[:n], self.send[:n], self.plan.splits, self.plan.splits, group=self.group)
+            check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.recv.data_ptr()),
+                                                     C.c_void_p(self.side.cuda_stream)))
+            self.ev_done.record()
+
+    def finish(self):
+        """Main stream waits for the accumulate of start()."""
+        import torch
+        if self.side is not None:
+            torch.cuda.current_stream().wait_event(self.ev_done)
+
+
 class DistributedLaplaceOperator:
     """LaplaceOperatorGpu over a box partition: vmult = local cell loop + interface exchange."""
 
-    def __init__(self, ctx, rank, world, dim, degree, r, dtype=np.float64, left=-1.0, right=1.0, variant=0, group=None):
+    def __init__(self, ctx, rank, world, dim, degree, r, dtype=np.float64, left=-1.0, right=1.0, variant=0, group=None, overlap=True):
         self.ctx, self.rank, self.world = ctx, rank, world
         box, self.me, self.grid = box_for_rank(rank, world, dim, r, left, right)
         self.mesh = HyperCubeMesh(ctx, dim, degree, box=box)
@@ -62,12 +88,20 @@ class DistributedLaplaceOperator:
             self.op.set_variant(variant)
         self.plan = build_exchange_plan(rank, world, dim, degree, r, self.mesh.lattice_to_dof, self.mesh.n_dofs)
         self.exchange = InterfaceExchange(ctx, self.plan, dtype, group)
+        # overlap: cell groups that touch exchanged DoFs run first, the rest while the exchange is in flight
+        self.n_iface_groups = self.op.set_interface_dofs(self.plan.pack_idx) if (overlap and world > 1 and self.plan.n_send) else 0
         self.n_local = self.mesh.n_dofs
         self.n_global = global_n_dofs(world, dim, degree, r)
 
     def vmult_ptr(self, dst_ptr, src_ptr):
-        self.op.vmult_ptr(dst_ptr, src_ptr)
-        self.exchange.add_interface_contributions(dst_ptr)
+        if self.n_iface_groups:
+            self.op.vmult_part_ptr(dst_ptr, src_ptr, 0)
+            self.exchange.start(dst_ptr)
+            self.op.vmult_part_ptr(dst_ptr, src_ptr, 1)   # writes no exchanged DoF
+            self.exchange.finish()
+        else:
+            self.op.vmult_ptr(dst_ptr, src_ptr)
+            self.exchange.add_interface_contributions(dst_ptr)
 
     def vmult(self, dst, src):
         self.vmult_ptr(dst.getData(), src.getData())

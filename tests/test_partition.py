@@ -158,8 +158,10 @@ def test_plan_counts_single_process(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,p,r,dtype", [(2, 4, 1, np.float64), (4, 2, 2, np.float64), (8, 4, 1, np.float64), (8, 3, 2, np.float32)])
-def test_partitions_emulated_on_one_gpu(ctx, world, p, r, dtype):
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("world,p,r,dtype", [(2, 4, 1, np.float64), (4, 2, 2, np.float64), (8, 4, 1, np.float64), (8, 3, 2, np.float32),
+                                             (2, 4, 3, np.float64), (4, 5, 2, np.float64)])
+def test_partitions_emulated_on_one_gpu(ctx, world, p, r, dtype, split):
     """All ranks' partitions live in this process; the collective is replaced by device-side slicing.
     Exercises mfg_mesh_create_box, the CUDA cell loop per partition, mfg_exchange_pack / _accumulate."""
     import torch
@@ -184,8 +186,17 @@ def test_partitions_emulated_on_one_gpu(ctx, world, p, r, dtype):
         ex = InterfaceExchange(ctx, plan, dtype)
         m = local_to_global_map(ol, og, me, p, r, dim)
         src = mf.GpuVector.from_numpy(ctx, u_g[m]); dst = mf.GpuVector(ctx, mesh.n_dofs, dtype)
-        op.vmult(dst, src)
-        mf.check(mf.lib.mfg_exchange_pack(ex.h, C.c_void_p(dst.getData()), C.c_void_p(ex.send.data_ptr())))
+        if split:
+            # the overlapped form: interface cell groups, pack, then the other groups (must not touch packed DoFs)
+            k = op.set_interface_dofs(plan.pack_idx)
+            assert (k > 0) == (op.active_variant() == 6 and plan.n_send > 0)
+            dst.fill(7.0)
+            op.vmult_part_ptr(dst.getData(), src.getData(), 0)
+            mf.check(mf.lib.mfg_exchange_pack(ex.h, C.c_void_p(dst.getData()), C.c_void_p(ex.send.data_ptr())))
+            op.vmult_part_ptr(dst.getData(), src.getData(), 1)
+        else:
+            op.vmult(dst, src)
+            mf.check(mf.lib.mfg_exchange_pack(ex.h, C.c_void_p(dst.getData()), C.c_void_p(ex.send.data_ptr())))
         parts.append(dict(mesh=mesh, op=op, plan=plan, ex=ex, map=m, dst=dst, src=src))
     ctx.synchronize(); torch.cuda.synchronize()
     # "all_to_all": recv buffer of rank a = concatenation over neighbours b (ascending) of b's block for a
