@@ -491,9 +491,10 @@ class LaplaceOperatorGpu:
         check(lib.mfg_laplace_set_interface_dofs(self.h, d.ctypes.data_as(C.POINTER(C.c_uint32)), d.size, C.byref(k)))
         return k.value
 
-    def vmult_part_ptr(self, dst_ptr, src_ptr, part):
-        """part 0: zero/constraint pass + interface cell groups, part 1: the other groups, -1: everything."""
-        check(lib.mfg_laplace_vmult_part_ptr(self.h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(part)))
+    def vmult_part_ptr(self, dst_ptr, src_ptr, part, stream=None):
+        """part 0: zero/constraint pass, 1: interface cell groups, 2: the other groups, -1: everything; stream: raw
+        CUDA stream to enqueue on (None: the context's)."""
+        check(lib.mfg_laplace_vmult_part_ptr(self.h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(part), C.c_void_p(stream or 0)))
 
     def vmult_host(self, dst, src):
         """dst, src: contiguous numpy arrays (or pinned torch CPU tensors via .numpy())."""

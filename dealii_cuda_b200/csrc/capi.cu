@@ -316,9 +316,9 @@ int mfg_laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, s
     if (n_interface_groups) *n_interface_groups = k;
   });
 }
-int mfg_laplace_vmult_part_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev, int part)
+int mfg_laplace_vmult_part_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev, int part, void *cuda_stream)
 {
-  return guarded([&] { MFG_REQUIRE(op && dst_dev && src_dev, "null argument"); laplace_vmult(op, dst_dev, src_dev, false, part); });
+  return guarded([&] { MFG_REQUIRE(op && dst_dev && src_dev, "null argument"); laplace_vmult(op, dst_dev, src_dev, false, part, cuda_stream); });
 }
 int mfg_laplace_vmult_host(mfg_laplace *op, void *dst_host, const void *src_host)
 {

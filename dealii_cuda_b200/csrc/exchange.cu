@@ -93,26 +93,34 @@ int mfg_exchange_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *pack_idx_hos
   });
 }
 int mfg_exchange_destroy(mfg_exchange *ex) { return guarded([&] { delete ex; }); }
+// tb = threads per block.  The overlapped form runs next to the persistent interior cell kernel, which leaves about
+// 1000 registers per SM free: only one-warp blocks with few registers find a slot there (pack and accumulate use < 24)
+static void pack_on(mfg_exchange *ex, const void *vec_dev, void *send_dev, cudaStream_t st, unsigned tb = 256)
+{
+  MFG_REQUIRE(ex && vec_dev && (send_dev || !ex->pack_idx.n), "null argument");
+  const size_t n = ex->pack_idx.n; if (!n) return;
+  const unsigned nb = (unsigned)((n + tb - 1) / tb);
+  if (ex->dt == MFG_F64) k_pack<double><<<nb, tb, 0, st>>>((const double *)vec_dev, ex->pack_idx.p, n, (double *)send_dev);
+  else k_pack<float><<<nb, tb, 0, st>>>((const float *)vec_dev, ex->pack_idx.p, n, (float *)send_dev);
+  MFG_CUDA_LAST();
+}
 int mfg_exchange_pack(mfg_exchange *ex, const void *vec_dev, void *send_dev)
 {
-  return guarded([&] {
-    MFG_REQUIRE(ex && vec_dev && (send_dev || !ex->pack_idx.n), "null argument");
-    const size_t n = ex->pack_idx.n; if (!n) return;
-    const unsigned nb = (unsigned)((n + 255) / 256);
-    if (ex->dt == MFG_F64) k_pack<double><<<nb, 256, 0, ex->ctx->stream>>>((const double *)vec_dev, ex->pack_idx.p, n, (double *)send_dev);
-    else k_pack<float><<<nb, 256, 0, ex->ctx->stream>>>((const float *)vec_dev, ex->pack_idx.p, n, (float *)send_dev);
-    MFG_CUDA_LAST();
-  });
+  return guarded([&] { MFG_REQUIRE(ex, "null argument"); pack_on(ex, vec_dev, send_dev, ex->ctx->stream); });
 }
-static void accumulate_on(mfg_exchange *ex, void *vec_dev, const void *recv_dev, cudaStream_t st)
+int mfg_exchange_pack_stream(mfg_exchange *ex, const void *vec_dev, void *send_dev, void *cuda_stream)
+{
+  return guarded([&] { pack_on(ex, vec_dev, send_dev, (cudaStream_t)cuda_stream, 32); });
+}
+static void accumulate_on(mfg_exchange *ex, void *vec_dev, const void *recv_dev, cudaStream_t st, unsigned tb = 256)
 {
   MFG_REQUIRE(ex && vec_dev, "null argument");
   const size_t n = ex->shared_dofs.n; if (!n) return;
-  const unsigned nb = (unsigned)((n + 255) / 256);
+  const unsigned nb = (unsigned)((n + tb - 1) / tb);
   if (ex->dt == MFG_F64)
-    k_accumulate<double><<<nb, 256, 0, st>>>((double *)vec_dev, (const double *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
+    k_accumulate<double><<<nb, tb, 0, st>>>((double *)vec_dev, (const double *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
   else
-    k_accumulate<float><<<nb, 256, 0, st>>>((float *)vec_dev, (const float *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
+    k_accumulate<float><<<nb, tb, 0, st>>>((float *)vec_dev, (const float *)recv_dev, ex->shared_dofs.p, ex->offsets.p, ex->slots.p, n);
   MFG_CUDA_LAST();
 }
 int mfg_exchange_accumulate(mfg_exchange *ex, void *vec_dev, const void *recv_dev)
@@ -121,7 +129,7 @@ int mfg_exchange_accumulate(mfg_exchange *ex, void *vec_dev, const void *recv_de
 }
 int mfg_exchange_accumulate_stream(mfg_exchange *ex, void *vec_dev, const void *recv_dev, void *cuda_stream)
 {
-  return guarded([&] { accumulate_on(ex, vec_dev, recv_dev, (cudaStream_t)cuda_stream); });
+  return guarded([&] { accumulate_on(ex, vec_dev, recv_dev, (cudaStream_t)cuda_stream, 32); });
 }
 int mfg_vec_dot_masked(const mfg_vec *a, const mfg_vec *b, const uint8_t *owned_mask_dev, double *out)
 {

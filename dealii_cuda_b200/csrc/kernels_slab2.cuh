@@ -234,7 +234,8 @@ template <int n, typename Number, int CFG>
 __global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n, Number, CFG>::MINB)
 laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
                    Number *__restrict__ dst, const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em,
-                   const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP, const uint32_t *__restrict__ glist)
+                   const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP, const uint32_t *__restrict__ glist,
+                   uint32_t *__restrict__ work_counter)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   using Tab = typename Cfg::Tab;
@@ -254,6 +255,9 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
   const uint32_t total_warps = gridDim.x * Cfg::WPB;
   // work list: groups glist[0 .. n_groups) (multi-GPU: interface groups first, interior groups while the exchange
   // runs) or simply 0 .. n_groups
+  // a launch that follows with programmatic stream serialization (the interior groups after the interface groups of a
+  // multi-GPU apply) may start right away: it reads nothing this one writes
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t k0 = blockIdx.x * Cfg::WPB + warp;
   if (k0 >= n_groups) return;
   const uint32_t g0 = glist ? __ldg(glist + k0) : k0;
@@ -301,11 +305,16 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
   if (Cfg::PF >= 1) load_ids(g0, id);
   if (Cfg::PF == 2) gather(id, un);
 
-  uint32_t g = g0;
-  for (uint32_t k = k0; k < n_groups; k += total_warps)
+  // Every warp starts with list entry k0; the following entries are handed out by an atomic counter when one is given
+  // (a warp that starts late -- its CTA waited for an SM slot next to another kernel -- then simply takes fewer groups),
+  // else with a fixed stride.  The entry after the current one is fetched one group ahead for the prefetches.
+  uint32_t g = g0, k = k0;
+  for (;;)
     {
-      const bool      more = k + total_warps < n_groups;
-      const uint32_t  gn   = more ? (glist ? __ldg(glist + k + total_warps) : k + total_warps) : 0;
+      // the atomic is issued here and its result is not looked at before the C phase: under the red traffic of the
+      // scatters an atomic with a return value takes microseconds (measured: 30 % slower when consumed at once)
+      uint32_t kn_raw = 0;
+      if (work_counter && lane == 0) kn_raw = total_warps + atomicAdd(work_counter, 1u);
       const uint32_t *irow = idxP + (size_t)g * NS * 32 + lane;
       Number u[NS], r[NS];
       if (Cfg::PF == 0) load_ids(g, id);
@@ -315,7 +324,6 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
           for (int s = 0; s < NS; ++s) u[s] = un[s];
         }
       else gather(id, u);
-      if (more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
       // ---- A: N_y, N_z ----
       slab2_apply<n, 1, n, false, Number, NOPC>(em.N, u);
       slab2_apply<n, n, 1, false, Number, NOPC>(em.N, u);
@@ -387,6 +395,10 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
       for (int k = 0; k < n; ++k)
 #pragma unroll
         for (int i = 0; i < n; ++i) u[i + n * k] = Q[bBCr + BC.SI * i + BC.SK * k];
+      const uint32_t kn   = work_counter ? __shfl_sync(0xffffffffu, kn_raw, 0) : k + total_warps;
+      const bool     more = kn < n_groups;
+      const uint32_t gn   = more ? (glist ? __ldg(glist + kn) : kn) : 0;
+      if (more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
       if (Cfg::PF >= 1)
         {
           if (more) load_ids(gn, id);
@@ -510,14 +522,16 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
               if (!(ii & CONSTRAINED_BIT) && !handed_over) red_add(dst + ii, u[s]);
             }
         }
+      if (!more) break;
       g = gn;
+      k = kn;
     }
 }
 
 template <typename Number>
 void launch_laplace_slab2(int degree, int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups,
                           const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0,
-                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr);
+                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr, uint32_t *work_counter = nullptr, bool pdl = false);
 // layout of the kernel's private arrays (for the builders in operators.cu)
 struct Slab2Geom { int n, cw, hc, cwf; Slab2Lay bc; };
 bool      slab2_supported(int dim, int degree, mfg_dtype dt);

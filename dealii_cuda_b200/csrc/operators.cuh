@@ -57,6 +57,7 @@ struct mfg_laplace
   mfg::DevBuf<uint32_t> mergeP; // [n_groups] face-merge mask
   mfg::DevBuf<uint32_t> glist;  // multi-GPU work list: groups touching interface DoFs first (laplace_set_interface_dofs)
   uint32_t              n_iface_groups = 0;
+  mfg::DevBuf<uint32_t> work_counters;  // dynamic group distribution of the slab2 kernel, one counter per concurrent part
   uint32_t              slab2_groups = 0;
   bool                  cwP_valid = false;
   // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer
@@ -93,7 +94,7 @@ void    ch_load_and_add(mfg_ch *ch, mfg_vec *v1, mfg_vec *v2);
 mfg_laplace *laplace_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter);
 mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const double *coef_host);
 void         laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host);
-void         laplace_vmult(mfg_laplace *op, void *dst, const void *src, bool add, int part = -1);
+void         laplace_vmult(mfg_laplace *op, void *dst, const void *src, bool add, int part = -1, void *cuda_stream = nullptr);
 uint32_t     laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, size_t n);
 void         laplace_compute_diagonal(mfg_laplace *op);
 int          laplace_launches_per_vmult(const mfg_laplace *op);

@@ -29,8 +29,9 @@ class InterfaceExchange:
         self.recv = torch.empty(max(1, plan.n_send), dtype=tdt, device="cuda")
         self.owned_mask = torch.from_numpy(plan.owned_mask).cuda()
         # second stream for the exchange when it is overlapped with the interior cells
-        self.side = torch.cuda.Stream() if plan.world > 1 and plan.n_send else None
-        self.ev_packed, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
+        # (high priority: its interface cell kernel gets SM slots before the interior kernel launched next to it)
+        self.side = torch.cuda.Stream(priority=-1) if plan.world > 1 and plan.n_send else None
+        self.ev_ready, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
 
     def __del__(self):
         try:
@@ -52,27 +53,27 @@ class InterfaceExchange:
         check(lib.mfg_exchange_accumulate(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.recv.data_ptr())))
 
 
-    def start(self, vec_ptr):
-        """After the interface cell groups: pack on the main stream, all_to_all + ordered accumulate on the side stream."""
+    def run_overlapped(self, op, dst_ptr, src_ptr):
+        """One apply with the exchange hidden behind the interior cells:
+        main stream:  zero/constraint pass | interface cell groups | interior cell groups (programmatic dependent launch:
+                                                                     its CTAs fill the SMs as the interface CTAs leave) | wait
+        side stream:                                               | pack, all_to_all, ordered accumulate |"""
         import torch
         import torch.distributed as dist
-        if self.side is None:
-            return
-        check(lib.mfg_exchange_pack(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.send.data_ptr())))
-        self.ev_packed.record()
+        main = torch.cuda.current_stream()
+        side = self.side
+        op.vmult_part_ptr(dst_ptr, src_ptr, 0)
+        op.vmult_part_ptr(dst_ptr, src_ptr, 1)
+        self.ev_ready.record(main)
+        op.vmult_part_ptr(dst_ptr, src_ptr, 2)   # adds into no exchanged DoF
+        side.wait_event(self.ev_ready)
+        check(lib.mfg_exchange_pack_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.send.data_ptr()), C.c_void_p(side.cuda_stream)))
         n = self.plan.n_send
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(self.ev_packed)
+        with torch.cuda.stream(side):
             dist.all_to_all_single(self.recv[:n], self.send[:n], self.plan.splits, self.plan.splits, group=self.group)
-            check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(vec_ptr), C.c_void_p(self.recv.data_ptr()),
-                                                     C.c_void_p(self.side.cuda_stream)))
-            self.ev_done.record()
-
-    def finish(self):
-        """Main stream waits for the accumulate of start()."""
-        import torch
-        if self.side is not None:
-            torch.cuda.current_stream().wait_event(self.ev_done)
+        check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.recv.data_ptr()), C.c_void_p(side.cuda_stream)))
+        self.ev_done.record(side)
+        main.wait_event(self.ev_done)
 
 
 class DistributedLaplaceOperator:
@@ -95,10 +96,7 @@ class DistributedLaplaceOperator:
 
     def vmult_ptr(self, dst_ptr, src_ptr):
         if self.n_iface_groups:
-            self.op.vmult_part_ptr(dst_ptr, src_ptr, 0)
-            self.exchange.start(dst_ptr)
-            self.op.vmult_part_ptr(dst_ptr, src_ptr, 1)   # writes no exchanged DoF
-            self.exchange.finish()
+            self.exchange.run_overlapped(self.op, dst_ptr, src_ptr)
         else:
             self.op.vmult_ptr(dst_ptr, src_ptr)
             self.exchange.add_interface_contributions(dst_ptr)
@@ -128,11 +126,19 @@ def bench_main(args, metric):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    # The exchange runs beside the persistent interior cell kernel, which leaves 4 CTA slots free (MFG_SLAB2_RESERVE):
+    # NCCL's send/recv kernel must fit into them, so few and narrow channels (measured on 2 x B200: 0.281 ms per apply
+    # against 0.287 with NCCL's defaults, profiles/r01_multigpu_overlap.txt)
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
+    os.environ.setdefault("NCCL_NTHREADS", "128")
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = Context(local_rank, stream)
+    # a non-default stream, so that a whole apply (cell kernels, pack, NCCL all_to_all on the side stream, accumulate)
+    # can be captured into a CUDA graph and replayed without per-step host work
+    main = torch.cuda.Stream()
+    torch.cuda.set_stream(main)
+    ctx = Context(local_rank, main.cuda_stream)
     dtype = np.float64 if args.dtype == "f64" else np.float32
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
     s = 8 if args.dtype == "f64" else 4
@@ -142,18 +148,39 @@ def bench_main(args, metric):
     tb = torch.zeros((n,), dtype=tdtype, device="cuda")
     pa, pb = ta.data_ptr(), tb.data_ptr()
 
+    graphs = {}
+
     def apply_steps(k):
         nonlocal pa, pb
         for _ in range(k):
             pa, pb = pb, pa
-            dop.vmult_ptr(pa, pb)
+            g = graphs.get((pa, pb))
+            if g is not None:
+                g.replay()
+            else:
+                dop.vmult_ptr(pa, pb)
 
     apply_steps(args.warmup)
     torch.cuda.synchronize()
+    use_graphs = os.environ.get("MFG_NO_GRAPH") is None
+    if use_graphs:
+        try:
+            for d_, s_ in ((pa, pb), (pb, pa)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=main):
+                    dop.vmult_ptr(d_, s_)
+                graphs[(d_, s_)] = g
+        except Exception as e:  # keep going without graphs, say so in the result
+            graphs.clear()
+            use_graphs = False
+            if rank == 0:
+                print("CUDA graph capture of the apply failed (%s): eager launches" % e, file=__import__("sys").stderr)
+        torch.cuda.synchronize()
+        apply_steps(2)
+        torch.cuda.synchronize()
     ta.fill_(0.1); tb.fill_(0.1)
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dop.op.enable_kernel_timing(True)
     if rank == 0:
         sampler.start()
     dist.barrier()
@@ -165,9 +192,17 @@ def bench_main(args, metric):
     dist.barrier()
     ms_local = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    # cell-kernel time per apply (both launches when the apply is split): CUDA events around every cell-kernel launch,
+    # on eager applies right after the timed region (events cannot be read back from inside a captured graph)
+    n_k = 20
+    dop.op.enable_kernel_timing(True)
+    for _ in range(n_k):
+        pa, pb = pb, pa
+        dop.vmult_ptr(pa, pb)
+    torch.cuda.synchronize()
     kernel_ms, kernel_launches = dop.op.kernel_time_ms()
     dop.op.enable_kernel_timing(False)
-    t = torch.tensor([ms_local, kernel_ms / max(1, kernel_launches)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_local, kernel_ms / n_k], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, k_avg_ms = float(t[0]), float(t[1])
 
@@ -208,12 +243,21 @@ def bench_main(args, metric):
                 "clocks": clocks,
                 "e2e": {"value": ng / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
                         "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
-                "gpu_launches": args.steps * (dop.op.launches_per_vmult() + 2) * world,
+                "gpu_launches": args.steps * (dop.op.launches_per_vmult() + (1 if dop.n_iface_groups else 0) + 2) * world,
+                "launch_mode": "CUDA graph replay of one apply (cell kernels + pack + all_to_all + accumulate)" if use_graphs else "eager",
+                "overlap": "interface cell groups first (%d of the groups), exchange on a side stream during the interior groups" % dop.n_iface_groups
+                           if dop.n_iface_groups else "none",
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "kernel": "laplace cell kernel (variant %d), per GPU, max over ranks" % dop.op.active_variant(),
+                             "kernel": "laplace cell kernel (variant %d), per GPU and apply (%d launches), max over ranks"
+                                       % (dop.op.active_variant(), kernel_launches // n_k),
                              "kernel_ms": k_avg_ms, "peak_source": peak_src},
                 "cpu_baseline": None}
-        print(json.dumps(line))
-    dist.barrier()
-    dist.destroy_process_group()
-    return 0
+        print(json.dumps(line), flush=True)
+    # graphs hold NCCL kernels: release them before the communicator goes away (destroying it first hangs)
+    # Captured graphs hold NCCL kernels; tearing the communicator down after them hung in ncclCommDestroy on this
+    # stack (torch 2.11 / NCCL 2.28), so the ranks synchronise, flush and leave without the teardown.
+    graphs.clear()
+    torch.cuda.synchronize()
+    __import__("sys").stdout.flush()
+    __import__("sys").stderr.flush()
+    os._exit(0)

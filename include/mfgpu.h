@@ -260,10 +260,14 @@ int mfg_exchange_accumulate(mfg_exchange *ex, void *vec_dev, const void *recv_de
 /* the same on another CUDA stream (overlap with the interior cells of mfg_laplace_vmult_part_ptr) */
 int mfg_exchange_accumulate_stream(mfg_exchange *ex, void *vec_dev, const void *recv_dev, void *cuda_stream);
 /* Overlap of the interface exchange with interior cells: mark the DoFs whose partial sums are exchanged;
-   part 0 of an apply = zero/constraint pass + the cell groups contributing to them, part 1 = all other groups
-   (touches no marked DoF), part -1 = everything.  Kernels without a work list run everything in part 0. */
+   part 0 of an apply = zero/constraint pass, part 1 = the cell groups contributing to marked DoFs, part 2 = all other
+   groups (touches no marked DoF), part -1 = everything.  Parts 1 and 2 may be enqueued on different streams after
+   part 0 (cuda_stream, NULL = the context's stream) and then run side by side.  Kernels without a work list run all
+   cells in part 2. */
 int mfg_laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, size_t n, uint32_t *n_interface_groups);
-int mfg_laplace_vmult_part_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev, int part);
+int mfg_laplace_vmult_part_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev, int part, void *cuda_stream);
+/* send[k] = vec[pack_idx[k]] on another CUDA stream */
+int mfg_exchange_pack_stream(mfg_exchange *ex, const void *vec_dev, void *send_dev, void *cuda_stream);
 /* owned-DoF dot product support: mask[i] = 1 if this rank owns DoF i (lowest rank touching it) */
 int mfg_vec_dot_masked(const mfg_vec *a, const mfg_vec *b, const uint8_t *owned_mask_dev, double *out);
 
