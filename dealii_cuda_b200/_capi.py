@@ -137,6 +137,7 @@ def _load():
         "mfg_laplace_set_interface_dofs": (C.c_int, [vp, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_uint32)]),
         "mfg_laplace_vmult_part_ptr": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "mfg_exchange_pack_stream": (C.c_int, [vp, vp, vp, vp]),
+        "mfg_exchange_push_stream": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_int, vp]),
         "mfg_vec_dot_masked": (C.c_int, [vp, vp, vp, dp]),
         "mfg_laplace_bmop": (C.c_int, [vp, vp, vp, C.c_int, C.c_double, C.POINTER(C.c_float)]),
     }

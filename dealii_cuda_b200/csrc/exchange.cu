@@ -19,6 +19,17 @@ template <typename T> __global__ void k_pack(const T *__restrict__ v, const uint
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) send[i] = v[pidx[i]];
 }
+// pack + send in one step over peer memory: entry i of this rank's send order belongs to chunk c (one chunk per
+// neighbour, ascending rank) and is stored straight into that neighbour's receive buffer through NVLink
+struct PushTable { unsigned long long dst[32]; uint32_t start[33]; int n; };
+template <typename T> __global__ void k_push(const T *__restrict__ v, const uint32_t *__restrict__ pidx, size_t n, const PushTable tb)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = 0;
+  while (c + 1 < tb.n && i >= tb.start[c + 1]) ++c;
+  reinterpret_cast<T *>(tb.dst[c])[i - tb.start[c]] = v[pidx[i]];
+}
 template <typename T>
 __global__ void k_accumulate(T *__restrict__ v, const T *__restrict__ recv, const uint32_t *__restrict__ dofs,
                              const uint32_t *__restrict__ offsets, const int32_t *__restrict__ slots, size_t n)
@@ -130,6 +141,25 @@ int mfg_exchange_accumulate(mfg_exchange *ex, void *vec_dev, const void *recv_de
 int mfg_exchange_accumulate_stream(mfg_exchange *ex, void *vec_dev, const void *recv_dev, void *cuda_stream)
 {
   return guarded([&] { accumulate_on(ex, vec_dev, recv_dev, (cudaStream_t)cuda_stream, 32); });
+}
+int mfg_exchange_push_stream(mfg_exchange *ex, const void *vec_dev, const uint64_t *peer_dst, const uint32_t *chunk_start, int n_chunks,
+                             void *cuda_stream)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ex && vec_dev && peer_dst && chunk_start, "null argument");
+    MFG_REQUIRE(n_chunks >= 1 && n_chunks <= 32, "between 1 and 32 neighbours");
+    const size_t n = ex->pack_idx.n; if (!n) return;
+    MFG_REQUIRE(chunk_start[0] == 0 && chunk_start[n_chunks] == n, "chunk starts do not span the send list");
+    PushTable tb;
+    tb.n = n_chunks;
+    for (int c = 0; c < n_chunks; ++c) { tb.dst[c] = peer_dst[c]; tb.start[c] = chunk_start[c]; }
+    tb.start[n_chunks] = chunk_start[n_chunks];
+    const unsigned tbk = 32, nb = (unsigned)((n + tbk - 1) / tbk);  // one-warp blocks: they run beside the persistent cell kernel
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->ctx->stream;
+    if (ex->dt == MFG_F64) k_push<double><<<nb, tbk, 0, st>>>((const double *)vec_dev, ex->pack_idx.p, n, tb);
+    else k_push<float><<<nb, tbk, 0, st>>>((const float *)vec_dev, ex->pack_idx.p, n, tb);
+    MFG_CUDA_LAST();
+  });
 }
 int mfg_vec_dot_masked(const mfg_vec *a, const mfg_vec *b, const uint8_t *owned_mask_dev, double *out)
 {

@@ -32,6 +32,39 @@ class InterfaceExchange:
         # (high priority: its interface cell kernel gets SM slots before the interior kernel launched next to it)
         self.side = torch.cuda.Stream(priority=-1) if plan.world > 1 and plan.n_send else None
         self.ev_ready, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
+        self.symm = None
+        import torch.distributed as dist
+        if self.side is not None and os.environ.get("MFG_NO_P2P") is None and dist.is_available() and dist.is_initialized() \
+                and dist.get_backend(group) == "nccl":
+            self._setup_p2p(tdt)
+
+    def _setup_p2p(self, tdt):
+        """Receive buffer in symmetric memory: the neighbours store their partial sums straight into it over NVLink
+        (mfg_exchange_push_stream) and a device-side barrier replaces the NCCL collective.  Falls back to NCCL
+        (self.symm stays None) where peer mapping is not available."""
+        import torch
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            plan = self.plan
+            cap = torch.tensor([max(1, plan.n_send)], dtype=torch.int64, device="cuda")
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+            recv = symm_mem.empty(int(cap.item()), dtype=tdt, device=torch.device("cuda", torch.cuda.current_device()))
+            hdl = symm_mem.rendezvous(recv, self.group if self.group is not None else dist.group.WORLD)
+            offs = [None] * plan.world
+            dist.all_gather_object(offs, plan.recv_off, group=self.group)
+            es = recv.element_size()
+            ptrs = list(hdl.buffer_ptrs)
+            nb = plan.neighbors
+            self._peer_dst = (C.c_uint64 * len(nb))(*[ptrs[q] + offs[q][plan.rank] * es for q in nb])
+            starts = np.concatenate([[0], np.cumsum([plan.splits[q] for q in nb])]).astype(np.uint32)
+            self._chunk_start = (C.c_uint32 * starts.size)(*starts.tolist())
+            self._n_chunks = len(nb)
+            self.recv, self.symm = recv, hdl
+        except Exception as e:  # no peer access / symmetric memory on this system
+            self.symm = None
+            if self.plan.rank == 0:
+                print("symmetric-memory exchange unavailable (%s: %s): NCCL all_to_all" % (type(e).__name__, e), file=__import__("sys").stderr)
 
     def __del__(self):
         try:
@@ -67,11 +100,22 @@ class InterfaceExchange:
         self.ev_ready.record(main)
         op.vmult_part_ptr(dst_ptr, src_ptr, 2)   # adds into no exchanged DoF
         side.wait_event(self.ev_ready)
-        check(lib.mfg_exchange_pack_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.send.data_ptr()), C.c_void_p(side.cuda_stream)))
-        n = self.plan.n_send
-        with torch.cuda.stream(side):
-            dist.all_to_all_single(self.recv[:n], self.send[:n], self.plan.splits, self.plan.splits, group=self.group)
-        check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.recv.data_ptr()), C.c_void_p(side.cuda_stream)))
+        if self.symm is not None:
+            # P2P: stores into the neighbours' receive buffers, barrier (all stores landed), ordered accumulate, barrier
+            # (everybody has read its buffer: the next apply may overwrite it).  No SM-hungry collective kernel.
+            check(lib.mfg_exchange_push_stream(self.h, C.c_void_p(dst_ptr), self._peer_dst, self._chunk_start, self._n_chunks,
+                                               C.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(side):
+                self.symm.barrier(0)
+            check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.recv.data_ptr()), C.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(side):
+                self.symm.barrier(1)
+        else:
+            check(lib.mfg_exchange_pack_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.send.data_ptr()), C.c_void_p(side.cuda_stream)))
+            n = self.plan.n_send
+            with torch.cuda.stream(side):
+                dist.all_to_all_single(self.recv[:n], self.send[:n], self.plan.splits, self.plan.splits, group=self.group)
+            check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.recv.data_ptr()), C.c_void_p(side.cuda_stream)))
         self.ev_done.record(side)
         main.wait_event(self.ev_done)
 
@@ -129,8 +173,9 @@ def bench_main(args, metric):
     # The exchange runs beside the persistent interior cell kernel, which leaves 4 CTA slots free (MFG_SLAB2_RESERVE):
     # NCCL's send/recv kernel must fit into them, so few and narrow channels (measured on 2 x B200: 0.281 ms per apply
     # against 0.287 with NCCL's defaults, profiles/r01_multigpu_overlap.txt)
-    os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
-    os.environ.setdefault("NCCL_NTHREADS", "128")
+    if os.environ.get("MFG_NO_P2P") is not None:  # only the NCCL fallback of the exchange needs this
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
+        os.environ.setdefault("NCCL_NTHREADS", "128")
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
@@ -162,6 +207,21 @@ def bench_main(args, metric):
 
     apply_steps(args.warmup)
     torch.cuda.synchronize()
+    # self-check: the overlapped apply (P2P stores or NCCL on the side stream) against the plain sequence
+    # cell loop -> pack -> NCCL all_to_all -> ordered accumulate on the same input (atomics: equal to rounding)
+    selfcheck = None
+    if dop.n_iface_groups:
+        y1, y2 = torch.empty_like(ta), torch.empty_like(ta)
+        xin = pa  # result of the warm-up applies: replicas of interface DoFs agree across ranks
+        dop.vmult_ptr(y1.data_ptr(), xin)
+        dop.op.vmult_ptr(y2.data_ptr(), xin)
+        dop.exchange.add_interface_contributions(y2.data_ptr())
+        torch.cuda.synchronize()
+        err = torch.stack([(y1 - y2).abs().max(), y2.abs().max()])
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        selfcheck = {"overlapped_vs_sequential_max_rel_diff": float(err[0] / err[1])}
+        assert selfcheck["overlapped_vs_sequential_max_rel_diff"] < (1e-12 if args.dtype == "f64" else 1e-5), selfcheck
+        del y1, y2
     use_graphs = os.environ.get("MFG_NO_GRAPH") is None
     if use_graphs:
         try:
@@ -245,6 +305,9 @@ def bench_main(args, metric):
                         "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
                 "gpu_launches": args.steps * (dop.op.launches_per_vmult() + (1 if dop.n_iface_groups else 0) + 2) * world,
                 "launch_mode": "CUDA graph replay of one apply (cell kernels + pack + all_to_all + accumulate)" if use_graphs else "eager",
+                "selfcheck": selfcheck,
+                "exchange": ("NVLink P2P stores into the neighbours' symmetric-memory receive buffers + device-side barriers"
+                             if dop.exchange.symm is not None else "NCCL all_to_all_single"),
                 "overlap": "interface cell groups first (%d of the groups), exchange on a side stream during the interior groups" % dop.n_iface_groups
                            if dop.n_iface_groups else "none",
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

@@ -59,6 +59,7 @@ class ExchangePlan:
         for q in self.neighbors:
             recv_off[q] = o
             o += self.lists[q].size
+        self.recv_off = {int(q): int(v) for q, v in recv_off.items()}  # where neighbour q's block starts in this rank's receive buffer
         # CSR of contributions per shared DoF, ascending rank order, -1 = own partial sum
         contrib = {}
         for q in self.neighbors:

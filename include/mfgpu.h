@@ -266,6 +266,11 @@ int mfg_exchange_accumulate_stream(mfg_exchange *ex, void *vec_dev, const void *
    cells in part 2. */
 int mfg_laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, size_t n, uint32_t *n_interface_groups);
 int mfg_laplace_vmult_part_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev, int part, void *cuda_stream);
+/* pack + send over peer memory (NVLink P2P stores): entry k of the send order lies in chunk c = the c-th neighbour,
+   chunk_start[c] <= k < chunk_start[c+1], and is written to ((Number *)peer_dst[c])[k - chunk_start[c]], a pointer into that
+   neighbour's receive buffer mapped into this process (CUDA IPC / symmetric memory) */
+int mfg_exchange_push_stream(mfg_exchange *ex, const void *vec_dev, const uint64_t *peer_dst, const uint32_t *chunk_start, int n_chunks,
+                             void *cuda_stream);
 /* send[k] = vec[pack_idx[k]] on another CUDA stream */
 int mfg_exchange_pack_stream(mfg_exchange *ex, const void *vec_dev, void *send_dev, void *cuda_stream);
 /* owned-DoF dot product support: mask[i] = 1 if this rank owns DoF i (lowest rank touching it) */
