@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n
 laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
                    Number *__restrict__ dst, const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em,
                    const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP, const uint32_t *__restrict__ glist,
-                   uint32_t *__restrict__ work_counter)
+                   uint32_t *__restrict__ work_counter, const int dep_wait)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   using Tab = typename Cfg::Tab;
@@ -507,6 +507,9 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
             }
         }
       if (Cfg::PF == 2 && more) gather(id, un);
+      // launched as programmatic dependent of the kernel that zeroes dst (single-GPU apply): everything above overlapped
+      // with its tail, the first red has to wait for it
+      if (dep_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
       // ---- distribute_local_to_global (fee_gpu.cuh:346-365): red.add straight from registers ----
 #pragma unroll
       for (int s = 0; s < NS; ++s)
@@ -531,7 +534,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
 template <typename Number>
 void launch_laplace_slab2(int degree, int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups,
                           const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0,
-                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr, uint32_t *work_counter = nullptr, bool pdl = false);
+                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr, uint32_t *work_counter = nullptr, bool pdl = false, bool dep_wait = false);
 // layout of the kernel's private arrays (for the builders in operators.cu)
 struct Slab2Geom { int n, cw, hc, cwf; Slab2Lay bc; };
 bool      slab2_supported(int dim, int degree, mfg_dtype dt);

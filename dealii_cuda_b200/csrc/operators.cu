@@ -609,6 +609,19 @@ int laplace_active_variant(const mfg_laplace *op)
   return slab_ok ? 2 : 1;
 }
 
+// dst = 0 as a kernel (16-byte stores) that releases its programmatic dependents at once: the cell kernel launched
+// behind it loads, gathers and contracts its first groups while this one drains, and waits (griddepcontrol.wait)
+// only before its first red
+template <typename Number> __global__ void zero_fill_pdl(Number *__restrict__ dst, size_t n)
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  constexpr int V = 16 / (int)sizeof(Number);
+  const size_t  nv = n / V, stride = (size_t)gridDim.x * blockDim.x;
+  float4 *d4 = reinterpret_cast<float4 *>(dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && threadIdx.x < n - nv * V) dst[nv * V + threadIdx.x] = Number(0);
+}
+
 // part: -1 = the whole apply; 0 = zero/constraint pass; 1 = the cell groups that touch interface DoFs (multi-GPU: what
 // the exchange waits for); 2 = the remaining groups.  Without an interface partition part 2 runs all cells, part 1 none.
 // Parts 1 and 2 may run concurrently on different streams (they write disjoint... they only add into dst).
@@ -619,7 +632,17 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
   cudaStream_t  s  = s_other ? s_other : op->ctx->stream;
   const bool split = part >= 1 && op->glist.n != 0 && laplace_active_variant(op) == 6;
   if (part == 1 && !split) return;
-  if (part <= 0)
+  // whole apply with the slab2 kernel: zero kernel -> cell kernel as its programmatic dependent -> constrained rows
+  static const bool pdl_fill_on = !(std::getenv("MFG_PDL_FILL") && std::atoi(std::getenv("MFG_PDL_FILL")) == 0);
+  const bool pdl_fill = pdl_fill_on && part == -1 && !add && laplace_active_variant(op) == 6 && mf->hn_mask.n == 0 &&
+                        (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  if (pdl_fill)
+    {
+      const unsigned nb = (unsigned)std::min<size_t>(((size_t)mf->n_dofs * sizeof(Number) / 16 + 255) / 256, (size_t)op->ctx->sm_count * 16);
+      zero_fill_pdl<Number><<<std::max(1u, nb), 256, 0, s>>>(dst, mf->n_dofs);
+      MFG_CUDA_LAST();
+    }
+  else if (part <= 0)
     {
   // vmult: dst = 0 (laplace_operator_gpu.h:221) fused with dst[c] = src[c];
   // vmult_add: dst[c] += src[c]  (load_and_add_constrained_values, :302)
@@ -682,7 +705,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       uint32_t *wc = dynamic ? op->work_counters.p + (part == 1 ? 1 : 0) : nullptr;
       time_begin();
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
-                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, wc, split && part == 2);
+                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, wc, (split && part == 2) || pdl_fill, pdl_fill);
       time_end();
     }
   else if (laplace_active_variant(op) == 2)
@@ -713,6 +736,8 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       launch_v0(n_plain, mf->n_cells, mf->hn_mask.p);
       time_end();
     }
+  // identity on the constrained rows (the cell kernel never writes them)
+  if (pdl_fill && op->ch->n()) { constrained_copy<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n()); MFG_CUDA_LAST(); }
 }
 
 void laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches)
