@@ -151,6 +151,14 @@ def test_plan_counts_single_process(world):
             assert a in plans[b].neighbors
             # both sides list the same global DoFs in the same order
             assert np.array_equal(maps[a][plans[a].lists[b]], maps[b][plans[b].lists[a]])
+    # receive offsets (what a neighbour needs to store straight into this rank's receive buffer, mfg_exchange_push_stream):
+    # the blocks of the neighbours tile [0, n_send) in ascending rank order
+    for a in range(world):
+        o = 0
+        for b in plans[a].neighbors:
+            assert plans[a].recv_off[b] == o and plans[b].lists[a].size == plans[a].lists[b].size
+            o += plans[a].lists[b].size
+        assert o == plans[a].n_send
     owned = np.zeros(og.n_dofs, dtype=int)
     for a in range(world):
         np.add.at(owned, maps[a][plans[a].owned_mask.astype(bool)], 1)
