@@ -386,7 +386,8 @@ class MatrixFreeGpu:
             invj = np.ascontiguousarray(a["inv_jac"], dtype=np.float64)
             d.dim, d.degree, d.dtype = int(a["dim"]), int(a["degree"]), self.code
             d.n_cells, d.n_dofs = l2g.shape[0], int(a["n_dofs"])
-            d.loc2glob, d.geometry, d.inv_jac = _u32p(l2g), 0, _dp(invj)
+            # inv_jac [n_cells]: uniform mesh; [n_cells][npc][dim][dim]: full inverse Jacobian per quadrature point
+            d.loc2glob, d.geometry, d.inv_jac = _u32p(l2g), (1 if invj.ndim == 4 else 0), _dp(invj)
             keep = [l2g, invj]
             if a.get("JxW") is not None:
                 jxw = np.ascontiguousarray(a["JxW"], dtype=np.float64)

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "kernels_slab.cuh"
 #include "kernels_slab2.cuh"
+#include "kernels_general.cuh"
 #include "operators.cuh"
 
 namespace mfg {
@@ -306,7 +307,12 @@ mfg_mf *mf_from_desc(mfg_ctx *ctx, const mfg_mf_desc &d)
   MFG_REQUIRE(d.dim == 2 || d.dim == 3, "dim must be 2 or 3");
   MFG_REQUIRE(d.degree >= 1 && d.degree <= 8, "degree must be in 1..8");
   MFG_REQUIRE(d.loc2glob != nullptr && d.inv_jac != nullptr, "loc2glob and inv_jac are required");
-  if (d.geometry != MFG_GEOM_UNIFORM) throw Error(MFG_ERR_UNSUPPORTED, "only MFG_GEOM_UNIFORM is implemented");
+  MFG_REQUIRE(d.geometry == MFG_GEOM_UNIFORM || d.geometry == MFG_GEOM_GENERAL, "unknown geometry kind");
+  if (d.geometry == MFG_GEOM_GENERAL)
+    {
+      MFG_REQUIRE(d.JxW != nullptr, "general geometry needs JxW per quadrature point");
+      if (d.constraint_mask) throw Error(MFG_ERR_UNSUPPORTED, "hanging nodes with general geometry are not implemented");
+    }
   MFG_REQUIRE(d.n_dofs < CONSTRAINED_BIT, "n_dofs must be < 2^31");
   std::unique_ptr<mfg_mf> mf(new mfg_mf);
   mf->ctx = ctx; mf->dim = d.dim; mf->p = d.degree; mf->n = d.degree + 1; mf->npc = ipow(mf->n, mf->dim);
@@ -344,6 +350,30 @@ mfg_mf *mf_from_desc(mfg_ctx *ctx, const mfg_mf_desc &d)
     }
   else
     mf->idx.upload(d.loc2glob, total, ctx->stream);
+  if (d.geometry == MFG_GEOM_GENERAL)
+    {
+      // G = JxW K K^T with K = J^-1 [cell][q][d1][d2] as FEValues::get_inverse_jacobians delivers it (matrix_free_gpu.cu:326-338):
+      // get_gradient applies K^T (fee_gpu.cuh:236-240), submit_gradient K and JxW (:276-280)
+      const int dim = mf->dim, nc = dim * (dim + 1) / 2;
+      static const int pairs3[6][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 1}, {0, 2}, {1, 2}}, pairs2[3][2] = {{0, 0}, {1, 1}, {0, 1}};
+      mf->general = true;
+      mf->gsym_host.resize(total * nc);
+      for (uint32_t c = 0; c < d.n_cells; ++c)
+        for (uint32_t q = 0; q < mf->npc; ++q)
+          {
+            const double *K = d.inv_jac + ((size_t)c * mf->npc + q) * dim * dim;
+            const double  jxw = d.JxW[(size_t)c * mf->npc + q];
+            for (int k = 0; k < nc; ++k)
+              {
+                const int a = dim == 3 ? pairs3[k][0] : pairs2[k][0], b = dim == 3 ? pairs3[k][1] : pairs2[k][1];
+                double    s = 0;
+                for (int e = 0; e < dim; ++e) s += K[a * dim + e] * K[b * dim + e];
+                mf->gsym_host[((size_t)c * nc + k) * mf->npc + q] = jxw * s;
+              }
+          }
+      if (d.quadrature_points) mf->qpoints_host.assign(d.quadrature_points, d.quadrature_points + total * mf->dim);
+      return mf.release();
+    }
   // merged geometry factor inv_jac^2 * JxW_q  (fee_gpu.cuh:228,270: grad = J0*g ; submit = grad*J0*jxw)
   mf->geom_host.resize(total);
   for (uint32_t c = 0; c < d.n_cells; ++c)
@@ -466,7 +496,7 @@ mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const dou
 {
   MFG_REQUIRE(mf && ch && coef_host, "mf, ch and coefficient are required");
   MFG_REQUIRE(mf->dt == ch->dt, "mf and ch dtypes differ");
-  MFG_REQUIRE(!mf->geom_host.empty() || mf->mesh, "mf has no geometry");
+  MFG_REQUIRE(!mf->geom_host.empty() || !mf->gsym_host.empty() || mf->mesh, "mf has no geometry");
   std::unique_ptr<mfg_laplace> op(new mfg_laplace);
   op->ctx = ctx; op->mf = mf; op->ch = ch;
   // mark constrained DoFs in the kernel index array (in place)
@@ -477,7 +507,7 @@ mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const dou
   build_kernel_indices<<<nblk(total), 256, 0, ctx->stream>>>(mf->idx.p, nullptr, flag.p, mf->npc, total, mf->idx.p);
   MFG_CUDA_LAST();
   laplace_finish_setup(op.get(), flag.p);
-  op->cw.alloc((total + 32 * (size_t)mf->npc) * (mf->dt == MFG_F64 ? 8 : 4));
+  op->cw.alloc((total * (mf->general ? mf->dim * (mf->dim + 1) / 2 : 1) + 32 * (size_t)mf->npc) * (mf->dt == MFG_F64 ? 8 : 4));
   MFG_CUDA(cudaMemsetAsync(op->cw.p, 0, op->cw.bytes(), ctx->stream));
   laplace_set_coefficient_host(op.get(), coef_host);
   MFG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -489,6 +519,26 @@ void laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host)
 {
   const mfg_mf *mf = op->mf;
   const size_t total = (size_t)mf->n_cells * mf->npc;
+  if (mf->general)
+    {
+      // merged tensor a(x_q) JxW K K^T, [cell][component][q]
+      const int nc = mf->dim * (mf->dim + 1) / 2;
+      std::vector<double> merged(total * nc);
+      for (uint32_t c = 0; c < mf->n_cells; ++c)
+        for (int k = 0; k < nc; ++k)
+          for (uint32_t q = 0; q < mf->npc; ++q)
+            merged[((size_t)c * nc + k) * mf->npc + q] = coef_host[(size_t)c * mf->npc + q] * mf->gsym_host[((size_t)c * nc + k) * mf->npc + q];
+      if (mf->dt == MFG_F64) MFG_CUDA(cudaMemcpyAsync(op->cw.p, merged.data(), merged.size() * 8, cudaMemcpyHostToDevice, op->ctx->stream));
+      else
+        {
+          std::vector<float> m32(merged.begin(), merged.end());
+          MFG_CUDA(cudaMemcpyAsync(op->cw.p, m32.data(), m32.size() * 4, cudaMemcpyHostToDevice, op->ctx->stream));
+          MFG_CUDA(cudaStreamSynchronize(op->ctx->stream));
+        }
+      MFG_CUDA(cudaStreamSynchronize(op->ctx->stream));
+      op->diagonal_is_available = false;
+      return;
+    }
   std::vector<uint32_t> perm;
   if (mf->cell_perm.n) { perm.resize(mf->n_cells); mf->cell_perm.download(perm.data(), op->ctx->stream); }
   std::vector<double> geom_q;  // uniform mesh: same factors for every cell
@@ -601,6 +651,11 @@ int laplace_active_variant(const mfg_laplace *op)
   const bool slab2_ok = slab2_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
   if (op->variant >= 6 && !slab2_ok) throw Error(MFG_ERR_UNSUPPORTED, "variants 6..9 (slab2 kernel) need dim 3, degree <= 5, atomic scatter");
   if (op->variant >= 2 && op->variant < 6 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3/4 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
+  if (mf->general)
+    {
+      if (op->variant > 1) throw Error(MFG_ERR_UNSUPPORTED, "general geometry has one kernel (variant 0 or 1)");
+      return 1;
+    }
   if (op->variant == 1) return 1;
   if (op->variant >= 6) return 6;
   if (op->variant >= 2) return 2;
@@ -718,6 +773,21 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
                                   mf->fe.colloc.data(), op->ctx->sm_count, s);
       time_end();
     }
+  else if (mf->general)
+    {
+      // full J^-1 per quadrature point (kernels_general.cuh), one launch per color
+      for (uint32_t c = 0; c + 1 < mf->color_offsets.size(); ++c)
+        {
+          time_begin();
+          if (mf->dim == 2)
+            launch_laplace_general_dim<2, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->color_offsets[c], mf->color_offsets[c + 1],
+                                                  mf->fe.val.data(), mf->fe.colloc.data(), s);
+          else
+            launch_laplace_general_dim<3, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, mf->color_offsets[c], mf->color_offsets[c + 1],
+                                                  mf->fe.val.data(), mf->fe.colloc.data(), s);
+          time_end();
+        }
+    }
   else
     {
       // cell_loop (matrix_free_gpu.h:369-380): one launch per color
@@ -819,6 +889,27 @@ void laplace_compute_diagonal(mfg_laplace *op)
       MFG_CUDA(cudaMalloc(&op->inv_diag->p, (size_t)mf->n_dofs * op->inv_diag->esize()));
     }
   vec_fill(op->inv_diag.get(), 0.0);
+  if (mf->general)
+    {
+      // diag_i = sum_q sum_de G_de(q) d_d phi_i(q) d_e phi_i(q) with the full metric tensor (kernels_general.cuh)
+      DevBuf<double> tv, tg;
+      tv.upload(mf->fe.val.data(), (size_t)mf->n * mf->n, s);
+      tg.upload(mf->fe.grad.data(), (size_t)mf->n * mf->n, s);
+      const int th = (int)std::min<uint32_t>(256, ((mf->npc + 31) / 32) * 32);
+      if (mf->n_cells)
+        {
+          if (mf->dt == MFG_F64 && mf->dim == 2) diagonal_general<2, double><<<mf->n_cells, th, 0, s>>>(mf->idx.p, (const double *)op->cw.p, mf->n, mf->n_cells, tv.p, tg.p, (double *)op->inv_diag->p);
+          else if (mf->dt == MFG_F64) diagonal_general<3, double><<<mf->n_cells, th, 0, s>>>(mf->idx.p, (const double *)op->cw.p, mf->n, mf->n_cells, tv.p, tg.p, (double *)op->inv_diag->p);
+          else if (mf->dim == 2) diagonal_general<2, float><<<mf->n_cells, th, 0, s>>>(mf->idx.p, (const float *)op->cw.p, mf->n, mf->n_cells, tv.p, tg.p, (float *)op->inv_diag->p);
+          else diagonal_general<3, float><<<mf->n_cells, th, 0, s>>>(mf->idx.p, (const float *)op->cw.p, mf->n, mf->n_cells, tv.p, tg.p, (float *)op->inv_diag->p);
+          MFG_CUDA_LAST();
+        }
+      MFG_CUDA(cudaStreamSynchronize(s));  // tv / tg go out of scope
+      ch_set(op->ch, op->inv_diag.get(), 1.0);
+      vec_invert(op->inv_diag.get());
+      op->diagonal_is_available = true;
+      return;
+    }
   DiagTables tb;
   for (int i = 0; i < mf->n * mf->n; ++i) { tb.val[i] = mf->fe.val[i]; tb.grad[i] = mf->fe.grad[i]; tb.hang[i] = mf->fe.hanging[i]; }
   const size_t dsm = 2 * (size_t)mf->npc * sizeof(double);

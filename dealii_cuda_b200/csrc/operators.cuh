@@ -26,6 +26,8 @@ struct mfg_mf
   // geometry: either a uniform mesh (origin/h/Morton map) or host arrays from the explicit description
   const mfg_mesh       *mesh = nullptr;         // not owned
   std::vector<double>   geom_host;              // [n_cells][npc]: inv_jac^2 * JxW_q, original cell order
+  bool                  general = false;        // MFG_GEOM_GENERAL: full J^-1 per quadrature point
+  std::vector<double>   gsym_host;              // general: [n_cells][dim(dim+1)/2][npc]: JxW_q K K^T (00, 11[, 22], 01[, 02, 12])
   std::vector<double>   qpoints_host;           // optional [n_cells][npc][dim]
   uint32_t              n_colors() const { return (uint32_t)color_offsets.size() - 1; }
 };

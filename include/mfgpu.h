@@ -131,7 +131,7 @@ int mfg_mesh_color_cells(const mfg_mesh *m, uint32_t *color_of_cell, uint32_t *n
 typedef enum mfg_geometry
 {
   MFG_GEOM_UNIFORM = 0, /* -DMATRIX_FREE_UNIFORM_MESH: scalar J^-1[0][0] per cell (matrix_free_gpu.cu:332-334) */
-  MFG_GEOM_GENERAL = 1  /* full J^-1 per quadrature point (not yet supported) */
+  MFG_GEOM_GENERAL = 1  /* full J^-1 per quadrature point (fee_gpu.cuh:236-240, 276-280; matrix_free_gpu.cu:326-338) */
 } mfg_geometry;
 
 typedef struct mfg_mf_desc
@@ -141,7 +141,8 @@ typedef struct mfg_mf_desc
   uint32_t        n_cells, n_dofs;
   const uint32_t *loc2glob;        /* host, [n_cells][(p+1)^dim], lexicographic, unpadded */
   mfg_geometry    geometry;
-  const double   *inv_jac;         /* host, UNIFORM: [n_cells] */
+  const double   *inv_jac;         /* host, UNIFORM: [n_cells]; GENERAL: [n_cells][(p+1)^dim][dim][dim], K[d1][d2] = d xi_d1 / d x_d2
+                                      (FEValues::get_inverse_jacobians order; JxW is then required) */
   const double   *JxW;             /* host, [n_cells][(p+1)^dim] or NULL: then JxW = inv_jac^-dim * w_q */
   const double   *quadrature_points; /* host, [n_cells][(p+1)^dim][dim] (for evaluate_on_cells) or NULL */
   mfg_scatter     scatter;
