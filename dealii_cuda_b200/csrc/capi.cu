@@ -308,6 +308,7 @@ int mfg_laplace_vmult(mfg_laplace *op, mfg_vec *dst, const mfg_vec *src) { retur
 int mfg_laplace_vmult_add(mfg_laplace *op, mfg_vec *dst, const mfg_vec *src) { return guarded([&] { check_vecs(op, dst, src); laplace_vmult(op, dst->p, src->p, true); }); }
 int mfg_laplace_vmult_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev) { return guarded([&] { MFG_REQUIRE(op && dst_dev && src_dev, "null argument"); laplace_vmult(op, dst_dev, src_dev, false); }); }
 int mfg_laplace_vmult_add_ptr(mfg_laplace *op, void *dst_dev, const void *src_dev) { return guarded([&] { MFG_REQUIRE(op && dst_dev && src_dev, "null argument"); laplace_vmult(op, dst_dev, src_dev, true); }); }
+int mfg_mf_get_gpu_data(mfg_mf *mf, mfg_gpu_data *out) { return guarded([&] { MFG_REQUIRE(mf && out, "null argument"); mf_get_gpu_data(mf, out); }); }
 int mfg_laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, size_t n, uint32_t *n_interface_groups)
 {
   return guarded([&] {

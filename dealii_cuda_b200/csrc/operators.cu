@@ -350,6 +350,8 @@ mfg_mf *mf_from_desc(mfg_ctx *ctx, const mfg_mf_desc &d)
     }
   else
     mf->idx.upload(d.loc2glob, total, ctx->stream);
+  if (d.JxW) mf->jxw_host.assign(d.JxW, d.JxW + total);
+  mf->invjac_host.assign(d.inv_jac, d.inv_jac + (d.geometry == MFG_GEOM_GENERAL ? total * d.dim * d.dim : (size_t)d.n_cells));
   if (d.geometry == MFG_GEOM_GENERAL)
     {
       // G = JxW K K^T with K = J^-1 [cell][q][d1][d2] as FEValues::get_inverse_jacobians delivers it (matrix_free_gpu.cu:326-338):
@@ -391,6 +393,109 @@ mfg_mf *mf_from_desc(mfg_ctx *ctx, const mfg_mf_desc &d)
       }
   if (d.quadrature_points) mf->qpoints_host.assign(d.quadrature_points, d.quadrature_points + total * mf->dim);
   return mf.release();
+}
+
+// ---------------------------------------------------------------------------
+// generic FEEvaluationGpu path: the per-cell arrays of MatrixFreeGpu::GpuData (matrix_free_gpu.h:261-278) on the device
+// ---------------------------------------------------------------------------
+template <typename Number>
+__global__ void fill_uniform_geometry(MortonMap mm, int dim, int n, uint32_t npc, uint32_t n_cells, const uint32_t *__restrict__ perm, double ox,
+                                      double oy, double oz, double h, QuadData qd, Number *__restrict__ jxw, Number *__restrict__ invjac,
+                                      Number *__restrict__ qpts)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n_cells * npc) return;
+  const uint32_t s = (uint32_t)(t / npc), q = (uint32_t)(t % npc);
+  const uint32_t c = perm ? perm[s] : s;
+  uint32_t x[3]; mm.decode(c, x);
+  const int qi[3] = {(int)(q % n), (int)((q / n) % n), (int)(q / (n * n))};
+  const double o[3] = {ox, oy, oz};
+  double w = 1;
+  for (int d = 0; d < dim; ++d)
+    {
+      qpts[t * dim + d] = (Number)(o[d] + h * ((double)x[d] + qd.xq[qi[d]]));
+      w *= h * qd.wq[qi[d]];
+    }
+  jxw[t] = (Number)w;
+  if (q == 0) invjac[s] = (Number)(1.0 / h);
+}
+
+void mf_get_gpu_data(mfg_mf *mf, mfg_gpu_data *out)
+{
+  cudaStream_t s = mf->ctx->stream;
+  const size_t total = (size_t)mf->n_cells * mf->npc, es = mf->dt == MFG_F64 ? 8 : 4;
+  if (mf->gd_jxw.n == 0 && total)
+    {
+      if (mf->mesh)
+        {
+          const mfg_mesh *mesh = mf->mesh;
+          mf->gd_jxw.alloc(total * es); mf->gd_invjac.alloc((size_t)mf->n_cells * es); mf->gd_qpts.alloc(total * mf->dim * es);
+          QuadData qd;
+          for (int i = 0; i < mesh->n; ++i) { qd.xq[i] = mesh->fe.qpts[i]; qd.wq[i] = mesh->fe.qwts[i]; }
+          MortonMap mm; mm.dim = mesh->dim; for (int d = 0; d < 3; ++d) mm.lg[d] = mesh->lg[d];
+          if (mf->dt == MFG_F64)
+            fill_uniform_geometry<double><<<nblk(total), 256, 0, s>>>(mm, mf->dim, mf->n, mf->npc, mf->n_cells, mf->cell_perm.p, mesh->origin[0], mesh->origin[1],
+                                                                      mesh->origin[2], mesh->h, qd, (double *)mf->gd_jxw.p, (double *)mf->gd_invjac.p, (double *)mf->gd_qpts.p);
+          else
+            fill_uniform_geometry<float><<<nblk(total), 256, 0, s>>>(mm, mf->dim, mf->n, mf->npc, mf->n_cells, mf->cell_perm.p, mesh->origin[0], mesh->origin[1],
+                                                                     mesh->origin[2], mesh->h, qd, (float *)mf->gd_jxw.p, (float *)mf->gd_invjac.p, (float *)mf->gd_qpts.p);
+          MFG_CUDA_LAST();
+        }
+      else
+        {
+          // arrays of mfg_mf_desc, permuted into the kernel cell order (hanging-node cells last) and converted to Number
+          MFG_REQUIRE(!mf->invjac_host.empty(), "mf has no geometry");
+          std::vector<uint32_t> perm;
+          if (mf->cell_perm.n) { perm.resize(mf->n_cells); mf->cell_perm.download(perm.data(), s); }
+          const size_t per_inv = mf->general ? (size_t)mf->npc * mf->dim * mf->dim : 1;
+          std::vector<double> jxw(total), inv((size_t)mf->n_cells * per_inv), qp;
+          if (!mf->qpoints_host.empty()) qp.resize(total * mf->dim);
+          for (uint32_t k = 0; k < mf->n_cells; ++k)
+            {
+              const uint32_t c = perm.empty() ? k : perm[k];
+              for (uint32_t q = 0; q < mf->npc; ++q)
+                {
+                  double w;
+                  if (!mf->jxw_host.empty()) w = mf->jxw_host[(size_t)c * mf->npc + q];
+                  else
+                    {
+                      w = 1.0; uint32_t qq = q;
+                      for (int d = 0; d < mf->dim; ++d) { w *= mf->fe.qwts[qq % mf->n] / mf->invjac_host[c]; qq /= mf->n; }
+                    }
+                  jxw[(size_t)k * mf->npc + q] = w;
+                }
+              std::copy(mf->invjac_host.begin() + (size_t)c * per_inv, mf->invjac_host.begin() + (size_t)(c + 1) * per_inv, inv.begin() + (size_t)k * per_inv);
+              if (!qp.empty())
+                std::copy(mf->qpoints_host.begin() + (size_t)c * mf->npc * mf->dim, mf->qpoints_host.begin() + (size_t)(c + 1) * mf->npc * mf->dim,
+                          qp.begin() + (size_t)k * mf->npc * mf->dim);
+            }
+          auto up = [&](DevBuf<uint8_t> &b, const std::vector<double> &v) {
+            if (v.empty()) return;
+            b.alloc(v.size() * es);
+            if (mf->dt == MFG_F64) MFG_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * 8, cudaMemcpyHostToDevice, s));
+            else
+              {
+                std::vector<float> f(v.begin(), v.end());
+                MFG_CUDA(cudaMemcpyAsync(b.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice, s));
+                MFG_CUDA(cudaStreamSynchronize(s));
+              }
+          };
+          up(mf->gd_jxw, jxw); up(mf->gd_invjac, inv); up(mf->gd_qpts, qp);
+        }
+      MFG_CUDA(cudaStreamSynchronize(s));
+    }
+  std::memset(out, 0, sizeof(*out));
+  out->loc2glob = mf->idx.p;
+  out->JxW = mf->gd_jxw.p; out->inv_jac = mf->gd_invjac.p; out->quadrature_points = mf->gd_qpts.n ? mf->gd_qpts.p : nullptr;
+  out->n_cells = mf->n_cells; out->n_dofs = mf->n_dofs; out->dim = mf->dim; out->degree = mf->p; out->dtype = mf->dt;
+  out->general = mf->general ? 1 : 0;
+  out->use_coloring = mf->scatter == MFG_SCATTER_COLOR ? 1 : 0;
+  out->n_colors = mf->n_colors();
+  out->color_offsets = mf->color_offsets.data();
+  out->n_plain_cells = mf->hn_mask.n ? mf->n_plain : mf->n_cells;
+  out->constraint_mask = mf->hn_mask.n ? mf->hn_mask.p : nullptr;
+  out->cuda_stream = (void *)s;
+  for (int i = 0; i < mf->n * mf->n; ++i) { out->shape_values[i] = mf->fe.val[i]; out->shape_gradients[i] = mf->fe.grad[i]; out->colloc_gradients[i] = mf->fe.colloc[i]; }
 }
 
 // ---------------------------------------------------------------------------

@@ -29,6 +29,10 @@ struct mfg_mf
   bool                  general = false;        // MFG_GEOM_GENERAL: full J^-1 per quadrature point
   std::vector<double>   gsym_host;              // general: [n_cells][dim(dim+1)/2][npc]: JxW_q K K^T (00, 11[, 22], 01[, 02, 12])
   std::vector<double>   qpoints_host;           // optional [n_cells][npc][dim]
+  // host copies of the geometry as given in mfg_mf_desc (original cell order) and the device arrays of the generic
+  // FEEvaluationGpu path (mfg_mf_get_gpu_data), built on first request in kernel cell order
+  std::vector<double>   jxw_host, invjac_host;
+  mfg::DevBuf<uint8_t>  gd_jxw, gd_invjac, gd_qpts;
   uint32_t              n_colors() const { return (uint32_t)color_offsets.size() - 1; }
 };
 
@@ -98,6 +102,7 @@ mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const dou
 void         laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host);
 void         laplace_vmult(mfg_laplace *op, void *dst, const void *src, bool add, int part = -1, void *cuda_stream = nullptr);
 uint32_t     laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, size_t n);
+void         mf_get_gpu_data(mfg_mf *mf, mfg_gpu_data *out);
 void         laplace_compute_diagonal(mfg_laplace *op);
 int          laplace_launches_per_vmult(const mfg_laplace *op);
 int          laplace_active_variant(const mfg_laplace *op);

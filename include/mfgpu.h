@@ -161,6 +161,26 @@ uint32_t mfg_mf_n_dofs(const mfg_mf *mf);
 uint32_t mfg_mf_n_cells(const mfg_mf *mf);
 uint32_t mfg_mf_n_colors(const mfg_mf *mf);
 size_t mfg_mf_memory_consumption(const mfg_mf *mf);                                   /* matrix_free_gpu.h:437-459 */
+/* MatrixFreeGpu::get_gpu_data (matrix_free_gpu.h:261-278): the device arrays a user-written cell functor needs, for the
+ * header-only generic path include/dealii_cuda_b200/fee_gpu.cuh (FEEvaluationGpu + cell_loop compiled with the user's
+ * LocalOperator).  Arrays are in the cell order of the kernels (cells sorted by color; cells with hanging nodes last) and
+ * stay valid until mfg_mf_destroy.  The first call builds JxW / inv_jac / quadrature points on the device. */
+typedef struct mfg_gpu_data
+{
+  const uint32_t *loc2glob;          /* device [n_cells][(p+1)^dim], lexicographic; bit 31 may flag a constrained DoF
+                                        (set once a LaplaceOperatorGpu was built on this mf): mask with 0x7fffffff */
+  const void     *JxW;               /* device Number [n_cells][(p+1)^dim] */
+  const void     *inv_jac;           /* device Number: uniform [n_cells]; general [n_cells][(p+1)^dim][dim][dim] */
+  const void     *quadrature_points; /* device Number [n_cells][(p+1)^dim][dim], NULL if the description had none */
+  const uint32_t *constraint_mask;   /* device [n_cells] hanging-node masks or NULL */
+  const uint32_t *color_offsets;     /* host [n_colors+1] */
+  uint32_t        n_cells, n_dofs, n_colors, n_plain_cells;
+  int             dim, degree, general, use_coloring;
+  mfg_dtype       dtype;
+  void           *cuda_stream;       /* the context's stream */
+  double          shape_values[81], shape_gradients[81], colloc_gradients[81]; /* [i*n+q], n = degree+1 */
+} mfg_gpu_data;
+int mfg_mf_get_gpu_data(mfg_mf *mf, mfg_gpu_data *out);
 /* shape tables handed to the kernels: [i*n+q] = phi_i(x_q), phi_i'(x_q) (matrix_free_gpu.cu:502-513) */
 int mfg_shape_info(int degree, double *shape_values, double *shape_gradients, double *q_points, double *q_weights);
 /* 1-D hanging-node interpolation weights W[k*n+i] = phi_i(xi_k/2) (setup_constraint_weights, hanging_nodes.cuh:580-598) */
