@@ -409,6 +409,13 @@ class MatrixFreeGpu:
         self.num_colors = lib.mfg_mf_n_colors(h)
         self.use_coloring = bool(use_coloring)
 
+    def get_gpu_data(self):
+        """MatrixFreeGpu::get_gpu_data (matrix_free_gpu.h:261-278): raw device pointers and counters for user kernels
+        (torch / cupy / the header-only FEEvaluationGpu path); valid until free()."""
+        g = _capi.GpuData()
+        check(lib.mfg_mf_get_gpu_data(self.h, C.byref(g)))
+        return g
+
     def free(self):
         if self.h:
             lib.mfg_mf_destroy(self.h)

@@ -31,6 +31,16 @@ class MfDesc(C.Structure):
                 ("n_colors", C.c_uint32), ("color_offsets", C.POINTER(C.c_uint32)), ("constraint_mask", C.POINTER(C.c_uint32))]
 
 
+class GpuData(C.Structure):
+    """mfg_gpu_data: device arrays of a MatrixFreeGpu object for user-written kernels (MatrixFreeGpu::get_gpu_data)."""
+    _fields_ = [("loc2glob", C.c_void_p), ("JxW", C.c_void_p), ("inv_jac", C.c_void_p), ("quadrature_points", C.c_void_p),
+                ("constraint_mask", C.c_void_p), ("color_offsets", C.POINTER(C.c_uint32)),
+                ("n_cells", C.c_uint32), ("n_dofs", C.c_uint32), ("n_colors", C.c_uint32), ("n_plain_cells", C.c_uint32),
+                ("dim", C.c_int), ("degree", C.c_int), ("general", C.c_int), ("use_coloring", C.c_int), ("dtype", C.c_int),
+                ("cuda_stream", C.c_void_p), ("shape_values", C.c_double * 81), ("shape_gradients", C.c_double * 81),
+                ("colloc_gradients", C.c_double * 81)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -91,6 +101,7 @@ def _load():
         "mfg_mf_n_cells": (C.c_uint32, [vp]),
         "mfg_mf_n_colors": (C.c_uint32, [vp]),
         "mfg_mf_memory_consumption": (sz, [vp]),
+        "mfg_mf_get_gpu_data": (C.c_int, [vp, C.POINTER(GpuData)]),
         "mfg_shape_info": (C.c_int, [C.c_int, dp, dp, dp, dp]),
         "mfg_hanging_node_weights": (C.c_int, [C.c_int, dp]),
         "mfg_ch_create": (C.c_int, [vp, C.c_int, u32p, sz, u32p, sz, pp]),
