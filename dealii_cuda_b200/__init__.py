@@ -273,6 +273,12 @@ class HyperCubeMesh:
         check(lib.mfg_mesh_get_cell_coords(self.h, _u32p(out)))
         return out
 
+    def support_points(self):
+        """[n_dofs][dim] support point of every DoF (DoFTools::map_dofs_to_support_points)."""
+        out = np.empty((self.n_dofs, self.dim), dtype=np.float64)
+        check(lib.mfg_mesh_get_support_points(self.h, _dp(out)))
+        return out
+
     def lattice_to_dof(self, xyz):
         xyz = np.ascontiguousarray(xyz, dtype=np.uint32).reshape(-1, 3)
         out = np.empty(xyz.shape[0], dtype=np.uint32)

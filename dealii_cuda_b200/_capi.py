@@ -91,6 +91,7 @@ def _load():
         "mfg_mesh_constrained_device": (vp, [vp]),
         "mfg_mesh_get_loc2glob": (C.c_int, [vp, u32p]),
         "mfg_mesh_get_constrained": (C.c_int, [vp, u32p]),
+        "mfg_mesh_get_support_points": (C.c_int, [vp, dp]),
         "mfg_mesh_get_cell_coords": (C.c_int, [vp, u32p]),
         "mfg_mesh_lattice_to_dof": (C.c_int, [vp, sz, u32p, u32p]),
         "mfg_mesh_color_cells": (C.c_int, [vp, u32p, u32p]),

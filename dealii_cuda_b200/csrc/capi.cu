@@ -186,6 +186,7 @@ const uint32_t *mfg_mesh_constrained_device(const mfg_mesh *m) { return m ? m->c
 int mfg_mesh_get_loc2glob(const mfg_mesh *m, uint32_t *host) { return guarded([&] { MFG_REQUIRE(m && host, "null argument"); m->l2g.download(host, m->ctx->stream); }); }
 int mfg_mesh_get_constrained(const mfg_mesh *m, uint32_t *host) { return guarded([&] { MFG_REQUIRE(m && (host || !m->n_constrained), "null argument"); m->constrained.download(host, m->ctx->stream); }); }
 int mfg_mesh_get_cell_coords(const mfg_mesh *m, uint32_t *host) { return guarded([&] { MFG_REQUIRE(m && host, "null argument"); mesh_cell_coords(m, host); }); }
+int mfg_mesh_get_support_points(const mfg_mesh *m, double *host) { return guarded([&] { MFG_REQUIRE(m && host, "null argument"); mesh_support_points(m, host); }); }
 int mfg_mesh_lattice_to_dof(const mfg_mesh *m, size_t n, const uint32_t *lattice_xyz, uint32_t *dof)
 {
   return guarded([&] {

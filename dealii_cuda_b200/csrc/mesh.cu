@@ -132,6 +132,21 @@ __global__ void cell_coords_kernel(MeshParams P, uint32_t *out)
   out[3 * (size_t)c + 0] = x[0]; out[3 * (size_t)c + 1] = x[1]; out[3 * (size_t)c + 2] = x[2];
 }
 
+// support point of every DoF: x = origin + h (cell + node_i); shared DoFs get the same value from each of their cells
+struct NodeTable { double x[9]; };
+__global__ void support_points_kernel(MeshParams P, const uint32_t *__restrict__ l2g, NodeTable nodes, double ox, double oy, double oz, double h,
+                                      double *__restrict__ out)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)P.n_cells * P.npc) return;
+  const uint32_t c = (uint32_t)(t / P.npc), e = (uint32_t)(t % P.npc);
+  uint32_t x[3]; P.mm.decode(c, x);
+  const int li[3] = {(int)(e % P.n), (int)((e / P.n) % P.n), (int)(e / (P.n * P.n))};
+  const double o[3] = {ox, oy, oz};
+  const uint32_t g = l2g[t];
+  for (int d = 0; d < P.dim; ++d) out[(size_t)g * P.dim + d] = o[d] + h * ((double)x[d] + nodes.x[li[d]]);
+}
+
 struct IotaOp { __host__ __device__ uint32_t operator()(uint32_t i) const { return i; } };
 
 MeshParams params_of(const mfg_mesh *m)
@@ -243,6 +258,18 @@ void mesh_lattice_to_dof_device(const mfg_mesh *m, size_t npts, const uint32_t *
   if (!npts) return;
   lattice_lookup<<<(unsigned)((npts + 255) / 256), 256, 0, m->ctx->stream>>>(params_of(m), m->cell_first.p, m->rank_table.p, npts, xyz_dev, out_dev);
   MFG_CUDA_LAST();
+}
+
+void mesh_support_points(const mfg_mesh *m, double *out_host)
+{
+  cudaStream_t s = m->ctx->stream;
+  DevBuf<double> out((size_t)m->n_dofs * m->dim);
+  NodeTable nt;
+  for (int i = 0; i < m->n; ++i) nt.x[i] = m->fe.nodes[i];
+  const size_t total = (size_t)m->n_cells * m->npc;
+  if (total) support_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(params_of(m), m->l2g.p, nt, m->origin[0], m->origin[1], m->origin[2], m->h, out.p);
+  MFG_CUDA_LAST();
+  out.download(out_host, s);
 }
 
 void mesh_cell_coords(const mfg_mesh *m, uint32_t *out_host)

@@ -85,6 +85,7 @@ namespace mfg {
 mfg_mesh *build_box_mesh(mfg_ctx *ctx, const mfg_box_desc &d);
 void      mesh_lattice_to_dof(const mfg_mesh *m, size_t npts, const uint32_t *xyz_host, uint32_t *out_host);
 void      mesh_cell_coords(const mfg_mesh *m, uint32_t *out_host);
+void      mesh_support_points(const mfg_mesh *m, double *out_host);
 void      mesh_parity_colors(const mfg_mesh *m, std::vector<uint32_t> &color_of_cell, uint32_t &n_colors);
 
 mfg_mf *mf_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter);

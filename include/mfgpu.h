@@ -120,6 +120,9 @@ const uint32_t *mfg_mesh_constrained_device(const mfg_mesh *m);  /* ascending */
 int mfg_mesh_get_loc2glob(const mfg_mesh *m, uint32_t *host);
 int mfg_mesh_get_constrained(const mfg_mesh *m, uint32_t *host);
 int mfg_mesh_get_cell_coords(const mfg_mesh *m, uint32_t *host /* [n_cells][3] */);
+/* support point of every DoF (DoFTools::map_dofs_to_support_points; VectorTools::interpolate_boundary_values needs them,
+   poisson.cu:155-158): host [n_dofs][dim] */
+int mfg_mesh_get_support_points(const mfg_mesh *m, double *host);
 /* global DoF index of lattice points (x,y,z in 0..p*N_d), host arrays, blocking */
 int mfg_mesh_lattice_to_dof(const mfg_mesh *m, size_t n, const uint32_t *lattice_xyz, uint32_t *dof);
 /* graph coloring of the cells (coloring.cc:20-33): color_of_cell[n_cells] to host; returns n_colors in *n_colors */
