@@ -180,8 +180,11 @@ template <int n, typename Number, int CFG> struct Slab2Cfg
   // and the rows needed by the scatter are re-read before N_y^T; 2 = in addition the gather of the next group is issued
   // before the scatter of the current one
   static constexpr int PF   = (CFG % 32) / 8;
+  // + 256: kernel with the in-group face merge of the scatter compiled in (costs registers: 24 bytes of spills at Q4 FP64
+  // with 168 registers, so the default FP64 kernel is built without it)
+  static constexpr bool MERGE = (CFG / 256) % 2 != 0;
   // measurement-only ablations (tools/ablate.py; results are wrong): 1 = no src gather, 2 = no scatter, 4 = no contractions
-  static constexpr int ABL  = CFG / 32;
+  static constexpr int ABL  = (CFG / 32) % 8;
   static constexpr int MINB = OCC == 1 ? 2 : OCC == 2 ? 4 : 3;
   static constexpr int NBUF = (OCC == 2 || OCC == 3) ? 1 : 2;
   static constexpr int F   = Tab::F;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n
 laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
                    Number *__restrict__ dst, const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em,
                    const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP, const uint32_t *__restrict__ glist,
-                   uint32_t *__restrict__ work_counter, const int dep_wait)
+                   const int dep_wait)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   using Tab = typename Cfg::Tab;
@@ -305,16 +308,14 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
   if (Cfg::PF >= 1) load_ids(g0, id);
   if (Cfg::PF == 2) gather(id, un);
 
-  // Every warp starts with list entry k0; the following entries are handed out by an atomic counter when one is given
-  // (a warp that starts late -- its CTA waited for an SM slot next to another kernel -- then simply takes fewer groups),
-  // else with a fixed stride.  The entry after the current one is fetched one group ahead for the prefetches.
-  uint32_t g = g0, k = k0;
-  for (;;)
+  // list entries k0, k0 + total_warps, ... (an atomic work counter instead of the fixed stride measured 27 % slower: the
+  // 4 warps of a CTA lose the lines shared by 4 adjacent groups, profiles/r01_multigpu_overlap.txt)
+  for (uint32_t k = k0; k < n_groups; k += total_warps)
     {
-      // the atomic is issued here and its result is not looked at before the C phase: under the red traffic of the
-      // scatters an atomic with a return value takes microseconds (measured: 30 % slower when consumed at once)
-      uint32_t kn_raw = 0;
-      if (work_counter && lane == 0) kn_raw = total_warps + atomicAdd(work_counter, 1u);
+      const uint32_t  g    = glist ? __ldg(glist + k) : k;
+      const bool      more = k + total_warps < n_groups;
+      const uint32_t  gn   = more ? (glist ? __ldg(glist + k + total_warps) : k + total_warps) : 0;
+      if (more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
       const uint32_t *irow = idxP + (size_t)g * NS * 32 + lane;
       Number u[NS], r[NS];
       if (Cfg::PF == 0) load_ids(g, id);
@@ -395,10 +396,6 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
       for (int k = 0; k < n; ++k)
 #pragma unroll
         for (int i = 0; i < n; ++i) u[i + n * k] = Q[bBCr + BC.SI * i + BC.SK * k];
-      const uint32_t kn   = work_counter ? __shfl_sync(0xffffffffu, kn_raw, 0) : k + total_warps;
-      const bool     more = kn < n_groups;
-      const uint32_t gn   = more ? (glist ? __ldg(glist + kn) : kn) : 0;
-      if (more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
       if (Cfg::PF >= 1)
         {
           if (more) load_ids(gn, id);
@@ -462,7 +459,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
       // ---- face merge inside the group: x (lanes i = n-1 -> i = 0 of cell c+1), y (slots j = n-1 -> j = 0 of cell c+2),
       //      z (slots k = n-1 -> k = 0 of cell c+4); a handed-over value is zeroed so that a later merge does not move it twice
       bool xs = false, ys = false, zs = false;  // this lane hands over its i = n-1 entries / its j = n-1 slots / its k = n-1 slots
-      if (Cfg::CW <= SLAB2_MERGE_MAX_CW)
+      if (Cfg::MERGE && Cfg::CW <= SLAB2_MERGE_MAX_CW)
         {
           const uint32_t mm = __ldg(mergeP + g);
           if (mm != 0)
@@ -525,16 +522,13 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
               if (!(ii & CONSTRAINED_BIT) && !handed_over) red_add(dst + ii, u[s]);
             }
         }
-      if (!more) break;
-      g = gn;
-      k = kn;
     }
 }
 
 template <typename Number>
 void launch_laplace_slab2(int degree, int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups,
                           const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0,
-                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr, uint32_t *work_counter = nullptr, bool pdl = false, bool dep_wait = false);
+                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr, bool pdl = false, bool dep_wait = false);
 // layout of the kernel's private arrays (for the builders in operators.cu)
 struct Slab2Geom { int n, cw, hc, cwf; Slab2Lay bc; };
 bool      slab2_supported(int dim, int degree, mfg_dtype dt);

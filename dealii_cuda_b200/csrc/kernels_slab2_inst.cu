@@ -41,7 +41,7 @@ template <typename Number, int n> static void make_eo(const double *M, bool TR, 
 
 template <int n, typename Number, int CFG>
 static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
-                     const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, uint32_t *work_counter, bool pdl, bool dep_wait)
+                     const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   if (n_groups == 0) return;
@@ -64,7 +64,6 @@ static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src,
     MFG_CUDA(cudaMemcpyToSymbolAsync(g_slab2_delay, d, sizeof(d), 0, cudaMemcpyHostToDevice, stream));
   }
 #endif
-  if (work_counter) MFG_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), stream));
   const uint32_t want = (n_groups + Cfg::WPB - 1) / Cfg::WPB;
   // pdl = interior groups of a multi-GPU apply: MFG_SLAB2_RESERVE CTA slots are left free for the kernels of the
   // exchange that runs beside it (pack, NCCL send/recv, accumulate): a persistent grid that fills every slot would
@@ -83,37 +82,40 @@ static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src,
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      MFG_CUDA(cudaLaunchKernelEx(&cfg, kern, idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, work_counter, (int)dep_wait));
+      MFG_CUDA(cudaLaunchKernelEx(&cfg, kern, idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, (int)dep_wait));
     }
   else
     {
-      kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, work_counter, 0);
+      kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, 0);
       MFG_CUDA_LAST();
     }
 }
 
 template <int n, typename Number>
 static void launch_cfg(int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
-                       const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, uint32_t *work_counter, bool pdl, bool dep_wait)
+                       const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait)
 {
   switch (cfg)
     {
-      case 1: launch_n<n, Number, 1>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 3: launch_n<n, Number, 3>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 4: launch_n<n, Number, 4>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 7: launch_n<n, Number, 7>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 9: launch_n<n, Number, 9>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 11: launch_n<n, Number, 11>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 13: launch_n<n, Number, 13>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 15: launch_n<n, Number, 15>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 17: launch_n<n, Number, 17>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 19: launch_n<n, Number, 19>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 21: launch_n<n, Number, 21>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 23: launch_n<n, Number, 23>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 0: launch_n<n, Number, 0>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 2: launch_n<n, Number, 2>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
+      case 1: launch_n<n, Number, 1>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 3: launch_n<n, Number, 3>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 4: launch_n<n, Number, 4>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 7: launch_n<n, Number, 7>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 9: launch_n<n, Number, 9>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 11: launch_n<n, Number, 11>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 13: launch_n<n, Number, 13>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 15: launch_n<n, Number, 15>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 17: launch_n<n, Number, 17>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 19: launch_n<n, Number, 19>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 21: launch_n<n, Number, 21>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 23: launch_n<n, Number, 23>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 0: launch_n<n, Number, 0>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 2: launch_n<n, Number, 2>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      // configurations 3 and 7 with the face merge compiled in
+      case 259: launch_n<n, Number, 259>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 263: launch_n<n, Number, 263>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
 #ifdef MFG_SLAB2_ABLATE
-#define MFG_ABL(a) case 7 + 32 * a: if constexpr (n == 5) launch_n<n, Number, 7 + 32 * a>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
+#define MFG_ABL(a) case 7 + 32 * a: if constexpr (n == 5) launch_n<n, Number, 7 + 32 * a>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
       MFG_ABL(1) MFG_ABL(2) MFG_ABL(3) MFG_ABL(4) MFG_ABL(5) MFG_ABL(6) MFG_ABL(7)
 #undef MFG_ABL
 #endif
@@ -123,15 +125,15 @@ static void launch_cfg(int cfg, const uint32_t *idxP, const Number *cwP, const N
 
 template <>
 void launch_laplace_slab2<inst_number>(int degree, int cfg, const uint32_t *idxP, const inst_number *cwP, const inst_number *src, inst_number *dst,
-                                       uint32_t n_groups, const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, uint32_t *work_counter, bool pdl, bool dep_wait)
+                                       uint32_t n_groups, const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait)
 {
   switch (degree)
     {
-      case 1: launch_cfg<2, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 2: launch_cfg<3, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 3: launch_cfg<4, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 4: launch_cfg<5, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
-      case 5: launch_cfg<6, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, work_counter, pdl, dep_wait); break;
+      case 1: launch_cfg<2, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 2: launch_cfg<3, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 3: launch_cfg<4, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 4: launch_cfg<5, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 5: launch_cfg<6, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
       default: throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: degree must be in 1..5");
     }
 }

@@ -705,6 +705,22 @@ static cudaTextureObject_t laplace_src_texture(mfg_laplace *op, const void *src)
 }
 
 // (re)build the slab2 kernel's private arrays from idx / cw
+// configuration of the slab2 kernel for the operator's variant; + 256 = the build with the face merge (configurations 3, 7)
+static int slab2_merge_dirs(const mfg_laplace *op)
+{
+  // MFG_SLAB2_MERGE: bit mask of the directions (1 x, 2 y, 4 z) whose in-group face merge is enabled.  Measured on
+  // B200 at 3D Q4 r=6 (profiles/r01_slab2_merge.txt): 22 % fewer red sectors, but the shuffles cost as many L1 data-pipe
+  // wavefronts as the removed sectors in FP64 (+4 % time), while FP32 gains 3.6 % -> on for FP32, off for FP64
+  const int base = op->variant >= 6 ? op->variant - 6 : 3;
+  if (base != 3 && base != 7) return 0;
+  return getenv("MFG_SLAB2_MERGE") ? atoi(getenv("MFG_SLAB2_MERGE")) & 7 : (op->mf->dt == MFG_F64 ? 0 : 7);
+}
+static int slab2_cfg(const mfg_laplace *op)
+{
+  const int base = op->variant >= 6 ? op->variant - 6 : 3;
+  return base + (slab2_merge_dirs(op) ? 256 : 0);
+}
+
 static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
 {
   const mfg_mf   *mf = op->mf;
@@ -717,15 +733,17 @@ static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
       op->idxP.alloc((size_t)n_groups * ns * 32);
       if (n_groups) build_slab2_indices<<<nblk(op->idxP.n), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm, op->idxP.p);
       MFG_CUDA_LAST();
-      // MFG_SLAB2_MERGE: bit mask of the directions (1 x, 2 y, 4 z) whose in-group face merge is enabled.  Measured on
-      // B200 at 3D Q4 r=6 (profiles/r01_slab2_merge.txt): 22 % fewer red sectors, but the shuffles cost as many L1 data-pipe
-      // wavefronts as the removed sectors in FP64 (+4 % time), while FP32 gains 3.6 % -> on for FP32, off for FP64
-      const int dirs = getenv("MFG_SLAB2_MERGE") ? atoi(getenv("MFG_SLAB2_MERGE")) : (mf->dt == MFG_F64 ? 0 : 7);
-      op->mergeP.alloc(n_groups);
-      if (n_groups) build_slab2_merge<<<nblk(n_groups), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm.cw, dirs, op->mergeP.p);
-      MFG_CUDA_LAST();
       op->slab2_groups = n_groups;
       op->cwP_valid = false;
+      op->merge_dirs_built = -1;
+    }
+  const int dirs = slab2_merge_dirs(op);
+  if (op->merge_dirs_built != dirs)
+    {
+      if (op->mergeP.n != n_groups) op->mergeP.alloc(n_groups);
+      if (n_groups) build_slab2_merge<<<nblk(n_groups), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm.cw, dirs, op->mergeP.p);
+      MFG_CUDA_LAST();
+      op->merge_dirs_built = dirs;
     }
   if (!op->cwP_valid)
     {
@@ -854,18 +872,13 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
     {
       laplace_prepare_slab2(op, n_plain);
       // auto = configuration 3 (3 blocks x 4 warps, 168 registers, one transpose buffer per warp, LSU gather)
-      const int cfg = op->variant >= 6 ? op->variant - 6 : 3;
+      const int cfg = slab2_cfg(op);
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
       const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
       const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
-      // MFG_SLAB2_DYNAMIC=1: groups handed out by an atomic counter (one per part: the parts may be in flight together)
-      // instead of a fixed stride.  Measured 27 % slower at 3D Q4 r=6 (0.346 vs 0.273 ms per apply) -- off by default.
-      static const bool dynamic = std::getenv("MFG_SLAB2_DYNAMIC") != nullptr;
-      if (dynamic && op->work_counters.n == 0) { op->work_counters.alloc(2); }
-      uint32_t *wc = dynamic ? op->work_counters.p + (part == 1 ? 1 : 0) : nullptr;
       time_begin();
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
-                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, wc, (split && part == 2) || pdl_fill, pdl_fill);
+                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill);
       time_end();
     }
   else if (laplace_active_variant(op) == 2)

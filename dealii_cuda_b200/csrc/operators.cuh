@@ -61,9 +61,9 @@ struct mfg_laplace
   mfg::DevBuf<uint32_t> idxP;   // [n_groups][n^2 slots][32 lanes]
   mfg::DevBuf<uint8_t>  cwP;    // [n_groups][shared-memory image]
   mfg::DevBuf<uint32_t> mergeP; // [n_groups] face-merge mask
+  int                   merge_dirs_built = -1;  // directions the mask was built for
   mfg::DevBuf<uint32_t> glist;  // multi-GPU work list: groups touching interface DoFs first (laplace_set_interface_dofs)
   uint32_t              n_iface_groups = 0;
-  mfg::DevBuf<uint32_t> work_counters;  // dynamic group distribution of the slab2 kernel, one counter per concurrent part
   uint32_t              slab2_groups = 0;
   bool                  cwP_valid = false;
   // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer
