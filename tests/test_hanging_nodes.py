@@ -149,3 +149,50 @@ def test_gpu_hanging_node_apply(ctx, dim, p, base, kind, dtype):
             op.set_variant(variant)
             op.vmult(dst, src)
             assert np.linalg.norm(dst.toVector() - want) <= tol * np.linalg.norm(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,p,base,kind", [(2, 3, 2, "disk"), (3, 3, 1, "corner"), (3, 4, 1, "corner")])
+def test_gpu_cg_solve_on_adaptive_mesh(ctx, dim, p, base, kind):
+    """BASELINE.json configs[3]: apply AND solve on an adaptively refined mesh with hanging-node constraints.  mfg_solver_cg
+    on the GPU operator against the same CG recurrence (poisson.cu:233-260 control flow) run in numpy on the oracle's operator:
+    same iteration count, iterates equal to rounding; the solution satisfies the oracle's operator equation."""
+    import dealii_cuda_b200 as mf
+    m = make_mesh(dim, p, base, kind)
+    arrays = dict(dim=dim, degree=p, n_dofs=m.n_dofs, loc2glob=m.l2g, inv_jac=m.inv_jac, constraint_mask=m.mask)
+    data = mf.MatrixFreeGpu(ctx, np.float64)
+    data.reinit(arrays)
+    ch = mf.ConstraintHandlerGpu(ctx, np.float64)
+    ch.reinit(m.constrained, m.n_dofs)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(data, ch, coefficient=m.coef)
+    ue = sm64(17, m.n_dofs)
+    b = m.vmult(ue)
+    tol = 1e-10 * np.linalg.norm(b)
+    # numpy restatement of SolverCG with the Jacobi preconditioner on the oracle operator
+    minv = m.inverse_diagonal()
+    x = np.zeros(m.n_dofs); g = -b.copy(); h = minv * g; d = -h; gh = g @ h
+    it_ref = 0
+    hist_ref = [np.linalg.norm(g)]
+    while hist_ref[-1] > tol and it_ref < 2000:
+        it_ref += 1
+        Ad = m.vmult(d)
+        alpha = gh / (d @ Ad)
+        x += alpha * d; g += alpha * Ad
+        hist_ref.append(np.linalg.norm(g))
+        if hist_ref[-1] <= tol:
+            break
+        h = minv * g
+        beta = (g @ h) / gh
+        gh = g @ h
+        d = beta * d - h
+    vb, vx = mf.GpuVector.from_numpy(ctx, b), mf.GpuVector(ctx, m.n_dofs)
+    it, res, hist = mf.solver_cg(op, vx, vb, tol, 2000, use_jacobi=True, history=True)
+    assert abs(it - it_ref) <= 1, (it, it_ref)
+    # CG amplifies rounding differences as orthogonality is lost: tight on the first half of the iterations, loose after
+    k = min(it, it_ref)
+    assert np.allclose(hist[:k // 2 + 1], hist_ref[:k // 2 + 1], rtol=1e-6)
+    assert np.allclose(hist[:k + 1], hist_ref[:k + 1], rtol=5e-2)
+    got = vx.toVector()
+    assert np.linalg.norm(m.vmult(got) - b) <= 2 * tol
+    assert np.linalg.norm(got - ue) <= 1e-6 * np.linalg.norm(ue)
