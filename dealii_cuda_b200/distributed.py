@@ -161,6 +161,58 @@ class DistributedLaplaceOperator:
         return float(t.item())
 
 
+def solver_cg_distributed(dop, x, b, abs_tol, max_iter=10000, use_jacobi=True):
+    """SolverCG over the box partition (poisson.cu:233-260 control flow; the single-GPU form is mfg_solver_cg): the operator is
+    DistributedLaplaceOperator.vmult (replicas of interface DoFs stay bit-identical), inner products run over owned DoFs
+    (mfg_vec_dot_masked) + all_reduce, the Jacobi diagonal is the exchanged sum of the local diagonals.  Vector updates are the
+    library's BLAS-1 kernels.  Returns (iterations, last residual)."""
+    ctx, n = dop.ctx, dop.n_local
+    dt = np.float64 if x.dtype == np.float64 else np.float32
+    g, d, h = GpuVector(ctx, n, dt), GpuVector(ctx, n, dt), GpuVector(ctx, n, dt)
+    minv = None
+    if use_jacobi:
+        if getattr(dop, "_inv_diag", None) is None:
+            dop.op.compute_diagonal()
+            diag = GpuVector(ctx, n, dt)
+            diag.assign(dop.op.get_diagonal_inverse())
+            diag.invert()                                        # local diagonal (constrained rows: 1)
+            dop.exchange.add_interface_contributions(diag.getData())   # interface rows: sum over the sharing ranks
+            diag.invert()
+            dop._inv_diag = diag
+        minv = dop._inv_diag
+    # g = A x - b
+    dop.vmult(g, x)
+    g.add(-1.0, b)
+
+    def precondition():
+        if minv is not None:
+            h.assign(g)
+            h.scale(minv)
+        else:
+            h.assign(g)
+
+    precondition()
+    gh = dop.dot(g, h)
+    res = dop.dot(g, g) ** 0.5
+    it = 0
+    if res > abs_tol:
+        d.equ(-1.0, h)
+        for it in range(1, max_iter + 1):
+            dop.vmult(h, d)
+            alpha = gh / dop.dot(d, h)
+            x.add(alpha, d)
+            g.add(alpha, h)
+            res = dop.dot(g, g) ** 0.5
+            if res <= abs_tol:
+                break
+            precondition()
+            gh_new = dop.dot(g, h)
+            beta = gh_new / gh
+            gh = gh_new
+            d.sadd(beta, -1.0, h)
+    return it, res
+
+
 def bench_main(args, metric):
     """bench.py --gpus N (N > 1): weak scaling, one 2^r cube of cells per GPU."""
     import torch
@@ -287,6 +339,32 @@ def bench_main(args, metric):
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
 
+    # CG solve over all GPUs (BASELINE metric "CG time"): b = A u for a vector u whose interface replicas agree
+    cg = None
+    if not args.no_cg:
+        from . import GpuVector as GV
+        ta.fill_(1.0)
+        dop.vmult_ptr(tb.data_ptr(), ta.data_ptr())      # tb = A 1: bit-identical on the replicas of interface DoFs
+        amax = tb.abs().max()
+        dist.all_reduce(amax, op=dist.ReduceOp.MAX)
+        uvec_t = tb / amax.clamp_min(1e-300) + 1.0       # u = 1 + A1 / max|A1|
+        ue = GV.wrap(ctx, uvec_t)
+        vb, vx = GV(ctx, n, dtype), GV(ctx, n, dtype)
+        dop.vmult(vb, ue)
+        vx.fill(0.0)
+        bnorm = dop.dot(vb, vb) ** 0.5
+        solver_cg_distributed(dop, vx, vb, 0.0, 3)
+        vx.fill(0.0)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        its, res = solver_cg_distributed(dop, vx, vb, (1e-12 if args.dtype == "f64" else 1e-5) * bnorm, 20000)
+        torch.cuda.synchronize(); dist.barrier()
+        cg_s = time.perf_counter() - t0
+        vx.add(-1.0, ue)
+        err = dop.dot(vx, vx) ** 0.5 / dop.dot(ue, ue) ** 0.5
+        cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "rel_error": err, "n_dofs": dop.n_global,
+              "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|",
+              "note": "host-orchestrated (distributed.solver_cg_distributed): library BLAS-1 kernels, masked dot + all_reduce"}
     if rank == 0:
         ng = dop.n_global
         peak, peak_src = measured_peaks()
@@ -314,7 +392,7 @@ def bench_main(args, metric):
                              "kernel": "laplace cell kernel (variant %d), per GPU and apply (%d launches), max over ranks"
                                        % (dop.op.active_variant(), kernel_launches // n_k),
                              "kernel_ms": k_avg_ms, "peak_source": peak_src},
-                "cpu_baseline": None}
+                "cpu_baseline": None, "cg_solve": cg}
         print(json.dumps(line), flush=True)
     # graphs hold NCCL kernels: release them before the communicator goes away (destroying it first hangs)
     # Captured graphs hold NCCL kernels; tearing the communicator down after them hung in ncclCommDestroy on this
