@@ -183,6 +183,10 @@ template <int n, typename Number, int CFG> struct Slab2Cfg
   // + 256: kernel with the in-group face merge of the scatter compiled in (costs registers: 24 bytes of spills at Q4 FP64
   // with 168 registers, so the default FP64 kernel is built without it)
   static constexpr bool MERGE = (CFG / 256) % 2 != 0;
+  // + 512: gather and scatter in plane layouts (one cell per pass, lane <-> a point of the (i,j) resp. (i,k) plane, the
+  // third index in registers): an instruction then covers contiguous runs of 9 and 3 DoFs instead of 3 and 1, 71 / 76
+  // sectors per cell instead of 94.  Dense cell-major transpose buffers; conflict free for n = 5.
+  static constexpr bool KGS = (CFG / 512) % 2 != 0;
   // measurement-only ablations (tools/ablate.py; results are wrong): 1 = no src gather, 2 = no scatter, 4 = no contractions
   static constexpr int ABL  = (CFG / 32) % 8;
   static constexpr int MINB = OCC == 1 ? 2 : OCC == 2 ? 4 : 3;
@@ -238,13 +242,17 @@ __global__ void __launch_bounds__(Slab2Cfg<n, Number, CFG>::WPB * 32, Slab2Cfg<n
 laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src,
                    Number *__restrict__ dst, const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em,
                    const cudaTextureObject_t tex, const uint32_t *__restrict__ mergeP, const uint32_t *__restrict__ glist,
-                   const int dep_wait)
+                   const int dep_wait, const uint32_t *__restrict__ idxLex, const uint32_t *__restrict__ idxJ, const uint32_t n_cells)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   using Tab = typename Cfg::Tab;
   constexpr int NS = Cfg::NS;
   constexpr bool NOPC = (Cfg::ABL & 4) != 0;
-  constexpr Slab2Lay AB = Tab::AB(), BC = Tab::BC(), CA = Tab::CA();
+  constexpr int HCn = (Cfg::CW % 2 == 0 ? Cfg::CW / 2 : Cfg::CW) * n * n * n;
+  // KGS: dense buffers, element (c,i,j,k) at n^3 c + n^2 k + n j + i (written by the gather planes, read by B) and at
+  // n^3 c + n^2 j + n k + i (written by C, read by the scatter planes)
+  constexpr Slab2Lay AB = Cfg::KGS ? Slab2Lay{n * n * n, HCn, 1, n, n * n} : Tab::AB(), BC = Tab::BC(),
+                     CA = Cfg::KGS ? Slab2Lay{n * n * n, HCn, 1, n * n, n} : Tab::CA();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw) + 2 * warp;
@@ -315,25 +323,62 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
       const uint32_t  g    = glist ? __ldg(glist + k) : k;
       const bool      more = k + total_warps < n_groups;
       const uint32_t  gn   = more ? (glist ? __ldg(glist + k + total_warps) : k + total_warps) : 0;
-      if (more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
+      if (!Cfg::KGS && more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)gn * NS + lane) * 32));
       const uint32_t *irow = idxP + (size_t)g * NS * 32 + lane;
       Number u[NS], r[NS];
-      if (Cfg::PF == 0) load_ids(g, id);
-      if (Cfg::PF == 2)
+      if (Cfg::KGS)
         {
+          // ---- K: one cell per pass, lane t <-> (i, j) = (t % n, t / n), k in registers: gather, N_z, store for B ----
+          // (all index rows first, then all gathers: two exposed memory latencies per group, not two per cell)
+          const bool pl = lane < NS;
+          constexpr int HC = Cfg::CW % 2 == 0 ? Cfg::CW / 2 : Cfg::CW;
+          uint32_t kid[Cfg::CW][n];
+          Number   kv[Cfg::CW][n];
 #pragma unroll
-          for (int s = 0; s < NS; ++s) u[s] = un[s];
+          for (int c = 0; c < Cfg::CW; ++c)
+            {
+              const uint32_t  cell = g * Cfg::CW + c;
+              const bool      ok = pl && cell < n_cells;
+              const uint32_t *row = idxLex + (size_t)cell * Cfg::NPC + lane;
+#pragma unroll
+              for (int k = 0; k < n; ++k) kid[c][k] = ok ? __ldg(row + NS * k) : CONSTRAINED_BIT;
+            }
+#pragma unroll
+          for (int c = 0; c < Cfg::CW; ++c)
+#pragma unroll
+            for (int k = 0; k < n; ++k) kv[c][k] = (kid[c][k] & CONSTRAINED_BIT) ? Number(0) : __ldg(src + kid[c][k]);
+#pragma unroll
+          for (int c = 0; c < Cfg::CW; ++c)
+            {
+              Number out[n];
+              eo_apply<n, false, Number, NOPC>(em.N, kv[c], out);
+              if (pl)
+                {
+                  Number *pc = P + AB.SL * (c % HC) + AB.SH * (c / HC) + lane;  // + i + n j = + lane
+#pragma unroll
+                  for (int k = 0; k < n; ++k) pc[AB.SK * k] = out[k];
+                }
+            }
         }
-      else gather(id, u);
-      // ---- A: N_y, N_z ----
-      slab2_apply<n, 1, n, false, Number, NOPC>(em.N, u);
-      slab2_apply<n, n, 1, false, Number, NOPC>(em.N, u);
-      if (active)
+      else
         {
+          if (Cfg::PF == 0) load_ids(g, id);
+          if (Cfg::PF == 2)
+            {
 #pragma unroll
-          for (int k = 0; k < n; ++k)
+              for (int s = 0; s < NS; ++s) u[s] = un[s];
+            }
+          else gather(id, u);
+          // ---- A: N_y, N_z ----
+          slab2_apply<n, 1, n, false, Number, NOPC>(em.N, u);
+          slab2_apply<n, n, 1, false, Number, NOPC>(em.N, u);
+          if (active)
+            {
 #pragma unroll
-            for (int j = 0; j < n; ++j) P[bABw + AB.SJ * j + AB.SK * k] = u[j + n * k];
+              for (int k = 0; k < n; ++k)
+#pragma unroll
+                for (int j = 0; j < n; ++j) P[bABw + AB.SJ * j + AB.SK * k] = u[j + n * k];
+            }
         }
       __syncwarp();
       // ---- B: N_x -> u at the quadrature points, u[i + n j] ----
@@ -343,6 +388,7 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
         for (int i = 0; i < n; ++i) u[i + n * j] = P[bABr + AB.SI * i + AB.SJ * j];
       __syncwarp();  // P consumed
       slab2_apply<n, 1, n, false, Number, NOPC>(em.N, u);
+      if (Cfg::KGS) slab2_apply<n, n, 1, false, Number, NOPC>(em.N, u);  // N_y (the plane gather only did N_z)
       if (active)
         {
 #pragma unroll
@@ -443,6 +489,44 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
             for (int i = 0; i < n; ++i) Q[bCAw + CA.SI * i + CA.SK * k] = u[i + n * k];
         }
       __syncwarp();
+      if (Cfg::KGS)
+        {
+          // ---- K': one cell per pass, lane t <-> (i, k) = (t % n, t / n), j in registers: N_y^T, red.add ----
+          const bool pl = lane < NS;
+          constexpr int HC = Cfg::CW % 2 == 0 ? Cfg::CW / 2 : Cfg::CW;
+          uint32_t jid[Cfg::CW][n];
+#pragma unroll
+          for (int c = 0; c < Cfg::CW; ++c)
+            {
+              const uint32_t  cell = g * Cfg::CW + c;
+              const bool      ok = pl && cell < n_cells;
+              const uint32_t *row = idxJ + (size_t)cell * Cfg::NPC + lane;
+#pragma unroll
+              for (int j = 0; j < n; ++j) jid[c][j] = ok ? __ldg(row + NS * j) : CONSTRAINED_BIT;
+            }
+          if (dep_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < Cfg::CW; ++c)
+            {
+              const Number *qc = Q + CA.SL * (c % HC) + CA.SH * (c / HC) + (pl ? lane : 0);  // + i + n k = + lane
+              Number in[n], out[n];
+#pragma unroll
+              for (int j = 0; j < n; ++j) in[j] = qc[CA.SJ * j];
+              eo_apply<n, false, Number, NOPC>(em.NT, in, out);
+#pragma unroll
+              for (int j = 0; j < n; ++j)
+                {
+                  if (Cfg::ABL & 2)
+                    {
+                      if (out[j] == Number(12345.678)) red_add(dst + jid[c][j], out[j]);
+                    }
+                  else if (!(jid[c][j] & CONSTRAINED_BIT)) red_add(dst + jid[c][j], out[j]);
+                }
+            }
+          if (Cfg::NBUF == 1) __syncwarp();  // the next group's first store goes to the same memory
+        }
+      else
+        {
       // ---- A: N_y^T ----
 #pragma unroll
       for (int k = 0; k < n; ++k)
@@ -522,13 +606,15 @@ laplace_cell_slab2(const uint32_t *__restrict__ idxP, const Number *__restrict__
               if (!(ii & CONSTRAINED_BIT) && !handed_over) red_add(dst + ii, u[s]);
             }
         }
+        }  // !KGS
     }
 }
 
 template <typename Number>
 void launch_laplace_slab2(int degree, int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups,
                           const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex = 0,
-                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr, bool pdl = false, bool dep_wait = false);
+                          const uint32_t *mergeP = nullptr, const uint32_t *glist = nullptr, bool pdl = false, bool dep_wait = false,
+                          const uint32_t *idxLex = nullptr, const uint32_t *idxJ = nullptr, uint32_t n_cells = 0);
 // layout of the kernel's private arrays (for the builders in operators.cu)
 struct Slab2Geom { int n, cw, hc, cwf; Slab2Lay bc; };
 bool      slab2_supported(int dim, int degree, mfg_dtype dt);

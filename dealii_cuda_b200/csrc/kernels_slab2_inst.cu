@@ -41,7 +41,7 @@ template <typename Number, int n> static void make_eo(const double *M, bool TR, 
 
 template <int n, typename Number, int CFG>
 static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
-                     const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait)
+                     const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait, const uint32_t *idxLex, const uint32_t *idxJ, uint32_t n_cells)
 {
   using Cfg = Slab2Cfg<n, Number, CFG>;
   if (n_groups == 0) return;
@@ -82,40 +82,49 @@ static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src,
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      MFG_CUDA(cudaLaunchKernelEx(&cfg, kern, idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, (int)dep_wait));
+      MFG_CUDA(cudaLaunchKernelEx(&cfg, kern, idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, (int)dep_wait, idxLex, idxJ, n_cells));
     }
   else
     {
-      kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, 0);
+      kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, tex, mergeP, glist, 0, idxLex, idxJ, n_cells);
       MFG_CUDA_LAST();
     }
 }
 
 template <int n, typename Number>
 static void launch_cfg(int cfg, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
-                       const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait)
+                       const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait, const uint32_t *idxLex, const uint32_t *idxJ, uint32_t n_cells)
 {
   switch (cfg)
     {
-      case 1: launch_n<n, Number, 1>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 3: launch_n<n, Number, 3>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 4: launch_n<n, Number, 4>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 7: launch_n<n, Number, 7>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 9: launch_n<n, Number, 9>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 11: launch_n<n, Number, 11>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 13: launch_n<n, Number, 13>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 15: launch_n<n, Number, 15>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 17: launch_n<n, Number, 17>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 19: launch_n<n, Number, 19>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 21: launch_n<n, Number, 21>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 23: launch_n<n, Number, 23>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 0: launch_n<n, Number, 0>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 2: launch_n<n, Number, 2>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 1: launch_n<n, Number, 1>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 3: launch_n<n, Number, 3>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 4: launch_n<n, Number, 4>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 7: launch_n<n, Number, 7>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 9: launch_n<n, Number, 9>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 11: launch_n<n, Number, 11>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 13: launch_n<n, Number, 13>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 15: launch_n<n, Number, 15>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 17: launch_n<n, Number, 17>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 19: launch_n<n, Number, 19>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 21: launch_n<n, Number, 21>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 23: launch_n<n, Number, 23>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 0: launch_n<n, Number, 0>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 2: launch_n<n, Number, 2>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
       // configurations 3 and 7 with the face merge compiled in
-      case 259: launch_n<n, Number, 259>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 263: launch_n<n, Number, 263>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 259: launch_n<n, Number, 259>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 263: launch_n<n, Number, 263>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      // plane-layout gather / scatter (dense transpose buffers are conflict free for n = 5 only)
+      case 515:
+        if constexpr (n == 5) launch_n<n, Number, 515>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells);
+        else throw Error(MFG_ERR_UNSUPPORTED, "slab2 plane-layout configuration exists for degree 4 only");
+        break;
+      case 513:
+        if constexpr (n == 5) launch_n<n, Number, 513>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells);
+        else throw Error(MFG_ERR_UNSUPPORTED, "slab2 plane-layout configuration exists for degree 4 only");
+        break;
 #ifdef MFG_SLAB2_ABLATE
-#define MFG_ABL(a) case 7 + 32 * a: if constexpr (n == 5) launch_n<n, Number, 7 + 32 * a>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+#define MFG_ABL(a) case 7 + 32 * a: if constexpr (n == 5) launch_n<n, Number, 7 + 32 * a>(idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
       MFG_ABL(1) MFG_ABL(2) MFG_ABL(3) MFG_ABL(4) MFG_ABL(5) MFG_ABL(6) MFG_ABL(7)
 #undef MFG_ABL
 #endif
@@ -125,15 +134,15 @@ static void launch_cfg(int cfg, const uint32_t *idxP, const Number *cwP, const N
 
 template <>
 void launch_laplace_slab2<inst_number>(int degree, int cfg, const uint32_t *idxP, const inst_number *cwP, const inst_number *src, inst_number *dst,
-                                       uint32_t n_groups, const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait)
+                                       uint32_t n_groups, const double *N, const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait, const uint32_t *idxLex, const uint32_t *idxJ, uint32_t n_cells)
 {
   switch (degree)
     {
-      case 1: launch_cfg<2, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 2: launch_cfg<3, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 3: launch_cfg<4, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 4: launch_cfg<5, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
-      case 5: launch_cfg<6, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait); break;
+      case 1: launch_cfg<2, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 2: launch_cfg<3, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 3: launch_cfg<4, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 4: launch_cfg<5, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
+      case 5: launch_cfg<6, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
       default: throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: degree must be in 1..5");
     }
 }

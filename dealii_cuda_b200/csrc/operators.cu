@@ -96,6 +96,17 @@ __global__ void build_slab2_merge(const uint32_t *__restrict__ idx, uint32_t n_c
   out[g] = m;
 }
 
+// slab2 plane-layout scatter: idxJ[cell][j][i + n k] = idx[cell][i + n j + n^2 k]
+__global__ void build_slab2_idxJ(const uint32_t *__restrict__ idx, size_t total, int n, uint32_t *__restrict__ out)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int    npc = n * n * n, e = (int)(t % npc);
+  const size_t cell = t / npc;
+  const int    i = e % n, j = (e / n) % n, k = e / (n * n);
+  out[cell * npc + (size_t)j * n * n + i + n * k] = idx[t];
+}
+
 // slab2 kernel: coefficient image of a group, element (c,i,j,k) at SC c + SI i + SJ j + SK k (padding stays zero)
 template <typename Number>
 __global__ void build_slab2_weights(const Number *__restrict__ cw, uint32_t n_cells, int n, Slab2Geom gm, Number *__restrict__ out)
@@ -712,7 +723,7 @@ static int slab2_merge_dirs(const mfg_laplace *op)
   // B200 at 3D Q4 r=6 (profiles/r01_slab2_merge.txt): 22 % fewer red sectors, but the shuffles cost as many L1 data-pipe
   // wavefronts as the removed sectors in FP64 (+4 % time), while FP32 gains 3.6 % -> on for FP32, off for FP64
   const int base = op->variant >= 6 ? op->variant - 6 : 3;
-  if (base != 3 && base != 7) return 0;
+  if (base != 3 && base != 7) return 0;  // (also excludes the plane-layout configurations 512 + c)
   return getenv("MFG_SLAB2_MERGE") ? atoi(getenv("MFG_SLAB2_MERGE")) & 7 : (op->mf->dt == MFG_F64 ? 0 : 7);
 }
 static int slab2_cfg(const mfg_laplace *op)
@@ -873,12 +884,19 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       laplace_prepare_slab2(op, n_plain);
       // auto = configuration 3 (3 blocks x 4 warps, 168 registers, one transpose buffer per warp, LSU gather)
       const int cfg = slab2_cfg(op);
+      if (cfg >= 512 && op->idxJ.n == 0 && n_plain)
+        {
+          const size_t total = (size_t)n_plain * mf->npc;
+          op->idxJ.alloc(total);
+          build_slab2_idxJ<<<nblk(total), 256, 0, s>>>(mf->idx.p, total, mf->n, op->idxJ.p);
+          MFG_CUDA_LAST();
+        }
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
       const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
       const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
       time_begin();
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
-                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill);
+                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill, mf->idx.p, op->idxJ.p, n_plain);
       time_end();
     }
   else if (laplace_active_variant(op) == 2)

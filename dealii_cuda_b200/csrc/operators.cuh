@@ -60,6 +60,7 @@ struct mfg_laplace
   // built on first use from idx / cw
   mfg::DevBuf<uint32_t> idxP;   // [n_groups][n^2 slots][32 lanes]
   mfg::DevBuf<uint8_t>  cwP;    // [n_groups][shared-memory image]
+  mfg::DevBuf<uint32_t> idxJ;   // plane-layout scatter (configurations 512 + c): idx with j as the slowest local index
   mfg::DevBuf<uint32_t> mergeP; // [n_groups] face-merge mask
   int                   merge_dirs_built = -1;  // directions the mask was built for
   mfg::DevBuf<uint32_t> glist;  // multi-GPU work list: groups touching interface DoFs first (laplace_set_interface_dofs)

@@ -152,6 +152,41 @@ def test_slab2_face_merge_f64(ctx, p, r, dirs, monkeypatch):
     assert rel_err(dst.toVector(), o.vmult(u)) <= TOL[np.float64]
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("variant", [519, 521])
+@pytest.mark.parametrize("r", [0, 1, 2, 3])
+def test_slab2_plane_layout_variants(ctx, r, variant, dtype):
+    """slab2 with the gather / scatter in plane layouts (configurations 512 + c, degree 4 only): tails, vmult_add,
+    constrained rows; other degrees are rejected."""
+    import dealii_cuda_b200 as mf
+    p = 4
+    o = OracleMesh(3, p, r)
+    m = mf.HyperCubeMesh(ctx, 3, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(m)
+    op.set_variant(variant)
+    u = sm64(7, o.n_dofs).astype(dtype)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs, dtype)
+    for _ in range(2):
+        dst.fill(-3.0)
+        op.vmult(dst, src)
+        got = dst.toVector()
+        assert rel_err(got, o.vmult(u.astype(np.float64))) <= TOL[dtype]
+        assert np.array_equal(got[o.constrained], u[o.constrained])
+    d0 = sm64(8, o.n_dofs).astype(dtype)
+    dst.fromHost(d0)
+    op.vmult_add(dst, src)
+    assert rel_err(dst.toVector(), o.vmult_add(d0.astype(np.float64), u.astype(np.float64))) <= TOL[dtype]
+    if r == 1:
+        m3 = mf.HyperCubeMesh(ctx, 3, 3, 1)
+        op3 = mf.LaplaceOperatorGpu(ctx, dtype)
+        op3.reinit(m3)
+        op3.set_variant(variant)
+        a, b = mf.GpuVector(ctx, m3.n_dofs, dtype), mf.GpuVector(ctx, m3.n_dofs, dtype)
+        with pytest.raises(mf.MfgError):
+            op3.vmult(a, b)
+
+
 def test_slab_variant_rejected_where_unsupported(ctx):
     import dealii_cuda_b200 as mf
     for dim, p, coloring, auto in [(2, 4, False, 1), (3, 5, False, 6), (3, 4, True, 1), (3, 6, False, 1)]:
