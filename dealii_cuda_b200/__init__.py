@@ -542,7 +542,8 @@ class LaplaceOperatorGpu:
         return lib.mfg_laplace_active_variant(self.h)
 
     def enable_kernel_timing(self, on):
-        check(lib.mfg_laplace_enable_kernel_timing(self.h, 1 if on else 0))
+        """on = True / k: bracket every (k-th) cell-kernel launch with CUDA events; False: off."""
+        check(lib.mfg_laplace_enable_kernel_timing(self.h, int(on)))
 
     def kernel_time_ms(self):
         ms, nl = C.c_double(), C.c_int()

@@ -399,7 +399,7 @@ size_t mfg_laplace_memory_consumption(const mfg_laplace *op)
 }
 int mfg_laplace_enable_kernel_timing(mfg_laplace *op, int on)
 {
-  return guarded([&] { MFG_REQUIRE(op, "null operator"); op->timing = on != 0; if (!on) op->ev_used = 0; });
+  return guarded([&] { MFG_REQUIRE(op, "null operator"); op->timing = on != 0; op->timing_stride = on > 1 ? on : 1; op->timing_counter = 0; if (!on) op->ev_used = 0; });
 }
 int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launches)
 {

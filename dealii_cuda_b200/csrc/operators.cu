@@ -861,14 +861,16 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
   if (part == 0) return;
   const bool     hanging = mf->hn_mask.n != 0;
   const uint32_t n_plain = hanging ? mf->n_plain : mf->n_cells;
+  bool timed = false;
   auto time_begin = [&]() {
-    if (!op->timing) return;
+    timed = op->timing && (op->timing_counter++ % (size_t)op->timing_stride) == 0;
+    if (!timed) return;
     if (op->ev_used + 2 > op->ev.size())
       for (int k = 0; k < 2; ++k) { cudaEvent_t e; MFG_CUDA(cudaEventCreate(&e)); op->ev.push_back(e); }
     MFG_CUDA(cudaEventRecord(op->ev[op->ev_used], s));
   };
   auto time_end = [&]() {
-    if (op->timing) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
+    if (timed) { MFG_CUDA(cudaEventRecord(op->ev[op->ev_used + 1], s)); op->ev_used += 2; }
   };
   const bool atomic = mf->scatter == MFG_SCATTER_ATOMIC;
   auto launch_v0 = [&](uint32_t c0, uint32_t c1, const uint32_t *mask) {

@@ -78,6 +78,8 @@ struct mfg_laplace
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // optional per-launch timing of the cell kernel (bench.py roofline figure)
   bool                     timing = false;
+  int                      timing_stride = 1;   // bracket every timing_stride-th cell-kernel launch
+  size_t                   timing_counter = 0;
   std::vector<cudaEvent_t> ev;        // pairs (start, stop)
   size_t                   ev_used = 0;
 };

@@ -235,8 +235,10 @@ size_t mfg_laplace_memory_consumption(const mfg_laplace *op);                   
 /* number of kernel launches one vmult enqueues (for bench.py's gpu_launches) */
 int mfg_laplace_launches_per_vmult(const mfg_laplace *op);
 int mfg_laplace_cell_launches_per_vmult(const mfg_laplace *op); /* cell-kernel launches among them */
-/* per-kernel device timing for the roofline figure: when enabled every cell-kernel launch is bracketed by
- * CUDA events on the context stream; kernel_time_ms (blocking) returns and resets the accumulated time. */
+/* per-kernel device timing for the roofline figure: on = k > 0 brackets every k-th cell-kernel launch by CUDA events on
+ * the context stream (k = 1: every launch; a bracketed launch cannot overlap its neighbours, so a sample keeps the
+ * measured loop honest); kernel_time_ms (blocking) returns and resets the accumulated time and the number of
+ * bracketed launches. */
 int mfg_laplace_enable_kernel_timing(mfg_laplace *op, int on);
 int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launches);
 int mfg_laplace_active_variant(const mfg_laplace *op);
