@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--coloring", action="store_true", help="graph-colored scatter instead of FP64 atomics")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-refine", type=int, default=5)
+    ap.add_argument("--cpu-refine", type=int, default=6, help="CPU baseline sample: global refinements (6 = the GPU workload itself)")
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
