@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include "../include/dealii_cuda_b200/matrix_free_gpu.h"
 
 using namespace dealii_cuda_b200;
@@ -39,12 +40,29 @@ template <int dim, int fe_degree> void run(int n_ref)
   std::printf("%d\t%d\t%u\t%g\n", dim, fe_degree, mesh.n_dofs(), sec / N_ITERATIONS);
 }
 
+// bmop_mg's transfer (bmop_mg.cu): prolongate / restrict_and_add between two levels through the facade; checks <P u, v> = <u, R v>
+template <int dim, int fe_degree> void mg_transfer_smoke()
+{
+  HyperCubeMesh<dim> coarse(fe_degree, 1), fine(fe_degree, 2);
+  MGTransferMatrixFreeGpu<dim, number> transfer;
+  transfer.build({&coarse, &fine}, 1);
+  GpuVector<number> uc(coarse.n_dofs()), vf(fine.n_dofs()), pu(fine.n_dofs()), rv(coarse.n_dofs());
+  uc = number(1);
+  vf = number(0.5);
+  transfer.prolongate(2, pu, uc);
+  rv = number(0);
+  transfer.restrict_and_add(2, rv, vf);
+  const double a = (double)(pu * vf), b = (double)(uc * rv);
+  std::printf("mg transfer adjointness: <Pu,v> = %.12g, <u,Rv> = %.12g\n", a, b);
+}
+
 int main(int argc, char **argv)
 {
   try
     {
       const int max_refinement = argc > 1 ? std::atoi(argv[1]) : 1;
       const int min_refinement = argc > 2 ? std::atoi(argv[2]) : 0;
+      if (argc > 3 && std::string(argv[3]) == "mg") { mg_transfer_smoke<DIMENSION, DEGREE_FE>(); return 0; }
       for (int r = min_refinement; r <= max_refinement; ++r) run<DIMENSION, DEGREE_FE>(r);
     }
   catch (std::exception &exc)

@@ -3,6 +3,7 @@
 // (matrix_free_gpu.h:81-229) and LaplaceOperatorGpu<dim,fe_degree,Number> (laplace_operator_gpu.h:35-96).
 #pragma once
 #include <memory>
+#include <vector>
 #include "gpu_vec.h"
 
 namespace dealii_cuda_b200 {
@@ -146,6 +147,48 @@ public:
 private:
   bool         use_coloring_;
   mfg_laplace *op_ = nullptr;
+};
+
+// MGTransferMatrixFreeGpu<dim,Number> (mg_transfer_matrix_free_gpu.h:64-307) for a globally refined hierarchy:
+// build(meshes of consecutive levels, coarsest first), prolongate(to_level, dst, src), restrict_and_add(from_level, dst, src);
+// copy_to_mg / copy_from_mg are plain copies there (the finest level is the active mesh, .cu:688-757).
+template <int dim, typename Number> class MGTransferMatrixFreeGpu
+{
+public:
+  MGTransferMatrixFreeGpu() {}
+  ~MGTransferMatrixFreeGpu() { clear(); }
+  MGTransferMatrixFreeGpu(const MGTransferMatrixFreeGpu &) = delete;
+  void clear()
+  {
+    for (mfg_mgt *t : t_) mfg_mgt_destroy(t);
+    t_.clear();
+  }
+  // levels[l] = mesh of level min_level + l
+  void build(const std::vector<const HyperCubeMesh<dim> *> &levels, unsigned int min_level = 0)
+  {
+    clear();
+    min_level_ = min_level;
+    for (std::size_t l = 0; l + 1 < levels.size(); ++l)
+      {
+        mfg_mgt *t = nullptr;
+        check(mfg_mgt_build(default_context(), levels[l]->handle(), levels[l + 1]->handle(), dtype_of<Number>(), &t));
+        t_.push_back(t);
+      }
+  }
+  void prolongate(const unsigned int to_level, GpuVector<Number> &dst, const GpuVector<Number> &src) const
+  {
+    check(mfg_mgt_prolongate(t_.at(to_level - min_level_ - 1), dst.handle(), src.handle()));
+  }
+  void restrict_and_add(const unsigned int from_level, GpuVector<Number> &dst, const GpuVector<Number> &src) const
+  {
+    check(mfg_mgt_restrict_and_add(t_.at(from_level - min_level_ - 1), dst.handle(), src.handle()));
+  }
+  void copy_to_mg(std::vector<GpuVector<Number>> &dst_levels, const GpuVector<Number> &src) const { dst_levels.back() = src; }
+  void copy_from_mg(GpuVector<Number> &dst, const std::vector<GpuVector<Number>> &src_levels) const { dst = src_levels.back(); }
+
+private:
+  std::vector<mfg_mgt *> t_;
+  unsigned int           min_level_ = 0;
 };
 
 }  // namespace dealii_cuda_b200
