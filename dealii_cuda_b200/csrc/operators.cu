@@ -894,7 +894,17 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
           MFG_CUDA_LAST();
         }
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
-      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
+      // experiment (tools/sweep.py): MFG_SLAB2_ALIAS=m maps work item k to group k % m, i.e. the same
+      // instruction stream on an L2-resident working set (results are then meaningless)
+      static const int alias = std::getenv("MFG_SLAB2_ALIAS") ? std::atoi(std::getenv("MFG_SLAB2_ALIAS")) : 0;
+      if (alias > 0 && op->glist.n == 0 && op->slab2_groups)
+        {
+          std::vector<uint32_t> al(op->slab2_groups);
+          for (uint32_t k = 0; k < op->slab2_groups; ++k) al[k] = k % (uint32_t)alias;
+          op->glist.upload(al.data(), al.size(), s);
+          op->n_iface_groups = 0;
+        }
+      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : (alias > 0 ? op->glist.p : nullptr);
       const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
       time_begin();
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
