@@ -97,6 +97,8 @@ def cpu_reference_run(args, steps, warmup):
     """The reference's CPU path (bmop-cpu.cc:138-155) restated: oracle port, OpenMP over colors, all host threads.
     Bounded sample: the same mesh family at a refinement the host finishes in seconds."""
     from oracle.oracle import OracleMesh, lib as olib
+    # all host threads this process may use (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    olib().orc_set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     r = min(args.refine, args.cpu_refine)
     m = OracleMesh(3, args.degree, r)
     u = np.full(m.n_dofs, 0.1)

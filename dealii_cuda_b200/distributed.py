@@ -221,6 +221,12 @@ def bench_main(args, metric):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL and the symmetric-memory rendezvous print to stdout; the contract is ONE JSON line there: everything else
+    # goes to stderr, the line is written to the saved descriptor at the end
+    import sys
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     # The exchange runs beside the persistent interior cell kernel, which leaves 4 CTA slots free (MFG_SLAB2_RESERVE):
     # NCCL's send/recv kernel must fit into them, so few and narrow channels (measured on 2 x B200: 0.281 ms per apply
@@ -393,8 +399,7 @@ def bench_main(args, metric):
                                        % (dop.op.active_variant(), kernel_launches // n_k),
                              "kernel_ms": k_avg_ms, "peak_source": peak_src},
                 "cpu_baseline": None, "cg_solve": cg}
-        print(json.dumps(line), flush=True)
-    # graphs hold NCCL kernels: release them before the communicator goes away (destroying it first hangs)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     # Captured graphs hold NCCL kernels; tearing the communicator down after them hung in ncclCommDestroy on this
     # stack (torch 2.11 / NCCL 2.28), so the ranks synchronise, flush and leave without the teardown.
     graphs.clear()

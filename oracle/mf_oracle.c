@@ -784,6 +784,16 @@ void orc_vmult_fast(const orc_mesh *m, double *dst, const double *src)
   }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU arm asks for the host's threads explicitly */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

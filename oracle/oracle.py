@@ -60,6 +60,8 @@ def lib():
         L.orc_shape_1d.argtypes = [C.c_int, dp, dp, dp, dp, dp]
         L.orc_hier_to_lex.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint32)]
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_threads.restype = None
+        L.orc_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
