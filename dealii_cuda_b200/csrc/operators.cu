@@ -773,7 +773,13 @@ static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
 }
 
 // kernels of this library one vmult enqueues (the cudaMemsetAsync of dst is not counted)
-int laplace_launches_per_vmult(const mfg_laplace *op) { return (op->ch->n() ? 1 : 0) + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0); }
+int laplace_launches_per_vmult(const mfg_laplace *op)
+{
+  // with the slab2 kernel the zero pass is a kernel of this library too (zero_fill_pdl)
+  const bool zero_kernel = !(std::getenv("MFG_PDL_FILL") && std::atoi(std::getenv("MFG_PDL_FILL")) == 0) && laplace_active_variant(op) == 6 &&
+                           op->mf->hn_mask.n == 0;
+  return (op->ch->n() ? 1 : 0) + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0) + (zero_kernel ? 1 : 0);
+}
 
 // kernel variants: 1 = column kernel (kernels_v0.cuh, every dim/degree/dtype/scatter),
 //                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter),

@@ -387,7 +387,9 @@ def bench_main(args, metric):
                 "clocks": clocks,
                 "e2e": {"value": ng / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
                         "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
-                "gpu_launches": args.steps * (dop.op.launches_per_vmult() + (1 if dop.n_iface_groups else 0) + 2) * world,
+                # per apply and rank: constraint pass + cell kernel(s) + push (or pack) + accumulate; the split apply zeroes
+                # dst with cudaMemsetAsync (no zero kernel) and launches the cell kernel twice
+                "gpu_launches": args.steps * world * ((dop.op.launches_per_vmult() if not dop.n_iface_groups else dop.op.launches_per_vmult()) + 2),
                 "launch_mode": "CUDA graph replay of one apply (cell kernels + pack + all_to_all + accumulate)" if use_graphs else "eager",
                 "selfcheck": selfcheck,
                 "exchange": ("NVLink P2P stores into the neighbours' symmetric-memory receive buffers + device-side barriers"
