@@ -254,7 +254,8 @@ template <typename Number> __global__ void k_load_add(Number *out, Number *in, c
   if (i < n) { const uint32_t c = list[i]; out[c] = tmp_out[i] + tmp_in[i]; in[c] = tmp_in[i]; }
 }
 
-inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+// (at least one block: every kernel launched with it checks its index, and an empty partition must not fail the launch)
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)std::max<size_t>(1, (n + t - 1) / t); }
 
 }  // namespace
 
@@ -612,7 +613,7 @@ mfg_laplace *laplace_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const dou
 {
   MFG_REQUIRE(mf && ch && coef_host, "mf, ch and coefficient are required");
   MFG_REQUIRE(mf->dt == ch->dt, "mf and ch dtypes differ");
-  MFG_REQUIRE(!mf->geom_host.empty() || !mf->gsym_host.empty() || mf->mesh, "mf has no geometry");
+  MFG_REQUIRE(mf->n_cells == 0 || !mf->geom_host.empty() || !mf->gsym_host.empty() || mf->mesh, "mf has no geometry");
   std::unique_ptr<mfg_laplace> op(new mfg_laplace);
   op->ctx = ctx; op->mf = mf; op->ch = ch;
   // mark constrained DoFs in the kernel index array (in place)
@@ -635,6 +636,7 @@ void laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host)
 {
   const mfg_mf *mf = op->mf;
   const size_t total = (size_t)mf->n_cells * mf->npc;
+  if (total == 0) { op->diagonal_is_available = false; op->cwP_valid = false; return; }  // empty partition
   if (mf->general)
     {
       // merged tensor a(x_q) JxW K K^T, [cell][component][q]
@@ -1069,7 +1071,8 @@ void laplace_compute_diagonal(mfg_laplace *op)
   const size_t dsm = 2 * (size_t)mf->npc * sizeof(double);
   const uint32_t *hmask = mf->hn_mask.n ? mf->hn_mask.p : nullptr;
   const int threads = (int)std::min<uint32_t>(256, ((mf->npc + 31) / 32) * 32);
-  if (mf->dt == MFG_F64)
+  if (mf->n_cells == 0) { /* empty partition: only the constrained rows below */ }
+  else if (mf->dt == MFG_F64)
     diagonal_kernel<double><<<mf->n_cells, threads, dsm, s>>>(mf->idx.p, (const double *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (double *)op->inv_diag->p, hmask);
   else
     diagonal_kernel<float><<<mf->n_cells, threads, dsm, s>>>(mf->idx.p, (const float *)op->cw.p, mf->dim, mf->n, mf->npc, mf->n_cells, tb, (float *)op->inv_diag->p, hmask);

@@ -449,3 +449,28 @@ def test_full_size_r6_properties(ctx):
     bcells = cflag[l2g].any(axis=1)
     touched[l2g[bcells].ravel()] = True
     assert np.abs(r[~touched]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,p", [(2, 2), (3, 4)])
+def test_empty_mesh_from_arrays(ctx, dim, p, dtype):
+    """an operator without cells (empty partition): vmult is the identity on the constrained rows and zero elsewhere,
+    vmult_add leaves dst + src[c]; the diagonal is 1 on constrained rows"""
+    import dealii_cuda_b200 as mf
+    npc = (p + 1) ** dim
+    data = dict(dim=dim, degree=p, n_dofs=7, loc2glob=np.zeros((0, npc), np.uint32), inv_jac=np.zeros(0))
+    mfree = mf.MatrixFreeGpu(ctx, dtype)
+    mfree.reinit(data)
+    ch = mf.ConstraintHandlerGpu(ctx, dtype)
+    ch.reinit(np.array([1, 4], np.uint32), 7)
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(mfree, ch, coefficient=np.zeros((0, npc)))
+    u = np.arange(1, 8).astype(dtype)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, 7, dtype)
+    dst.fill(9.0)
+    op.vmult(dst, src)
+    assert np.array_equal(dst.toVector(), np.array([0, 2, 0, 0, 5, 0, 0], dtype))
+    op.vmult_add(dst, src)
+    assert np.array_equal(dst.toVector(), np.array([0, 4, 0, 0, 10, 0, 0], dtype))
+    op.compute_diagonal()
+    assert np.array_equal(op.get_diagonal_inverse().toVector()[[1, 4]], np.ones(2, dtype))
