@@ -2,7 +2,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include "kernels_slab2.cuh"
+#include "kernels_slab2_ws.cuh"
 
 #ifndef MFG_INST_F64
 #error "compile with -DMFG_INST_F64=0|1"
@@ -144,6 +144,49 @@ void launch_laplace_slab2<inst_number>(int degree, int cfg, const uint32_t *idxP
       case 4: launch_cfg<5, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
       case 5: launch_cfg<6, inst_number>(cfg, idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, tex, mergeP, glist, pdl, dep_wait, idxLex, idxJ, n_cells); break;
       default: throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: degree must be in 1..5");
+    }
+}
+
+template <int NCW, int NLW, int MINB>
+static void launch_ws(const uint32_t *idxLex, const uint32_t *idxJ, const inst_number *cwP, const inst_number *src, inst_number *dst, uint32_t n_groups,
+                      uint32_t n_cells, const double *N, const double *D, int sm_count, cudaStream_t stream)
+{
+  constexpr int n = 5;
+  using Cfg = Slab2WsCfg<n, inst_number, NCW, NLW, MINB>;
+  if (n_groups == 0) return;
+  EoMats<inst_number, n> em;
+  make_eo<inst_number, n>(N, false, +1, em.N);
+  make_eo<inst_number, n>(N, true, +1, em.NT);
+  make_eo<inst_number, n>(D, false, -1, em.D);
+  make_eo<inst_number, n>(D, true, -1, em.DT);
+  auto       kern = laplace_cell_slab2_ws<n, inst_number, NCW, NLW, MINB>;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0)
+    {
+      MFG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+      MFG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, Cfg::THREADS, Cfg::SMEM));
+      if (blocks_per_sm < 1) throw Error(MFG_ERR_CUDA, "warp-specialised slab2 kernel does not fit on an SM");
+    }
+  const uint32_t want = (n_groups + Cfg::NCW - 1) / Cfg::NCW;
+  const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sm_count * blocks_per_sm));
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, em);
+  MFG_CUDA_LAST();
+}
+
+// shape: 0 = 2 CTAs x (4 contraction + 2 loader warps), 1 = 3 CTAs x (3 + 1), 2 = 2 CTAs x (4 + 1), 3 = 2 CTAs x (4 + 4)
+template <>
+void launch_laplace_slab2_ws<inst_number>(int degree, int shape, const uint32_t *idxLex, const uint32_t *idxJ, const inst_number *cwP,
+                                          const inst_number *src, inst_number *dst, uint32_t n_groups, uint32_t n_cells, const double *N,
+                                          const double *D, int sm_count, cudaStream_t stream)
+{
+  if (degree != 4) throw Error(MFG_ERR_UNSUPPORTED, "the warp-specialised slab2 kernel exists for degree 4 only");
+  switch (shape)
+    {
+      case 0: launch_ws<4, 2, 2>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 1: launch_ws<3, 1, 3>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 2: launch_ws<4, 1, 2>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 3: launch_ws<4, 4, 1>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      default: throw Error(MFG_ERR_UNSUPPORTED, "warp-specialised slab2 kernel: unknown shape");
     }
 }
 

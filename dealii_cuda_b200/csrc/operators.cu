@@ -3,7 +3,7 @@
 #include <numeric>
 #include <cstdlib>
 #include "kernels_slab.cuh"
-#include "kernels_slab2.cuh"
+#include "kernels_slab2_ws.cuh"
 #include "kernels_general.cuh"
 #include "operators.cuh"
 
@@ -901,6 +901,17 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
           build_slab2_idxJ<<<nblk(total), 256, 0, s>>>(mf->idx.p, total, mf->n, op->idxJ.p);
           MFG_CUDA_LAST();
         }
+      if (cfg >= 1024)
+        {
+          // warp-specialised kernel (kernels_slab2_ws.cuh): variants 1030 + shape
+          if (split) throw Error(MFG_ERR_UNSUPPORTED, "the warp-specialised slab2 kernel has no work list");
+          time_begin();
+          launch_laplace_slab2_ws<Number>(mf->p, cfg - 1024, mf->idx.p, op->idxJ.p, (const Number *)op->cwP.p, src, dst, op->slab2_groups, n_plain,
+                                          mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s);
+          time_end();
+        }
+      else
+        {
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
       // experiment (tools/sweep.py): MFG_SLAB2_ALIAS=m maps work item k to group k % m, i.e. the same
       // instruction stream on an L2-resident working set (results are then meaningless)
@@ -918,6 +929,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
                                    mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill, mf->idx.p, op->idxJ.p, n_plain);
       time_end();
+        }
     }
   else if (laplace_active_variant(op) == 2)
     {
