@@ -147,19 +147,19 @@ void launch_laplace_slab2<inst_number>(int degree, int cfg, const uint32_t *idxP
     }
 }
 
-template <int NCW, int NLW, int MINB>
+template <int NCW, int NLW, int MINB, bool LS, int RC = 0, int RL = 0>
 static void launch_ws(const uint32_t *idxLex, const uint32_t *idxJ, const inst_number *cwP, const inst_number *src, inst_number *dst, uint32_t n_groups,
                       uint32_t n_cells, const double *N, const double *D, int sm_count, cudaStream_t stream)
 {
   constexpr int n = 5;
-  using Cfg = Slab2WsCfg<n, inst_number, NCW, NLW, MINB>;
+  using Cfg = Slab2WsCfg<n, inst_number, NCW, NLW, MINB, LS, RC, RL>;
   if (n_groups == 0) return;
   EoMats<inst_number, n> em;
   make_eo<inst_number, n>(N, false, +1, em.N);
   make_eo<inst_number, n>(N, true, +1, em.NT);
   make_eo<inst_number, n>(D, false, -1, em.D);
   make_eo<inst_number, n>(D, true, -1, em.DT);
-  auto       kern = laplace_cell_slab2_ws<n, inst_number, NCW, NLW, MINB>;
+  auto       kern = laplace_cell_slab2_ws<n, inst_number, NCW, NLW, MINB, LS, RC, RL>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0)
     {
@@ -182,10 +182,15 @@ void launch_laplace_slab2_ws<inst_number>(int degree, int shape, const uint32_t 
   if (degree != 4) throw Error(MFG_ERR_UNSUPPORTED, "the warp-specialised slab2 kernel exists for degree 4 only");
   switch (shape)
     {
-      case 0: launch_ws<4, 2, 2>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
-      case 1: launch_ws<3, 1, 3>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
-      case 2: launch_ws<4, 1, 2>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
-      case 3: launch_ws<4, 4, 1>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 0: launch_ws<4, 2, 2, false>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 1: launch_ws<3, 1, 3, false>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 2: launch_ws<4, 1, 2, false>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 3: launch_ws<4, 4, 1, false>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      // 4, 5: the loader warps also scatter (contraction warps touch global memory only through the coefficient copy)
+      case 4: launch_ws<4, 2, 2, true>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      case 5: launch_ws<4, 4, 1, true>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
+      // 6: two CTAs of 4 + 4 warps at 128 registers; setmaxnreg gives the contraction warps 168, the loader / scatter warps 88
+      case 6: launch_ws<4, 4, 2, true, 168, 88>(idxLex, idxJ, cwP, src, dst, n_groups, n_cells, N, D, sm_count, stream); break;
       default: throw Error(MFG_ERR_UNSUPPORTED, "warp-specialised slab2 kernel: unknown shape");
     }
 }

@@ -13,7 +13,7 @@
 
 namespace mfg {
 
-template <int n, typename Number, int NCW_ = 4, int NLW_ = 2, int MINB_ = 2> struct Slab2WsCfg
+template <int n, typename Number, int NCW_ = 4, int NLW_ = 2, int MINB_ = 2, bool LS_ = false, int RC_ = 0, int RL_ = 0> struct Slab2WsCfg
 {
   static constexpr int WB = (int)sizeof(Number);
   using Tab = Slab2Tab<n, WB>;
@@ -21,6 +21,11 @@ template <int n, typename Number, int NCW_ = 4, int NLW_ = 2, int MINB_ = 2> str
   static constexpr int NCW = NCW_;              // contraction warps per CTA
   static constexpr int NLW = NLW_;              // loader warps per CTA (each serves NCW / NLW contraction warps)
   static constexpr int MINB = MINB_;            // CTAs per SM
+  static constexpr bool LS = LS_;               // the loader warps also run the scatter (N_y^T + red) of the groups they loaded
+  // register reallocation between the warp groups (setmaxnreg, needs NCW = NLW = 4: one warp group each): the contraction
+  // warps grow to RC registers, the loader warps shrink to RL; 0 = every warp keeps the launch allocation
+  static constexpr int RC = RC_, RL = RL_;
+  static_assert(RC_ == 0 || (NCW_ == 4 && NLW_ == 4), "setmaxnreg works on warp groups of 4 warps");
   static_assert(NCW % NLW == 0, "every loader serves the same number of contraction warps");
   static constexpr int THREADS = (NCW + NLW) * 32;
   static constexpr int F = Tab::F;              // elements of one transpose buffer / of the coefficient image
@@ -45,13 +50,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-template <int n, typename Number, int NCW_, int NLW_, int MINB_>
-__global__ void __launch_bounds__((Slab2WsCfg<n, Number, NCW_, NLW_, MINB_>::THREADS), MINB_)
+template <int n, typename Number, int NCW_, int NLW_, int MINB_, bool LS_, int RC_, int RL_>
+__global__ void __launch_bounds__((Slab2WsCfg<n, Number, NCW_, NLW_, MINB_, LS_, RC_, RL_>::THREADS), MINB_)
 laplace_cell_slab2_ws(const uint32_t *__restrict__ idxLex, const uint32_t *__restrict__ idxJ, const Number *__restrict__ cwP,
                       const Number *__restrict__ src, Number *__restrict__ dst, const uint32_t n_groups, const uint32_t n_cells,
                       const __grid_constant__ EoMats<Number, n> em)
 {
-  using Cfg = Slab2WsCfg<n, Number, NCW_, NLW_, MINB_>;
+  using Cfg = Slab2WsCfg<n, Number, NCW_, NLW_, MINB_, LS_, RC_, RL_>;
   using Tab = typename Cfg::Tab;
   constexpr int NS = Cfg::NS, CW = Cfg::CW, NPC = Cfg::NPC, F = Cfg::F;
   constexpr int HC = CW % 2 == 0 ? CW / 2 : CW, HCn = HC * NPC;
@@ -76,6 +81,92 @@ laplace_cell_slab2_ws(const uint32_t *__restrict__ idxLex, const uint32_t *__res
   if (warp >= Cfg::NCW)
     {
       // ------------------------------------------------ loader ------------------------------------------------
+      if (Cfg::RL > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::RL));
+      if (Cfg::RL > 0)
+        {
+          // ---- lean loader / scatter warp (fits the shrunk register allocation): it serves ONE contraction warp and has that
+          //      warp's whole contraction time per group, so the group is handled in two halves of CW / 2 cells ----
+          static_assert(Cfg::RL == 0 || (Cfg::LS && Cfg::NCW == Cfg::NLW && CW % 2 == 0), "lean helper: one warp each, LS mode");
+          constexpr int HCELLS = CW / 2;
+          const int      w = warp - Cfg::NCW;
+          uint64_t      *bars = bars_of(w);
+          Number        *Pb = bufs_of(w) + F;
+          const uint32_t kw = blockIdx.x * Cfg::NCW + w;
+          if (kw >= n_groups) return;
+          const uint32_t n_it = (n_groups - kw + total_cw - 1) / total_cw;
+          auto half_ids = [&](uint32_t g, int h, const uint32_t *base, uint32_t (&id)[HCELLS][n]) {
+#pragma unroll
+            for (int c = 0; c < HCELLS; ++c)
+              {
+                const uint32_t  cell = g * CW + h * HCELLS + c;
+                const bool      ok = pl && cell < n_cells;
+                const uint32_t *row = base + (size_t)cell * NPC + lane;
+#pragma unroll
+                for (int kk = 0; kk < n; ++kk) id[c][kk] = ok ? __ldg(row + NS * kk) : CONSTRAINED_BIT;
+              }
+          };
+          auto tail = [&](uint32_t t) {  // scatter of iteration t from its buffer
+            const uint32_t g = kw + t * total_cw;
+            const Number  *P = Pb + F * (t & 1);
+            bool waited = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              {
+                uint32_t jid[HCELLS][n];
+                half_ids(g, h, idxJ, jid);
+                if (!waited) { mbar_wait(bars + 2 + (t & 1), (t >> 1) & 1); waited = true; }
+#pragma unroll
+                for (int c = 0; c < HCELLS; ++c)
+                  {
+                    const int     cc = h * HCELLS + c;
+                    const Number *qc = P + CK.SL * (cc % HC) + CK.SH * (cc / HC) + (pl ? lane : 0);
+                    Number in[n], out[n];
+#pragma unroll
+                    for (int j = 0; j < n; ++j) in[j] = qc[CK.SJ * j];
+                    eo_apply<n, false>(em.NT, in, out);
+#pragma unroll
+                    for (int j = 0; j < n; ++j)
+                      if (!(jid[c][j] & CONSTRAINED_BIT)) red_add(dst + jid[c][j], out[j]);
+                  }
+              }
+            __syncwarp();
+          };
+          for (uint32_t it = 0; it < n_it; ++it)
+            {
+              const uint32_t g = kw + it * total_cw;
+              Number        *P = Pb + F * (it & 1);
+              uint32_t kid[HCELLS][n];
+              half_ids(g, 0, idxLex, kid);           // in flight during the scatter of the buffer's previous group
+              if (it >= 2) tail(it - 2);
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                {
+                  Number kv[HCELLS][n];
+#pragma unroll
+                  for (int c = 0; c < HCELLS; ++c)
+#pragma unroll
+                    for (int kk = 0; kk < n; ++kk) kv[c][kk] = (kid[c][kk] & CONSTRAINED_BIT) ? Number(0) : __ldg(src + kid[c][kk]);
+                  if (h == 0) half_ids(g, 1, idxLex, kid);   // the second half's index rows travel with the first half's values
+#pragma unroll
+                  for (int c = 0; c < HCELLS; ++c)
+                    {
+                      const int cc = h * HCELLS + c;
+                      Number out[n];
+                      eo_apply<n, false>(em.N, kv[c], out);
+                      if (pl)
+                        {
+                          Number *pc = P + KB.SL * (cc % HC) + KB.SH * (cc / HC) + lane;
+#pragma unroll
+                          for (int kk = 0; kk < n; ++kk) pc[KB.SK * kk] = out[kk];
+                        }
+                    }
+                }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bars + (it & 1));  // full[b]
+            }
+          for (uint32_t t = n_it >= 2 ? n_it - 2 : 0; t < n_it; ++t) tail(t);
+          return;
+        }
       const int l = warp - Cfg::NCW;
       constexpr int SERVE = Cfg::NCW / Cfg::NLW;
       // work items q = 0, 1, ...: iteration it = q / SERVE of contraction warp w = l SERVE + q % SERVE.  The index rows of
@@ -92,11 +183,60 @@ laplace_cell_slab2_ws(const uint32_t *__restrict__ idxLex, const uint32_t *__res
             for (int kk = 0; kk < n; ++kk) id[c][kk] = ok ? __ldg(row + NS * kk) : CONSTRAINED_BIT;
           }
       };
+      // LS: scatter of one group from its buffer (written by the contraction warp in the C -> K' layout), lane t <-> (i, k)
+      auto scatter_tail = [&](int w, uint32_t g, uint32_t it) {
+        const int b = it & 1;
+        uint64_t *bars = bars_of(w);
+        const Number *P = bufs_of(w) + F * (1 + b);
+        uint32_t jid[CW][n];
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+          {
+            const uint32_t  cell = g * CW + c;
+            const bool      ok = pl && cell < n_cells;
+            const uint32_t *row = idxJ + (size_t)cell * NPC + lane;
+#pragma unroll
+            for (int j = 0; j < n; ++j) jid[c][j] = ok ? __ldg(row + NS * j) : CONSTRAINED_BIT;
+          }
+        mbar_wait(bars + 2 + b, (it >> 1) & 1);  // tail[b]: the contraction warp has stored the group's result planes
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+          {
+            const Number *qc = P + CK.SL * (c % HC) + CK.SH * (c / HC) + (pl ? lane : 0);
+            Number in[n], out[n];
+#pragma unroll
+            for (int j = 0; j < n; ++j) in[j] = qc[CK.SJ * j];
+            eo_apply<n, false>(em.NT, in, out);
+#pragma unroll
+            for (int j = 0; j < n; ++j)
+              if (!(jid[c][j] & CONSTRAINED_BIT)) red_add(dst + jid[c][j], out[j]);
+          }
+        __syncwarp();  // every lane has read the buffer: it may be refilled
+      };
       uint32_t kid[CW][n], kidn[CW][n];
       load_ids(item_group(0), kid);
       for (uint32_t q = 0;; ++q)
         {
-          if (item_group(q - q % SERVE) >= n_groups) break;  // no served warp has work in this iteration
+          if (item_group(q - q % SERVE) >= n_groups)
+            {
+              if (Cfg::LS)
+                {
+                  // the last two groups of every served warp are still waiting for their scatter
+                  const uint32_t it_end = q / SERVE;  // first iteration without work for anybody
+#pragma unroll
+                  for (int sw = 0; sw < SERVE; ++sw)
+                    {
+                      const int      w = l * SERVE + sw;
+                      const uint32_t kw = blockIdx.x * Cfg::NCW + w;
+                      if (kw >= n_groups) continue;
+                      const uint32_t n_it = (n_groups - kw + total_cw - 1) / total_cw;  // iterations of warp w
+                      // in the loop the scatter of iteration t ran together with the fill of t + 2 (if that one existed)
+                      for (uint32_t t = n_it >= 2 ? n_it - 2 : 0; t < n_it; ++t) scatter_tail(w, kw + t * total_cw, t);
+                      (void)it_end;
+                    }
+                }
+              break;  // no served warp has work in this iteration
+            }
           const uint32_t g = item_group(q);
           const bool     valid = g < n_groups;
           Number kv[CW][n];
@@ -114,8 +254,14 @@ laplace_cell_slab2_ws(const uint32_t *__restrict__ idxLex, const uint32_t *__res
               const int      w = l * SERVE + q % SERVE, b = it & 1;
               uint64_t      *bars = bars_of(w);
               Number        *P = bufs_of(w) + F * (1 + b);
-              // the buffer must have been released by the contraction warp (its use two iterations ago)
-              mbar_wait(bars + 2 + b, ((it >> 1) & 1) ^ 1);
+              if (Cfg::LS)
+                {
+                  // the buffer still holds the result planes of the group of two iterations ago: scatter them first
+                  if (it >= 2) scatter_tail(w, g - 2 * total_cw, it - 2);
+                }
+              else
+                // the buffer must have been released by the contraction warp (its use two iterations ago)
+                mbar_wait(bars + 2 + b, ((it >> 1) & 1) ^ 1);
 #pragma unroll
               for (int c = 0; c < CW; ++c)
                 {
@@ -140,6 +286,7 @@ laplace_cell_slab2_ws(const uint32_t *__restrict__ idxLex, const uint32_t *__res
     }
 
   // ------------------------------------------------ contraction warp ------------------------------------------------
+  if (Cfg::RC > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::RC));
   uint64_t *bars = bars_of(warp);
   Number   *W = bufs_of(warp), *Q = W + 3 * F;
   const Slab2Lane lm = slab2_lane<n>(lane);
@@ -232,45 +379,63 @@ laplace_cell_slab2_ws(const uint32_t *__restrict__ idxLex, const uint32_t *__res
       __syncwarp();  // P, Q and the coefficient image are consumed
       if (lane == 0)
         {
-          mbar_arrive(bars + 2 + b);  // empty[b]
+          if (!Cfg::LS) mbar_arrive(bars + 2 + b);  // empty[b]
           if (more) bulk_load(W, cwP + (size_t)(k + total_cw) * F, Cfg::CW_BYTES, bars + 4);
         }
-      // the scatter's index rows: issued here (r is dead), their latency hides behind N_x^T N_z^T and the transpose
-      uint32_t jid[CW][n];
-#pragma unroll
-      for (int c = 0; c < CW; ++c)
+      if (Cfg::LS)
         {
-          const uint32_t  cell = g * CW + c;
-          const bool      ok = pl && cell < n_cells;
-          const uint32_t *row = idxJ + (size_t)cell * NPC + lane;
+          // ---- N_x^T, N_z^T, result planes into the group's buffer: the loader warp scatters them (tail[b]) ----
+          slab2_apply<n, 1, n, false>(em.NT, u);
+          slab2_apply<n, n, 1, false>(em.NT, u);
+          if (active)
+            {
 #pragma unroll
-          for (int j = 0; j < n; ++j) jid[c][j] = ok ? __ldg(row + NS * j) : CONSTRAINED_BIT;
+              for (int kk = 0; kk < n; ++kk)
+#pragma unroll
+                for (int i = 0; i < n; ++i) P[bCKw + CK.SI * i + CK.SK * kk] = u[i + n * kk];
+            }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + 2 + b);  // tail[b]
         }
-      slab2_apply<n, 1, n, false>(em.NT, u);
-      slab2_apply<n, n, 1, false>(em.NT, u);
-      if (active)
+      else
         {
+          // the scatter's index rows: issued here (r is dead), their latency hides behind N_x^T N_z^T and the transpose
+          uint32_t jid[CW][n];
 #pragma unroll
-          for (int kk = 0; kk < n; ++kk)
+          for (int c = 0; c < CW; ++c)
+            {
+              const uint32_t  cell = g * CW + c;
+              const bool      ok = pl && cell < n_cells;
+              const uint32_t *row = idxJ + (size_t)cell * NPC + lane;
 #pragma unroll
-            for (int i = 0; i < n; ++i) Q[bCKw + CK.SI * i + CK.SK * kk] = u[i + n * kk];
+              for (int j = 0; j < n; ++j) jid[c][j] = ok ? __ldg(row + NS * j) : CONSTRAINED_BIT;
+            }
+          slab2_apply<n, 1, n, false>(em.NT, u);
+          slab2_apply<n, n, 1, false>(em.NT, u);
+          if (active)
+            {
+#pragma unroll
+              for (int kk = 0; kk < n; ++kk)
+#pragma unroll
+                for (int i = 0; i < n; ++i) Q[bCKw + CK.SI * i + CK.SK * kk] = u[i + n * kk];
+            }
+          __syncwarp();
+          // ---- K': one cell per pass, lane t <-> (i, k), j in registers: N_y^T, red.add ----
+          // (loading and contracting all cells first and issuing the 30 reds back to back measured 4 % slower)
+#pragma unroll
+          for (int c = 0; c < CW; ++c)
+            {
+              const Number *qc = Q + CK.SL * (c % HC) + CK.SH * (c / HC) + (pl ? lane : 0);
+              Number in[n], out[n];
+#pragma unroll
+              for (int j = 0; j < n; ++j) in[j] = qc[CK.SJ * j];
+              eo_apply<n, false>(em.NT, in, out);
+#pragma unroll
+              for (int j = 0; j < n; ++j)
+                if (!(jid[c][j] & CONSTRAINED_BIT)) red_add(dst + jid[c][j], out[j]);
+            }
+          __syncwarp();  // Q is written again by the next group
         }
-      __syncwarp();
-      // ---- K': one cell per pass, lane t <-> (i, k), j in registers: N_y^T, red.add ----
-      // (loading and contracting all cells first and issuing the 30 reds back to back measured 4 % slower)
-#pragma unroll
-      for (int c = 0; c < CW; ++c)
-        {
-          const Number *qc = Q + CK.SL * (c % HC) + CK.SH * (c / HC) + (pl ? lane : 0);
-          Number in[n], out[n];
-#pragma unroll
-          for (int j = 0; j < n; ++j) in[j] = qc[CK.SJ * j];
-          eo_apply<n, false>(em.NT, in, out);
-#pragma unroll
-          for (int j = 0; j < n; ++j)
-            if (!(jid[c][j] & CONSTRAINED_BIT)) red_add(dst + jid[c][j], out[j]);
-        }
-      __syncwarp();  // Q is written again by the next group
     }
 }
 

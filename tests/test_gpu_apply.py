@@ -153,7 +153,7 @@ def test_slab2_face_merge_f64(ctx, p, r, dirs, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("variant", [519, 521, 1030])
+@pytest.mark.parametrize("variant", [519, 521, 1030, 1031, 1034, 1035, 1036])
 @pytest.mark.parametrize("r", [0, 1, 2, 3])
 def test_slab2_plane_layout_variants(ctx, r, variant, dtype):
     """slab2 with the gather / scatter in plane layouts (configurations 512 + c) and its warp-specialised form (1030),
