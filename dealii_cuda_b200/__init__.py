@@ -541,6 +541,14 @@ class LaplaceOperatorGpu:
     def active_variant(self):
         return lib.mfg_laplace_active_variant(self.h)
 
+    def stage_stats(self):
+        """plan of the staged kernel (variant 40) after the first apply; per-group figures are averages over the staged groups"""
+        st = (C.c_uint32 * 8)()
+        check(lib.mfg_laplace_stage_stats(self.h, st))
+        g = max(1, st[1])
+        return dict(groups=st[0], staged=st[1], fallback=st[0] - st[1], patterns=st[2], own_per_group=st[3] / 16.0, halo_per_group=st[4] / 16.0,
+                    plain_per_group=st[5] / 16.0, red_per_group=st[6] / 16.0, smem_wavefronts_per_group=st[7] / 16.0)
+
     def enable_kernel_timing(self, on):
         """on = True / k: bracket every (k-th) cell-kernel launch with CUDA events; False: off."""
         check(lib.mfg_laplace_enable_kernel_timing(self.h, int(on)))

@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" entry points of libmfgpu.so (include/mfgpu.h).
 #include <cstdlib>
 #include "operators.cuh"
+#include "kernels_stage.cuh"
 
 namespace mfg {
 static thread_local std::string g_last_error;
@@ -406,6 +407,48 @@ int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launche
   return guarded([&] { MFG_REQUIRE(op, "null operator"); laplace_kernel_time(op, total_ms, n_launches); });
 }
 int mfg_laplace_active_variant(const mfg_laplace *op) { return op ? laplace_active_variant(op) : 0; }
+int mfg_laplace_stage_stats(const mfg_laplace *op, uint32_t out[8])
+{
+  return guarded([&] { MFG_REQUIRE(op && out, "null argument"); for (int i = 0; i < 8; ++i) out[i] = op->st_stats[i]; });
+}
+struct mfg_stage_plan { mfg::StagePlan plan; mfg::StageGeom geom; };
+int mfg_stage_plan_build(int degree, mfg_dtype dt, uint32_t n_plain, uint32_t n_cells, uint32_t n_dofs, const uint32_t *idx_host, int merge_dirs,
+                         mfg_stage_plan **out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(out && idx_host, "null argument");
+    MFG_REQUIRE(n_plain <= n_cells, "n_plain must not exceed n_cells");
+    std::unique_ptr<mfg_stage_plan> p(new mfg_stage_plan);
+    p->geom = stage_geom(degree, dt);
+    StagePlanIn in;
+    in.n = p->geom.n; in.cw = p->geom.cw; in.hc = p->geom.hc; in.wb = dt == MFG_F64 ? 8 : 4; in.xcap = p->geom.xcap; in.hmax = p->geom.hmax; in.ocap = p->geom.ocap; in.lcap = p->geom.lcap;
+    in.n_plain = n_plain; in.n_cells = n_cells; in.n_dofs = n_dofs; in.idx = idx_host; in.merge_dirs = merge_dirs;
+    build_stage_plan(in, p->plan);
+    *out = p.release();
+  });
+}
+int mfg_stage_plan_info(const mfg_stage_plan *p, uint32_t info[16])
+{
+  return guarded([&] {
+    MFG_REQUIRE(p && info, "null argument");
+    const uint32_t v[16] = {p->plan.n_groups, p->plan.n_patterns, (uint32_t)p->plan.pstride, (uint32_t)p->plan.halo.size(), (uint32_t)p->plan.fallback.size(),
+                            (uint32_t)p->geom.cw, (uint32_t)p->geom.hc, (uint32_t)p->geom.xcap, (uint32_t)p->geom.n, p->plan.n_staged, (uint32_t)p->geom.lcap, (uint32_t)p->geom.ocap,
+                            (uint32_t)(p->plan.rd_wavefronts / std::max<uint32_t>(1, p->plan.n_staged)), (uint32_t)(p->plan.wr_wavefronts / std::max<uint32_t>(1, p->plan.n_staged)),
+                            (uint32_t)(p->plan.cp_wavefronts / std::max<uint32_t>(1, p->plan.n_staged)), 0};
+    for (int i = 0; i < 16; ++i) info[i] = v[i];
+  });
+}
+int mfg_stage_plan_get(const mfg_stage_plan *p, uint32_t *gdesc, uint32_t *halo, uint16_t *ptab, uint32_t *fallback)
+{
+  return guarded([&] {
+    MFG_REQUIRE(p, "null argument");
+    if (gdesc) std::copy(p->plan.gdesc.begin(), p->plan.gdesc.end(), gdesc);
+    if (halo) std::copy(p->plan.halo.begin(), p->plan.halo.end(), halo);
+    if (ptab) std::copy(p->plan.ptab.begin(), p->plan.ptab.end(), ptab);
+    if (fallback) std::copy(p->plan.fallback.begin(), p->plan.fallback.end(), fallback);
+  });
+}
+int mfg_stage_plan_destroy(mfg_stage_plan *p) { return guarded([&] { delete p; }); }
 int mfg_laplace_launches_per_vmult(const mfg_laplace *op) { return op ? laplace_launches_per_vmult(op) : 0; }
 int mfg_laplace_cell_launches_per_vmult(const mfg_laplace *op) { return op ? (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0) : 0; }
 int mfg_laplace_bmop(mfg_laplace *op, mfg_vec *dst, mfg_vec *src, int k, double init, float *elapsed_ms)

@@ -29,6 +29,7 @@
 //   gather -> A: N_y N_z -> B: N_x, quadrature phases x and y -> C: quadrature phase z, sum, N_x^T N_z^T
 //          -> A: N_y^T -> red.add
 #pragma once
+#include <cmath>
 #include "kernels_v0.cuh"
 
 namespace mfg {
@@ -100,6 +101,37 @@ template <typename Number, int n> struct EoTab
   Number Co[h * m];
 };
 template <typename Number, int n> struct EoMats { EoTab<Number, n> N, NT, D, DT; };
+
+// even-odd tables of M (TR: of its transpose); sign = +1 centro-symmetric, -1 centro-antisymmetric
+template <typename Number, int n> inline void make_eo(const double *M, bool TR, int sign, EoTab<Number, n> &T)
+{
+  constexpr int h = n / 2, m = (n + 1) / 2;
+  auto at = [&](int k, int q) { return TR ? M[q * n + k] : M[k * n + q]; };
+  double scale = 0;
+  for (int i = 0; i < n * n; ++i) scale = std::max(scale, std::fabs(M[i]));
+  for (int k = 0; k < n; ++k)
+    for (int q = 0; q < n; ++q)
+      if (std::fabs(at(k, q) - sign * at(n - 1 - k, n - 1 - q)) > 1e-12 * scale)
+        throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: 1-D shape matrices are not centro-(anti)symmetric");
+  for (int i = 0; i < (h + 1) * m; ++i) T.Ce[i] = 0;
+  for (int i = 0; i < h * m; ++i) T.Co[i] = 0;
+  for (int k = 0; k < h; ++k)
+    for (int q = 0; q < m; ++q)
+      {
+        T.Ce[k * m + q] = (Number)(0.5 * (at(k, q) + at(n - 1 - k, q)));
+        T.Co[k * m + q] = (Number)(0.5 * (at(k, q) - at(n - 1 - k, q)));
+      }
+  if (n & 1)
+    for (int q = 0; q < m; ++q) T.Ce[h * m + q] = (Number)at(h, q);
+}
+
+template <typename Number, int n> inline void make_eo_tables(const double *N, const double *D, EoMats<Number, n> &em)
+{
+  make_eo<Number, n>(N, false, +1, em.N);
+  make_eo<Number, n>(N, true, +1, em.NT);
+  make_eo<Number, n>(D, false, -1, em.D);
+  make_eo<Number, n>(D, true, -1, em.DT);
+}
 
 // out = M^T-contraction of one line.  ANTI = false: centro-symmetric M (interpolation), true: centro-antisymmetric
 // (collocation derivative)

@@ -16,29 +16,6 @@ typedef double inst_number;
 typedef float inst_number;
 #endif
 
-// even-odd tables of M (TR: of its transpose); sign = +1 centro-symmetric, -1 centro-antisymmetric
-template <typename Number, int n> static void make_eo(const double *M, bool TR, int sign, EoTab<Number, n> &T)
-{
-  constexpr int h = n / 2, m = (n + 1) / 2;
-  auto at = [&](int k, int q) { return TR ? M[q * n + k] : M[k * n + q]; };
-  double scale = 0;
-  for (int i = 0; i < n * n; ++i) scale = std::max(scale, std::fabs(M[i]));
-  for (int k = 0; k < n; ++k)
-    for (int q = 0; q < n; ++q)
-      if (std::fabs(at(k, q) - sign * at(n - 1 - k, n - 1 - q)) > 1e-12 * scale)
-        throw Error(MFG_ERR_UNSUPPORTED, "slab2 kernel: 1-D shape matrices are not centro-(anti)symmetric");
-  for (int i = 0; i < (h + 1) * m; ++i) T.Ce[i] = 0;
-  for (int i = 0; i < h * m; ++i) T.Co[i] = 0;
-  for (int k = 0; k < h; ++k)
-    for (int q = 0; q < m; ++q)
-      {
-        T.Ce[k * m + q] = (Number)(0.5 * (at(k, q) + at(n - 1 - k, q)));
-        T.Co[k * m + q] = (Number)(0.5 * (at(k, q) - at(n - 1 - k, q)));
-      }
-  if (n & 1)
-    for (int q = 0; q < m; ++q) T.Ce[h * m + q] = (Number)at(h, q);
-}
-
 template <int n, typename Number, int CFG>
 static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
                      const double *D, int sm_count, cudaStream_t stream, cudaTextureObject_t tex, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait, const uint32_t *idxLex, const uint32_t *idxJ, uint32_t n_cells)
@@ -46,10 +23,7 @@ static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src,
   using Cfg = Slab2Cfg<n, Number, CFG>;
   if (n_groups == 0) return;
   EoMats<Number, n> em;
-  make_eo<Number, n>(N, false, +1, em.N);
-  make_eo<Number, n>(N, true, +1, em.NT);
-  make_eo<Number, n>(D, false, -1, em.D);
-  make_eo<Number, n>(D, true, -1, em.DT);
+  make_eo_tables<Number, n>(N, D, em);
   auto       kern          = laplace_cell_slab2<n, Number, CFG>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0)
@@ -155,10 +129,7 @@ static void launch_ws(const uint32_t *idxLex, const uint32_t *idxJ, const inst_n
   using Cfg = Slab2WsCfg<n, inst_number, NCW, NLW, MINB, LS, RC, RL>;
   if (n_groups == 0) return;
   EoMats<inst_number, n> em;
-  make_eo<inst_number, n>(N, false, +1, em.N);
-  make_eo<inst_number, n>(N, true, +1, em.NT);
-  make_eo<inst_number, n>(D, false, -1, em.D);
-  make_eo<inst_number, n>(D, true, -1, em.DT);
+  make_eo_tables<inst_number, n>(N, D, em);
   auto       kern = laplace_cell_slab2_ws<n, inst_number, NCW, NLW, MINB, LS, RC, RL>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0)

@@ -5,6 +5,7 @@
 #include "kernels_slab.cuh"
 #include "kernels_slab2_ws.cuh"
 #include "kernels_general.cuh"
+#include "kernels_stage.cuh"
 #include "operators.cuh"
 
 namespace mfg {
@@ -774,23 +775,64 @@ static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
     }
 }
 
+// grouped kernels (one warp per group of 32 / n cells, work list, programmatic dependent launch): slab2 and staged
+static inline bool grouped_variant(int v) { return v == 6 || v == 40; }
+
+// plan of the staged kernel (stage_plan.cu), built once per operator from the index array
+static void laplace_prepare_stage(mfg_laplace *op, uint32_t n_plain)
+{
+  laplace_prepare_slab2(op, n_plain);  // coefficient images (shared layout), index rows for the groups the plan leaves over
+  if (op->st_built) return;
+  const mfg_mf   *mf = op->mf;
+  const StageGeom sg = stage_geom(mf->p, mf->dt);
+  cudaStream_t    s = op->ctx->stream;
+  std::vector<uint32_t> idx((size_t)mf->n_cells * mf->npc);
+  mf->idx.download(idx.data(), s);
+  StagePlanIn in;
+  in.n = sg.n; in.cw = sg.cw; in.hc = sg.hc; in.wb = mf->dt == MFG_F64 ? 8 : 4; in.xcap = sg.xcap; in.hmax = sg.hmax; in.ocap = sg.ocap; in.lcap = sg.lcap;
+  in.n_plain = n_plain; in.n_cells = mf->n_cells; in.n_dofs = mf->n_dofs; in.idx = idx.data();
+  in.merge_dirs = getenv("MFG_STAGE_MERGE") ? atoi(getenv("MFG_STAGE_MERGE")) & 7 : 7;
+  StagePlan plan;
+  build_stage_plan(in, plan);
+  op->st_gdesc.upload(plan.gdesc.data(), plan.gdesc.size(), s);
+  op->st_halo.upload(plan.halo.data(), plan.halo.size(), s);
+  op->st_ptab.upload(plan.ptab.data(), plan.ptab.size(), s);
+  op->st_fallback.upload(plan.fallback.data(), plan.fallback.size(), s);
+  op->st_fb_iface = 0;
+  op->st_pstride = plan.pstride;
+  const uint64_t ns = std::max<uint32_t>(1, plan.n_staged);
+  const uint32_t st[8] = {plan.n_groups, plan.n_staged, plan.n_patterns, (uint32_t)(16 * plan.n_own / ns), (uint32_t)(16 * plan.n_halo / ns),
+                          (uint32_t)(16 * plan.n_plain_dofs / ns), (uint32_t)(16 * plan.n_red_dofs / ns),
+                          (uint32_t)(16 * (plan.rd_wavefronts + plan.wr_wavefronts + 2 * plan.cp_wavefronts) / ns)};
+  std::copy(st, st + 8, op->st_stats);
+  op->st_built = true;
+}
+
 // kernels of this library one vmult enqueues (the cudaMemsetAsync of dst is not counted)
 int laplace_launches_per_vmult(const mfg_laplace *op)
 {
   // with the slab2 kernel the zero pass is a kernel of this library too (zero_fill_pdl)
-  const bool zero_kernel = !(std::getenv("MFG_PDL_FILL") && std::atoi(std::getenv("MFG_PDL_FILL")) == 0) && laplace_active_variant(op) == 6 &&
-                           op->mf->hn_mask.n == 0;
-  return (op->ch->n() ? 1 : 0) + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0) + (zero_kernel ? 1 : 0);
+  const int  v = laplace_active_variant(op);
+  const bool zero_kernel = !(std::getenv("MFG_PDL_FILL") && std::atoi(std::getenv("MFG_PDL_FILL")) == 0) && grouped_variant(v) && op->mf->hn_mask.n == 0;
+  return (op->ch->n() ? 1 : 0) + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0) + (zero_kernel ? 1 : 0) +
+         (v == 40 && op->st_built && op->st_fallback.n ? 1 : 0);
 }
 
 // kernel variants: 1 = column kernel (kernels_v0.cuh, every dim/degree/dtype/scatter),
 //                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter),
-//                  6 = slab2 kernel (kernels_slab2.cuh: 3D, degree <= 5, atomic scatter). 0 = auto.
+//                  6 = slab2 kernel (kernels_slab2.cuh: 3D, degree <= 5, atomic scatter),
+//                  40 = staged kernel (kernels_stage.cuh: 3D, degree 2..5, atomic scatter). 0 = auto.
 int laplace_active_variant(const mfg_laplace *op)
 {
   const mfg_mf *mf = op->mf;
   const bool slab_ok = slab_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
   const bool slab2_ok = slab2_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
+  const bool stage_ok = stage_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC && !mf->general;
+  if (op->variant == 40)
+    {
+      if (!stage_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 40 (staged kernel) needs dim 3, degree 2..5, atomic scatter, uniform geometry");
+      return 40;
+    }
   if (op->variant >= 6 && !slab2_ok) throw Error(MFG_ERR_UNSUPPORTED, "variants 6..9 (slab2 kernel) need dim 3, degree <= 5, atomic scatter");
   if (op->variant >= 2 && op->variant < 6 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3/4 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
   if (mf->general)
@@ -801,7 +843,8 @@ int laplace_active_variant(const mfg_laplace *op)
   if (op->variant == 1) return 1;
   if (op->variant >= 6) return 6;
   if (op->variant >= 2) return 2;
-  // auto: measured on B200 (profiles/r01_sweep_slab2.jsonl): slab2 wins for degree 1, 3, 4, 5, the first slab kernel for degree 2
+  // auto: the staged kernel where it exists (3D degree 2..5), slab2 for 3D degree 1
+  if (stage_ok) return 40;
   if (slab2_ok && mf->p != 2) return 6;
   return slab_ok ? 2 : 1;
 }
@@ -827,11 +870,12 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
 {
   const mfg_mf *mf = op->mf;
   cudaStream_t  s  = s_other ? s_other : op->ctx->stream;
-  const bool split = part >= 1 && op->glist.n != 0 && laplace_active_variant(op) == 6;
+  const int  av = laplace_active_variant(op);
+  const bool split = part >= 1 && op->glist.n != 0 && grouped_variant(av);
   if (part == 1 && !split) return;
   // whole apply with the slab2 kernel: zero kernel -> cell kernel as its programmatic dependent -> constrained rows
   static const bool pdl_fill_on = !(std::getenv("MFG_PDL_FILL") && std::atoi(std::getenv("MFG_PDL_FILL")) == 0);
-  const bool pdl_fill = pdl_fill_on && part == -1 && !add && laplace_active_variant(op) == 6 && mf->hn_mask.n == 0 &&
+  const bool pdl_fill = pdl_fill_on && part == -1 && !add && grouped_variant(av) && mf->hn_mask.n == 0 &&
                         (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
   if (pdl_fill)
     {
@@ -889,7 +933,24 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       launch_laplace_v0_dim<3, Number>(mf->p, atomic, mf->idx.p, (const Number *)op->cw.p, src, dst, c0, c1, mf->fe.val.data(),
                                        mf->fe.colloc.data(), s, mask, mf->fe.hanging.data());
   };
-  if (laplace_active_variant(op) == 6)
+  if (av == 40)
+    {
+      // staged kernel; the groups its plan leaves over run on the slab2 kernel (work list) right behind it
+      laplace_prepare_stage(op, n_plain);
+      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
+      const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
+      const uint32_t *fl = op->st_fallback.p + (split && part == 2 ? op->st_fb_iface : 0);
+      const uint32_t  nf = (uint32_t)(!split ? op->st_fallback.n : part == 2 ? op->st_fallback.n - op->st_fb_iface : op->st_fb_iface);
+      time_begin();
+      launch_laplace_stage<Number>(mf->p, op->st_gdesc.p, op->st_halo.p, op->st_ptab.p, op->st_pstride, (const Number *)op->cwP.p, src, dst, ng,
+                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, gl, (split && part == 2) || pdl_fill, pdl_fill,
+                                   op->ctx->device);
+      if (nf)
+        launch_laplace_slab2<Number>(mf->p, 3, op->idxP.p, (const Number *)op->cwP.p, src, dst, nf, mf->fe.val.data(), mf->fe.colloc.data(),
+                                     op->ctx->sm_count, s, 0, op->mergeP.p, fl, false, false, mf->idx.p, op->idxJ.p, n_plain);
+      time_end();
+    }
+  else if (av == 6)
     {
       laplace_prepare_slab2(op, n_plain);
       // auto = configuration 3 (3 blocks x 4 warps, 168 registers, one transpose buffer per warp, LSU gather)
@@ -931,7 +992,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       time_end();
         }
     }
-  else if (laplace_active_variant(op) == 2)
+  else if (av == 2)
     {
       // variant 3 = 2 blocks x 4 warps per SM with up to 255 registers (no spills); measured faster than 3 x 4 x 168
       // for degree 4 in FP64 (profiles/r01_*), which is therefore what "auto" picks there
@@ -1019,10 +1080,14 @@ uint32_t laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, 
   const mfg_mf *mf = op->mf;
   op->glist.release();
   op->n_iface_groups = 0;
-  if (laplace_active_variant(op) != 6 || n == 0) return 0;
+  const int av = laplace_active_variant(op);
+  if (!grouped_variant(av) || n == 0) return 0;
+  // cells with hanging nodes always run in part 2 and could add into an exchanged DoF while it is packed
+  if (mf->hn_mask.n != 0) throw Error(MFG_ERR_UNSUPPORTED, "interface split is not available for meshes with hanging nodes");
   cudaStream_t   s = op->ctx->stream;
   const uint32_t n_plain = mf->hn_mask.n ? mf->n_plain : mf->n_cells;
-  laplace_prepare_slab2(op, n_plain);
+  if (av == 40) laplace_prepare_stage(op, n_plain);
+  else laplace_prepare_slab2(op, n_plain);
   const uint32_t ng = op->slab2_groups;
   if (ng == 0) return 0;
   for (size_t i = 0; i < n; ++i) MFG_REQUIRE(dofs_host[i] < mf->n_dofs, "interface DoF index out of range");
@@ -1043,6 +1108,16 @@ uint32_t laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, 
   op->n_iface_groups = (uint32_t)order.size();
   for (uint32_t g = 0; g < ng; ++g) if (!gf[g]) order.push_back(g);
   op->glist.upload(order.data(), ng, s);
+  if (av == 40 && op->st_fallback.n)
+    {
+      // left-over groups of the staged plan in the same two parts
+      std::vector<uint32_t> fb(op->st_fallback.n), fo;
+      op->st_fallback.download(fb.data(), s);
+      for (uint32_t g : fb) if (gf[g]) fo.push_back(g);
+      op->st_fb_iface = (uint32_t)fo.size();
+      for (uint32_t g : fb) if (!gf[g]) fo.push_back(g);
+      op->st_fallback.upload(fo.data(), fo.size(), s);
+    }
   return op->n_iface_groups;
 }
 

@@ -67,6 +67,14 @@ struct mfg_laplace
   uint32_t              n_iface_groups = 0;
   uint32_t              slab2_groups = 0;
   bool                  cwP_valid = false;
+  // staged kernel (kernels_stage.cuh): plan built on first use from idx (stage_plan.cu)
+  mfg::DevBuf<uint32_t> st_gdesc, st_halo;   // [n_groups][4] ; halo DoF lists
+  mfg::DevBuf<uint16_t> st_ptab;             // deduplicated position tables
+  mfg::DevBuf<uint32_t> st_fallback;         // groups the plan leaves to the slab2 kernel (interface groups first)
+  uint32_t              st_fb_iface = 0;     // how many of them touch interface DoFs
+  int                   st_pstride = 0;
+  bool                  st_built = false;
+  uint32_t              st_stats[8] = {0};   // groups, staged, patterns, own, halo, plain, red, smem wavefronts (per staged group, x 16)
   // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer
   struct SrcTex { const void *p; size_t n; cudaTextureObject_t tex; };
   std::vector<SrcTex>   src_tex;

@@ -242,6 +242,22 @@ int mfg_laplace_cell_launches_per_vmult(const mfg_laplace *op); /* cell-kernel l
 int mfg_laplace_enable_kernel_timing(mfg_laplace *op, int on);
 int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launches);
 int mfg_laplace_active_variant(const mfg_laplace *op);
+/* staged cell kernel (variant 40): numbers of its plan after the first apply: out[0..7] = groups, staged groups, patterns,
+ * and per staged group x 16: own DoFs, halo entries, plain-stored DoFs, red.add DoFs, shared-memory wavefronts of the
+ * staged reads + writes */
+int mfg_laplace_stage_stats(const mfg_laplace *op, uint32_t out[8]);
+/* The plan of the staged kernel for a host index array (pure host code, no device needed): what the kernel's copy lists,
+ * position tables and merge masks are for [n_cells][(degree+1)^3] lexicographic indices with bit 31 = constrained DoF.
+ * Used by the CPU tests, which replay the kernel's data movement with numpy and compare with a plain gather / scatter.
+ * info[0..14] = groups, patterns, pattern stride (uint16), halo entries, fallback groups, cells per group, cells per
+ * half warp, staging slots, points per direction, staged groups, load-list capacity, own-range capacity, and per staged
+ * group the shared-memory wavefronts of the slab reads, of the staged writes and of one pass over the load list */
+typedef struct mfg_stage_plan mfg_stage_plan;
+int mfg_stage_plan_build(int degree, mfg_dtype dt, uint32_t n_plain, uint32_t n_cells, uint32_t n_dofs, const uint32_t *idx_host,
+                         int merge_dirs, mfg_stage_plan **out);
+int mfg_stage_plan_info(const mfg_stage_plan *p, uint32_t info[16]);
+int mfg_stage_plan_get(const mfg_stage_plan *p, uint32_t *gdesc, uint32_t *halo, uint16_t *ptab, uint32_t *fallback);
+int mfg_stage_plan_destroy(mfg_stage_plan *p);
 /* bmop loop (bmop.cu:135-153): dst=init; k times {swap; vmult}; result left in *dst.
  * Returns device milliseconds measured with CUDA events on the context stream. */
 int mfg_laplace_bmop(mfg_laplace *op, mfg_vec *dst, mfg_vec *src, int k, double init, float *elapsed_ms);

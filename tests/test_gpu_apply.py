@@ -188,13 +188,62 @@ def test_slab2_plane_layout_variants(ctx, r, variant, dtype):
             op3.vmult(a, b)
 
 
+STAGE_CASES = [(2, 2), (2, 3), (3, 2), (3, 3), (4, 0), (4, 1), (4, 2), (4, 3), (5, 1), (5, 2)]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("p,r", STAGE_CASES)
+def test_staged_kernel_matches_oracle(ctx, p, r, dtype):
+    """variant 40 = staged kernel (kernels_stage.cuh: asynchronous staged gather, register face merges, staged scatter with
+    plain stores for group-interior DoFs), the default for 3D degree 2..5: vmult into a dirty vector (the plain stores and
+    the zero pass must cover every DoF), vmult_add, and agreement with the slab2 kernel it shares its contractions with"""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, p, r)
+    m = mf.HyperCubeMesh(ctx, 3, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(m)
+    assert op.active_variant() == 40
+    u = sm64(3, o.n_dofs).astype(dtype)
+    src = mf.GpuVector.from_numpy(ctx, u)
+    dst = mf.GpuVector(ctx, o.n_dofs, dtype)
+    dst.fill(-7.5)
+    op.vmult(dst, src)
+    want = o.vmult(u.astype(np.float64))
+    assert rel_err(dst.toVector(), want) <= TOL[dtype]
+    assert np.array_equal(src.toVector(), u)  # src untouched
+    op.vmult_add(dst, src)
+    assert rel_err(dst.toVector(), 2.0 * want) <= 2 * TOL[dtype]
+    st = op.stage_stats()
+    assert st["groups"] == (o.n_cells + 32 // (p + 1) - 1) // (32 // (p + 1)) and st["staged"] + st["fallback"] == st["groups"]
+    op6 = mf.LaplaceOperatorGpu(ctx, dtype)
+    op6.reinit(m)
+    op6.set_variant(9)
+    d6 = mf.GpuVector(ctx, o.n_dofs, dtype)
+    op6.vmult(d6, src)
+    assert rel_err(dst.toVector(), 2.0 * d6.toVector().astype(np.float64)) <= (1e-14 if dtype == np.float64 else 1e-5)
+
+
+def test_staged_kernel_repeated_applies_and_box(ctx):
+    """the bmop loop (bmop.cu:135-153) on a non-cubic box whose last group is partial, against the oracle"""
+    import dealii_cuda_b200 as mf
+    box = dict(log2_cells=(2, 1, 3), origin=(-1.0, -0.5, 0.0), h=0.25)
+    o = OracleMesh(3, 4, box=box)
+    m = mf.HyperCubeMesh(ctx, 3, 4, box=box)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(m)
+    assert op.active_variant() == 40
+    a, b = mf.GpuVector(ctx, o.n_dofs), mf.GpuVector(ctx, o.n_dofs)
+    op.bmop(a, b, 3, 0.1)
+    assert rel_err(a.toVector(), o.bmop(3, 0.1)) <= 1e-12
+
+
 def test_slab_variant_rejected_where_unsupported(ctx):
     import dealii_cuda_b200 as mf
-    for dim, p, coloring, auto in [(2, 4, False, 1), (3, 5, False, 6), (3, 4, True, 1), (3, 6, False, 1)]:
+    for dim, p, coloring, auto in [(2, 4, False, 1), (3, 5, False, 40), (3, 1, False, 6), (3, 4, True, 1), (3, 6, False, 1)]:
         m = mf.HyperCubeMesh(ctx, dim, p, 1)
         op = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=coloring)
         op.reinit(m)
-        assert op.active_variant() == auto  # auto: slab2 for 3D degree 1, 3, 4, 5 with atomics, slab for degree 2
+        assert op.active_variant() == auto  # auto: staged kernel for 3D degree 2..5 with atomics, slab2 for degree 1
         op.set_variant(2)
         a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs)
         with pytest.raises(mf.MfgError):
@@ -410,6 +459,23 @@ def test_full_size_r5_against_threaded_oracle(ctx, coloring):
     op.vmult(dst, src)
     want = o.vmult(u, threaded=True)
     assert rel_err(dst.toVector(), want) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_full_size_r6_against_threaded_oracle(ctx, dtype):
+    """the headline configuration itself (3D Q4 r=6, 16,974,593 DoFs) against the oracle, default kernel"""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, 4, 6)
+    m = mf.HyperCubeMesh(ctx, 3, 4, 6)
+    assert m.n_dofs == o.n_dofs == 16974593
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(m)
+    u = sm64(1, o.n_dofs).astype(dtype)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs, dtype)
+    op.vmult(dst, src)
+    want = o.vmult(u.astype(np.float64), threaded=True)
+    assert rel_err(dst.toVector(), want) <= TOL[dtype]
+    assert max_rel_err(dst.toVector(), want) <= 10 * TOL[dtype]
 
 
 def test_full_size_r6_properties(ctx):
