@@ -421,7 +421,7 @@ int mfg_stage_plan_build(int degree, mfg_dtype dt, uint32_t n_plain, uint32_t n_
     std::unique_ptr<mfg_stage_plan> p(new mfg_stage_plan);
     p->geom = stage_geom(degree, dt);
     StagePlanIn in;
-    in.n = p->geom.n; in.cw = p->geom.cw; in.hc = p->geom.hc; in.wb = dt == MFG_F64 ? 8 : 4; in.xcap = p->geom.xcap; in.hmax = p->geom.hmax; in.ocap = p->geom.ocap; in.lcap = p->geom.lcap;
+    in.n = p->geom.n; in.cw = p->geom.cw; in.hc = p->geom.hc; in.wb = dt == MFG_F64 ? 8 : 4; in.xcap = p->geom.xcap; in.hmax = p->geom.hmax; in.ocap = p->geom.ocap; in.lcap = p->geom.lcap; in.nclass = p->geom.nclass;
     in.n_plain = n_plain; in.n_cells = n_cells; in.n_dofs = n_dofs; in.idx = idx_host; in.merge_dirs = merge_dirs;
     build_stage_plan(in, p->plan);
     *out = p.release();

@@ -789,7 +789,7 @@ static void laplace_prepare_stage(mfg_laplace *op, uint32_t n_plain)
   std::vector<uint32_t> idx((size_t)mf->n_cells * mf->npc);
   mf->idx.download(idx.data(), s);
   StagePlanIn in;
-  in.n = sg.n; in.cw = sg.cw; in.hc = sg.hc; in.wb = mf->dt == MFG_F64 ? 8 : 4; in.xcap = sg.xcap; in.hmax = sg.hmax; in.ocap = sg.ocap; in.lcap = sg.lcap;
+  in.n = sg.n; in.cw = sg.cw; in.hc = sg.hc; in.wb = mf->dt == MFG_F64 ? 8 : 4; in.xcap = sg.xcap; in.hmax = sg.hmax; in.ocap = sg.ocap; in.lcap = sg.lcap; in.nclass = sg.nclass;
   in.n_plain = n_plain; in.n_cells = mf->n_cells; in.n_dofs = mf->n_dofs; in.idx = idx.data();
   in.merge_dirs = getenv("MFG_STAGE_MERGE") ? atoi(getenv("MFG_STAGE_MERGE")) & 7 : 7;
   StagePlan plan;
@@ -800,6 +800,8 @@ static void laplace_prepare_stage(mfg_laplace *op, uint32_t n_plain)
   op->st_fallback.upload(plan.fallback.data(), plan.fallback.size(), s);
   op->st_fb_iface = 0;
   op->st_pstride = plan.pstride;
+  MFG_REQUIRE(plan.pstride == sg.pstride, "stage plan: table layout differs from the kernel's");
+  std::copy(plan.class_pat, plan.class_pat + 8, op->st_class_pat);
   const uint64_t ns = std::max<uint32_t>(1, plan.n_staged);
   const uint32_t st[8] = {plan.n_groups, plan.n_staged, plan.n_patterns, (uint32_t)(16 * plan.n_own / ns), (uint32_t)(16 * plan.n_halo / ns),
                           (uint32_t)(16 * plan.n_plain_dofs / ns), (uint32_t)(16 * plan.n_red_dofs / ns),
@@ -937,14 +939,14 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
     {
       // staged kernel; the groups its plan leaves over run on the slab2 kernel (work list) right behind it
       laplace_prepare_stage(op, n_plain);
-      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
-      const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
       const uint32_t *fl = op->st_fallback.p + (split && part == 2 ? op->st_fb_iface : 0);
       const uint32_t  nf = (uint32_t)(!split ? op->st_fallback.n : part == 2 ? op->st_fallback.n - op->st_fb_iface : op->st_fb_iface);
+      // whole apply: every group; multi-GPU: the interface groups from the work list, then all groups without the interface flag
+      const int mode = !split ? 0 : part == 1 ? 1 : 2;
       time_begin();
-      launch_laplace_stage<Number>(mf->p, op->st_gdesc.p, op->st_halo.p, op->st_ptab.p, op->st_pstride, (const Number *)op->cwP.p, src, dst, ng,
-                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, gl, (split && part == 2) || pdl_fill, pdl_fill,
-                                   op->ctx->device);
+      launch_laplace_stage<Number>(mf->p, op->st_gdesc.p, op->st_halo.p, op->st_ptab.p, op->st_pstride, op->st_class_pat, (const Number *)op->cwP.p, src, dst,
+                                   op->slab2_groups, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, op->glist.p, op->n_iface_groups, mode,
+                                   (split && part == 2) || pdl_fill, pdl_fill, add, op->ctx->device);
       if (nf)
         launch_laplace_slab2<Number>(mf->p, 3, op->idxP.p, (const Number *)op->cwP.p, src, dst, nf, mf->fe.val.data(), mf->fe.colloc.data(),
                                      op->ctx->sm_count, s, 0, op->mergeP.p, fl, false, false, mf->idx.p, op->idxJ.p, n_plain);
@@ -1072,6 +1074,13 @@ __global__ void mark_interface_groups(const uint32_t *__restrict__ idxP, size_t 
   if (!(id & CONSTRAINED_BIT) && flag[id]) gflag[t / per_group] = 1;
 }
 
+// staged kernel: bit 31 of the fourth descriptor word = the group contributes to an exchanged DoF
+__global__ void set_interface_bits(uint32_t *__restrict__ gdesc, const uint8_t *__restrict__ gflag, uint32_t ng)
+{
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ng) gdesc[4 * (size_t)g + 3] = (gdesc[4 * (size_t)g + 3] & 0x7fffffffu) | (gflag && gflag[g] ? 0x80000000u : 0u);
+}
+
 // Multi-GPU: the DoFs whose partial sums are exchanged after the cell loop.  Splits the cell groups of the
 // slab2 kernel into those that contribute to such a DoF (launched first) and the rest (launched while the exchange
 // runs); returns the number of groups in the first set, 0 if the active kernel has no work list.
@@ -1080,6 +1089,12 @@ uint32_t laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, 
   const mfg_mf *mf = op->mf;
   op->glist.release();
   op->n_iface_groups = 0;
+  op->st_fb_iface = 0;
+  if (op->st_built && op->slab2_groups)
+    {
+      set_interface_bits<<<nblk(op->slab2_groups), 256, 0, op->ctx->stream>>>(op->st_gdesc.p, nullptr, op->slab2_groups);
+      MFG_CUDA_LAST();
+    }
   const int av = laplace_active_variant(op);
   if (!grouped_variant(av) || n == 0) return 0;
   // cells with hanging nodes always run in part 2 and could add into an exchanged DoF while it is packed
@@ -1108,6 +1123,12 @@ uint32_t laplace_set_interface_dofs(mfg_laplace *op, const uint32_t *dofs_host, 
   op->n_iface_groups = (uint32_t)order.size();
   for (uint32_t g = 0; g < ng; ++g) if (!gf[g]) order.push_back(g);
   op->glist.upload(order.data(), ng, s);
+  if (av == 40)
+    {
+      set_interface_bits<<<nblk(ng), 256, 0, s>>>(op->st_gdesc.p, gflag.p, ng);
+      MFG_CUDA_LAST();
+      MFG_CUDA(cudaStreamSynchronize(s));
+    }
   if (av == 40 && op->st_fallback.n)
     {
       // left-over groups of the staged plan in the same two parts

@@ -73,6 +73,7 @@ struct mfg_laplace
   mfg::DevBuf<uint32_t> st_fallback;         // groups the plan leaves to the slab2 kernel (interface groups first)
   uint32_t              st_fb_iface = 0;     // how many of them touch interface DoFs
   int                   st_pstride = 0;
+  uint32_t              st_class_pat[8] = {0};  // tables the kernel keeps in shared memory, per class of groups
   bool                  st_built = false;
   uint32_t              st_stats[8] = {0};   // groups, staged, patterns, own, halo, plain, red, smem wavefronts (per staged group, x 16)
   // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer

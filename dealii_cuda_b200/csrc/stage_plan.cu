@@ -404,8 +404,9 @@ void build_stage_plan(const StagePlanIn &in, StagePlan &out)
 {
   MFG_REQUIRE(in.n >= 2 && in.cw >= 1 && in.cw * in.n <= 32, "stage plan: bad group shape");
   MFG_REQUIRE(in.ocap % 32 == 0 && in.ocap >= in.cw * in.n * in.n * in.n && in.lcap == in.ocap + in.hmax && in.lcap < 0x7fff, "stage plan: bad list capacities");
-  MFG_REQUIRE(in.xcap >= 64 && in.xcap < 0x4000 && in.xcap % 2 == 0, "stage plan: bad staging capacity");
+  MFG_REQUIRE(in.xcap >= 64 && in.xcap * in.wb <= 0x8000 && in.xcap % 2 == 0, "stage plan: bad staging capacity");
   out = StagePlan();
+  for (int a = 0; a < 8; ++a) out.class_pat[a] = STAGE_NOPAT;
   Builder B(in);
   const uint32_t ng = (in.n_plain + in.cw - 1) / in.cw;
   out.n_groups = ng;
@@ -477,6 +478,23 @@ void build_stage_plan(const StagePlanIn &in, StagePlan &out)
       out.cp_wavefronts += p.cp;
     }
   }
+  // most frequent pattern of every class of groups: the kernel keeps its tables in shared memory
+  {
+    const int nc = std::max(1, std::min(in.nclass, 8));
+    for (int a = 0; a < 8; ++a) out.class_pat[a] = STAGE_NOPAT;
+    std::vector<std::vector<uint32_t>> hist(nc, std::vector<uint32_t>(pats.size(), 0));
+    for (uint32_t g = 0; g < ng; ++g)
+      {
+        const uint32_t pat = out.gdesc[(size_t)g * 4 + 2] >> 16;
+        if (pat != STAGE_NOPAT) ++hist[g % nc][pat];
+      }
+    for (int a = 0; a < nc; ++a)
+      {
+        uint32_t best = 0;
+        for (size_t k = 0; k < pats.size(); ++k)
+          if (hist[a][k] > best) { best = hist[a][k]; out.class_pat[a] = (uint32_t)k; }
+      }
+  }
   // the kernel reads whole 32-entry rows of the halo list
   out.halo.resize(out.halo.size() + 32, 0);
   out.n_patterns = (uint32_t)pats.size();
@@ -492,15 +510,17 @@ void build_stage_plan(const StagePlanIn &in, StagePlan &out)
       for (int s2 = 0; s2 < ns2; ++s2)
         for (int l = 0; l < 32; ++l)
           {
-            const uint32_t lo = p.fin[(size_t)(2 * s2) * 32 + l];
-            const uint32_t hi = 2 * s2 + 1 < B.ns ? p.fin[(size_t)(2 * s2 + 1) * 32 + l] : (uint32_t)((in.xcap - 1) | STAGE_DEAD);
+            // (slot * sizeof(Number) | dead flag)
+            auto enc = [&](uint16_t v) { return (uint32_t)(((v & 0x7fffu) * in.wb) | (v & STAGE_DEAD)); };
+            const uint32_t lo = enc(p.fin[(size_t)(2 * s2) * 32 + l]);
+            const uint32_t hi = enc(2 * s2 + 1 < B.ns ? p.fin[(size_t)(2 * s2 + 1) * 32 + l] : (uint16_t)((in.xcap - 1) | STAGE_DEAD));
             pos32[s2 * 32 + l] = lo | (hi << 16);
           }
       // own [ocap] uint32: slot | flag << 16 ; halo slots [hmax] uint16
       uint32_t *own32 = pos32 + ns2 * 32;
-      for (int e = 0; e < in.ocap; ++e) own32[e] = (uint32_t)(e < (int)p.own_total ? p.st[e] | ((uint32_t)p.oflag[e] << 16) : (uint32_t)(in.xcap - 1));
+      for (int e = 0; e < in.ocap; ++e) own32[e] = (uint32_t)(e < (int)p.own_total ? (uint32_t)p.st[e] * in.wb | ((uint32_t)p.oflag[e] << 16) : (uint32_t)(in.xcap - 1) * in.wb);
       uint16_t *hs = t + STAGE_PH + 2 * ns2 * 32 + 2 * in.ocap;
-      for (int h = 0; h < in.hmax; ++h) hs[h] = h < (int)p.n_halo ? p.st[p.own_total + h] : (uint16_t)(in.xcap - 1);
+      for (int h = 0; h < in.hmax; ++h) hs[h] = (uint16_t)((h < (int)p.n_halo ? p.st[p.own_total + h] : (uint16_t)(in.xcap - 1)) * in.wb);
     }
 }
 

@@ -34,6 +34,7 @@ struct StagePlanIn
   uint32_t        n_dofs = 0;
   const uint32_t *idx = nullptr;  // [n_cells][n^3] lexicographic, bit 31 = constrained
   int             merge_dirs = 7; // bit d: merge faces in direction d inside a group
+  int             nclass = 1;     // groups g and g + nclass have the same position in the cell order (same tables on a uniform mesh)
 };
 
 struct StagePlan
@@ -45,6 +46,7 @@ struct StagePlan
   std::vector<uint32_t> halo;         // halo DoF lists of all groups
   std::vector<uint16_t> ptab;         // [n_patterns][pstride]
   std::vector<uint32_t> fallback;     // groups the staged kernel skips
+  uint32_t              class_pat[8];  // most frequent pattern among the groups g % nclass == a (STAGE_NOPAT: none)
   // statistics (per staged group averages x 1000 are computed by the caller)
   uint64_t n_own = 0, n_halo = 0, n_plain_dofs = 0, n_red_dofs = 0, rd_wavefronts = 0, wr_wavefronts = 0, cp_wavefronts = 0;
 };

@@ -39,6 +39,7 @@ class Plan:
         rc = lib.mfg_stage_plan_build(degree, _capi.F64 if dtype == np.float64 else _capi.F32, n_plain, idx.shape[0], n_dofs,
                                       idx.ctypes.data_as(C.POINTER(C.c_uint32)), merge_dirs, C.byref(h))
         assert rc == 0, lib.mfg_last_error()
+        self.wb = 8 if dtype == np.float64 else 4
         info = (C.c_uint32 * 16)()
         assert lib.mfg_stage_plan_info(h, info) == 0
         (self.n_groups, self.n_patterns, self.pstride, n_halo, n_fb, self.cw, self.hc, self.xcap, self.n, self.n_staged, self.lcap, self.ocap,
@@ -85,9 +86,10 @@ def replay(plan, idx, n_plain, n_dofs, rng):
         pos32 = t[PH:PH + 2 * ns2 * 32].view(np.uint32).reshape(ns2, 32)
         pos = np.empty((2 * ns2, 32), int)
         pos[0::2], pos[1::2] = pos32 & 0xffff, pos32 >> 16
+        pos = (pos & 0x7fff) // plan.wb | (pos & DEAD)  # (the tables hold byte offsets)
         own32 = t[PH + 2 * ns2 * 32:PH + 2 * ns2 * 32 + 2 * plan.ocap].view(np.uint32)
         hs = t[PH + 2 * ns2 * 32 + 2 * plan.ocap:PH + 2 * ns2 * 32 + 2 * plan.ocap + (plan.lcap - plan.ocap)].astype(int)
-        st = np.concatenate([(own32 & 0xffff).astype(int)[:hdr[H_OWN]], hs])
+        st = np.concatenate([(own32 & 0xffff).astype(int)[:hdr[H_OWN]], hs]) // plan.wb
         oflag = (own32 >> 16).astype(np.uint8)
         own_total = hdr[H_OWN]
         assert hdr[H_NHALO] == n_halo and own_total + n_halo <= xcap - 1
