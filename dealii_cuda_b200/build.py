@@ -27,6 +27,7 @@ for dim in (2, 3):
 for f64 in (0, 1):
     UNITS.append(("kernels_slab_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
     UNITS.append(("kernels_stage_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
+    UNITS.append(("kernels_slab3_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
     # MFG_SLAB2_ABLATE=1 in the environment adds the measurement-only ablation kernels (tools/ablate.py)
     UNITS.append(("kernels_slab2_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"] + (["-DMFG_SLAB2_ABLATE"] if os.environ.get("MFG_SLAB2_ABLATE") else [])))
 

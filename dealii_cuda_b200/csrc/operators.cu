@@ -6,6 +6,7 @@
 #include "kernels_slab2_ws.cuh"
 #include "kernels_general.cuh"
 #include "kernels_stage.cuh"
+#include "kernels_slab3.cuh"
 #include "operators.cuh"
 
 namespace mfg {
@@ -67,8 +68,9 @@ __global__ void build_slab2_indices(const uint32_t *__restrict__ idx, uint32_t n
 // direction d and the lower face of cell c + 2^d of the same group carry identical index entries.  A merge whose receiving
 // entries would themselves be handed over by an earlier direction without the sender doing the same is dropped, so that
 // no contribution can be lost whatever the cell order of the mesh is.
+// xzy: the merges run in the order x, z, y (slab3 kernel: x and z in layout C, y in layout A) instead of x, y, z.
 __global__ void build_slab2_merge(const uint32_t *__restrict__ idx, uint32_t n_cells, uint32_t n_groups, int n, int cw, int dirs,
-                                  uint32_t *__restrict__ out)
+                                  uint32_t *__restrict__ out, bool xzy)
 {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
@@ -90,6 +92,15 @@ __global__ void build_slab2_merge(const uint32_t *__restrict__ idx, uint32_t n_c
           }
       }
   auto bit = [&](int d, int c) { return c < SLAB2_MERGE_MAX_CW && ((m >> (10 * d + c)) & 1u); };
+  if (xzy)
+    {
+      for (int c = 0; c + 4 < cw && cw <= SLAB2_MERGE_MAX_CW; ++c)
+        if (bit(2, c) && bit(0, c + 4) && !bit(0, c)) m &= ~(1u << (20 + c));
+      for (int c = 0; c + 2 < cw && cw <= SLAB2_MERGE_MAX_CW; ++c)
+        if (bit(1, c) && ((bit(0, c + 2) && !bit(0, c)) || (bit(2, c + 2) && !bit(2, c)))) m &= ~(1u << (10 + c));
+      out[g] = m;
+      return;
+    }
   for (int c = 0; c + 2 < cw && cw <= SLAB2_MERGE_MAX_CW; ++c)
     if (bit(1, c) && bit(0, c + 2) && !bit(0, c)) m &= ~(1u << (10 + c));
   for (int c = 0; c + 4 < cw && cw <= SLAB2_MERGE_MAX_CW; ++c)
@@ -720,8 +731,20 @@ static cudaTextureObject_t laplace_src_texture(mfg_laplace *op, const void *src)
 
 // (re)build the slab2 kernel's private arrays from idx / cw
 // configuration of the slab2 kernel for the operator's variant; + 256 = the build with the face merge (configurations 3, 7)
+static inline bool slab3_variant(int v) { return v >= 50 && v <= 54; }  // 50 = default (asynchronous gather + early merges); 51..53: flavours 0..2
+
+// flavour of the slab3 kernel: bit 0 = asynchronous gather, bit 1 = early face merges.  auto (variant 0 / 50): early merges
+// except for degree 4 in FP64, no asynchronous gather (measured on B200, profiles/r02_slab3_flavours.txt: the merges gain
+// 3-11 % for FP32 and for degree 2, 3; the cp.async gather costs 10-15 % everywhere); 51..54 select flavour 0..3
+static int slab3_flavour(const mfg_laplace *op)
+{
+  if (op->variant >= 51 && op->variant <= 54) return op->variant - 51;
+  return (op->mf->p == 4 && op->mf->dt == MFG_F64) ? 0 : 2;
+}
+
 static int slab2_merge_dirs(const mfg_laplace *op)
 {
+  if (slab3_variant(op->variant) || (op->variant == 0 && laplace_active_variant(op) == 50)) return 8 + 7;  // slab3: every direction, order x, z, y
   // MFG_SLAB2_MERGE: bit mask of the directions (1 x, 2 y, 4 z) whose in-group face merge is enabled.  Measured on
   // B200 at 3D Q4 r=6 (profiles/r01_slab2_merge.txt): 22 % fewer red sectors, but the shuffles cost as many L1 data-pipe
   // wavefronts as the removed sectors in FP64 (+4 % time), while FP32 gains 3.6 % -> on for FP32, off for FP64
@@ -755,7 +778,7 @@ static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
   if (op->merge_dirs_built != dirs)
     {
       if (op->mergeP.n != n_groups) op->mergeP.alloc(n_groups);
-      if (n_groups) build_slab2_merge<<<nblk(n_groups), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm.cw, dirs, op->mergeP.p);
+      if (n_groups) build_slab2_merge<<<nblk(n_groups), 256, 0, s>>>(mf->idx.p, n_plain, n_groups, mf->n, gm.cw, dirs & 7, op->mergeP.p, (dirs & 8) != 0);
       MFG_CUDA_LAST();
       op->merge_dirs_built = dirs;
     }
@@ -776,7 +799,7 @@ static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
 }
 
 // grouped kernels (one warp per group of 32 / n cells, work list, programmatic dependent launch): slab2 and staged
-static inline bool grouped_variant(int v) { return v == 6 || v == 40; }
+static inline bool grouped_variant(int v) { return v == 6 || v == 40 || v == 50; }
 
 // plan of the staged kernel (stage_plan.cu), built once per operator from the index array
 static void laplace_prepare_stage(mfg_laplace *op, uint32_t n_plain)
@@ -815,15 +838,17 @@ int laplace_launches_per_vmult(const mfg_laplace *op)
 {
   // with the slab2 kernel the zero pass is a kernel of this library too (zero_fill_pdl)
   const int  v = laplace_active_variant(op);
-  const bool zero_kernel = !(std::getenv("MFG_PDL_FILL") && std::atoi(std::getenv("MFG_PDL_FILL")) == 0) && grouped_variant(v) && op->mf->hn_mask.n == 0;
-  return (op->ch->n() ? 1 : 0) + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0) + (zero_kernel ? 1 : 0) +
+  const bool zero_kernel = grouped_variant(v) && op->mf->hn_mask.n == 0;
+  // (the slab3 kernel copies the constrained rows itself when it runs behind the zero kernel)
+  return (op->ch->n() && !(v == 50 && zero_kernel) ? 1 : 0) + (int)op->mf->n_colors() + (op->mf->hn_mask.n ? 1 : 0) + (zero_kernel ? 1 : 0) +
          (v == 40 && op->st_built && op->st_fallback.n ? 1 : 0);
 }
 
 // kernel variants: 1 = column kernel (kernels_v0.cuh, every dim/degree/dtype/scatter),
 //                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter),
 //                  6 = slab2 kernel (kernels_slab2.cuh: 3D, degree <= 5, atomic scatter),
-//                  40 = staged kernel (kernels_stage.cuh: 3D, degree 2..5, atomic scatter). 0 = auto.
+//                  40 = staged kernel (kernels_stage.cuh: 3D, degree 2..5, atomic scatter),
+//                  50 = slab3 kernel (kernels_slab3.cuh: 3D, degree <= 5, atomic scatter). 0 = auto.
 int laplace_active_variant(const mfg_laplace *op)
 {
   const mfg_mf *mf = op->mf;
@@ -835,6 +860,11 @@ int laplace_active_variant(const mfg_laplace *op)
       if (!stage_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 40 (staged kernel) needs dim 3, degree 2..5, atomic scatter, uniform geometry");
       return 40;
     }
+  if (slab3_variant(op->variant))
+    {
+      if (!slab2_ok || mf->general) throw Error(MFG_ERR_UNSUPPORTED, "variant 50 (slab3 kernel) needs dim 3, degree <= 5, atomic scatter, uniform geometry");
+      return 50;
+    }
   if (op->variant >= 6 && !slab2_ok) throw Error(MFG_ERR_UNSUPPORTED, "variants 6..9 (slab2 kernel) need dim 3, degree <= 5, atomic scatter");
   if (op->variant >= 2 && op->variant < 6 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3/4 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
   if (mf->general)
@@ -845,9 +875,8 @@ int laplace_active_variant(const mfg_laplace *op)
   if (op->variant == 1) return 1;
   if (op->variant >= 6) return 6;
   if (op->variant >= 2) return 2;
-  // auto: the staged kernel where it exists (3D degree 2..5), slab2 for 3D degree 1
-  if (stage_ok) return 40;
-  if (slab2_ok && mf->p != 2) return 6;
+  // auto: the slab3 kernel where it exists (measured on B200, profiles/r02_sweep_*.jsonl)
+  if (slab2_ok) return 50;
   return slab_ok ? 2 : 1;
 }
 
@@ -876,8 +905,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
   const bool split = part >= 1 && op->glist.n != 0 && grouped_variant(av);
   if (part == 1 && !split) return;
   // whole apply with the slab2 kernel: zero kernel -> cell kernel as its programmatic dependent -> constrained rows
-  static const bool pdl_fill_on = !(std::getenv("MFG_PDL_FILL") && std::atoi(std::getenv("MFG_PDL_FILL")) == 0);
-  const bool pdl_fill = pdl_fill_on && part == -1 && !add && grouped_variant(av) && mf->hn_mask.n == 0 &&
+  const bool pdl_fill = part == -1 && !add && grouped_variant(av) && mf->hn_mask.n == 0 &&
                         (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
   if (pdl_fill)
     {
@@ -891,20 +919,10 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
   // vmult_add: dst[c] += src[c]  (load_and_add_constrained_values, :302)
   if (!add)
     {
-      // cudaMemsetAsync + a kernel over the constraint list measured 14 us faster per apply at 17 M DoFs than the
-      // fused vmult_prepare kernel (kept behind MFG_PREPARE_FUSED for comparison)
-      static const bool use_memset = std::getenv("MFG_PREPARE_FUSED") == nullptr;
-      if (use_memset)
-        {
-          MFG_CUDA(cudaMemsetAsync(dst, 0, (size_t)mf->n_dofs * sizeof(Number), s));
-          if (op->ch->n()) { constrained_copy<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n()); MFG_CUDA_LAST(); }
-        }
-      else
-        {
-          const unsigned nb = (unsigned)std::min<size_t>((mf->n_dofs + 2047) / 2048, (size_t)op->ctx->sm_count * 8);
-          vmult_prepare<Number><<<std::max(1u, nb), 256, 0, s>>>(dst, src, op->cbits.p, mf->n_dofs);
-          MFG_CUDA_LAST();
-        }
+      // (cudaMemsetAsync + a kernel over the constraint list measured 14 us faster per apply at 17 M DoFs than one fused
+      // pass with a bit mask, profiles/r01_*)
+      MFG_CUDA(cudaMemsetAsync(dst, 0, (size_t)mf->n_dofs * sizeof(Number), s));
+      if (op->ch->n()) { constrained_copy<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n()); MFG_CUDA_LAST(); }
     }
   else if (op->ch->n())
     {
@@ -915,7 +933,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
   if (part == 0) return;
   const bool     hanging = mf->hn_mask.n != 0;
   const uint32_t n_plain = hanging ? mf->n_plain : mf->n_cells;
-  bool timed = false;
+  bool timed = false, fused_ccopy = false;
   auto time_begin = [&]() {
     timed = op->timing && (op->timing_counter++ % (size_t)op->timing_stride) == 0;
     if (!timed) return;
@@ -952,6 +970,18 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
                                      op->ctx->sm_count, s, 0, op->mergeP.p, fl, false, false, mf->idx.p, op->idxJ.p, n_plain);
       time_end();
     }
+  else if (av == 50)
+    {
+      laplace_prepare_slab2(op, n_plain);
+      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
+      const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
+      time_begin();
+      launch_laplace_slab3<Number>(mf->p, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s,
+                                   op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill, op->ctx->device, slab3_flavour(op),
+                                   pdl_fill ? op->ch->constrained.p : nullptr, pdl_fill ? (uint32_t)op->ch->n() : 0u);
+      fused_ccopy = pdl_fill;
+      time_end();
+    }
   else if (av == 6)
     {
       laplace_prepare_slab2(op, n_plain);
@@ -976,17 +1006,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       else
         {
       const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
-      // experiment (tools/sweep.py): MFG_SLAB2_ALIAS=m maps work item k to group k % m, i.e. the same
-      // instruction stream on an L2-resident working set (results are then meaningless)
-      static const int alias = std::getenv("MFG_SLAB2_ALIAS") ? std::atoi(std::getenv("MFG_SLAB2_ALIAS")) : 0;
-      if (alias > 0 && op->glist.n == 0 && op->slab2_groups)
-        {
-          std::vector<uint32_t> al(op->slab2_groups);
-          for (uint32_t k = 0; k < op->slab2_groups; ++k) al[k] = k % (uint32_t)alias;
-          op->glist.upload(al.data(), al.size(), s);
-          op->n_iface_groups = 0;
-        }
-      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : (alias > 0 ? op->glist.p : nullptr);
+      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
       const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
       time_begin();
       launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
@@ -1037,8 +1057,8 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       launch_v0(n_plain, mf->n_cells, mf->hn_mask.p);
       time_end();
     }
-  // identity on the constrained rows (the cell kernel never writes them)
-  if (pdl_fill && op->ch->n()) { constrained_copy<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n()); MFG_CUDA_LAST(); }
+  // identity on the constrained rows (the cell kernel never writes them; the slab3 kernel does this copy itself)
+  if (pdl_fill && op->ch->n() && !fused_ccopy) { constrained_copy<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n()); MFG_CUDA_LAST(); }
 }
 
 void laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches)

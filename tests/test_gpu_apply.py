@@ -195,13 +195,14 @@ STAGE_CASES = [(2, 2), (2, 3), (3, 2), (3, 3), (4, 0), (4, 1), (4, 2), (4, 3), (
 @pytest.mark.parametrize("p,r", STAGE_CASES)
 def test_staged_kernel_matches_oracle(ctx, p, r, dtype):
     """variant 40 = staged kernel (kernels_stage.cuh: asynchronous staged gather, register face merges, staged scatter with
-    plain stores for group-interior DoFs), the default for 3D degree 2..5: vmult into a dirty vector (the plain stores and
-    the zero pass must cover every DoF), vmult_add, and agreement with the slab2 kernel it shares its contractions with"""
+    plain stores for group-interior DoFs): vmult into a dirty vector (the plain stores and the zero pass must cover every
+    DoF), vmult_add, and agreement with the slab2 kernel it shares its contractions with"""
     import dealii_cuda_b200 as mf
     o = OracleMesh(3, p, r)
     m = mf.HyperCubeMesh(ctx, 3, p, r)
     op = mf.LaplaceOperatorGpu(ctx, dtype)
     op.reinit(m)
+    op.set_variant(40)
     assert op.active_variant() == 40
     u = sm64(3, o.n_dofs).astype(dtype)
     src = mf.GpuVector.from_numpy(ctx, u)
@@ -223,7 +224,8 @@ def test_staged_kernel_matches_oracle(ctx, p, r, dtype):
     assert rel_err(dst.toVector(), 2.0 * d6.toVector().astype(np.float64)) <= (1e-14 if dtype == np.float64 else 1e-5)
 
 
-def test_staged_kernel_repeated_applies_and_box(ctx):
+@pytest.mark.parametrize("variant", [40, 50])
+def test_grouped_kernels_repeated_applies_and_box(ctx, variant):
     """the bmop loop (bmop.cu:135-153) on a non-cubic box whose last group is partial, against the oracle"""
     import dealii_cuda_b200 as mf
     box = dict(log2_cells=(2, 1, 3), origin=(-1.0, -0.5, 0.0), h=0.25)
@@ -231,19 +233,43 @@ def test_staged_kernel_repeated_applies_and_box(ctx):
     m = mf.HyperCubeMesh(ctx, 3, 4, box=box)
     op = mf.LaplaceOperatorGpu(ctx, np.float64)
     op.reinit(m)
-    assert op.active_variant() == 40
+    op.set_variant(variant)
+    assert op.active_variant() == variant
     a, b = mf.GpuVector(ctx, o.n_dofs), mf.GpuVector(ctx, o.n_dofs)
     op.bmop(a, b, 3, 0.1)
     assert rel_err(a.toVector(), o.bmop(3, 0.1)) <= 1e-12
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("p,r", [(1, 2), (1, 3), (2, 2), (2, 3), (3, 2), (3, 3), (4, 0), (4, 1), (4, 2), (4, 3), (5, 1), (5, 2)])
+def test_slab3_kernel_matches_oracle(ctx, p, r, dtype):
+    """variant 50 = slab3 kernel (kernels_slab3.cuh: asynchronous gather one group ahead, face merges in registers right
+    after the contraction across the face), the default for 3D degree 1..5 with the atomic scatter"""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, p, r)
+    m = mf.HyperCubeMesh(ctx, 3, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(m)
+    assert op.active_variant() == 50
+    u = sm64(4, o.n_dofs).astype(dtype)
+    src = mf.GpuVector.from_numpy(ctx, u)
+    dst = mf.GpuVector(ctx, o.n_dofs, dtype)
+    dst.fill(-7.5)
+    op.vmult(dst, src)
+    want = o.vmult(u.astype(np.float64))
+    assert rel_err(dst.toVector(), want) <= TOL[dtype]
+    assert np.array_equal(src.toVector(), u)
+    op.vmult_add(dst, src)
+    assert rel_err(dst.toVector(), 2.0 * want) <= 2 * TOL[dtype]
+
+
 def test_slab_variant_rejected_where_unsupported(ctx):
     import dealii_cuda_b200 as mf
-    for dim, p, coloring, auto in [(2, 4, False, 1), (3, 5, False, 40), (3, 4, True, 1), (3, 6, False, 1)]:
+    for dim, p, coloring, auto in [(2, 4, False, 1), (3, 5, False, 50), (3, 4, True, 1), (3, 6, False, 1)]:
         m = mf.HyperCubeMesh(ctx, dim, p, 1)
         op = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=coloring)
         op.reinit(m)
-        assert op.active_variant() == auto  # auto: staged kernel for 3D degree 2..5 with atomics, slab2 for degree 1
+        assert op.active_variant() == auto  # auto: slab3 kernel for 3D degree 1..5 with atomics, column kernel otherwise
         op.set_variant(2)
         a, b = mf.GpuVector(ctx, m.n_dofs), mf.GpuVector(ctx, m.n_dofs)
         with pytest.raises(mf.MfgError):

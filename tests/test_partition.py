@@ -197,7 +197,7 @@ def test_partitions_emulated_on_one_gpu(ctx, world, p, r, dtype, split):
         if split:
             # the overlapped form: interface cell groups, pack, then the other groups (must not touch packed DoFs)
             k = op.set_interface_dofs(plan.pack_idx)
-            assert (k > 0) == (op.active_variant() in (6, 40) and plan.n_send > 0)
+            assert (k > 0) == (op.active_variant() in (6, 40, 50) and plan.n_send > 0)
             dst.fill(7.0)
             op.vmult_part_ptr(dst.getData(), src.getData(), 0)
             op.vmult_part_ptr(dst.getData(), src.getData(), 1)
