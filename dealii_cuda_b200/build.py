@@ -25,11 +25,8 @@ for dim in (2, 3):
         UNITS.append(("kernels_v0_inst.cu", f"_d{dim}_f{f64}", [f"-DMFG_INST_DIM={dim}", f"-DMFG_INST_F64={f64}"]))
         UNITS.append(("kernels_general_inst.cu", f"_d{dim}_f{f64}", [f"-DMFG_INST_DIM={dim}", f"-DMFG_INST_F64={f64}"]))
 for f64 in (0, 1):
-    UNITS.append(("kernels_slab_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
     UNITS.append(("kernels_stage_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
     UNITS.append(("kernels_slab3_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"]))
-    # MFG_SLAB2_ABLATE=1 in the environment adds the measurement-only ablation kernels (tools/ablate.py)
-    UNITS.append(("kernels_slab2_inst.cu", f"_f{f64}", [f"-DMFG_INST_F64={f64}"] + (["-DMFG_SLAB2_ABLATE"] if os.environ.get("MFG_SLAB2_ABLATE") else [])))
 
 
 def _headers():

@@ -16,7 +16,7 @@
 //     shuffled values per lane and direction instead of n^2 for the x face at the end; the remaining contractions act
 //     along the face and are the same for both cells), which removes a fifth of the red.global.add sectors.
 #pragma once
-#include "kernels_slab2.cuh"
+#include "slab_common.cuh"
 
 namespace mfg {
 

@@ -91,4 +91,28 @@ void launch_laplace_slab3<inst_number>(int degree, const uint32_t *idxP, const i
 #undef MFG_A
 }
 
+#if MFG_INST_F64
+bool slab2_supported(int dim, int degree, mfg_dtype) { return dim == 3 && degree >= 1 && degree <= 5; }
+
+template <int n, int WB> static Slab2Geom geom_of()
+{
+  using Tab = Slab2Tab<n, WB>;
+  constexpr int CW = 32 / n;
+  return Slab2Geom{n, CW, CW % 2 == 0 ? CW / 2 : CW, Tab::F, Tab::BC()};
+}
+Slab2Geom slab2_geom(int degree, mfg_dtype dt)
+{
+  const bool f64 = dt == MFG_F64;
+  switch (degree)
+    {
+      case 1: return f64 ? geom_of<2, 8>() : geom_of<2, 4>();
+      case 2: return f64 ? geom_of<3, 8>() : geom_of<3, 4>();
+      case 3: return f64 ? geom_of<4, 8>() : geom_of<4, 4>();
+      case 4: return f64 ? geom_of<5, 8>() : geom_of<5, 4>();
+      case 5: return f64 ? geom_of<6, 8>() : geom_of<6, 4>();
+      default: throw Error(MFG_ERR_UNSUPPORTED, "slab kernels: degree must be in 1..5");
+    }
+}
+#endif
+
 }  // namespace mfg

@@ -17,7 +17,7 @@
 //     which writes it to the staging buffer; the warp writes the buffer out in memory order: plain coalesced stores
 //     for DoFs no cell outside the group touches, red.add for the rest.
 #pragma once
-#include "kernels_slab2.cuh"
+#include "slab_common.cuh"
 #include "stage_plan.h"
 
 namespace mfg {

@@ -2,8 +2,6 @@
 #include <algorithm>
 #include <numeric>
 #include <cstdlib>
-#include "kernels_slab.cuh"
-#include "kernels_slab2_ws.cuh"
 #include "kernels_general.cuh"
 #include "kernels_stage.cuh"
 #include "kernels_slab3.cuh"
@@ -106,17 +104,6 @@ __global__ void build_slab2_merge(const uint32_t *__restrict__ idx, uint32_t n_c
   for (int c = 0; c + 4 < cw && cw <= SLAB2_MERGE_MAX_CW; ++c)
     if (bit(2, c) && ((bit(0, c + 4) && !bit(0, c)) || (bit(1, c + 4) && !bit(1, c)))) m &= ~(1u << (20 + c));
   out[g] = m;
-}
-
-// slab2 plane-layout scatter: idxJ[cell][j][i + n k] = idx[cell][i + n j + n^2 k]
-__global__ void build_slab2_idxJ(const uint32_t *__restrict__ idx, size_t total, int n, uint32_t *__restrict__ out)
-{
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int    npc = n * n * n, e = (int)(t % npc);
-  const size_t cell = t / npc;
-  const int    i = e % n, j = (e / n) % n, k = e / (n * n);
-  out[cell * npc + (size_t)j * n * n + i + n * k] = idx[t];
 }
 
 // slab2 kernel: coefficient image of a group, element (c,i,j,k) at SC c + SI i + SJ j + SK k (padding stays zero)
@@ -703,35 +690,9 @@ void laplace_set_coefficient_host(mfg_laplace *op, const double *coef_host)
   op->cwP_valid = false;
 }
 
-// texture object over a source vector (cached per pointer; a handful of vectors alternate in solvers and in bmop)
-static cudaTextureObject_t laplace_src_texture(mfg_laplace *op, const void *src)
-{
-  const mfg_mf *mf = op->mf;
-  for (auto &t : op->src_tex)
-    if (t.p == src && t.n == mf->n_dofs) return t.tex;
-  if (op->src_tex.size() >= 16)
-    {
-      for (auto &t : op->src_tex) cudaDestroyTextureObject(t.tex);
-      op->src_tex.clear();
-    }
-  cudaResourceDesc rd;
-  std::memset(&rd, 0, sizeof(rd));
-  rd.resType = cudaResourceTypeLinear;
-  rd.res.linear.devPtr = const_cast<void *>(src);
-  rd.res.linear.desc = mf->dt == MFG_F64 ? cudaCreateChannelDesc<int2>() : cudaCreateChannelDesc<float>();
-  rd.res.linear.sizeInBytes = (size_t)mf->n_dofs * (mf->dt == MFG_F64 ? 8 : 4);
-  cudaTextureDesc td;
-  std::memset(&td, 0, sizeof(td));
-  td.readMode = cudaReadModeElementType;
-  cudaTextureObject_t tex = 0;
-  MFG_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-  op->src_tex.push_back({src, mf->n_dofs, tex});
-  return tex;
-}
-
 // (re)build the slab2 kernel's private arrays from idx / cw
 // configuration of the slab2 kernel for the operator's variant; + 256 = the build with the face merge (configurations 3, 7)
-static inline bool slab3_variant(int v) { return v >= 50 && v <= 54; }  // 50 = default (asynchronous gather + early merges); 51..53: flavours 0..2
+static inline bool slab3_variant(int v) { return v >= 50 && v <= 54; }  // 50 = flavour chosen by measurement; 51..54: flavours 0..3
 
 // flavour of the slab3 kernel: bit 0 = asynchronous gather, bit 1 = early face merges.  auto (variant 0 / 50): early merges
 // except for degree 4 in FP64, no asynchronous gather (measured on B200, profiles/r02_slab3_flavours.txt: the merges gain
@@ -742,21 +703,9 @@ static int slab3_flavour(const mfg_laplace *op)
   return (op->mf->p == 4 && op->mf->dt == MFG_F64) ? 0 : 2;
 }
 
-static int slab2_merge_dirs(const mfg_laplace *op)
-{
-  if (slab3_variant(op->variant) || (op->variant == 0 && laplace_active_variant(op) == 50)) return 8 + 7;  // slab3: every direction, order x, z, y
-  // MFG_SLAB2_MERGE: bit mask of the directions (1 x, 2 y, 4 z) whose in-group face merge is enabled.  Measured on
-  // B200 at 3D Q4 r=6 (profiles/r01_slab2_merge.txt): 22 % fewer red sectors, but the shuffles cost as many L1 data-pipe
-  // wavefronts as the removed sectors in FP64 (+4 % time), while FP32 gains 3.6 % -> on for FP32, off for FP64
-  const int base = op->variant >= 6 ? op->variant - 6 : 3;
-  if (base != 3 && base != 7) return 0;  // (also excludes the plane-layout configurations 512 + c)
-  return getenv("MFG_SLAB2_MERGE") ? atoi(getenv("MFG_SLAB2_MERGE")) & 7 : (op->mf->dt == MFG_F64 ? 0 : 7);
-}
-static int slab2_cfg(const mfg_laplace *op)
-{
-  const int base = op->variant >= 6 ? op->variant - 6 : 3;
-  return base + (slab2_merge_dirs(op) ? 256 : 0);
-}
+// face merges of the slab kernels: bit d = direction d, bit 3 = order x, z, y (slab3, staged); the staged kernel keeps its
+// own masks in its plan and runs its left-over groups on the slab3 kernel without merges
+static int slab2_merge_dirs(const mfg_laplace *op) { return laplace_active_variant(op) == 50 && (slab3_flavour(op) & 2) ? 8 + 7 : 0; }
 
 static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
 {
@@ -799,7 +748,7 @@ static void laplace_prepare_slab2(mfg_laplace *op, uint32_t n_plain)
 }
 
 // grouped kernels (one warp per group of 32 / n cells, work list, programmatic dependent launch): slab2 and staged
-static inline bool grouped_variant(int v) { return v == 6 || v == 40 || v == 50; }
+static inline bool grouped_variant(int v) { return v == 40 || v == 50; }
 
 // plan of the staged kernel (stage_plan.cu), built once per operator from the index array
 static void laplace_prepare_stage(mfg_laplace *op, uint32_t n_plain)
@@ -844,16 +793,14 @@ int laplace_launches_per_vmult(const mfg_laplace *op)
          (v == 40 && op->st_built && op->st_fallback.n ? 1 : 0);
 }
 
-// kernel variants: 1 = column kernel (kernels_v0.cuh, every dim/degree/dtype/scatter),
-//                  2 = slab kernel (kernels_slab.cuh: 3D, degree <= 4, atomic scatter),
-//                  6 = slab2 kernel (kernels_slab2.cuh: 3D, degree <= 5, atomic scatter),
+// kernel variants: 1 = column kernel (kernels_v0.cuh: every dim / degree / dtype / scatter, hanging-node cells),
 //                  40 = staged kernel (kernels_stage.cuh: 3D, degree 2..5, atomic scatter),
-//                  50 = slab3 kernel (kernels_slab3.cuh: 3D, degree <= 5, atomic scatter). 0 = auto.
+//                  50 = slab3 kernel (kernels_slab3.cuh: 3D, degree <= 5, atomic scatter), 51..54 = its flavours 0..3.
+//                  0 = auto: slab3 where it exists, else the column kernel (general geometry: its own kernel).
 int laplace_active_variant(const mfg_laplace *op)
 {
   const mfg_mf *mf = op->mf;
-  const bool slab_ok = slab_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
-  const bool slab2_ok = slab2_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC;
+  const bool slab_ok = slab2_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC && !mf->general;
   const bool stage_ok = stage_supported(mf->dim, mf->p, mf->dt) && mf->scatter == MFG_SCATTER_ATOMIC && !mf->general;
   if (op->variant == 40)
     {
@@ -862,22 +809,12 @@ int laplace_active_variant(const mfg_laplace *op)
     }
   if (slab3_variant(op->variant))
     {
-      if (!slab2_ok || mf->general) throw Error(MFG_ERR_UNSUPPORTED, "variant 50 (slab3 kernel) needs dim 3, degree <= 5, atomic scatter, uniform geometry");
+      if (!slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variants 50..54 (slab3 kernel) need dim 3, degree <= 5, atomic scatter, uniform geometry");
       return 50;
     }
-  if (op->variant >= 6 && !slab2_ok) throw Error(MFG_ERR_UNSUPPORTED, "variants 6..9 (slab2 kernel) need dim 3, degree <= 5, atomic scatter");
-  if (op->variant >= 2 && op->variant < 6 && !slab_ok) throw Error(MFG_ERR_UNSUPPORTED, "variant 2/3/4 (slab kernel) needs dim 3, degree <= 4, atomic scatter");
-  if (mf->general)
-    {
-      if (op->variant > 1) throw Error(MFG_ERR_UNSUPPORTED, "general geometry has one kernel (variant 0 or 1)");
-      return 1;
-    }
-  if (op->variant == 1) return 1;
-  if (op->variant >= 6) return 6;
-  if (op->variant >= 2) return 2;
-  // auto: the slab3 kernel where it exists (measured on B200, profiles/r02_sweep_*.jsonl)
-  if (slab2_ok) return 50;
-  return slab_ok ? 2 : 1;
+  if (op->variant != 0 && op->variant != 1) throw Error(MFG_ERR_UNSUPPORTED, "unknown kernel variant (0 auto, 1 column, 40 staged, 50..54 slab3)");
+  if (mf->general || op->variant == 1) return 1;
+  return slab_ok ? 50 : 1;
 }
 
 // dst = 0 as a kernel (16-byte stores) that releases its programmatic dependents at once: the cell kernel launched
@@ -966,8 +903,8 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
                                    op->slab2_groups, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, op->glist.p, op->n_iface_groups, mode,
                                    (split && part == 2) || pdl_fill, pdl_fill, add, op->ctx->device);
       if (nf)
-        launch_laplace_slab2<Number>(mf->p, 3, op->idxP.p, (const Number *)op->cwP.p, src, dst, nf, mf->fe.val.data(), mf->fe.colloc.data(),
-                                     op->ctx->sm_count, s, 0, op->mergeP.p, fl, false, false, mf->idx.p, op->idxJ.p, n_plain);
+        launch_laplace_slab3<Number>(mf->p, op->idxP.p, (const Number *)op->cwP.p, src, dst, nf, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s,
+                                     op->mergeP.p, fl, false, false, op->ctx->device, 0, nullptr, 0u);
       time_end();
     }
   else if (av == 50)
@@ -978,50 +915,8 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       time_begin();
       launch_laplace_slab3<Number>(mf->p, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s,
                                    op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill, op->ctx->device, slab3_flavour(op),
-                                   pdl_fill ? op->ch->constrained.p : nullptr, pdl_fill ? (uint32_t)op->ch->n() : 0u);
-      fused_ccopy = pdl_fill;
-      time_end();
-    }
-  else if (av == 6)
-    {
-      laplace_prepare_slab2(op, n_plain);
-      // auto = configuration 3 (3 blocks x 4 warps, 168 registers, one transpose buffer per warp, LSU gather)
-      const int cfg = slab2_cfg(op);
-      if (cfg >= 512 && op->idxJ.n == 0 && n_plain)
-        {
-          const size_t total = (size_t)n_plain * mf->npc;
-          op->idxJ.alloc(total);
-          build_slab2_idxJ<<<nblk(total), 256, 0, s>>>(mf->idx.p, total, mf->n, op->idxJ.p);
-          MFG_CUDA_LAST();
-        }
-      if (cfg >= 1024)
-        {
-          // warp-specialised kernel (kernels_slab2_ws.cuh): variants 1030 + shape
-          if (split) throw Error(MFG_ERR_UNSUPPORTED, "the warp-specialised slab2 kernel has no work list");
-          time_begin();
-          launch_laplace_slab2_ws<Number>(mf->p, cfg - 1024, mf->idx.p, op->idxJ.p, (const Number *)op->cwP.p, src, dst, op->slab2_groups, n_plain,
-                                          mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s);
-          time_end();
-        }
-      else
-        {
-      const cudaTextureObject_t tex = (cfg / 4) % 2 ? laplace_src_texture(op, src) : 0;
-      const uint32_t *gl = split ? op->glist.p + (part == 2 ? op->n_iface_groups : 0) : nullptr;
-      const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
-      time_begin();
-      launch_laplace_slab2<Number>(mf->p, cfg, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng,
-                                   mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, tex, op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill, mf->idx.p, op->idxJ.p, n_plain);
-      time_end();
-        }
-    }
-  else if (av == 2)
-    {
-      // variant 3 = 2 blocks x 4 warps per SM with up to 255 registers (no spills); measured faster than 3 x 4 x 168
-      // for degree 4 in FP64 (profiles/r01_*), which is therefore what "auto" picks there
-      const bool two_blocks = op->variant == 3 || (op->variant == 0 && mf->p == 4 && mf->dt == MFG_F64);
-      time_begin();
-      launch_laplace_slab<Number>(mf->p, op->variant == 4 ? 15 : op->variant == 5 ? 12 : two_blocks ? 2 : 0, mf->idx.p, (const Number *)op->cw.p, src, dst, n_plain, mf->fe.val.data(),
-                                  mf->fe.colloc.data(), op->ctx->sm_count, s);
+                                   pdl_fill && ng ? op->ch->constrained.p : nullptr, pdl_fill && ng ? (uint32_t)op->ch->n() : 0u);
+      fused_ccopy = pdl_fill && ng;  // (no groups: no kernel, the copy below runs)
       time_end();
     }
   else if (mf->general)

@@ -56,11 +56,10 @@ struct mfg_laplace
   std::unique_ptr<mfg_vec> inv_diag;
   bool     diagonal_is_available = false;
   int      variant = 0;
-  // slab2 kernel (kernels_slab2.cuh): the index map and the merged weights in the order its threads consume them,
-  // built on first use from idx / cw
+  // slab kernels (kernels_slab3.cuh, kernels_stage.cuh): the index map and the merged weights in the order their threads
+  // consume them, built on first use from idx / cw
   mfg::DevBuf<uint32_t> idxP;   // [n_groups][n^2 slots][32 lanes]
   mfg::DevBuf<uint8_t>  cwP;    // [n_groups][shared-memory image]
-  mfg::DevBuf<uint32_t> idxJ;   // plane-layout scatter (configurations 512 + c): idx with j as the slowest local index
   mfg::DevBuf<uint32_t> mergeP; // [n_groups] face-merge mask
   int                   merge_dirs_built = -1;  // directions the mask was built for
   mfg::DevBuf<uint32_t> glist;  // multi-GPU work list: groups touching interface DoFs first (laplace_set_interface_dofs)
@@ -76,9 +75,6 @@ struct mfg_laplace
   uint32_t              st_class_pat[8] = {0};  // tables the kernel keeps in shared memory, per class of groups
   bool                  st_built = false;
   uint32_t              st_stats[8] = {0};   // groups, staged, patterns, own, halo, plain, red, smem wavefronts (per staged group, x 16)
-  // texture objects over source vectors (slab2 variants that gather through the texture pipe), keyed by pointer
-  struct SrcTex { const void *p; size_t n; cudaTextureObject_t tex; };
-  std::vector<SrcTex>   src_tex;
   mfg::DevBuf<uint8_t> solver_work;  // mfg_solver_cg: residual, direction, A*direction, device-resident scalars (reused across solves)
   mfg::DevBuf<uint8_t> host_stage_src, host_stage_dst;  // device staging for vmult_host
   // pipelined host API (mfg_laplace_vmult_host_async): 2 slots x {src,dst} staging, copy streams, events
