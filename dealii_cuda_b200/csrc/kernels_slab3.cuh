@@ -45,13 +45,18 @@ template <int BYTES> __device__ __forceinline__ void slab3_cp_zfill(void *smem_d
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(gsrc), "n"(BYTES), "r"(sz) : "memory");
 }
 
-// ASYNC: gather through cp.async one group ahead (false: register gather at the start of the group, as the slab2 kernel);
-// EARLY: face merges right after the contraction across the face (false: no merges)
-template <int n, typename Number, bool ASYNC, bool EARLY>
+// ASYNC: gather through cp.async one group ahead (false: register gather at the start of the group);
+// EARLY: face merges right after the contraction across the face (false: no merges);
+// DOT:   the kernel also emits src . (A src) (conjugate gradients: the denominator of alpha without a pass of its own):
+//        src . (A src) = sum over the quadrature points of w |grad src|^2 (+ src_c^2 on the constrained rows), which is at hand in
+//        registers in the quadrature phases: every warp sums its share in a fixed order and stores one partial sum; dot_out[w] is
+//        written by the same warp w in every launch
+template <int n, typename Number, bool ASYNC, bool EARLY, bool DOT>
 __global__ void __launch_bounds__(Slab3Cfg<n, Number, ASYNC>::WPB * 32) __maxnreg__((Slab3Cfg<n, Number, ASYNC>::REGS))
 laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__ cwP, const Number *__restrict__ src, Number *__restrict__ dst,
                    const uint32_t n_groups, const __grid_constant__ EoMats<Number, n> em, const uint32_t *__restrict__ mergeP,
-                   const uint32_t *__restrict__ glist, const int dep_wait, const uint32_t *__restrict__ clist, const uint32_t n_clist)
+                   const uint32_t *__restrict__ glist, const int dep_wait, const uint32_t *__restrict__ clist, const uint32_t n_clist,
+                   double *__restrict__ dot_out)
 {
   using Cfg = Slab3Cfg<n, Number, ASYNC>;
   using Tab = typename Cfg::Tab;
@@ -68,6 +73,9 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
   const int  cl = lm.cl, ch = lm.ch, x = lm.x, cc = lm.c;
   const uint32_t total_warps = gridDim.x * Cfg::WPB;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // dep_wait: 1 = the kernel in front only writes dst (zero pass): wait before the first write; 2 = it also writes src
+  // (fused CG: d = beta d - z): wait before the first read
+  if (dep_wait == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t k0 = blockIdx.x * Cfg::WPB + warp;
   if (k0 >= n_groups) return;
   auto group_of = [&](uint32_t k) { return glist ? __ldg(glist + k) : k; };
@@ -91,6 +99,7 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
   uint32_t g = group_of(k0);
   if (lane == 0) bulk_load(W, cwP + (size_t)g * Cfg::F, Cfg::CW_BYTES, bar);
   unsigned phase = 0;
+  double   dacc = 0;  // DOT: this lane's share of src . (A src)
   if (ASYNC)
     {
       uint32_t id[NS];
@@ -110,6 +119,7 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
       const uint32_t *irow = idxP + (size_t)g * NS * 32 + lane;
       if (more && lane < NS) asm volatile("prefetch.global.L2 [%0];" ::"l"(idxP + ((size_t)(more ? gn : g) * NS + lane) * 32));
       Number u[NS], r[NS];
+      Number eacc = Number(0);  // DOT: sum of w |grad src|^2 over this lane's quadrature points of the group
       // ---- read_dof_values: the slab u[j + n k] arrived in this lane's rows one group ago ----
       uint32_t id[NS];
       if (ASYNC)
@@ -164,7 +174,12 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
           for (int i = 0; i < n; ++i) in[i] = u[i + n * j];
           eo_apply<n, true, Number>(em.D, in, gq);
 #pragma unroll
-          for (int i = 0; i < n; ++i) gq[i] *= W[bBCw + BC.SI * i + BC.SJ * j];
+          for (int i = 0; i < n; ++i)
+            {
+              const Number wg = gq[i] * W[bBCw + BC.SI * i + BC.SJ * j];
+              if (DOT) eacc = fma(gq[i], wg, eacc);
+              gq[i] = wg;
+            }
           eo_apply<n, true, Number>(em.DT, gq, t);
 #pragma unroll
           for (int i = 0; i < n; ++i) r[i + n * j] = t[i];
@@ -177,7 +192,12 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
           for (int j = 0; j < n; ++j) in[j] = u[i + n * j];
           eo_apply<n, true, Number>(em.D, in, gq);
 #pragma unroll
-          for (int j = 0; j < n; ++j) gq[j] *= W[bBCw + BC.SI * i + BC.SJ * j];
+          for (int j = 0; j < n; ++j)
+            {
+              const Number wg = gq[j] * W[bBCw + BC.SI * i + BC.SJ * j];
+              if (DOT) eacc = fma(gq[j], wg, eacc);
+              gq[j] = wg;
+            }
           eo_apply<n, true, Number>(em.DT, gq, t);
 #pragma unroll
           for (int j = 0; j < n; ++j) r[i + n * j] += t[j];
@@ -204,7 +224,12 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
           for (int kk = 0; kk < n; ++kk) in[kk] = u[i + n * kk];
           eo_apply<n, true, Number>(em.D, in, gq);
 #pragma unroll
-          for (int kk = 0; kk < n; ++kk) gq[kk] *= W[bBCr + BC.SI * i + BC.SK * kk];
+          for (int kk = 0; kk < n; ++kk)
+            {
+              const Number wg = gq[kk] * W[bBCr + BC.SI * i + BC.SK * kk];
+              if (DOT) eacc = fma(gq[kk], wg, eacc);
+              gq[kk] = wg;
+            }
           eo_apply<n, true, Number>(em.DT, gq, t);
 #pragma unroll
           for (int kk = 0; kk < n; ++kk) u[i + n * kk] = t[kk] + P[bBCr + BC.SI * i + BC.SK * kk];
@@ -271,14 +296,16 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
               if (ys) u[(n - 1) + n * kk] = Number(0);
             }
         }
-      if (dep_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+      if (dep_wait == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
       // whole vmult: identity on the constrained rows (load_and_add_constrained_values, constraint_handler_gpu.cu:277-289):
       // dst is zero now, the cells never write these rows, so any warp may copy its share once
       if (clist != nullptr && k == k0)
         for (uint32_t t = k0 * 32 + lane; t < n_clist; t += (total_warps < n_groups ? total_warps : n_groups) * 32)  // (warps with work)
           {
             const uint32_t c = __ldg(clist + t);
-            dst[c] = __ldg(src + c);
+            const Number   v = __ldg(src + c);
+            dst[c] = v;
+            if (DOT) dacc += (double)v * (double)v;
           }
       // ---- distribute_local_to_global: red.add straight from registers; what was handed over is not written ----
       const bool xdead = xs && x == n - 1;
@@ -286,15 +313,25 @@ laplace_cell_slab3(const uint32_t *__restrict__ idxP, const Number *__restrict__
       for (int s = 0; s < NS; ++s)
         {
           const bool handed_over = xdead || (s % n == n - 1 && ys) || (s / n == n - 1 && zs);
-          if (!(idc[s] & CONSTRAINED_BIT) && !handed_over) red_add(dst + idc[s], u[s]);
+          if (!(idc[s] & CONSTRAINED_BIT) && !handed_over)
+            red_add(dst + idc[s], u[s]);
         }
+      if (DOT && active) dacc += (double)eacc;
       g = gn;
+    }
+  if (DOT)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dacc += __shfl_down_sync(0xffffffffu, dacc, o);
+      if (lane == 0) dot_out[k0] = dacc;
     }
 }
 
 template <typename Number>
 void launch_laplace_slab3(int degree, const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N,
-                          const double *D, int sm_count, cudaStream_t stream, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait,
-                          int device, int flavour, const uint32_t *clist, uint32_t n_clist);  // flavour: bit 0 = asynchronous gather, bit 1 = early face merges
+                          const double *D, int sm_count, cudaStream_t stream, const uint32_t *mergeP, const uint32_t *glist, bool pdl, int dep_wait,
+                          int device, int flavour, const uint32_t *clist, uint32_t n_clist, double *dot_out = nullptr,
+                          uint32_t *n_dot = nullptr);  // flavour: bit 0 = asynchronous gather, bit 1 = early face merges;
+                                                       // dot_out: per-warp partial sums of src . (A src), *n_dot of them (register gather only)
 
 }  // namespace mfg

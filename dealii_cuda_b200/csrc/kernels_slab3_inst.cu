@@ -15,16 +15,16 @@ typedef double inst_number;
 typedef float inst_number;
 #endif
 
-template <int n, typename Number, bool ASYNC, bool EARLY>
+template <int n, typename Number, bool ASYNC, bool EARLY, bool DOT = false>
 static void launch_f(const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N, const double *D,
-                     int sm_count, cudaStream_t stream, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait, int device,
-                     const uint32_t *clist, uint32_t n_clist)
+                     int sm_count, cudaStream_t stream, const uint32_t *mergeP, const uint32_t *glist, bool pdl, int dep_wait, int device,
+                     const uint32_t *clist, uint32_t n_clist, double *dot_out, uint32_t *n_dot)
 {
   using Cfg = Slab3Cfg<n, Number, ASYNC>;
   if (n_groups == 0) return;
   EoMats<Number, n> em;
   make_eo_tables<Number, n>(N, D, em);
-  auto       kern = laplace_cell_slab3<n, Number, ASYNC, EARLY>;
+  auto       kern = laplace_cell_slab3<n, Number, ASYNC, EARLY, DOT>;
   static int blocks_per_sm[64] = {0};  // (function attributes are per device)
   MFG_REQUIRE(device >= 0 && device < 64, "device index out of range");
   if (blocks_per_sm[device] == 0)
@@ -39,6 +39,7 @@ static void launch_f(const uint32_t *idxP, const Number *cwP, const Number *src,
   // pdl without dep_wait = interior groups of a multi-GPU apply: a few CTA slots stay free for the exchange kernels
   const uint32_t reserve = 4, full = (uint32_t)(sm_count * blocks_per_sm[device]);
   const uint32_t grid = std::min<uint32_t>(want, pdl && !dep_wait && full > reserve + 1 ? full - reserve : full);
+  if (n_dot) *n_dot = std::min<uint32_t>(grid * Cfg::WPB, n_groups);  // warps with work = partial sums written
   if (pdl)
     {
       cudaLaunchConfig_t cfg;
@@ -48,21 +49,30 @@ static void launch_f(const uint32_t *idxP, const Number *cwP, const Number *src,
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      MFG_CUDA(cudaLaunchKernelEx(&cfg, kern, idxP, cwP, src, dst, n_groups, em, mergeP, glist, (int)dep_wait, clist, n_clist));
+      MFG_CUDA(cudaLaunchKernelEx(&cfg, kern, idxP, cwP, src, dst, n_groups, em, mergeP, glist, dep_wait, clist, n_clist, dot_out));
     }
   else
     {
-      kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, mergeP, glist, 0, clist, n_clist);
+      kern<<<grid, Cfg::WPB * 32, Cfg::SMEM, stream>>>(idxP, cwP, src, dst, n_groups, em, mergeP, glist, 0, clist, n_clist, dot_out);
       MFG_CUDA_LAST();
     }
 }
 
 template <int n, typename Number>
 static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N, const double *D,
-                     int sm_count, cudaStream_t stream, const uint32_t *mergeP, const uint32_t *glist, bool pdl, bool dep_wait, int device, int flavour,
-                     const uint32_t *clist, uint32_t n_clist)
+                     int sm_count, cudaStream_t stream, const uint32_t *mergeP, const uint32_t *glist, bool pdl, int dep_wait, int device, int flavour,
+                     const uint32_t *clist, uint32_t n_clist, double *dot_out, uint32_t *n_dot)
 {
-#define MFG_B idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, mergeP, glist, pdl, dep_wait, device, clist, n_clist
+  if (dot_out)
+    {
+      if (flavour & 1) throw Error(MFG_ERR_UNSUPPORTED, "slab3 kernel: the fused dot product exists for the register gather only");
+#define MFG_B2 idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, mergeP, glist, pdl, dep_wait, device, clist, n_clist, dot_out, n_dot
+      if (flavour & 2) launch_f<n, Number, false, true, true>(MFG_B2);
+      else launch_f<n, Number, false, false, true>(MFG_B2);
+#undef MFG_B2
+      return;
+    }
+#define MFG_B idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, mergeP, glist, pdl, dep_wait, device, clist, n_clist, dot_out, n_dot
   switch (flavour & 3)
     {
       case 0: launch_f<n, Number, false, false>(MFG_B); break;
@@ -76,9 +86,10 @@ static void launch_n(const uint32_t *idxP, const Number *cwP, const Number *src,
 template <>
 void launch_laplace_slab3<inst_number>(int degree, const uint32_t *idxP, const inst_number *cwP, const inst_number *src, inst_number *dst,
                                        uint32_t n_groups, const double *N, const double *D, int sm_count, cudaStream_t stream, const uint32_t *mergeP,
-                                       const uint32_t *glist, bool pdl, bool dep_wait, int device, int flavour, const uint32_t *clist, uint32_t n_clist)
+                                       const uint32_t *glist, bool pdl, int dep_wait, int device, int flavour, const uint32_t *clist, uint32_t n_clist, double *dot_out,
+                                       uint32_t *n_dot)
 {
-#define MFG_A idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, mergeP, glist, pdl, dep_wait, device, flavour, clist, n_clist
+#define MFG_A idxP, cwP, src, dst, n_groups, N, D, sm_count, stream, mergeP, glist, pdl, dep_wait, device, flavour, clist, n_clist, dot_out, n_dot
   switch (degree)
     {
       case 1: launch_n<2, inst_number>(MFG_A); break;

@@ -904,7 +904,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
                                    (split && part == 2) || pdl_fill, pdl_fill, add, op->ctx->device);
       if (nf)
         launch_laplace_slab3<Number>(mf->p, op->idxP.p, (const Number *)op->cwP.p, src, dst, nf, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s,
-                                     op->mergeP.p, fl, false, false, op->ctx->device, 0, nullptr, 0u);
+                                     op->mergeP.p, fl, false, 0, op->ctx->device, 0, nullptr, 0u);
       time_end();
     }
   else if (av == 50)
@@ -914,7 +914,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       const uint32_t  ng = !split ? op->slab2_groups : part == 2 ? op->slab2_groups - op->n_iface_groups : op->n_iface_groups;
       time_begin();
       launch_laplace_slab3<Number>(mf->p, op->idxP.p, (const Number *)op->cwP.p, src, dst, ng, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s,
-                                   op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill, op->ctx->device, slab3_flavour(op),
+                                   op->mergeP.p, gl, (split && part == 2) || pdl_fill, pdl_fill ? 1 : 0, op->ctx->device, slab3_flavour(op),
                                    pdl_fill && ng ? op->ch->constrained.p : nullptr, pdl_fill && ng ? (uint32_t)op->ch->n() : 0u);
       fused_ccopy = pdl_fill && ng;  // (no groups: no kernel, the copy below runs)
       time_end();
@@ -954,6 +954,28 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
     }
   // identity on the constrained rows (the cell kernel never writes them; the slab3 kernel does this copy itself)
   if (pdl_fill && op->ch->n() && !fused_ccopy) { constrained_copy<Number><<<nblk(op->ch->n()), 256, 0, s>>>(dst, src, op->ch->constrained.p, op->ch->n()); MFG_CUDA_LAST(); }
+}
+
+// Cell loop of the slab3 kernel alone, for the fused CG loop (solver.cu): dst must be ZERO on entry and written by the
+// kernel in front of this one in the stream (the cell kernel is launched as its programmatic dependent and waits for it
+// before its first write); the kernel also copies the constrained rows (dst[c] = src[c]) and stores per-warp partial
+// sums of src . (A src) to dot_out (returns how many).  False if the operator's active kernel cannot do this.
+bool laplace_cell_dot(mfg_laplace *op, void *dst, const void *src, double *dot_out, uint32_t *n_dot)
+{
+  const mfg_mf *mf = op->mf;
+  if (laplace_active_variant(op) != 50 || mf->hn_mask.n != 0 || (slab3_flavour(op) & 1)) return false;
+  laplace_prepare_slab2(op, mf->n_cells);
+  if (op->slab2_groups == 0) return false;
+  cudaStream_t s = op->ctx->stream;
+  if (mf->dt == MFG_F64)
+    launch_laplace_slab3<double>(mf->p, op->idxP.p, (const double *)op->cwP.p, (const double *)src, (double *)dst, op->slab2_groups, mf->fe.val.data(),
+                                 mf->fe.colloc.data(), op->ctx->sm_count, s, op->mergeP.p, nullptr, true, 2, op->ctx->device, slab3_flavour(op),
+                                 op->ch->constrained.p, (uint32_t)op->ch->n(), dot_out, n_dot);
+  else
+    launch_laplace_slab3<float>(mf->p, op->idxP.p, (const float *)op->cwP.p, (const float *)src, (float *)dst, op->slab2_groups, mf->fe.val.data(),
+                                mf->fe.colloc.data(), op->ctx->sm_count, s, op->mergeP.p, nullptr, true, 2, op->ctx->device, slab3_flavour(op),
+                                op->ch->constrained.p, (uint32_t)op->ch->n(), dot_out, n_dot);
+  return true;
 }
 
 void laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches)

@@ -75,6 +75,7 @@ struct mfg_laplace
   uint32_t              st_class_pat[8] = {0};  // tables the kernel keeps in shared memory, per class of groups
   bool                  st_built = false;
   uint32_t              st_stats[8] = {0};   // groups, staged, patterns, own, halo, plain, red, smem wavefronts (per staged group, x 16)
+  mfg::DevBuf<double>  solver_dot;   // fused CG: per-warp partial sums of d . (A d) written by the cell kernel
   mfg::DevBuf<uint8_t> solver_work;  // mfg_solver_cg: residual, direction, A*direction, device-resident scalars (reused across solves)
   mfg::DevBuf<uint8_t> host_stage_src, host_stage_dst;  // device staging for vmult_host
   // pipelined host API (mfg_laplace_vmult_host_async): 2 slots x {src,dst} staging, copy streams, events
@@ -116,4 +117,5 @@ void         laplace_compute_diagonal(mfg_laplace *op);
 int          laplace_launches_per_vmult(const mfg_laplace *op);
 int          laplace_active_variant(const mfg_laplace *op);
 void         laplace_kernel_time(mfg_laplace *op, double *total_ms, int *n_launches);
+bool         laplace_cell_dot(mfg_laplace *op, void *dst, const void *src, double *dot_out, uint32_t *n_dot);
 }  // namespace mfg

@@ -1,9 +1,13 @@
 // solver.cu -- conjugate gradients on GpuVectors with the Laplace operator: the control flow of deal.II's
-// SolverCG<GpuVector> as the reference instantiates it (poisson.cu:233-260), with the
-// BLAS-1 of every iteration fused into three kernels (12 vector passes) instead of the reference's five
-// (operator*, add, add_and_dot, DiagonalMatrix::vmult -> scale, sadd; gpu_vec.cu:306-617), each of which
-// cudaMallocs and blocks on a D2H copy there; here alpha, beta and the residual stay on the device and the host
-// never waits inside the loop.  Preconditioner: the inverse diagonal (PreconditionChebyshev with
+// SolverCG<GpuVector> as the reference instantiates it (poisson.cu:233-260).  The reference runs
+// five BLAS-1 kernels per iteration (operator*, add, add_and_dot, DiagonalMatrix::vmult -> scale, sadd;
+// gpu_vec.cu:306-617), each of which cudaMallocs and blocks on a D2H copy.  Here alpha, beta and the residual stay on the
+// device, the host never waits inside the loop, and an iteration is THREE kernels:
+//   cell kernel   h = A d (constrained rows included) and, in the same pass, the per-warp partial sums of d . h
+//   cg_residual   alpha = g.z / d.h ; g += alpha h ; z = Minv g (into h) ; |g|^2, g.z ; convergence ; beta
+//   cg_advance    x += alpha d ; d = beta d - z ; h = 0 -- the zero pass of the NEXT operator application
+// 11 vector passes beside the operator's own (the reference: 15 + the operator's zero pass and two constraint kernels).
+// Operators whose kernel cannot emit the dot product (column kernel, hanging nodes) use vmult + cg_dot instead.  Preconditioner: the inverse diagonal (PreconditionChebyshev with
 // its default degree 0 is a scaled Jacobi step; the scaling does not change the CG iterates).
 #include <chrono>
 #include <cstdio>
@@ -94,16 +98,44 @@ __global__ void cg_dot(const T *__restrict__ d, const T *__restrict__ h, size_t 
 }
 // g += alpha h ; z = Minv .* g (z overwrites h) ; |g|, g.z ; convergence test ; beta = g.z / gh_old
 // (first = true: alpha = 0, h holds nothing yet: only z and the sums, the start of the iteration)
+// dotp != nullptr: alpha = gh / (sum of the n_dot partial sums of d . h the cell kernel left), summed by every block in the
+// same fixed order, so that all blocks use the same bits
 template <typename T>
 __global__ void cg_residual(T *__restrict__ g, T *__restrict__ h, const T *__restrict__ minv, size_t n, double *__restrict__ partial, CgState *st,
-                            int it, double *__restrict__ history)
+                            int it, double *__restrict__ history, const double *__restrict__ dotp, unsigned n_dot)
 {
   if (st->converged_at >= 0) return;
   const bool first = it == 0;
-  const T alpha = first ? T(0) : (T)st->alpha;
+  __shared__ double s_alpha;
+  if (dotp != nullptr && !first)
+    {
+      double a = 0, b = 0;
+      for (unsigned i = threadIdx.x; i < n_dot; i += blockDim.x) a += dotp[i];
+      block_sum2(a, b);
+      if (threadIdx.x == 0) s_alpha = st->gh / a;
+      __syncthreads();
+    }
+  const T alpha = first ? T(0) : (T)(dotp != nullptr ? s_alpha : st->alpha);
   double gg = 0, gz = 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride)  // four independent elements per thread in flight
+    {
+      T gv[4], hv[4], mv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { gv[k] = g[i + k * stride]; hv[k] = first ? T(0) : h[i + k * stride]; mv[k] = minv ? minv[i + k * stride] : T(1); }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        {
+          const T gi = first ? gv[k] : gv[k] + alpha * hv[k];
+          if (!first) g[i + k * stride] = gi;
+          const T zi = mv[k] * gi;
+          h[i + k * stride] = zi;
+          gg += (double)gi * (double)gi;
+          gz += (double)gi * (double)zi;
+        }
+    }
+  for (; i < n; i += stride)
     {
       const T gi = first ? g[i] : g[i] + alpha * h[i];
       if (!first) g[i] = gi;
@@ -124,25 +156,43 @@ __global__ void cg_residual(T *__restrict__ g, T *__restrict__ h, const T *__res
           if (history) history[it] = res;
           if (res <= st->tol) st->converged_at = it;
           st->beta = first ? 0.0 : gz / st->gh;
+          if (dotp != nullptr && !first) st->alpha = s_alpha;  // (for cg_advance)
           st->gh = gz;
           st->ticket = 0;
         }
     }
 }
 // x += alpha d (also in the iteration that converged, as SolverCG updates the solution before the check) ;
-// d = beta d - z ; h = 0 is left to the operator
-template <typename T> __global__ void cg_advance(T *__restrict__ x, T *__restrict__ d, const T *__restrict__ z, size_t n, const CgState *st, int it)
+// d = beta d - z ; zero_z: z = 0, the zero pass of the next operator application, whose cell kernel is launched as the
+// programmatic dependent of this kernel
+template <typename T> __global__ void cg_advance(T *__restrict__ x, T *__restrict__ d, T *__restrict__ z, size_t n, const CgState *st, int it, bool zero_z)
 {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int c = st->converged_at;
   if (c >= 0 && c < it) return;
   const bool first = it == 0, done = c == it;
   const T alpha = (T)st->alpha, beta = (T)st->beta;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride)
+    {
+      T dv[4], xv[4], zv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { dv[k] = first ? T(0) : d[i + k * stride]; xv[k] = first ? T(0) : x[i + k * stride]; zv[k] = done ? T(0) : z[i + k * stride]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        {
+          if (!first) x[i + k * stride] = xv[k] + alpha * dv[k];
+          if (!done) d[i + k * stride] = beta * dv[k] - zv[k];
+          if (zero_z) z[i + k * stride] = T(0);
+        }
+    }
+  for (; i < n; i += stride)
     {
       const T di = first ? T(0) : d[i];
       if (!first) x[i] += alpha * di;
       if (!done) d[i] = beta * di - z[i];
+      if (zero_z) z[i] = T(0);
     }
 }
 
@@ -187,10 +237,16 @@ void cg_solve(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double tol, int max
     MFG_CUDA(cudaMemcpyAsync(mirror + it % (LAG + 1), st.p, sizeof(CgState), cudaMemcpyDeviceToHost, s));
     MFG_CUDA(cudaEventRecord(ev[it % (LAG + 1)], s));
   };
+  // fused loop: the cell kernel emits d . (A d) and runs behind cg_advance, which zeroes its destination
+  uint32_t n_dot = 0;
+  if (op->solver_dot.n < 8192) op->solver_dot.alloc(8192);
+  MFG_CUDA(cudaMemsetAsync(op->solver_dot.p, 0, op->solver_dot.bytes(), s));
+  const bool fused = std::getenv("MFG_CG_UNFUSED") == nullptr && laplace_active_variant(op) == 50 && op->mf->hn_mask.n == 0 && op->mf->n_cells > 0 &&
+                     (size_t)ctx->sm_count * 3 * 4 <= op->solver_dot.n;
   // iteration 0: h = Minv g, |g|, g.h ; d = -h
-  cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, 0, hist.p);
+  cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, 0, hist.p, nullptr, 0u);
   MFG_CUDA_LAST();
-  cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, 0);
+  cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, 0, fused);
   MFG_CUDA_LAST();
   snapshot(0);
   const bool dbg = getenv("MFG_CG_DEBUG") != nullptr;
@@ -205,13 +261,14 @@ void cg_solve(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double tol, int max
           if (mirror[(it - LAG) % (LAG + 1)].converged_at >= 0) break;
         }
       const double tb = dbg ? now() : 0;
-      laplace_vmult(op, h.p, d.p, false);                                   // h = A d
+      bool with_dot = false;
+      if (fused) with_dot = laplace_cell_dot(op, h.p, d.p, op->solver_dot.p, &n_dot);   // h = A d and the partial sums of d . h
+      if (!with_dot) laplace_vmult(op, h.p, d.p, false);                                  // h = A d
       const double tc = dbg ? now() : 0;
-      cg_dot<T><<<nb, TH, 0, s>>>(d.p, h.p, n, partial, st.p);             // alpha
+      if (!with_dot) { cg_dot<T><<<nb, TH, 0, s>>>(d.p, h.p, n, partial, st.p); MFG_CUDA_LAST(); }  // alpha
+      cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, it, hist.p, with_dot ? op->solver_dot.p : nullptr, n_dot);
       MFG_CUDA_LAST();
-      cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, it, hist.p);
-      MFG_CUDA_LAST();
-      cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, it);
+      cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, it, fused);
       MFG_CUDA_LAST();
       snapshot(it);
       if (dbg) { const double td = now(); t_wait += tb - ta; t_vmult += tc - tb; t_rest += td - tc; }

@@ -32,7 +32,7 @@ class InterfaceExchange:
         # (high priority: its interface cell kernel gets SM slots before the interior kernel launched next to it)
         self.side = torch.cuda.Stream(priority=-1) if plan.world > 1 and plan.n_send else None
         self.ev_ready, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
-        self.symm = None
+        self.symm, self.recv_p2p = None, None
         import torch.distributed as dist
         if self.side is not None and os.environ.get("MFG_NO_P2P") is None and dist.is_available() and dist.is_initialized() \
                 and dist.get_backend(group) == "nccl":
@@ -60,7 +60,8 @@ class InterfaceExchange:
             starts = np.concatenate([[0], np.cumsum([plan.splits[q] for q in nb])]).astype(np.uint32)
             self._chunk_start = (C.c_uint32 * starts.size)(*starts.tolist())
             self._n_chunks = len(nb)
-            self.recv, self.symm = recv, hdl
+            # (the NCCL path keeps its own receive buffer: a neighbour that is one apply ahead may already push into this one)
+            self.recv_p2p, self.symm = recv, hdl
         except Exception as e:  # no peer access / symmetric memory on this system
             self.symm = None
             if self.plan.rank == 0:
@@ -107,7 +108,7 @@ class InterfaceExchange:
                                                C.c_void_p(side.cuda_stream)))
             with torch.cuda.stream(side):
                 self.symm.barrier(0)
-            check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.recv.data_ptr()), C.c_void_p(side.cuda_stream)))
+            check(lib.mfg_exchange_accumulate_stream(self.h, C.c_void_p(dst_ptr), C.c_void_p(self.recv_p2p.data_ptr()), C.c_void_p(side.cuda_stream)))
             with torch.cuda.stream(side):
                 self.symm.barrier(1)
         else:

@@ -75,3 +75,34 @@ def test_cg_fp32_and_nonzero_start(ctx):
     it, res = mf.solver_cg(op, x, vb, 1e-4 * np.linalg.norm(b), 500)
     assert 0 < it < 500
     assert np.linalg.norm(x.toVector() - u_exact) <= 1e-3 * np.linalg.norm(u_exact)
+
+
+@pytest.mark.parametrize("p,r", [(4, 2), (3, 3), (2, 3), (5, 1)])
+def test_cg_fused_loop_equals_unfused_loop(ctx, p, r, monkeypatch):
+    """the fused loop (d . A d emitted by the cell kernel, the operator's zero pass done by cg_advance; solver.cu) against the
+    loop with vmult + cg_dot: same iteration count, residual histories equal to rounding, and the first iterates within
+    1e-12 of the numpy restatement of SolverCG on the oracle operator"""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(3, p, r)
+    u_exact = sm64(13, o.n_dofs)
+    b = o.vmult(u_exact)
+    tol = 1e-10 * np.linalg.norm(b)
+    m = mf.HyperCubeMesh(ctx, 3, p, r)
+    runs = []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("MFG_CG_UNFUSED", "1")
+        op = mf.LaplaceOperatorGpu(ctx, np.float64)
+        op.reinit(m)
+        assert op.active_variant() == 50
+        x, vb = mf.GpuVector(ctx, o.n_dofs), mf.GpuVector.from_numpy(ctx, b)
+        it, res, hist = mf.solver_cg(op, x, vb, tol, 2000, history=True)
+        runs.append((it, np.asarray(hist), x.toVector()))
+    (it_f, h_f, x_f), (it_u, h_u, x_u) = runs
+    assert abs(it_f - it_u) <= 1
+    k = min(12, it_f, it_u)
+    assert np.allclose(h_f[:k], h_u[:k], rtol=1e-11)
+    assert np.linalg.norm(x_f - x_u) <= 1e-9 * np.linalg.norm(x_u)
+    xr, itr, hr = numpy_cg(o, b, tol, 2000, True)
+    assert np.allclose(h_f[:6], hr[:6], rtol=1e-12)
+    assert np.linalg.norm(x_f - u_exact) <= 1e-8 * np.linalg.norm(u_exact)
