@@ -137,6 +137,12 @@ def _load():
         "mfg_laplace_kernel_time_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int)]),
         "mfg_laplace_active_variant": (C.c_int, [vp]),
         "mfg_laplace_stage_stats": (C.c_int, [vp, u32p]),
+        "mfg_cgd_init": (C.c_int, [vp, vp]),
+        "mfg_cgd_dot": (C.c_int, [vp, C.c_int, vp, vp, vp, sz, vp]),
+        "mfg_cgd_alpha": (C.c_int, [vp, vp]),
+        "mfg_cgd_residual": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, sz, vp, C.c_int]),
+        "mfg_cgd_beta": (C.c_int, [vp, vp, C.c_double, C.c_int]),
+        "mfg_cgd_advance": (C.c_int, [vp, C.c_int, vp, vp, vp, sz, vp, C.c_int]),
         "mfg_stage_plan_build": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u32p, C.c_int, pp]),
         "mfg_stage_plan_info": (C.c_int, [vp, u32p]),
         "mfg_stage_plan_get": (C.c_int, [vp, u32p, u32p, C.POINTER(C.c_uint16), u32p]),

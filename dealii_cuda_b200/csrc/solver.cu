@@ -196,6 +196,134 @@ template <typename T> __global__ void cg_advance(T *__restrict__ x, T *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Building blocks of the CG loop over a partition (one process per GPU): the same three vector kernels with
+// sums over the OWNED DoFs only; the scalars live in a block of 8 doubles on the device that the caller all-reduces in
+// stream order between the kernels (NCCL), so the host never reads a scalar inside the loop.
+//   scal[0] = d.h   scal[1] = g.g   scal[2] = g.z   scal[4] = g.z of the previous iterate   scal[5] = alpha
+//   scal[6] = beta  scal[7] = iteration at which |g| <= tol was met (-1 before)   scal[3] = |g|   scal[9] = iteration counter
+// (it < 0 in cgd_beta / cgd_advance: the iteration number is the device counter, so that one captured CUDA graph serves every iteration)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ inline void block_partial_store(double a, double b, double *partial)
+{
+  block_sum2(a, b);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b; }
+}
+template <typename T>
+__global__ void cgd_dot(const T *__restrict__ d, const T *__restrict__ h, const uint8_t *__restrict__ owned, size_t n, double *__restrict__ partial,
+                        double *scal, unsigned *ticket)
+{
+  if (scal[7] >= 0) return;
+  double s0 = 0, s1 = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride)  // four independent elements per thread in flight
+    {
+      T dv[4], hv[4];
+      uint8_t ov[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { dv[k] = d[i + k * stride]; hv[k] = h[i + k * stride]; ov[k] = owned[i + k * stride]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ov[k]) s0 += (double)dv[k] * (double)hv[k];
+    }
+  for (; i < n; i += stride)
+    if (owned[i]) s0 += (double)d[i] * (double)h[i];
+  block_partial_store(s0, s1, partial);
+  if (last_block_done(ticket))
+    {
+      sum_partials2(partial, s0, s1);
+      if (threadIdx.x == 0) { scal[0] = s0; *ticket = 0; }
+    }
+}
+// one thread: alpha = g.z / d.h (after the all-reduce of scal[0])
+__global__ void cgd_alpha(double *scal) { if (scal[7] < 0) scal[5] = scal[4] / scal[0]; }
+template <typename T>
+__global__ void cgd_residual(T *__restrict__ g, T *__restrict__ h, const T *__restrict__ minv, const uint8_t *__restrict__ owned, size_t n,
+                             double *__restrict__ partial, double *scal, unsigned *ticket, int first)
+{
+  if (scal[7] >= 0) return;
+  const T alpha = first ? T(0) : (T)scal[5];
+  double gg = 0, gz = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride)
+    {
+      T gv[4], hv[4], mv[4];
+      uint8_t ov[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        {
+          gv[k] = g[i + k * stride]; hv[k] = first ? T(0) : h[i + k * stride]; mv[k] = minv ? minv[i + k * stride] : T(1);
+          ov[k] = owned[i + k * stride];
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        {
+          const T gi = first ? gv[k] : gv[k] + alpha * hv[k];
+          if (!first) g[i + k * stride] = gi;
+          const T zi = mv[k] * gi;
+          h[i + k * stride] = zi;
+          if (ov[k]) { gg += (double)gi * (double)gi; gz += (double)gi * (double)zi; }
+        }
+    }
+  for (; i < n; i += stride)
+    {
+      const T gi = first ? g[i] : g[i] + alpha * h[i];
+      if (!first) g[i] = gi;
+      const T zi = minv ? minv[i] * gi : gi;
+      h[i] = zi;
+      if (owned[i]) { gg += (double)gi * (double)gi; gz += (double)gi * (double)zi; }
+    }
+  block_partial_store(gg, gz, partial);
+  if (last_block_done(ticket))
+    {
+      sum_partials2(partial, gg, gz);
+      if (threadIdx.x == 0) { scal[1] = gg; scal[2] = gz; *ticket = 0; }
+    }
+}
+// one thread: |g|, convergence, beta (after the all-reduce of scal[1..2])
+__global__ void cgd_beta(double *scal, double tol, int it, double *history)
+{
+  if (scal[7] >= 0) return;
+  if (it < 0) it = (int)scal[9] + 1;
+  scal[9] = (double)it;
+  const double res = sqrt(scal[1]);
+  scal[3] = res;
+  if (history) history[it] = res;
+  scal[6] = it == 0 ? 0.0 : scal[2] / scal[4];
+  scal[4] = scal[2];
+  if (res <= tol) scal[7] = (double)it;
+}
+template <typename T> __global__ void cgd_advance(T *__restrict__ x, T *__restrict__ d, const T *__restrict__ z, size_t n, const double *scal, int it)
+{
+  if (it < 0) it = (int)scal[9];
+  const double c = scal[7];
+  if (c >= 0 && c < it) return;
+  const bool first = it == 0, done = c == (double)it;
+  const T alpha = (T)scal[5], beta = (T)scal[6];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride)
+    {
+      T dv[4], xv[4], zv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { dv[k] = first ? T(0) : d[i + k * stride]; xv[k] = first ? T(0) : x[i + k * stride]; zv[k] = done ? T(0) : z[i + k * stride]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        {
+          if (!first) x[i + k * stride] = xv[k] + alpha * dv[k];
+          if (!done) d[i + k * stride] = beta * dv[k] - zv[k];
+        }
+    }
+  for (; i < n; i += stride)
+    {
+      const T di = first ? T(0) : d[i];
+      if (!first) x[i] += alpha * di;
+      if (!done) d[i] = beta * di - z[i];
+    }
+}
+
 template <typename T>
 void cg_solve(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double tol, int max_iter, bool jacobi, int *iters, double *last_res,
               double *history)
@@ -299,5 +427,60 @@ extern "C" int mfg_solver_cg(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, doub
     MFG_REQUIRE(max_iter >= 0, "max_iter must be non-negative");
     if (op->mf->dt == MFG_F64) cg_solve<double>(op, x, b, abs_tol, max_iter, use_jacobi != 0, iters, last_residual, residual_history);
     else cg_solve<float>(op, x, b, abs_tol, max_iter, use_jacobi != 0, iters, last_residual, residual_history);
+  });
+}
+
+// ---- CG over a partition: kernels on device pointers; `scal` = 8 doubles on the device (+ 1 unsigned ticket behind them) ----
+static int cgd_blocks(const mfg_ctx *ctx, size_t n)
+{
+  return (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((RED_SCRATCH_DOUBLES - 8) / 2, (size_t)ctx->sm_count * 8), (n + 256 * 8 - 1) / (256 * 8)));
+}
+extern "C" int mfg_cgd_init(mfg_ctx *ctx, double *scal_dev)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && scal_dev, "null argument");
+    const double init[10] = {0, 0, 0, 0, 0, 0, 0, -1.0, 0, 0};  // ([8] holds the ticket counter: zero bits)
+    MFG_CUDA(cudaMemcpyAsync(scal_dev, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    MFG_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+extern "C" int mfg_cgd_dot(mfg_ctx *ctx, mfg_dtype dt, const void *d, const void *h, const uint8_t *owned_dev, size_t n, double *scal_dev)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && d && h && owned_dev && scal_dev, "null argument");
+    unsigned *ticket = reinterpret_cast<unsigned *>(scal_dev + 8);
+    const int nb = cgd_blocks(ctx, n);
+    if (dt == MFG_F64) cgd_dot<double><<<nb, 256, 0, ctx->stream>>>((const double *)d, (const double *)h, owned_dev, n, ctx->red_dev + 8, scal_dev, ticket);
+    else cgd_dot<float><<<nb, 256, 0, ctx->stream>>>((const float *)d, (const float *)h, owned_dev, n, ctx->red_dev + 8, scal_dev, ticket);
+    MFG_CUDA_LAST();
+  });
+}
+extern "C" int mfg_cgd_alpha(mfg_ctx *ctx, double *scal_dev)
+{
+  return guarded([&] { MFG_REQUIRE(ctx && scal_dev, "null argument"); cgd_alpha<<<1, 1, 0, ctx->stream>>>(scal_dev); MFG_CUDA_LAST(); });
+}
+extern "C" int mfg_cgd_residual(mfg_ctx *ctx, mfg_dtype dt, void *g, void *h, const void *minv, const uint8_t *owned_dev, size_t n, double *scal_dev, int first)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && g && h && owned_dev && scal_dev, "null argument");
+    unsigned *ticket = reinterpret_cast<unsigned *>(scal_dev + 8);
+    const int nb = cgd_blocks(ctx, n);
+    if (dt == MFG_F64) cgd_residual<double><<<nb, 256, 0, ctx->stream>>>((double *)g, (double *)h, (const double *)minv, owned_dev, n, ctx->red_dev + 8, scal_dev, ticket, first);
+    else cgd_residual<float><<<nb, 256, 0, ctx->stream>>>((float *)g, (float *)h, (const float *)minv, owned_dev, n, ctx->red_dev + 8, scal_dev, ticket, first);
+    MFG_CUDA_LAST();
+  });
+}
+extern "C" int mfg_cgd_beta(mfg_ctx *ctx, double *scal_dev, double tol, int it)
+{
+  return guarded([&] { MFG_REQUIRE(ctx && scal_dev, "null argument"); cgd_beta<<<1, 1, 0, ctx->stream>>>(scal_dev, tol, it, nullptr); MFG_CUDA_LAST(); });
+}
+extern "C" int mfg_cgd_advance(mfg_ctx *ctx, mfg_dtype dt, void *x, void *d, const void *z, size_t n, const double *scal_dev, int it)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && x && d && z && scal_dev, "null argument");
+    const int nb = cgd_blocks(ctx, n);
+    if (dt == MFG_F64) cgd_advance<double><<<nb, 256, 0, ctx->stream>>>((double *)x, (double *)d, (const double *)z, n, scal_dev, it);
+    else cgd_advance<float><<<nb, 256, 0, ctx->stream>>>((float *)x, (float *)d, (const float *)z, n, scal_dev, it);
+    MFG_CUDA_LAST();
   });
 }

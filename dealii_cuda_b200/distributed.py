@@ -149,6 +149,29 @@ class DistributedLaplaceOperator:
     def vmult(self, dst, src):
         self.vmult_ptr(dst.getData(), src.getData())
 
+    def vmult_graphed(self, dst_ptr, src_ptr):
+        """the apply (cell kernels, pushes, barriers, accumulate on two streams) replayed as ONE CUDA graph per (dst, src) pair:
+        eager launches from Python are host-bound.  Needs a non-default current stream; falls back to eager launches."""
+        import torch
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get((dst_ptr, src_ptr))
+        if g is None:
+            self.vmult_ptr(dst_ptr, src_ptr)  # (this call computes the result; the capture below only records)
+            if graphs.get("disabled") or os.environ.get("MFG_NO_GRAPH") is not None:
+                return
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+                    self.vmult_ptr(dst_ptr, src_ptr)
+                graphs[(dst_ptr, src_ptr)] = g
+            except Exception as e:
+                graphs["disabled"] = True
+                if self.rank == 0:
+                    print("CUDA graph capture of the apply failed (%s): eager launches" % e, file=__import__("sys").stderr)
+            return
+        g.replay()
+
     def dot(self, a, b):
         """Global dot product: owned DoFs locally (deterministic two-pass reduction), then all_reduce."""
         import torch
@@ -162,13 +185,18 @@ class DistributedLaplaceOperator:
         return float(t.item())
 
 
-def solver_cg_distributed(dop, x, b, abs_tol, max_iter=10000, use_jacobi=True):
-    """SolverCG over the box partition (poisson.cu:233-260 control flow; the single-GPU form is mfg_solver_cg): the operator is
-    DistributedLaplaceOperator.vmult (replicas of interface DoFs stay bit-identical), inner products run over owned DoFs
-    (mfg_vec_dot_masked) + all_reduce, the Jacobi diagonal is the exchanged sum of the local diagonals.  Vector updates are the
-    library's BLAS-1 kernels.  Returns (iterations, last residual)."""
+def solver_cg_distributed(dop, x, b, abs_tol, max_iter=10000, use_jacobi=True, check_every=8):
+    """SolverCG over the box partition (poisson.cu:233-260 control flow; the single-GPU form is mfg_solver_cg).  The operator is
+    DistributedLaplaceOperator.vmult (replicas of interface DoFs stay bit-identical), the vector kernels are mfg_cgd_*: sums
+    over the owned DoFs, scalars in a device block that is all-reduced in stream order (NCCL) -- no rank reads a scalar on the
+    host inside the loop.  Every `check_every` iterations all ranks read the (identical) convergence flag; kernels of
+    iterations behind the converged one return at once, so x is the iterate of the converged iteration.  The Jacobi
+    diagonal is the exchanged sum of the local diagonals.  Returns (iterations, last residual)."""
+    import torch
+    import torch.distributed as dist
     ctx, n = dop.ctx, dop.n_local
     dt = np.float64 if x.dtype == np.float64 else np.float32
+    code = _capi.F64 if dt == np.float64 else _capi.F32
     g, d, h = GpuVector(ctx, n, dt), GpuVector(ctx, n, dt), GpuVector(ctx, n, dt)
     minv = None
     if use_jacobi:
@@ -181,44 +209,77 @@ def solver_cg_distributed(dop, x, b, abs_tol, max_iter=10000, use_jacobi=True):
             diag.invert()
             dop._inv_diag = diag
         minv = dop._inv_diag
-    # g = A x - b
+    world, group = dop.world, dop.exchange.group
+    scal = torch.zeros(16, dtype=torch.float64, device="cuda")   # (kept alive by the captured graph)
+    sp, own = C.c_void_p(scal.data_ptr()), C.c_void_p(dop.exchange.owned_mask.data_ptr())
+    check(lib.mfg_cgd_init(ctx.h, sp))
+    vp = lambda v: C.c_void_p(v.getData())
+
+    def allreduce(lo, hi):
+        if world > 1:
+            dist.all_reduce(scal[lo:hi], group=group)
+
+    # g = A x - b ; iteration 0: z = Minv g, |g|, g.z ; d = -z
     dop.vmult(g, x)
     g.add(-1.0, b)
+    check(lib.mfg_cgd_residual(ctx.h, code, vp(g), vp(h), vp(minv) if minv is not None else None, own, n, sp, 1))
+    allreduce(1, 3)
+    check(lib.mfg_cgd_beta(ctx.h, sp, float(abs_tol), 0))
+    check(lib.mfg_cgd_advance(ctx.h, code, vp(x), vp(d), vp(h), n, sp, 0))
+    def iteration(it):
+        dop.vmult_graphed(h.getData(), d.getData())                              # h = A d
+        check(lib.mfg_cgd_dot(ctx.h, code, vp(d), vp(h), own, n, sp))
+        allreduce(0, 1)
+        check(lib.mfg_cgd_alpha(ctx.h, sp))
+        check(lib.mfg_cgd_residual(ctx.h, code, vp(g), vp(h), vp(minv) if minv is not None else None, own, n, sp, 0))
+        allreduce(1, 3)
+        check(lib.mfg_cgd_beta(ctx.h, sp, float(abs_tol), it))
+        check(lib.mfg_cgd_advance(ctx.h, code, vp(x), vp(d), vp(h), n, sp, it))
 
-    def precondition():
-        if minv is not None:
-            h.assign(g)
-            h.scale(minv)
-        else:
-            h.assign(g)
-
-    precondition()
-    gh = dop.dot(g, h)
-    res = dop.dot(g, g) ** 0.5
+    # One iteration (apply, vector kernels, the two all-reduces) as ONE CUDA graph: the Python loop with its NCCL calls is
+    # host-bound (1.05 ms per iteration at 2 x 17 M DoFs against 0.6 ms of device work).  it = -1: device-side counter.
+    graph = None
     it = 0
-    if res > abs_tol:
-        d.equ(-1.0, h)
-        for it in range(1, max_iter + 1):
-            dop.vmult(h, d)
-            alpha = gh / dop.dot(d, h)
-            x.add(alpha, d)
-            g.add(alpha, h)
-            res = dop.dot(g, g) ** 0.5
-            if res <= abs_tol:
-                break
-            precondition()
-            gh_new = dop.dot(g, h)
-            beta = gh_new / gh
-            gh = gh_new
-            d.sadd(beta, -1.0, h)
-    return it, res
+    if max_iter >= 2 and os.environ.get("MFG_NO_GRAPH") is None and torch.cuda.current_stream() != torch.cuda.default_stream():
+        iteration(1)                       # eager: warms every kernel and the apply's own graph
+        it = 1
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=torch.cuda.current_stream()):
+                dop.vmult_ptr(h.getData(), d.getData())
+                check(lib.mfg_cgd_dot(ctx.h, code, vp(d), vp(h), own, n, sp))
+                allreduce(0, 1)
+                check(lib.mfg_cgd_alpha(ctx.h, sp))
+                check(lib.mfg_cgd_residual(ctx.h, code, vp(g), vp(h), vp(minv) if minv is not None else None, own, n, sp, 0))
+                allreduce(1, 3)
+                check(lib.mfg_cgd_beta(ctx.h, sp, float(abs_tol), -1))
+                check(lib.mfg_cgd_advance(ctx.h, code, vp(x), vp(d), vp(h), n, sp, -1))
+        except Exception as e:
+            graph = None
+            if dop.rank == 0:
+                print("CUDA graph capture of the CG iteration failed (%s): eager launches" % e, file=__import__("sys").stderr)
+    done = False
+    state = scal[:8].cpu()
+    done = float(state[7]) >= 0
+    while it < max_iter and not done:
+        for _ in range(min(check_every, max_iter - it)):
+            it += 1
+            if graph is not None:
+                graph.replay()
+            else:
+                iteration(it)
+        state = scal[:8].cpu()                     # the only host read: identical on all ranks
+        done = float(state[7]) >= 0
+    its = int(state[7]) if done else it
+    return its, float(state[3])
 
 
 def bench_main(args, metric):
     """bench.py --gpus N (N > 1): weak scaling, one 2^r cube of cells per GPU."""
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, b_alg, measured_peaks, cpu_reference_run
+    from bench import ClockSampler, b_alg, measured_peaks, cpu_reference_run, PROFILED_TRAFFIC
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -302,6 +363,11 @@ def bench_main(args, metric):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if rank == 0:
         sampler.start()
+    t_lead = time.perf_counter()   # clock samples (20 ms period) start 0.3 s before the timed region, under the same load
+    while time.perf_counter() - t_lead < 0.3:
+        apply_steps(50)
+        torch.cuda.synchronize()
+    ta.fill_(0.1); tb.fill_(0.1)
     dist.barrier()
     torch.cuda.synchronize()
     e0.record()
@@ -325,26 +391,56 @@ def bench_main(args, metric):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, k_avg_ms = float(t[0]), float(t[1])
 
-    # end to end: pinned host src -> H2D -> vmult (+exchange) -> D2H
-    hs = torch.full((n,), 0.1, dtype=tdtype).pin_memory()
-    hd = torch.empty((n,), dtype=tdtype).pin_memory()
+    # end to end: pinned host src -> H2D -> vmult (+exchange) -> D2H, two slots per rank pipelined on three streams (PCIe is
+    # full duplex: step k's D2H overlaps step k+1's H2D; the applies stay on the main stream).  Blocking figure next to it.
+    hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
+    hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
+    ds = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
+    dd = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]; ev_ap = [torch.cuda.Event() for _ in range(2)]; ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        ta.copy_(hs, non_blocking=True)
-        dop.vmult_ptr(tb.data_ptr(), ta.data_ptr())
-        hd.copy_(tb, non_blocking=True)
+    def e2e_blocking():
+        ds[0].copy_(hs[0], non_blocking=True)
+        dop.vmult_ptr(dd[0].data_ptr(), ds[0].data_ptr())
+        hd[0].copy_(dd[0], non_blocking=True)
         torch.cuda.synchronize()
 
-    e2e_step()
+    def e2e_pipelined(steps):
+        for k in range(steps):
+            sl = k % 2
+            s_h2d.wait_event(ev_ap[sl])                      # the apply that read this slot's source two steps ago is done
+            with torch.cuda.stream(s_h2d):
+                ds[sl].copy_(hs[sl], non_blocking=True)
+                ev_in[sl].record(s_h2d)
+            main.wait_event(ev_in[sl])
+            main.wait_event(ev_out[sl])                      # this slot's previous result has left the device
+            dop.vmult_graphed(dd[sl].data_ptr(), ds[sl].data_ptr())
+            ev_ap[sl].record(main)
+            s_d2h.wait_event(ev_ap[sl])
+            with torch.cuda.stream(s_d2h):
+                hd[sl].copy_(dd[sl], non_blocking=True)
+                ev_out[sl].record(s_d2h)
+        torch.cuda.synchronize()
+
+    e2e_blocking()
     dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
+    for _ in range(3):
+        e2e_blocking()
     dist.barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    e2e_block_s = (time.perf_counter() - t0) / 3
+    e2e_pipelined(4)   # warm-up: captures the two graphs
+    n_e2e = max(args.e2e_steps, 6)
+    dist.barrier()
+    t0 = time.perf_counter()
+    e2e_pipelined(n_e2e)
+    dist.barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    te = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
+    e2e_s, e2e_block_s = float(te[0]), float(te[1])
+    del hs, hd, ds, dd
 
     # CG solve over all GPUs (BASELINE metric "CG time"): b = A u for a vector u whose interface replicas agree
     cg = None
@@ -371,7 +467,8 @@ def bench_main(args, metric):
         err = dop.dot(vx, vx) ** 0.5 / dop.dot(ue, ue) ** 0.5
         cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "rel_error": err, "n_dofs": dop.n_global,
               "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|",
-              "note": "host-orchestrated (distributed.solver_cg_distributed): library BLAS-1 kernels, masked dot + all_reduce"}
+              "loop": "distributed.solver_cg_distributed: graph-replayed apply + mfg_cgd_* kernels, scalars all-reduced on the device (NCCL, "
+                      "in stream order), one host read of the convergence flag every 8 iterations"}
     if rank == 0:
         ng = dop.n_global
         peak, peak_src = measured_peaks()
@@ -382,12 +479,13 @@ def bench_main(args, metric):
                 "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": "bmop: 3D variable-coefficient Laplace apply, FE_Q(%d), one refine_global(%d) cube of %d cells per GPU, "
                                        "%s grid of cubes, %d global DoFs (%d per GPU incl. interface replicas), atomic scatter, "
-                                       "NCCL all_to_all interface exchange" % (args.degree, args.refine, dop.mesh.n_cells,
-                                                                               "x".join(map(str, dop.grid)), ng, n),
+                                       "interface exchange: %s" % (args.degree, args.refine, dop.mesh.n_cells, "x".join(map(str, dop.grid)), ng, n,
+                                                                   "NVLink P2P stores + device-side barriers" if dop.exchange.symm is not None
+                                                                   else "NCCL all_to_all_single"),
                            "l2": "inputs larger than L2"},
                 "clocks": clocks,
                 "e2e": {"value": ng / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
-                        "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
+                        "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3},
                 # per apply and rank: constraint pass + cell kernel(s) + push (or pack) + accumulate; the split apply zeroes
                 # dst with cudaMemsetAsync (no zero kernel) and launches the cell kernel twice
                 "gpu_launches": args.steps * world * ((dop.op.launches_per_vmult() if not dop.n_iface_groups else dop.op.launches_per_vmult()) + 2),
@@ -397,16 +495,25 @@ def bench_main(args, metric):
                              if dop.exchange.symm is not None else "NCCL all_to_all_single"),
                 "overlap": "interface cell groups first (%d of the groups), exchange on a side stream during the interior groups" % dop.n_iface_groups
                            if dop.n_iface_groups else "none",
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             # same kernel and per-GPU workload as the N = 1 line: the committed single-GPU ncu capture applies
+                             "traffic": PROFILED_TRAFFIC.get((args.dim, args.degree, args.dtype, args.refine, dop.op.active_variant())),
                              "kernel": "laplace cell kernel (variant %d), per GPU and apply (%d launches), max over ranks"
                                        % (dop.op.active_variant(), kernel_launches // n_k),
                              "kernel_ms": k_avg_ms, "peak_source": peak_src},
                 "cpu_baseline": None, "cg_solve": cg}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    # Captured graphs hold NCCL kernels; tearing the communicator down after them hung in ncclCommDestroy on this
-    # stack (torch 2.11 / NCCL 2.28), so the ranks synchronise, flush and leave without the teardown.
+    # Teardown: ncclCommDestroy hung on this stack (torch 2.11 / NCCL 2.28) after captured graphs that hold NCCL kernels had
+    # run; the graphs are released first and the teardown gets 20 s on a watchdog thread before the ranks leave without it.
     graphs.clear()
+    getattr(dop, "_graphs", {}).clear()
     torch.cuda.synchronize()
     __import__("sys").stdout.flush()
     __import__("sys").stderr.flush()
-    os._exit(0)
+    import threading
+    threading.Timer(20.0, lambda: os._exit(0)).start()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)

@@ -317,6 +317,19 @@ int mfg_exchange_push_stream(mfg_exchange *ex, const void *vec_dev, const uint64
 int mfg_exchange_pack_stream(mfg_exchange *ex, const void *vec_dev, void *send_dev, void *cuda_stream);
 /* owned-DoF dot product support: mask[i] = 1 if this rank owns DoF i (lowest rank touching it) */
 int mfg_vec_dot_masked(const mfg_vec *a, const mfg_vec *b, const uint8_t *owned_mask_dev, double *out);
+/* CG over the partition (SolverCG control flow, poisson.cu:233-260, one process per GPU): the three vector kernels of
+ * mfg_solver_cg with sums over the OWNED DoFs, and the scalars in a device block `scal` of 9 doubles ([0] d.h, [1] g.g,
+ * [2] g.z, [3] |g|, [4] previous g.z, [5] alpha, [6] beta, [7] iteration of convergence or -1, [8] scratch) that the caller
+ * all-reduces in stream order (NCCL) between the kernels -- entries [0] after mfg_cgd_dot, [1..2] after mfg_cgd_residual --
+ * so that no rank reads a scalar on the host inside the loop.  scal needs 10 doubles ([9] = iteration counter on the device: with
+ * it < 0 mfg_cgd_beta / mfg_cgd_advance take the iteration number from it, so one captured CUDA graph serves every iteration).
+ * All kernels run on the context stream. */
+int mfg_cgd_init(mfg_ctx *ctx, double *scal_dev);
+int mfg_cgd_dot(mfg_ctx *ctx, mfg_dtype dt, const void *d, const void *h, const uint8_t *owned_dev, size_t n, double *scal_dev);
+int mfg_cgd_alpha(mfg_ctx *ctx, double *scal_dev);                 /* alpha = g.z / d.h */
+int mfg_cgd_residual(mfg_ctx *ctx, mfg_dtype dt, void *g, void *h, const void *minv, const uint8_t *owned_dev, size_t n, double *scal_dev, int first);
+int mfg_cgd_beta(mfg_ctx *ctx, double *scal_dev, double tol, int it);  /* |g|, convergence flag, beta */
+int mfg_cgd_advance(mfg_ctx *ctx, mfg_dtype dt, void *x, void *d, const void *z, size_t n, const double *scal_dev, int it);
 
 #ifdef __cplusplus
 }
