@@ -137,6 +137,17 @@ def _load():
         "mfg_laplace_kernel_time_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int)]),
         "mfg_laplace_active_variant": (C.c_int, [vp]),
         "mfg_laplace_stage_stats": (C.c_int, [vp, u32p]),
+        "mfg_chebyshev_create": (C.c_int, [vp, C.c_int, C.c_double, C.c_int, pp]),
+        "mfg_chebyshev_destroy": (C.c_int, [vp]),
+        "mfg_chebyshev_vmult": (C.c_int, [vp, vp, vp]),
+        "mfg_chebyshev_step": (C.c_int, [vp, vp, vp]),
+        "mfg_chebyshev_info": (C.c_int, [vp, dp, dp, dp, dp, C.POINTER(C.c_int)]),
+        "mfg_mg_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, pp]),
+        "mfg_mg_destroy": (C.c_int, [vp]),
+        "mfg_mg_vcycle": (C.c_int, [vp, vp, vp]),
+        "mfg_mg_level_operator": (C.c_int, [vp, C.c_int, pp]),
+        "mfg_mg_info": (C.c_int, [vp, C.c_int, dp, C.POINTER(C.c_long), C.POINTER(sz)]),
+        "mfg_mg_solve_cg": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(C.c_int), dp, dp]),
         "mfg_cgd_init": (C.c_int, [vp, vp]),
         "mfg_cgd_dot": (C.c_int, [vp, C.c_int, vp, vp, vp, sz, vp]),
         "mfg_cgd_alpha": (C.c_int, [vp, vp]),

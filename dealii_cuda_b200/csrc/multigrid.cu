@@ -1,0 +1,368 @@
+// multigrid.cu -- PreconditionChebyshev, the multigrid V-cycle and the V-cycle-preconditioned CG of the reference's
+// poisson_mg.cu / bmop_mg.cu (poisson_mg.cu:430-552, bmop_mg.cu:300-340) behind the C ABI.
+//
+// In the reference this is deal.II template code instantiated on GpuVector (PreconditionChebyshev, Multigrid,
+// PreconditionMG, MGSmootherPrecondition, MGCoarseIterative = SolverCG to a 1e-10 reduction, SolverCG outside), every
+// vector operation a separate BLAS-1 kernel.  Here it is C++ host code over the same library objects (level
+// LaplaceOperatorGpu, MGTransferMatrixFreeGpu) with ONE fused vector kernel per Chebyshev matrix-vector product:
+//   t = Dinv (b - A x);  d = f1 d + f2 t;  x += d              (PreconditionChebyshev::vector_updates)
+// deal.II conventions restated (deal.II 8.5 precondition.h, from memory -- deal.II is not available):
+//   * eigenvalue estimate: eig_cg_n_iterations steps of SolverCG on Dinv A from x = 0 with the right-hand side
+//     1/sqrt(n) (entry 0 set to 0), stopping early at |g| <= 1e-2 (eig_cg_residual); lambda_max / lambda_min = largest /
+//     smallest eigenvalue of the Lanczos tridiagonal matrix built from the CG coefficients;
+//   * beta = 1.2 lambda_max, alpha = lambda_max / smoothing_range (range > 1), delta = (beta - alpha) / 2,
+//     theta = (beta + alpha) / 2, rho_0 = delta / theta, sigma = theta / delta, rho_{k+1} = 1 / (2 sigma - rho_k);
+//   * vmult (zero initial guess): x = d = Dinv b / theta, then `degree` products; step (given x): the same with the
+//     first update d = Dinv (b - A x) / theta;
+//   * V-cycle (Multigrid::level_v_step): pre-smooth from zero, t = b - A x, restrict_and_add into a zeroed defect,
+//     recurse, prolongate, x += t, post-smooth (step); coarsest level: unpreconditioned CG to 1e-10 |b|.
+// Globally refined meshes: there are no refinement edges, so the edge matrices (vmult_interface_down / up,
+// laplace_operator_gpu.h:306-352) are the zero operator and are not called.
+#include <cmath>
+#include <memory>
+#include <vector>
+#include "operators.cuh"
+
+using namespace mfg;
+
+extern "C" int mfg_solver_cg(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter, int use_jacobi, int *iters,
+                             double *last_residual, double *residual_history);
+
+namespace {
+
+#define MG_CHECK(call)                                                                    \
+  do {                                                                                    \
+    const int rc__ = (call);                                                              \
+    if (rc__ != MFG_OK) throw Error(rc__, std::string(mfg_last_error()));                 \
+  } while (0)
+
+struct Vec  // owning GpuVector
+{
+  mfg_vec *v = nullptr;
+  Vec() = default;
+  Vec(mfg_ctx *ctx, mfg_dtype dt, size_t n) { MG_CHECK(mfg_vec_create(ctx, dt, n, &v)); }
+  Vec(const Vec &) = delete;
+  Vec &operator=(const Vec &) = delete;
+  Vec(Vec &&o) noexcept : v(o.v) { o.v = nullptr; }
+  Vec &operator=(Vec &&o) noexcept { if (this != &o) { if (v) mfg_vec_destroy(v); v = o.v; o.v = nullptr; } return *this; }
+  ~Vec() { if (v) mfg_vec_destroy(v); }
+};
+
+// x, d: updated; ax = A x on entry (first: ignored when zero_start); b: right-hand side
+// zero_start: d = f2 Dinv b, x = d;   else: t = Dinv (b - ax), d = f1 d + f2 t, x += d
+template <typename T>
+__global__ void cheb_update(T *__restrict__ x, T *__restrict__ d, const T *__restrict__ ax, const T *__restrict__ b, const T *__restrict__ dinv, size_t n,
+                            T f1, T f2, bool zero_start, bool first)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+      const T r = zero_start ? b[i] : b[i] - ax[i];
+      const T di = (first ? T(0) : f1 * d[i]) + f2 * dinv[i] * r;
+      d[i] = di;
+      x[i] = zero_start ? di : x[i] + di;
+    }
+}
+
+// eigenvalues of the symmetric tridiagonal matrix (diag a, off-diagonal b) by bisection on the Sturm count
+int sturm_count(const std::vector<double> &a, const std::vector<double> &b, double x)
+{
+  int    cnt = 0;
+  double q = a[0] - x;
+  if (q < 0) ++cnt;
+  for (size_t i = 1; i < a.size(); ++i)
+    {
+      q = a[i] - x - b[i - 1] * b[i - 1] / (q != 0 ? q : 1e-300);
+      if (q < 0) ++cnt;
+    }
+  return cnt;  // number of eigenvalues < x
+}
+double tridiag_eigenvalue(const std::vector<double> &a, const std::vector<double> &b, int k)  // k-th smallest (0-based)
+{
+  double lo = 1e300, hi = -1e300;
+  for (size_t i = 0; i < a.size(); ++i)
+    {
+      const double r = (i ? std::fabs(b[i - 1]) : 0) + (i + 1 < a.size() ? std::fabs(b[i]) : 0);
+      lo = std::min(lo, a[i] - r); hi = std::max(hi, a[i] + r);
+    }
+  for (int it = 0; it < 200; ++it)
+    {
+      const double mid = 0.5 * (lo + hi);
+      if (sturm_count(a, b, mid) > k) hi = mid; else lo = mid;
+    }
+  return 0.5 * (lo + hi);
+}
+
+}  // namespace
+
+struct mfg_cheb
+{
+  mfg_laplace *op = nullptr;
+  int          degree = 0;
+  double       smoothing_range = 0, lambda_max = 0, lambda_min = 0, theta = 0, delta = 0;
+  int          eig_iterations_done = 0;
+  Vec          d, t;  // update1, update2
+
+  void update(mfg_vec *x, const mfg_vec *b, double f1, double f2, bool zero_start, bool first)
+  {
+    const mfg_mf *mf = op->mf;
+    const size_t  n = mf->n_dofs;
+    const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)op->ctx->sm_count * 16));
+    cudaStream_t  s = op->ctx->stream;
+    if (mf->dt == MFG_F64)
+      cheb_update<double><<<nb, 256, 0, s>>>((double *)x->p, (double *)d.v->p, (const double *)t.v->p, (const double *)b->p, (const double *)op->inv_diag->p, n, f1, f2, zero_start, first);
+    else
+      cheb_update<float><<<nb, 256, 0, s>>>((float *)x->p, (float *)d.v->p, (const float *)t.v->p, (const float *)b->p, (const float *)op->inv_diag->p, n, (float)f1, (float)f2, zero_start, first);
+    MFG_CUDA_LAST();
+  }
+  // PreconditionChebyshev::vmult (zero_start) / ::step
+  void apply(mfg_vec *x, const mfg_vec *b, bool zero_start)
+  {
+    double rhok = delta / theta;
+    const double sigma = theta / delta;
+    if (!zero_start) laplace_vmult(op, t.v->p, x->p, false);
+    update(x, b, 0.0, 1.0 / theta, zero_start, true);
+    for (int k = 0; k < degree; ++k)
+      {
+        laplace_vmult(op, t.v->p, x->p, false);
+        const double rhokp = 1.0 / (2.0 * sigma - rhok), f1 = rhokp * rhok, f2 = 2.0 * rhokp / delta;
+        rhok = rhokp;
+        update(x, b, f1, f2, false, false);
+      }
+  }
+  // eigenvalue estimate: CG (SolverCG control flow) on Dinv A, Lanczos matrix from its coefficients
+  void estimate(int n_iterations, double eig_cg_residual)
+  {
+    mfg_ctx *ctx = op->ctx;
+    const mfg_mf *mf = op->mf;
+    const size_t n = mf->n_dofs;
+    Vec g(ctx, mf->dt, n), h(ctx, mf->dt, n), dd(ctx, mf->dt, n), rhs(ctx, mf->dt, n);
+    vec_fill(rhs.v, 1.0 / std::sqrt((double)n));
+    if (n) MFG_CUDA(cudaMemsetAsync(rhs.v->p, 0, rhs.v->esize(), ctx->stream));  // entry 0 = 0: triggers the high frequencies
+    vec_equ(g.v, -1.0, rhs.v);                                                    // x = 0: g = -b
+    auto precondition = [&]() { MG_CHECK(mfg_vec_copy(h.v, g.v)); vec_scale(h.v, op->inv_diag.get()); };
+    precondition();
+    vec_equ(dd.v, -1.0, h.v);
+    double gh = vec_dot(g.v, h.v), res = std::sqrt(vec_dot(g.v, g.v));
+    std::vector<double> alphas, betas;
+    for (int it = 1; it <= n_iterations && res > eig_cg_residual; ++it)
+      {
+        laplace_vmult(op, h.v->p, dd.v->p, false);
+        const double alpha = gh / vec_dot(dd.v, h.v);
+        alphas.push_back(alpha);
+        res = std::sqrt(vec_add_and_dot(g.v, alpha, h.v, g.v));
+        precondition();
+        const double gh_new = vec_dot(g.v, h.v), beta = gh_new / gh;
+        gh = gh_new;
+        betas.push_back(beta);
+        vec_sadd(dd.v, beta, -1.0, h.v);
+      }
+    eig_iterations_done = (int)alphas.size();
+    if (alphas.empty()) { lambda_max = lambda_min = 1.0; return; }
+    const size_t k = alphas.size();
+    std::vector<double> a(k), b(k > 1 ? k - 1 : 0);
+    for (size_t j = 0; j < k; ++j)
+      {
+        a[j] = 1.0 / alphas[j] + (j ? betas[j - 1] / alphas[j - 1] : 0.0);
+        if (j + 1 < k) b[j] = std::sqrt(betas[j]) / alphas[j];
+      }
+    lambda_max = tridiag_eigenvalue(a, b, (int)k - 1);
+    lambda_min = tridiag_eigenvalue(a, b, 0);
+  }
+};
+
+struct mfg_mg
+{
+  mfg_ctx *ctx = nullptr;
+  mfg_dtype dt = MFG_F64;
+  int min_level = 0, max_level = 0;
+  std::vector<mfg_mesh *>    meshes;
+  std::vector<mfg_laplace *> ops;
+  std::vector<mfg_mgt *>     transfers;   // [l]: level l-1 -> l (l > min_level)
+  std::vector<std::unique_ptr<mfg_cheb>> smoothers;
+  std::vector<Vec> x, b, t;
+  long coarse_iterations = 0;
+  int  L(int level) const { return level - min_level; }
+  ~mfg_mg()
+  {
+    smoothers.clear();
+    for (auto *p : transfers) if (p) mfg_mgt_destroy(p);
+    for (auto *p : ops) if (p) mfg_laplace_destroy(p);
+    for (auto *p : meshes) if (p) mfg_mesh_destroy(p);
+  }
+  void cycle(int level)  // Multigrid::level_v_step
+  {
+    const int l = L(level);
+    mfg_laplace *op = ops[l];
+    if (level == min_level)
+      {
+        vec_fill(x[l].v, 0.0);
+        const double bn = std::sqrt(vec_dot(b[l].v, b[l].v));
+        int its = 0;
+        MG_CHECK(mfg_solver_cg(op, x[l].v, b[l].v, 1e-10 * std::max(bn, 1e-300), 10000, 0, &its, nullptr, nullptr));
+        coarse_iterations += its;
+        return;
+      }
+    smoothers[l]->apply(x[l].v, b[l].v, true);                       // pre-smoothing from a zero guess
+    laplace_vmult(op, t[l].v->p, x[l].v->p, false);
+    vec_sadd(t[l].v, -1.0, 1.0, b[l].v);                             // t = b - A x
+    vec_fill(b[l - 1].v, 0.0);
+    MG_CHECK(mfg_mgt_restrict_and_add(transfers[l], b[l - 1].v, t[l].v));
+    cycle(level - 1);
+    MG_CHECK(mfg_mgt_prolongate(transfers[l], t[l].v, x[l - 1].v));
+    vec_sadd(x[l].v, 1.0, 1.0, t[l].v);
+    smoothers[l]->apply(x[l].v, b[l].v, false);                      // post-smoothing
+  }
+  void vmult(mfg_vec *dst, const mfg_vec *src)  // PreconditionMG::vmult: copy_to_mg, cycle, copy_from_mg
+  {
+    const int top = L(max_level);
+    MG_CHECK(mfg_vec_copy(b[top].v, src));
+    cycle(max_level);
+    MG_CHECK(mfg_vec_copy(dst, x[top].v));
+  }
+};
+
+extern "C" {
+
+int mfg_chebyshev_create(mfg_laplace *op, int degree, double smoothing_range, int eig_cg_n_iterations, mfg_cheb **out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(op && out, "null argument");
+    MFG_REQUIRE(degree >= 0 && eig_cg_n_iterations >= 0, "degree and eig_cg_n_iterations must be non-negative");
+    std::unique_ptr<mfg_cheb> c(new mfg_cheb);
+    c->op = op; c->degree = degree; c->smoothing_range = smoothing_range;
+    if (!op->diagonal_is_available) laplace_compute_diagonal(op);
+    c->d = Vec(op->ctx, op->mf->dt, op->mf->n_dofs);
+    c->t = Vec(op->ctx, op->mf->dt, op->mf->n_dofs);
+    if (eig_cg_n_iterations > 0) c->estimate(eig_cg_n_iterations, 1e-2);
+    else c->lambda_max = c->lambda_min = 1.0;  // (AdditionalData::max_eigenvalue default)
+    const double beta = 1.2 * c->lambda_max;
+    const double alpha = smoothing_range > 1.0 ? c->lambda_max / smoothing_range : std::min(0.9 * c->lambda_max, c->lambda_min);
+    c->delta = 0.5 * (beta - alpha); c->theta = 0.5 * (beta + alpha);
+    *out = c.release();
+  });
+}
+int mfg_chebyshev_destroy(mfg_cheb *c) { return guarded([&] { delete c; }); }
+int mfg_chebyshev_vmult(mfg_cheb *c, mfg_vec *dst, const mfg_vec *src)
+{
+  return guarded([&] {
+    MFG_REQUIRE(c && dst && src && dst != src, "null or aliased argument");
+    MFG_REQUIRE(dst->n == c->op->mf->n_dofs && src->n == dst->n && dst->dt == c->op->mf->dt && src->dt == dst->dt, "vector does not fit the operator");
+    c->apply(dst, src, true);
+  });
+}
+int mfg_chebyshev_step(mfg_cheb *c, mfg_vec *dst, const mfg_vec *src)
+{
+  return guarded([&] {
+    MFG_REQUIRE(c && dst && src && dst != src, "null or aliased argument");
+    MFG_REQUIRE(dst->n == c->op->mf->n_dofs && src->n == dst->n && dst->dt == c->op->mf->dt && src->dt == dst->dt, "vector does not fit the operator");
+    c->apply(dst, src, false);
+  });
+}
+int mfg_chebyshev_info(const mfg_cheb *c, double *lambda_max, double *lambda_min, double *theta, double *delta, int *eig_iterations)
+{
+  return guarded([&] {
+    MFG_REQUIRE(c, "null argument");
+    if (lambda_max) *lambda_max = c->lambda_max;
+    if (lambda_min) *lambda_min = c->lambda_min;
+    if (theta) *theta = c->theta;
+    if (delta) *delta = c->delta;
+    if (eig_iterations) *eig_iterations = c->eig_iterations_done;
+  });
+}
+
+int mfg_mg_create(mfg_ctx *ctx, int dim, int degree, int min_level, int max_level, mfg_dtype dt, double left, double right, int smoother_degree,
+                  double smoothing_range, int eig_cg_n_iterations, mfg_mg **out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && out, "null argument");
+    MFG_REQUIRE(min_level >= 0 && max_level >= min_level, "levels must satisfy 0 <= min_level <= max_level");
+    std::unique_ptr<mfg_mg> mg(new mfg_mg);
+    mg->ctx = ctx; mg->dt = dt; mg->min_level = min_level; mg->max_level = max_level;
+    const int nl = max_level - min_level + 1;
+    mg->meshes.assign(nl, nullptr); mg->ops.assign(nl, nullptr); mg->transfers.assign(nl, nullptr);
+    mg->smoothers.resize(nl);
+    for (int l = 0; l < nl; ++l)
+      {
+        MG_CHECK(mfg_mesh_hyper_cube(ctx, dim, degree, min_level + l, left, right, &mg->meshes[l]));
+        MG_CHECK(mfg_laplace_create(ctx, mg->meshes[l], dt, MFG_SCATTER_ATOMIC, &mg->ops[l]));
+        if (l > 0) MG_CHECK(mfg_mgt_build(ctx, mg->meshes[l - 1], mg->meshes[l], dt, &mg->transfers[l]));
+        const size_t n = mg->meshes[l]->n_dofs;
+        mg->x.emplace_back(ctx, dt, n); mg->b.emplace_back(ctx, dt, n); mg->t.emplace_back(ctx, dt, n);
+        if (l > 0)
+          {
+            mfg_cheb *c = nullptr;
+            MG_CHECK(mfg_chebyshev_create(mg->ops[l], smoother_degree, smoothing_range, eig_cg_n_iterations, &c));
+            mg->smoothers[l].reset(c);
+          }
+      }
+    *out = mg.release();
+  });
+}
+int mfg_mg_destroy(mfg_mg *mg) { return guarded([&] { delete mg; }); }
+int mfg_mg_vcycle(mfg_mg *mg, mfg_vec *dst, const mfg_vec *src)
+{
+  return guarded([&] {
+    MFG_REQUIRE(mg && dst && src, "null argument");
+    const size_t n = mg->meshes.back()->n_dofs;
+    MFG_REQUIRE(dst->n == n && src->n == n && dst->dt == mg->dt && src->dt == mg->dt, "vector does not fit the finest level");
+    mg->vmult(dst, src);
+  });
+}
+int mfg_mg_level_operator(mfg_mg *mg, int level, mfg_laplace **op)
+{
+  return guarded([&] {
+    MFG_REQUIRE(mg && op && level >= mg->min_level && level <= mg->max_level, "bad level");
+    *op = mg->ops[mg->L(level)];
+  });
+}
+int mfg_mg_info(const mfg_mg *mg, int level, double *lambda_max, long *coarse_iterations, size_t *n_dofs)
+{
+  return guarded([&] {
+    MFG_REQUIRE(mg && level >= mg->min_level && level <= mg->max_level, "bad level");
+    const int l = mg->L(level);
+    if (lambda_max) *lambda_max = mg->smoothers[l] ? mg->smoothers[l]->lambda_max : 0.0;
+    if (coarse_iterations) *coarse_iterations = mg->coarse_iterations;
+    if (n_dofs) *n_dofs = mg->meshes[l]->n_dofs;
+  });
+}
+// SolverCG preconditioned by one V-cycle per iteration (poisson_mg.cu:504-518), on the finest level operator
+int mfg_mg_solve_cg(mfg_mg *mg, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter, int *iters, double *last_residual, double *history)
+{
+  return guarded([&] {
+    MFG_REQUIRE(mg && x && b, "null argument");
+    mfg_laplace *op = mg->ops.back();
+    const size_t n = op->mf->n_dofs;
+    MFG_REQUIRE(x->n == n && b->n == n && x->dt == mg->dt && b->dt == mg->dt, "vector does not fit the finest level");
+    Vec g(mg->ctx, mg->dt, n), h(mg->ctx, mg->dt, n), d(mg->ctx, mg->dt, n);
+    if (vec_all_zero(x)) vec_equ(g.v, -1.0, b);
+    else { laplace_vmult(op, g.v->p, x->p, false); vec_sadd(g.v, 1.0, -1.0, b); }
+    double res = std::sqrt(vec_dot(g.v, g.v));
+    int it = 0;
+    if (history) history[0] = res;
+    if (res > abs_tol)
+      {
+        mg->vmult(h.v, g.v);
+        vec_equ(d.v, -1.0, h.v);
+        double gh = vec_dot(g.v, h.v);
+        for (it = 1; it <= max_iter; ++it)
+          {
+            laplace_vmult(op, h.v->p, d.v->p, false);
+            const double alpha = gh / vec_dot(d.v, h.v);
+            vec_sadd(x, 1.0, alpha, d.v);
+            res = std::sqrt(vec_add_and_dot(g.v, alpha, h.v, g.v));
+            if (history) history[it] = res;
+            if (res <= abs_tol) break;
+            mg->vmult(h.v, g.v);
+            const double gh_new = vec_dot(g.v, h.v), beta = gh_new / gh;
+            gh = gh_new;
+            vec_sadd(d.v, beta, -1.0, h.v);
+          }
+        if (it > max_iter) it = max_iter;
+      }
+    if (iters) *iters = it;
+    if (last_residual) *last_residual = res;
+  });
+}
+
+}  // extern "C"

@@ -55,100 +55,99 @@ class MGTransferMatrixFreeGpu:
 
 
 class ChebyshevSmoother:
-    """PreconditionChebyshev on D^-1 A (poisson_mg.cu:461-470: degree 5, smoothing range 15, 15 iterations for the
-    eigenvalue estimate).  lambda_max is estimated by power iteration on D^-1 A with a 1.2 safety factor."""
+    """PreconditionChebyshev on Dinv A (poisson_mg.cu:461-470: degree 5, smoothing range 15, 15 CG/Lanczos iterations for the
+    eigenvalue estimate, deal.II's procedure): binding of mfg_chebyshev_* (csrc/multigrid.cu)."""
 
     def __init__(self, ctx, op, degree=5, smoothing_range=15.0, eig_iterations=15, dtype=np.float64):
         self.ctx, self.op, self.degree = ctx, op, degree
-        n = op.m()
-        op.compute_diagonal()
-        self.dinv = op.get_diagonal_inverse()
-        self.r, self.d, self.t = (GpuVector(ctx, n, dtype) for _ in range(3))
-        v = GpuVector.from_numpy(ctx, (1.0 + (np.arange(n) % 11) / 11.0).astype(dtype))
-        lam = 1.0
-        for _ in range(eig_iterations):
-            op.vmult(self.t, v)
-            self.t.scale(self.dinv)
-            lam = self.t.l2_norm() / v.l2_norm()
-            v.equ(1.0 / self.t.l2_norm(), self.t)
-        self.lambda_max = lam
-        beta, alpha = 1.2 * lam, 1.2 * lam / smoothing_range
-        self.theta, self.delta = 0.5 * (beta + alpha), 0.5 * (beta - alpha)
+        h = C.c_void_p()
+        check(lib.mfg_chebyshev_create(op.h, int(degree), float(smoothing_range), int(eig_iterations), C.byref(h)))
+        self.h = h
+        lmax, lmin, theta, delta, its = C.c_double(), C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        check(lib.mfg_chebyshev_info(h, C.byref(lmax), C.byref(lmin), C.byref(theta), C.byref(delta), C.byref(its)))
+        self.lambda_max, self.lambda_min, self.theta, self.delta, self.eig_iterations = lmax.value, lmin.value, theta.value, delta.value, its.value
 
-    def step(self, x, b, zero_guess):
-        """one Chebyshev sweep of the given degree on A x = b"""
-        op, r, d, t = self.op, self.r, self.d, self.t
-        theta, delta = self.theta, self.delta
-        sigma = theta / delta
-        rho = 1.0 / sigma
-        if zero_guess:
-            r.assign(b)
-        else:
-            op.vmult(r, x)
-            r.sadd(-1.0, 1.0, b)                    # r = b - A x
-        d.assign(r); d.scale(self.dinv); d *= 1.0 / theta
-        if zero_guess:
-            x.assign(d)
-        else:
-            x.add(d)
-        for _ in range(self.degree):
-            op.vmult(r, x)
-            r.sadd(-1.0, 1.0, b)
-            rho_new = 1.0 / (2.0 * sigma - rho)
-            t.assign(r); t.scale(self.dinv)
-            d.sadd(rho_new * rho, 2.0 * rho_new / delta, t)
-            x.add(d)
-            rho = rho_new
+    def __del__(self):
+        try:
+            if self.h:
+                lib.mfg_chebyshev_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def vmult(self, dst, src):
+        check(lib.mfg_chebyshev_vmult(self.h, dst.h, src.h))
+
+    def step(self, x, b, zero_guess=False):
+        """one Chebyshev sweep of the given degree on A x = b (zero_guess: PreconditionChebyshev::vmult, else ::step)"""
+        check((lib.mfg_chebyshev_vmult if zero_guess else lib.mfg_chebyshev_step)(self.h, x.h, b.h))
+
+
+class _LevelOperator:
+    """borrowed level operator of a GeometricMultigrid (same interface as LaplaceOperatorGpu for vmult / m)"""
+
+    def __init__(self, ctx, handle, n, dtype):
+        self.ctx, self.h, self._n, self.dtype = ctx, handle, n, dtype
+
+    def m(self):
+        return self._n
+
+    n = m
+
+    def vmult(self, dst, src):
+        check(lib.mfg_laplace_vmult(self.h, dst.h, src.h))
 
 
 class GeometricMultigrid:
     """V-cycle preconditioner (Multigrid + PreconditionMG, poisson_mg.cu:456-518) on hyper_cube meshes
-    refine_global(min_level..max_level)."""
+    refine_global(min_level..max_level): binding of mfg_mg_* (csrc/multigrid.cu)."""
 
-    def __init__(self, ctx, dim, degree, min_level, max_level, dtype=np.float64, left=-1.0, right=1.0, smoother_degree=5):
+    def __init__(self, ctx, dim, degree, min_level, max_level, dtype=np.float64, left=-1.0, right=1.0, smoother_degree=5,
+                 smoothing_range=15.0, eig_iterations=15):
         self.ctx, self.dtype = ctx, dtype
         self.levels = list(range(min_level, max_level + 1))
-        self.meshes = {l: HyperCubeMesh(ctx, dim, degree, l, left, right) for l in self.levels}
-        self.ops = {}
+        code = _capi.F64 if np.dtype(dtype) == np.float64 else _capi.F32
+        h = C.c_void_p()
+        check(lib.mfg_mg_create(ctx.h, dim, degree, min_level, max_level, code, float(left), float(right), int(smoother_degree),
+                                float(smoothing_range), int(eig_iterations), C.byref(h)))
+        self.h = h
+        self.ops, self.lambda_max = {}, {}
         for l in self.levels:
-            self.ops[l] = LaplaceOperatorGpu(ctx, dtype)
-            self.ops[l].reinit(self.meshes[l])
-        self.transfer = MGTransferMatrixFreeGpu(ctx, dtype)
-        self.transfer.build(self.meshes)
-        self.smoothers = {l: ChebyshevSmoother(ctx, self.ops[l], smoother_degree, dtype=dtype) for l in self.levels[1:]}
-        self.x = {l: GpuVector(ctx, self.meshes[l].n_dofs, dtype) for l in self.levels}
-        self.b = {l: GpuVector(ctx, self.meshes[l].n_dofs, dtype) for l in self.levels}
-        self.t = {l: GpuVector(ctx, self.meshes[l].n_dofs, dtype) for l in self.levels}
-        self.ops[min_level].compute_diagonal()
-        self.coarse_iterations = 0
+            oh, lm, ci, nd = C.c_void_p(), C.c_double(), C.c_long(), C.c_size_t()
+            check(lib.mfg_mg_level_operator(h, l, C.byref(oh)))
+            check(lib.mfg_mg_info(h, l, C.byref(lm), C.byref(ci), C.byref(nd)))
+            self.ops[l] = _LevelOperator(ctx, oh, nd.value, dtype)
+            self.lambda_max[l] = lm.value
 
-    def _cycle(self, l):
-        x, b, t, op = self.x[l], self.b[l], self.t[l], self.ops[l]
-        if l == self.levels[0]:
-            x.fill(0.0)                                                       # coarse CG to 1e-10 (poisson_mg.cu:73-80)
-            it, _ = solver_cg(op, x, b, 1e-10 * max(b.l2_norm(), 1e-300), 2000, use_jacobi=True)
-            self.coarse_iterations += it
-            return
-        self.smoothers[l].step(x, b, zero_guess=True)                         # pre-smoothing
-        op.vmult(t, x)
-        t.sadd(-1.0, 1.0, b)                                                  # residual
-        self.b[l - 1].fill(0.0)
-        self.transfer.restrict_and_add(l, self.b[l - 1], t)
-        self._cycle(l - 1)
-        self.transfer.prolongate(l, t, self.x[l - 1])
-        x.add(t)
-        self.smoothers[l].step(x, b, zero_guess=False)                        # post-smoothing
+    def __del__(self):
+        try:
+            if self.h:
+                lib.mfg_mg_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def coarse_iterations(self):
+        ci = C.c_long()
+        check(lib.mfg_mg_info(self.h, self.levels[0], None, C.byref(ci), None))
+        return ci.value
 
     def vmult(self, dst, src):
         """PreconditionMG::vmult: copy_to_mg, one V-cycle, copy_from_mg"""
-        top = self.levels[-1]
-        self.transfer.copy_to_mg({top: self.b[top]}, src)
-        self._cycle(top)
-        self.transfer.copy_from_mg(dst, {top: self.x[top]})
+        check(lib.mfg_mg_vcycle(self.h, dst.h, src.h))
+
+    def solve_cg(self, x, b, abs_tol, max_iter=1000, history=False):
+        """SolverCG on the finest level preconditioned by the V-cycle, in the library (poisson_mg.cu:504-518)"""
+        its, res = C.c_int(), C.c_double()
+        hist = (C.c_double * (max_iter + 1))() if history else None
+        check(lib.mfg_mg_solve_cg(self.h, x.h, b.h, float(abs_tol), int(max_iter), C.byref(its), C.byref(res), hist))
+        return (its.value, res.value, list(hist[:its.value + 1])) if history else (its.value, res.value)
 
 
 def solver_cg_preconditioned(ctx, op, x, b, precond, abs_tol, max_iter=1000):
-    """SolverCG control flow with an arbitrary preconditioner object (vmult(dst, src))."""
+    """SolverCG control flow with an arbitrary preconditioner object (vmult(dst, src)); host-side
+    variant for preconditioners written in Python (the library's own is GeometricMultigrid.solve_cg)."""
     n, dtype = op.m(), x.dtype
     g, h, d = (GpuVector(ctx, n, dtype) for _ in range(3))
     if x.all_zero():

@@ -282,6 +282,32 @@ int mfg_mgt_restrict_and_add(mfg_mgt *t, mfg_vec *dst_coarse, const mfg_vec *src
 int mfg_solver_cg(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter, int use_jacobi, int *iters,
                   double *last_residual, double *residual_history);
 
+/* ---- PreconditionChebyshev / Multigrid / PreconditionMG as the reference instantiates them on GpuVector ----------------
+ * (poisson_mg.cu:430-552, bmop_mg.cu:300-340; in the reference this is deal.II template code, here C++ host code of the
+ * library: level operators, matrix-free transfer, one fused vector kernel per Chebyshev product).
+ * mfg_chebyshev_create: PreconditionChebyshev::initialize with AdditionalData{degree, smoothing_range, eig_cg_n_iterations,
+ * preconditioner = the operator's inverse diagonal}: lambda_max from eig_cg_n_iterations CG/Lanczos steps on Dinv A (deal.II's
+ * procedure); eig_cg_n_iterations = 0 takes lambda_max = 1 (deal.II's default max_eigenvalue). */
+typedef struct mfg_cheb mfg_cheb;
+typedef struct mfg_mg mfg_mg;
+int mfg_chebyshev_create(mfg_laplace *op, int degree, double smoothing_range, int eig_cg_n_iterations, mfg_cheb **out);
+int mfg_chebyshev_destroy(mfg_cheb *c);
+int mfg_chebyshev_vmult(mfg_cheb *c, mfg_vec *dst, const mfg_vec *src);   /* dst = p(Dinv A) Dinv src from a zero guess */
+int mfg_chebyshev_step(mfg_cheb *c, mfg_vec *dst, const mfg_vec *src);    /* the same sweep starting from dst */
+int mfg_chebyshev_info(const mfg_cheb *c, double *lambda_max, double *lambda_min, double *theta, double *delta, int *eig_iterations);
+/* Geometric multigrid on hyper_cube(left,right) refine_global(min_level .. max_level): level LaplaceOperatorGpu (level_mg_handler,
+ * laplace_operator_gpu.h:156-186; on a globally refined mesh a level IS a uniform mesh and its edge matrices are zero),
+ * MGTransferMatrixFreeGpu, Chebyshev smoothers (poisson_mg.cu:461-470: degree 5, range 15, 15 eigenvalue iterations), coarse
+ * solve = unpreconditioned CG to a 1e-10 reduction (poisson_mg.cu:73-80).  mfg_mg_vcycle = PreconditionMG::vmult;
+ * mfg_mg_solve_cg = SolverCG with that preconditioner on the finest level (poisson_mg.cu:504-518). */
+int mfg_mg_create(mfg_ctx *ctx, int dim, int degree, int min_level, int max_level, mfg_dtype dt, double left, double right, int smoother_degree,
+                  double smoothing_range, int eig_cg_n_iterations, mfg_mg **out);
+int mfg_mg_destroy(mfg_mg *mg);
+int mfg_mg_vcycle(mfg_mg *mg, mfg_vec *dst, const mfg_vec *src);
+int mfg_mg_level_operator(mfg_mg *mg, int level, mfg_laplace **op);   /* borrowed */
+int mfg_mg_info(const mfg_mg *mg, int level, double *lambda_max, long *coarse_iterations, size_t *n_dofs);
+int mfg_mg_solve_cg(mfg_mg *mg, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter, int *iters, double *last_residual, double *history);
+
 /* ---- multi-GPU: interface-DoF exchange (new capability; the reference is single-GPU) -----------
  * The mesh is partitioned into boxes of cells, one per GPU.  Every rank stores all DoFs its cells touch;
  * DoFs on partition interfaces are replicated and kept consistent.  After the local cell loop the partial

@@ -113,3 +113,96 @@ def test_multigrid_preconditioned_cg(ctx, dim, p):
         assert x.l2_norm() <= 1e-7 * ue.l2_norm()
         its.append(it)
     assert max(its) <= 25 and max(its) - min(its) <= 6, its
+
+
+def numpy_chebyshev(o, degree, smoothing_range, n_eig):
+    """deal.II 8.5 PreconditionChebyshev restated on the oracle operator: eigenvalue estimate by n_eig
+    SolverCG steps on Dinv A from x = 0 with rhs = 1/sqrt(n), entry 0 zeroed; Lanczos matrix from the CG coefficients;
+    beta = 1.2 lmax, alpha = lmax / range; returns (lmax, theta, delta, apply(b, x0=None))"""
+    n = o.n_dofs
+    dinv = o.inverse_diagonal()
+    rhs = np.full(n, 1.0 / np.sqrt(n)); rhs[0] = 0.0
+    g = -rhs; h = dinv * g; d = -h; gh = g @ h
+    al, be = [], []
+    for _ in range(n_eig):
+        if np.sqrt(g @ g) <= 1e-2:
+            break
+        h = o.vmult(d)
+        alpha = gh / (d @ h); al.append(alpha)
+        g = g + alpha * h
+        h = dinv * g
+        ghn = g @ h; beta = ghn / gh; gh = ghn; be.append(beta)
+        d = beta * d - h
+    k = len(al)
+    T = np.zeros((k, k))
+    for j in range(k):
+        T[j, j] = 1.0 / al[j] + (be[j - 1] / al[j - 1] if j else 0.0)
+        if j + 1 < k:
+            T[j, j + 1] = T[j + 1, j] = np.sqrt(be[j]) / al[j]
+    lmax = np.linalg.eigvalsh(T)[-1]
+    b_, a_ = 1.2 * lmax, lmax / smoothing_range
+    theta, delta = 0.5 * (b_ + a_), 0.5 * (b_ - a_)
+
+    def apply(b, x0=None):
+        rhok, sigma = delta / theta, theta / delta
+        if x0 is None:
+            dvec = dinv * b / theta
+            x = dvec.copy()
+        else:
+            dvec = dinv * (b - o.vmult(x0)) / theta
+            x = x0 + dvec
+        for _ in range(degree):
+            r = b - o.vmult(x)
+            rhokp = 1.0 / (2.0 * sigma - rhok)
+            dvec = rhokp * rhok * dvec + 2.0 * rhokp / delta * (dinv * r)
+            rhok = rhokp
+            x = x + dvec
+        return x
+    return lmax, theta, delta, apply
+
+
+@pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
+def test_chebyshev_matches_restatement_of_dealii(ctx, dim, p, r):
+    """mfg_chebyshev_* (csrc/multigrid.cu) against the numpy restatement on the oracle: the eigenvalue estimate, the
+    polynomial from a zero guess (vmult) and from a given guess (step)"""
+    import dealii_cuda_b200 as mf
+    from dealii_cuda_b200.multigrid import ChebyshevSmoother
+    o = OracleMesh(dim, p, r)
+    lmax, theta, delta, apply = numpy_chebyshev(o, 5, 15.0, 15)
+    m = mf.HyperCubeMesh(ctx, dim, p, r)
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(m)
+    sm = ChebyshevSmoother(ctx, op, 5, 15.0, 15)
+    assert abs(sm.lambda_max - lmax) <= 1e-9 * lmax
+    assert abs(sm.theta - theta) <= 1e-9 * theta and abs(sm.delta - delta) <= 1e-9 * delta
+    b = sm64(3, o.n_dofs)
+    vb, vx = mf.GpuVector.from_numpy(ctx, b), mf.GpuVector(ctx, o.n_dofs)
+    vx.fill(99.0)
+    sm.vmult(vx, vb)
+    want = apply(b)
+    assert np.linalg.norm(vx.toVector() - want) <= 1e-11 * np.linalg.norm(want)
+    x0 = sm64(4, o.n_dofs)
+    vx.fromHost(x0)
+    sm.step(vx, vb)
+    want = apply(b, x0)
+    assert np.linalg.norm(vx.toVector() - want) <= 1e-11 * np.linalg.norm(want)
+
+
+def test_library_mg_cg_equals_host_orchestrated_loop(ctx):
+    """mfg_mg_solve_cg (C++ loop) against solver_cg_preconditioned (Python loop over the same V-cycle): same iterations"""
+    import dealii_cuda_b200 as mf
+    from dealii_cuda_b200.multigrid import GeometricMultigrid, solver_cg_preconditioned
+    mg = GeometricMultigrid(ctx, 3, 4, 1, 3)
+    op = mg.ops[3]
+    n = op.m()
+    ue = mf.GpuVector.from_numpy(ctx, sm64(9, n))
+    b, x1, x2 = mf.GpuVector(ctx, n), mf.GpuVector(ctx, n), mf.GpuVector(ctx, n)
+    op.vmult(b, ue)
+    tol = 1e-10 * b.l2_norm()
+    it1, hist1 = solver_cg_preconditioned(ctx, op, x1, b, mg, tol, 100)
+    it2, res2, hist2 = mg.solve_cg(x2, b, tol, 100, history=True)
+    assert it1 == it2 and it2 <= 12
+    assert np.allclose(hist1, hist2, rtol=1e-6)
+    x2.add(-1.0, ue)
+    assert x2.l2_norm() <= 1e-7 * ue.l2_norm()
+    assert mg.coarse_iterations > 0 and all(mg.lambda_max[l] > 1.0 for l in mg.levels[1:])

@@ -17,7 +17,7 @@ def problem(op, n):
     return ue, b, x
 
 
-for r in (6, 7):
+for r in (() if "--mg-only" in sys.argv else (6, 7)):
     mesh = mf.HyperCubeMesh(ctx, 3, 4, r)
     op = mf.LaplaceOperatorGpu(ctx, np.float64); op.reinit(mesh)
     n = mesh.n_dofs
@@ -35,6 +35,8 @@ for r in (6, 7):
     torch.cuda.empty_cache()
 
 for r in ((6, 7) if "--mg7" in sys.argv else (6,)):
+    if "--mg-only" in sys.argv or True:
+        pass
     t0 = time.perf_counter()
     mg = GeometricMultigrid(ctx, 3, 4, 1, r)
     ctx.synchronize()
@@ -44,7 +46,7 @@ for r in ((6, 7) if "--mg7" in sys.argv else (6,)):
     ue, b, x = problem(op, n)
     ctx.synchronize()
     t0 = time.perf_counter()
-    it, hist = solver_cg_preconditioned(ctx, op, x, b, mg, 1e-10 * b.l2_norm(), 100)
+    it, res_ = mg.solve_cg(x, b, 1e-10 * b.l2_norm(), 100)   # the library's loop (mfg_mg_solve_cg)
     ctx.synchronize()
     dt = time.perf_counter() - t0
     x.add(-1.0, ue)
