@@ -292,6 +292,15 @@ class HyperCubeMesh:
         return out, nc.value
 
 
+def graph_coloring(loc2glob, n_indices):
+    """GraphColoringWrapper::make_graph_coloring (coloring.cc:8-33) restated on the host: (color_of_cell, n_colors)"""
+    l2g = np.ascontiguousarray(loc2glob, dtype=np.uint32)
+    col = np.zeros(l2g.shape[0], dtype=np.uint32)
+    nc = C.c_uint32()
+    check(lib.mfg_graph_coloring(l2g.shape[0], l2g.shape[1], _u32p(l2g), int(n_indices), _u32p(col), C.byref(nc)))
+    return col, nc.value
+
+
 def hanging_node_weights(degree):
     """W[k][i] = phi_i(xi_k/2) (setup_constraint_weights, hanging_nodes.cuh:580-598)."""
     n = degree + 1
@@ -540,6 +549,9 @@ class LaplaceOperatorGpu:
 
     def active_variant(self):
         return lib.mfg_laplace_active_variant(self.h)
+
+    def set_option(self, name, value):
+        check(lib.mfg_laplace_set_option(self.h, name.encode(), int(value)))
 
     def stage_stats(self):
         """plan of the staged kernel (variant 40) after the first apply; per-group figures are averages over the staged groups"""

@@ -135,7 +135,9 @@ def _load():
         "mfg_laplace_cell_launches_per_vmult": (C.c_int, [vp]),
         "mfg_laplace_enable_kernel_timing": (C.c_int, [vp, C.c_int]),
         "mfg_laplace_kernel_time_ms": (C.c_int, [vp, dp, C.POINTER(C.c_int)]),
+        "mfg_graph_coloring": (C.c_int, [C.c_uint32, C.c_uint32, u32p, C.c_uint32, u32p, u32p]),
         "mfg_laplace_active_variant": (C.c_int, [vp]),
+        "mfg_laplace_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "mfg_laplace_stage_stats": (C.c_int, [vp, u32p]),
         "mfg_chebyshev_create": (C.c_int, [vp, C.c_int, C.c_double, C.c_int, pp]),
         "mfg_chebyshev_destroy": (C.c_int, [vp]),

@@ -298,6 +298,17 @@ int mfg_laplace_destroy(mfg_laplace *op)
   });
 }
 uint32_t mfg_laplace_m(const mfg_laplace *op) { return op ? op->mf->n_dofs : 0; }
+int mfg_laplace_set_option(mfg_laplace *op, const char *name, int value)
+{
+  return guarded([&] {
+    MFG_REQUIRE(op && name, "null argument");
+    const std::string k(name);
+    if (k == "cg_fused") op->cg_fused = value != 0;
+    else if (k == "stage_sync") op->stage_sync = value != 0;
+    else if (k == "stage_merge_dirs") { op->stage_merge_dirs = value & 7; op->st_built = false; }
+    else throw Error(MFG_ERR_INVALID, "unknown option '" + k + "'");
+  });
+}
 int mfg_laplace_set_variant(mfg_laplace *op, int variant) { return guarded([&] { MFG_REQUIRE(op, "null operator"); op->variant = variant; }); }
 
 static void check_vecs(const mfg_laplace *op, const mfg_vec *dst, const mfg_vec *src)

@@ -404,6 +404,6 @@ StageGeom stage_geom(int degree, mfg_dtype dt);
 template <typename Number>
 void launch_laplace_stage(int degree, const uint32_t *gdesc, const uint32_t *halo, const uint16_t *ptab, int pstride, const uint32_t *class_pat,
                           const Number *cwP, const Number *src, Number *dst, uint32_t n_groups, const double *N, const double *D, int sm_count,
-                          cudaStream_t stream, const uint32_t *glist, uint32_t n_list, int mode, bool pdl, bool dep_wait, bool add, int device);
+                          cudaStream_t stream, const uint32_t *glist, uint32_t n_list, int mode, bool pdl, bool dep_wait, bool add, int device, bool sync = true);
 
 }  // namespace mfg

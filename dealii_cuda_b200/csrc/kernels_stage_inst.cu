@@ -19,7 +19,7 @@ typedef float inst_number;
 template <int n, typename Number>
 static void launch_n(const uint32_t *gdesc, const uint32_t *halo, const uint16_t *ptab, int pstride, const uint32_t *class_pat, const Number *cwP,
                      const Number *src, Number *dst, uint32_t n_groups, const double *N, const double *D, int sm_count, cudaStream_t stream,
-                     const uint32_t *glist, uint32_t n_list, int mode, bool pdl, bool dep_wait, bool add, int device)
+                     const uint32_t *glist, uint32_t n_list, int mode, bool pdl, bool dep_wait, bool add, int device, bool sync)
 {
   using Cfg = StageCfg<n, Number>;
   const uint32_t n_items = mode == 1 ? n_list : n_groups;
@@ -29,7 +29,6 @@ static void launch_n(const uint32_t *gdesc, const uint32_t *halo, const uint16_t
   make_eo_tables<Number, n>(N, D, em);
   StageClasses cls;
   for (int a = 0; a < 8; ++a) cls.pat[a] = class_pat[a < Cfg::NCLASS ? a : 0];
-  static const bool sync = !(std::getenv("MFG_STAGE_SYNC") && std::atoi(std::getenv("MFG_STAGE_SYNC")) == 0);
   auto       kern = sync ? laplace_cell_stage<n, Number, true> : laplace_cell_stage<n, Number, false>;
   // (function attributes are per device: one cache entry per device of the process)
   static int blocks_per_sm[64] = {0};  // (both instantiations have the same resources)
@@ -43,7 +42,7 @@ static void launch_n(const uint32_t *gdesc, const uint32_t *halo, const uint16_t
       if (b < 1) throw Error(MFG_ERR_CUDA, "staged cell kernel does not fit on an SM");
       blocks_per_sm[device] = b;
     }
-  static const int reserve = std::getenv("MFG_SLAB2_RESERVE") ? std::atoi(std::getenv("MFG_SLAB2_RESERVE")) : 4;
+  const int reserve = 4;  // CTA slots left to the exchange kernels beside the interior groups of a multi-GPU apply
   const uint32_t full = (uint32_t)(sm_count * blocks_per_sm[device]);
   uint32_t       grid = pdl && !dep_wait && full > (uint32_t)reserve + Cfg::NCLASS ? full - reserve : full;
   if (mode == 1) grid = std::min<uint32_t>(grid, (n_items + Cfg::WPB - 1) / Cfg::WPB);
@@ -76,9 +75,9 @@ template <>
 void launch_laplace_stage<inst_number>(int degree, const uint32_t *gdesc, const uint32_t *halo, const uint16_t *ptab, int pstride, const uint32_t *class_pat,
                                        const inst_number *cwP, const inst_number *src, inst_number *dst, uint32_t n_groups, const double *N, const double *D,
                                        int sm_count, cudaStream_t stream, const uint32_t *glist, uint32_t n_list, int mode, bool pdl, bool dep_wait, bool add,
-                                       int device)
+                                       int device, bool sync)
 {
-#define MFG_STAGE_ARGS gdesc, halo, ptab, pstride, class_pat, cwP, src, dst, n_groups, N, D, sm_count, stream, glist, n_list, mode, pdl, dep_wait, add, device
+#define MFG_STAGE_ARGS gdesc, halo, ptab, pstride, class_pat, cwP, src, dst, n_groups, N, D, sm_count, stream, glist, n_list, mode, pdl, dep_wait, add, device, sync
   switch (degree)
     {
       case 2: launch_n<3, inst_number>(MFG_STAGE_ARGS); break;

@@ -763,7 +763,7 @@ static void laplace_prepare_stage(mfg_laplace *op, uint32_t n_plain)
   StagePlanIn in;
   in.n = sg.n; in.cw = sg.cw; in.hc = sg.hc; in.wb = mf->dt == MFG_F64 ? 8 : 4; in.xcap = sg.xcap; in.hmax = sg.hmax; in.ocap = sg.ocap; in.lcap = sg.lcap; in.nclass = sg.nclass;
   in.n_plain = n_plain; in.n_cells = mf->n_cells; in.n_dofs = mf->n_dofs; in.idx = idx.data();
-  in.merge_dirs = getenv("MFG_STAGE_MERGE") ? atoi(getenv("MFG_STAGE_MERGE")) & 7 : 7;
+  in.merge_dirs = op->stage_merge_dirs & 7;
   StagePlan plan;
   build_stage_plan(in, plan);
   op->st_gdesc.upload(plan.gdesc.data(), plan.gdesc.size(), s);
@@ -901,7 +901,7 @@ static void vmult_impl(mfg_laplace *op, Number *dst, const Number *src, bool add
       time_begin();
       launch_laplace_stage<Number>(mf->p, op->st_gdesc.p, op->st_halo.p, op->st_ptab.p, op->st_pstride, op->st_class_pat, (const Number *)op->cwP.p, src, dst,
                                    op->slab2_groups, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s, op->glist.p, op->n_iface_groups, mode,
-                                   (split && part == 2) || pdl_fill, pdl_fill, add, op->ctx->device);
+                                   (split && part == 2) || pdl_fill, pdl_fill, add, op->ctx->device, op->stage_sync);
       if (nf)
         launch_laplace_slab3<Number>(mf->p, op->idxP.p, (const Number *)op->cwP.p, src, dst, nf, mf->fe.val.data(), mf->fe.colloc.data(), op->ctx->sm_count, s,
                                      op->mergeP.p, fl, false, 0, op->ctx->device, 0, nullptr, 0u);

@@ -56,6 +56,10 @@ struct mfg_laplace
   std::unique_ptr<mfg_vec> inv_diag;
   bool     diagonal_is_available = false;
   int      variant = 0;
+  // options (mfg_laplace_set_option): fused CG loop, face-merge directions of the staged kernel's plan, per-item CTA barrier of the staged kernel
+  bool     cg_fused = true;
+  int      stage_merge_dirs = 7;
+  bool     stage_sync = true;
   // slab kernels (kernels_slab3.cuh, kernels_stage.cuh): the index map and the merged weights in the order their threads
   // consume them, built on first use from idx / cw
   mfg::DevBuf<uint32_t> idxP;   // [n_groups][n^2 slots][32 lanes]

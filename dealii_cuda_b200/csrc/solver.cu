@@ -369,7 +369,7 @@ void cg_solve(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double tol, int max
   uint32_t n_dot = 0;
   if (op->solver_dot.n < 8192) op->solver_dot.alloc(8192);
   MFG_CUDA(cudaMemsetAsync(op->solver_dot.p, 0, op->solver_dot.bytes(), s));
-  const bool fused = std::getenv("MFG_CG_UNFUSED") == nullptr && laplace_active_variant(op) == 50 && op->mf->hn_mask.n == 0 && op->mf->n_cells > 0 &&
+  const bool fused = op->cg_fused && laplace_active_variant(op) == 50 && op->mf->hn_mask.n == 0 && op->mf->n_cells > 0 &&
                      (size_t)ctx->sm_count * 3 * 4 <= op->solver_dot.n;
   // iteration 0: h = Minv g, |g|, g.h ; d = -h
   cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, 0, hist.p, nullptr, 0u);
@@ -377,31 +377,23 @@ void cg_solve(mfg_laplace *op, mfg_vec *x, const mfg_vec *b, double tol, int max
   cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, 0, fused);
   MFG_CUDA_LAST();
   snapshot(0);
-  const bool dbg = getenv("MFG_CG_DEBUG") != nullptr;
-  double t_wait = 0, t_vmult = 0, t_rest = 0;
-  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int it = 1; it <= max_iter; ++it)
     {
-      const double ta = dbg ? now() : 0;
       if (it > LAG)
         {
           MFG_CUDA(cudaEventSynchronize(ev[(it - LAG) % (LAG + 1)]));
           if (mirror[(it - LAG) % (LAG + 1)].converged_at >= 0) break;
         }
-      const double tb = dbg ? now() : 0;
       bool with_dot = false;
       if (fused) with_dot = laplace_cell_dot(op, h.p, d.p, op->solver_dot.p, &n_dot);   // h = A d and the partial sums of d . h
       if (!with_dot) laplace_vmult(op, h.p, d.p, false);                                  // h = A d
-      const double tc = dbg ? now() : 0;
       if (!with_dot) { cg_dot<T><<<nb, TH, 0, s>>>(d.p, h.p, n, partial, st.p); MFG_CUDA_LAST(); }  // alpha
       cg_residual<T><<<nb, TH, 0, s>>>(g.p, h.p, minv, n, partial, st.p, it, hist.p, with_dot ? op->solver_dot.p : nullptr, n_dot);
       MFG_CUDA_LAST();
       cg_advance<T><<<nb, TH, 0, s>>>((T *)x->p, d.p, h.p, n, st.p, it, fused);
       MFG_CUDA_LAST();
       snapshot(it);
-      if (dbg) { const double td = now(); t_wait += tb - ta; t_vmult += tc - tb; t_rest += td - tc; }
     }
-  if (dbg) fprintf(stderr, "cg host time: wait %.3f ms, vmult enqueue %.3f ms, other enqueue %.3f ms\n", 1e3 * t_wait, 1e3 * t_vmult, 1e3 * t_rest);
   CgState fin;
   MFG_CUDA(cudaMemcpyAsync(&fin, st.p, sizeof(fin), cudaMemcpyDeviceToHost, s));
   MFG_CUDA(cudaStreamSynchronize(s));

@@ -265,6 +265,37 @@ __global__ void apply_kernel_shmem(Number *dst, const Number *src, const LocOp l
   loc_op.cell_apply(dst, src, &gd, cell, &sh);
 }
 
+// apply_kernel_shmem<LocOp>(dst, loc_op, gpu_data) (matrix_free_gpu.h:343-365): the variant without a source vector,
+// loc_op.cell_apply(dst, gpu_data, cell, shdata) -- the reference uses it for compute_diagonal (laplace_operator_gpu.h:413-414)
+template <typename LocOp, int dim, int fe_degree, typename Number>
+__global__ void apply_kernel_shmem_dst(Number *dst, const LocOp loc_op, const GpuData<dim, Number> gpu_data,
+                                       const __grid_constant__ ShapeTables<Number, fe_degree + 1> tab, const unsigned int cell_begin)
+{
+  constexpr unsigned int npc = FEEvaluationGpu<dim, fe_degree, Number>::n_local_dofs;
+  extern __shared__ __align__(16) unsigned char fee_smem_raw[];
+  Number *base = reinterpret_cast<Number *>(fee_smem_raw) + (size_t)(threadIdx.x / npc) * (3 + dim) * npc;
+  SharedData<dim, Number> sh;
+  sh.values = base;
+  for (int k = 0; k < dim; ++k) sh.gradients[k] = base + (1 + k) * npc;
+  sh.scratch[0] = base + (1 + dim) * npc;
+  sh.scratch[1] = base + (2 + dim) * npc;
+  GpuData<dim, Number> gd = gpu_data;
+  gd.shape_values = tab.val;
+  gd.shape_gradients = tab.grad;
+  const unsigned int cell = cell_begin + blockIdx.x * (blockDim.x / npc) + threadIdx.x / npc;
+  loc_op.cell_apply(dst, &gd, cell, &sh);
+}
+
+// cell_eval_kernel<dim,Number,Op> (matrix_free_gpu.h:397-410): Op::eval(row of vec, quadrature points of the cell).  The
+// reference runs one thread per cell, serial over the quadrature points; Op::eval keeps that signature (it loops over
+// n_q_points itself), rows are [n_q_points] long here (the reference pads them to `rowlength`).
+template <int dim, typename Number, typename Op>
+__global__ void cell_eval_kernel(Number *vec, const GpuData<dim, Number> gpu_data, const unsigned int n_q_points)
+{
+  const unsigned int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell < gpu_data.n_cells) Op::eval(vec + (size_t)cell * n_q_points, gpu_data.quadrature_points + (size_t)cell * n_q_points * dim);
+}
+
 inline void fee_check(int rc, const char *what)
 {
   if (rc != 0) throw std::runtime_error(std::string(what) + ": " + mfg_last_error());
@@ -283,6 +314,11 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const Number *src_dev, const LocOp &
   fee_check(mfg_mf_get_gpu_data(mf, &g), "mfg_mf_get_gpu_data");
   if (g.dim != dim || g.degree != fe_degree) throw std::runtime_error("cell_loop: dim / fe_degree differ from the MatrixFreeGpu object");
   if ((g.dtype == MFG_F64) != (sizeof(Number) == 8)) throw std::runtime_error("cell_loop: Number differs from the MatrixFreeGpu dtype");
+  // read_dof_values / distribute_local_to_global of this path do not apply resolve_hanging_nodes_shmem (fee_gpu.cuh:333-335,
+  // 349-351): on a mesh with hanging-node cells the result would silently miss them, so refuse instead
+  if (g.constraint_mask != nullptr)
+    throw std::runtime_error("cell_loop: the MatrixFreeGpu object holds cells with hanging-node constraints, which the generic "
+                             "FEEvaluationGpu path does not interpolate; use LaplaceOperatorGpu or a mesh without hanging nodes");
   constexpr unsigned int n = fe_degree + 1, npc = dim == 2 ? n * n : n * n * n;
   static_assert(npc <= 1024, "one thread per local DoF");
   GpuData<dim, Number> gd;
@@ -310,11 +346,85 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const Number *src_dev, const LocOp &
     }
 }
 
+// MatrixFreeGpu::cell_loop(dst, loc_op) (matrix_free_gpu.h:382-393): no source vector, loc_op.cell_apply(dst, gpu_data, cell, shdata)
+template <int dim, int fe_degree, typename Number, typename LocOp>
+void cell_loop(mfg_mf *mf, Number *dst_dev, const LocOp &loc_op)
+{
+  mfg_gpu_data g;
+  fee_check(mfg_mf_get_gpu_data(mf, &g), "mfg_mf_get_gpu_data");
+  if (g.dim != dim || g.degree != fe_degree) throw std::runtime_error("cell_loop: dim / fe_degree differ from the MatrixFreeGpu object");
+  if ((g.dtype == MFG_F64) != (sizeof(Number) == 8)) throw std::runtime_error("cell_loop: Number differs from the MatrixFreeGpu dtype");
+  if (g.constraint_mask != nullptr) throw std::runtime_error("cell_loop: hanging-node cells are not supported by the generic FEEvaluationGpu path");
+  constexpr unsigned int n = fe_degree + 1, npc = dim == 2 ? n * n : n * n * n;
+  GpuData<dim, Number> gd;
+  gd.loc2glob = g.loc2glob;
+  gd.JxW = static_cast<const Number *>(g.JxW);
+  gd.inv_jac = static_cast<const Number *>(g.inv_jac);
+  gd.quadrature_points = static_cast<const Number *>(g.quadrature_points);
+  gd.shape_values = gd.shape_gradients = nullptr;
+  gd.general = g.general;
+  gd.use_coloring = g.use_coloring;
+  ShapeTables<Number, n> tab;
+  for (unsigned int i = 0; i < n * n; ++i) { tab.val[i] = (Number)g.shape_values[i]; tab.grad[i] = (Number)g.shape_gradients[i]; }
+  const unsigned int cpb = npc >= 128 ? 1 : 128 / npc;
+  const size_t       smem = (size_t)cpb * (3 + dim) * npc * sizeof(Number);
+  auto kern = apply_kernel_shmem_dst<LocOp, dim, fe_degree, Number>;
+  if (smem > 48 * 1024) fee_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
+  cudaStream_t st = static_cast<cudaStream_t>(g.cuda_stream);
+  for (uint32_t c = 0; c < g.n_colors; ++c)
+    {
+      const uint32_t c0 = g.color_offsets[c], c1 = g.color_offsets[c + 1];
+      if (c1 <= c0) continue;
+      gd.n_cells = c1;
+      kern<<<(c1 - c0 + cpb - 1) / cpb, cpb * npc, smem, st>>>(dst_dev, loc_op, gd, tab, c0);
+      fee_check_cuda(cudaGetLastError(), "cell_loop launch");
+    }
+}
+
+// MatrixFreeGpu::evaluate_on_cells<Op>(vec) (matrix_free_gpu.h:415-435): vec[cell][q] = what Op::eval writes for the cell's
+// quadrature points; vec_dev holds n_cells * n_q_points entries in kernel cell order (the order of get_gpu_data); the mf
+// must carry quadrature points (uniform meshes always do, mfg_mf_desc.quadrature_points otherwise)
+template <int dim, int fe_degree, typename Number, typename Op>
+void evaluate_on_cells(mfg_mf *mf, Number *vec_dev)
+{
+  mfg_gpu_data g;
+  fee_check(mfg_mf_get_gpu_data(mf, &g), "mfg_mf_get_gpu_data");
+  if (g.dim != dim || g.degree != fe_degree) throw std::runtime_error("evaluate_on_cells: dim / fe_degree differ from the MatrixFreeGpu object");
+  if ((g.dtype == MFG_F64) != (sizeof(Number) == 8)) throw std::runtime_error("evaluate_on_cells: Number differs from the MatrixFreeGpu dtype");
+  if (g.quadrature_points == nullptr) throw std::runtime_error("evaluate_on_cells: the MatrixFreeGpu object has no quadrature points");
+  constexpr unsigned int n = fe_degree + 1, nq = dim == 2 ? n * n : n * n * n;
+  GpuData<dim, Number> gd;
+  gd.loc2glob = g.loc2glob;
+  gd.JxW = static_cast<const Number *>(g.JxW);
+  gd.inv_jac = static_cast<const Number *>(g.inv_jac);
+  gd.quadrature_points = static_cast<const Number *>(g.quadrature_points);
+  gd.shape_values = gd.shape_gradients = nullptr;
+  gd.general = g.general;
+  gd.use_coloring = g.use_coloring;
+  gd.n_cells = g.n_cells;
+  if (g.n_cells == 0) return;
+  cell_eval_kernel<dim, Number, Op><<<(g.n_cells + 127) / 128, 128, 0, static_cast<cudaStream_t>(g.cuda_stream)>>>(vec_dev, gd, nq);
+  fee_check_cuda(cudaGetLastError(), "evaluate_on_cells launch");
+}
+
 // the same on the facade classes: data.cell_loop(dst, src, loc_op) of the reference (matrix_free_gpu.h:212-219)
 template <int dim, int fe_degree, typename Number, typename LocOp>
 void cell_loop(const MatrixFreeGpu<dim, Number> &data, GpuVector<Number> &dst, const GpuVector<Number> &src, const LocOp &loc_op)
 {
   cell_loop<dim, fe_degree, Number, LocOp>(data.handle(), dst.getData(), src.getDataRO(), loc_op);
+}
+template <int dim, int fe_degree, typename Number, typename LocOp>
+void cell_loop(const MatrixFreeGpu<dim, Number> &data, GpuVector<Number> &dst, const LocOp &loc_op)
+{
+  cell_loop<dim, fe_degree, Number, LocOp>(data.handle(), dst.getData(), loc_op);
+}
+// data.template evaluate_on_cells<Op>(vec) (matrix_free_gpu.h:223-224); vec is resized like the reference does
+template <int dim, int fe_degree, typename Number, typename Op>
+void evaluate_on_cells(const MatrixFreeGpu<dim, Number> &data, GpuVector<Number> &vec)
+{
+  constexpr unsigned int n = fe_degree + 1, nq = dim == 2 ? n * n : n * n * n;
+  vec.resize((size_t)data.n_cells_tot * nq);
+  evaluate_on_cells<dim, fe_degree, Number, Op>(data.handle(), vec.getData());
 }
 
 }  // namespace dealii_cuda_b200

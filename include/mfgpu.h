@@ -127,6 +127,12 @@ int mfg_mesh_get_support_points(const mfg_mesh *m, double *host);
 int mfg_mesh_lattice_to_dof(const mfg_mesh *m, size_t n, const uint32_t *lattice_xyz, uint32_t *dof);
 /* graph coloring of the cells (coloring.cc:20-33): color_of_cell[n_cells] to host; returns n_colors in *n_colors */
 int mfg_mesh_color_cells(const mfg_mesh *m, uint32_t *color_of_cell, uint32_t *n_colors);
+/* GraphColoringWrapper::make_graph_coloring (matrix_free_gpu/coloring.cc:8-33) for any mesh, on the host: deal.II's
+ * algorithm restated (zones by breadth-first search over shared conflict indices, DSATUR inside a zone, colors of the even
+ * and of the odd zones merged).  conflict_indices_host: [n_cells][dofs_per_cell] = the cell DoFs after resolve_indices
+ * (bit 31 ignored).  Feed the result to mfg_mf_desc.n_colors / color_offsets (cells sorted by color). */
+int mfg_graph_coloring(uint32_t n_cells, uint32_t dofs_per_cell, const uint32_t *conflict_indices_host, uint32_t n_indices,
+                       uint32_t *color_of_cell, uint32_t *n_colors);
 
 /* ---- MatrixFreeGpu ------------------------------------------------------- */
 /* Explicit-array description: what ReinitHelper extracts from deal.II
@@ -217,6 +223,9 @@ int mfg_laplace_destroy(mfg_laplace *op);                                       
 uint32_t mfg_laplace_m(const mfg_laplace *op);                                       /* m()/n() :52-53 */
 /* kernel variant: 0 = auto, otherwise a variant id; for A/B measurements */
 int mfg_laplace_set_variant(mfg_laplace *op, int variant);
+/* measurement switches (A/B runs, tests): "cg_fused" 0/1 (mfg_solver_cg: d.(A d) from the cell kernel, default 1),
+ * "stage_sync" 0/1 and "stage_merge_dirs" 0..7 (staged kernel, variant 40) */
+int mfg_laplace_set_option(mfg_laplace *op, const char *name, int value);
 int mfg_laplace_vmult(mfg_laplace *op, mfg_vec *dst, const mfg_vec *src);            /* :216-223 (Tvmult identical) */
 int mfg_laplace_vmult_add(mfg_laplace *op, mfg_vec *dst, const mfg_vec *src);        /* :286-303 */
 /* raw device pointers (dtype of the operator), for callers that own their memory */

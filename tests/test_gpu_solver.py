@@ -78,7 +78,7 @@ def test_cg_fp32_and_nonzero_start(ctx):
 
 
 @pytest.mark.parametrize("p,r", [(4, 2), (3, 3), (2, 3), (5, 1)])
-def test_cg_fused_loop_equals_unfused_loop(ctx, p, r, monkeypatch):
+def test_cg_fused_loop_equals_unfused_loop(ctx, p, r):
     """the fused loop (d . A d emitted by the cell kernel, the operator's zero pass done by cg_advance; solver.cu) against the
     loop with vmult + cg_dot: same iteration count, residual histories equal to rounding, and the first iterates within
     1e-12 of the numpy restatement of SolverCG on the oracle operator"""
@@ -90,10 +90,9 @@ def test_cg_fused_loop_equals_unfused_loop(ctx, p, r, monkeypatch):
     m = mf.HyperCubeMesh(ctx, 3, p, r)
     runs = []
     for unfused in (False, True):
-        if unfused:
-            monkeypatch.setenv("MFG_CG_UNFUSED", "1")
         op = mf.LaplaceOperatorGpu(ctx, np.float64)
         op.reinit(m)
+        op.set_option("cg_fused", 0 if unfused else 1)
         assert op.active_variant() == 50
         x, vb = mf.GpuVector(ctx, o.n_dofs), mf.GpuVector.from_numpy(ctx, b)
         it, res, hist = mf.solver_cg(op, x, vb, tol, 2000, history=True)
