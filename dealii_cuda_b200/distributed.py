@@ -124,20 +124,21 @@ class InterfaceExchange:
 class DistributedLaplaceOperator:
     """LaplaceOperatorGpu over a box partition: vmult = local cell loop + interface exchange."""
 
-    def __init__(self, ctx, rank, world, dim, degree, r, dtype=np.float64, left=-1.0, right=1.0, variant=0, group=None, overlap=True):
-        self.ctx, self.rank, self.world = ctx, rank, world
-        box, self.me, self.grid = box_for_rank(rank, world, dim, r, left, right)
+    def __init__(self, ctx, rank, world, dim, degree, r, dtype=np.float64, left=-1.0, right=1.0, variant=0, group=None, overlap=True,
+                 strong=False):
+        self.ctx, self.rank, self.world, self.strong = ctx, rank, world, strong
+        box, self.me, self.grid = box_for_rank(rank, world, dim, r, left, right, strong)
         self.mesh = HyperCubeMesh(ctx, dim, degree, box=box)
         self.op = LaplaceOperatorGpu(ctx, dtype)
         self.op.reinit(self.mesh)
         if variant:
             self.op.set_variant(variant)
-        self.plan = build_exchange_plan(rank, world, dim, degree, r, self.mesh.lattice_to_dof, self.mesh.n_dofs)
+        self.plan = build_exchange_plan(rank, world, dim, degree, r, self.mesh.lattice_to_dof, self.mesh.n_dofs, strong)
         self.exchange = InterfaceExchange(ctx, self.plan, dtype, group)
         # overlap: cell groups that touch exchanged DoFs run first, the rest while the exchange is in flight
         self.n_iface_groups = self.op.set_interface_dofs(self.plan.pack_idx) if (overlap and world > 1 and self.plan.n_send) else 0
         self.n_local = self.mesh.n_dofs
-        self.n_global = global_n_dofs(world, dim, degree, r)
+        self.n_global = global_n_dofs(world, dim, degree, r, strong)
 
     def vmult_ptr(self, dst_ptr, src_ptr):
         if self.n_iface_groups:
@@ -307,7 +308,8 @@ def bench_main(args, metric):
     dtype = np.float64 if args.dtype == "f64" else np.float32
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
     s = 8 if args.dtype == "f64" else 4
-    dop = DistributedLaplaceOperator(ctx, rank, world, args.dim, args.degree, args.refine, dtype, variant=args.variant)
+    strong = getattr(args, "scaling", "weak") == "strong"
+    dop = DistributedLaplaceOperator(ctx, rank, world, args.dim, args.degree, args.refine, dtype, variant=args.variant, strong=strong)
     n = dop.n_local
     ta = torch.full((n,), 0.1, dtype=tdtype, device="cuda")
     tb = torch.zeros((n,), dtype=tdtype, device="cuda")
@@ -363,10 +365,11 @@ def bench_main(args, metric):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if rank == 0:
         sampler.start()
-    t_lead = time.perf_counter()   # clock samples (20 ms period) start 0.3 s before the timed region, under the same load
-    while time.perf_counter() - t_lead < 0.3:
-        apply_steps(50)
-        torch.cuda.synchronize()
+    # Clock samples (20 ms period) start before the timed region, under the same load.  The number of lead-in applies must be
+    # THE SAME ON EVERY RANK (an apply synchronises with its neighbours through the exchange barriers: a rank that runs one
+    # more apply than its peers waits for ever), so it is a fixed count, not a time: about 0.3 s at the r = 6 rate.
+    apply_steps(1000 if n <= 20000000 else 150)
+    torch.cuda.synchronize()
     ta.fill_(0.1); tb.fill_(0.1)
     dist.barrier()
     torch.cuda.synchronize()
@@ -391,56 +394,60 @@ def bench_main(args, metric):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, k_avg_ms = float(t[0]), float(t[1])
 
-    # end to end: pinned host src -> H2D -> vmult (+exchange) -> D2H, two slots per rank pipelined on three streams (PCIe is
-    # full duplex: step k's D2H overlaps step k+1's H2D; the applies stay on the main stream).  Blocking figure next to it.
-    hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
-    hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
-    ds = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
-    dd = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
-    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]; ev_ap = [torch.cuda.Event() for _ in range(2)]; ev_out = [torch.cuda.Event() for _ in range(2)]
+    e2e_s = e2e_block_s = float("nan")
+    n_e2e = 0
+    if not getattr(args, "no_e2e", False):
+        # end to end: pinned host src -> H2D -> vmult (+exchange) -> D2H, two slots per rank pipelined on three streams (PCIe is
+        # full duplex: step k's D2H overlaps step k+1's H2D; the applies stay on the main stream).  Blocking figure next to it.
+        hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
+        hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
+        ds = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
+        dd = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
+        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]; ev_ap = [torch.cuda.Event() for _ in range(2)]; ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_blocking():
-        ds[0].copy_(hs[0], non_blocking=True)
-        dop.vmult_ptr(dd[0].data_ptr(), ds[0].data_ptr())
-        hd[0].copy_(dd[0], non_blocking=True)
-        torch.cuda.synchronize()
+        def e2e_blocking():
+            ds[0].copy_(hs[0], non_blocking=True)
+            dop.vmult_ptr(dd[0].data_ptr(), ds[0].data_ptr())
+            hd[0].copy_(dd[0], non_blocking=True)
+            torch.cuda.synchronize()
 
-    def e2e_pipelined(steps):
-        for k in range(steps):
-            sl = k % 2
-            s_h2d.wait_event(ev_ap[sl])                      # the apply that read this slot's source two steps ago is done
-            with torch.cuda.stream(s_h2d):
-                ds[sl].copy_(hs[sl], non_blocking=True)
-                ev_in[sl].record(s_h2d)
-            main.wait_event(ev_in[sl])
-            main.wait_event(ev_out[sl])                      # this slot's previous result has left the device
-            dop.vmult_graphed(dd[sl].data_ptr(), ds[sl].data_ptr())
-            ev_ap[sl].record(main)
-            s_d2h.wait_event(ev_ap[sl])
-            with torch.cuda.stream(s_d2h):
-                hd[sl].copy_(dd[sl], non_blocking=True)
-                ev_out[sl].record(s_d2h)
-        torch.cuda.synchronize()
+        def e2e_pipelined(steps):
+            for k in range(steps):
+                sl = k % 2
+                s_h2d.wait_event(ev_ap[sl])                      # the apply that read this slot's source two steps ago is done
+                with torch.cuda.stream(s_h2d):
+                    ds[sl].copy_(hs[sl], non_blocking=True)
+                    ev_in[sl].record(s_h2d)
+                main.wait_event(ev_in[sl])
+                main.wait_event(ev_out[sl])                      # this slot's previous result has left the device
+                dop.vmult_graphed(dd[sl].data_ptr(), ds[sl].data_ptr())
+                ev_ap[sl].record(main)
+                s_d2h.wait_event(ev_ap[sl])
+                with torch.cuda.stream(s_d2h):
+                    hd[sl].copy_(dd[sl], non_blocking=True)
+                    ev_out[sl].record(s_d2h)
+            torch.cuda.synchronize()
 
-    e2e_blocking()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(3):
         e2e_blocking()
-    dist.barrier()
-    e2e_block_s = (time.perf_counter() - t0) / 3
-    e2e_pipelined(4)   # warm-up: captures the two graphs
-    n_e2e = max(args.e2e_steps, 6)
-    dist.barrier()
-    t0 = time.perf_counter()
-    e2e_pipelined(n_e2e)
-    dist.barrier()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    te = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_block_s = float(te[0]), float(te[1])
-    del hs, hd, ds, dd
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_blocking()
+        dist.barrier()
+        e2e_block_s = (time.perf_counter() - t0) / 3
+        e2e_pipelined(4)   # warm-up: captures the two graphs
+        n_e2e = max(args.e2e_steps, 6)
+        dist.barrier()
+        t0 = time.perf_counter()
+        e2e_pipelined(n_e2e)
+        dist.barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        te = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s, e2e_block_s = float(te[0]), float(te[1])
+        del hs, hd, ds, dd
+
 
     # CG solve over all GPUs (BASELINE metric "CG time"): b = A u for a vector u whose interface replicas agree
     cg = None
@@ -474,18 +481,21 @@ def bench_main(args, metric):
         peak, peak_src = measured_peaks()
         alg_bytes = b_alg(args.degree, args.dim, s) * n
         achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+        workload = ("bmop: 3D variable-coefficient Laplace apply, FE_Q(%d), " % args.degree
+                    + (("the refine_global(%d) cube cut into boxes of %d cells per GPU, " if strong else "one refine_global(%d) cube of %d cells per GPU, ")
+                       % (args.refine, dop.mesh.n_cells))
+                    + "%s grid of boxes, %d global DoFs (%d per GPU incl. interface replicas), atomic scatter, interface exchange: %s"
+                    % ("x".join(map(str, dop.grid)), ng, n,
+                       "NVLink P2P stores + device-side barriers" if dop.exchange.symm is not None else "NCCL all_to_all_single"))
         line = {"metric": metric, "value": ng * args.steps / (ms * 1e-3), "unit": "DoFs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": "bmop: 3D variable-coefficient Laplace apply, FE_Q(%d), one refine_global(%d) cube of %d cells per GPU, "
-                                       "%s grid of cubes, %d global DoFs (%d per GPU incl. interface replicas), atomic scatter, "
-                                       "interface exchange: %s" % (args.degree, args.refine, dop.mesh.n_cells, "x".join(map(str, dop.grid)), ng, n,
-                                                                   "NVLink P2P stores + device-side barriers" if dop.exchange.symm is not None
-                                                                   else "NCCL all_to_all_single"),
+                "config": {"workload": workload,
                            "l2": "inputs larger than L2"},
                 "clocks": clocks,
-                "e2e": {"value": ng / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
-                        "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3},
+                "e2e": ({"value": ng / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
+                         "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3}
+                        if n_e2e else None),
                 # per apply and rank: constraint pass + cell kernel(s) + push (or pack) + accumulate; the split apply zeroes
                 # dst with cudaMemsetAsync (no zero kernel) and launches the cell kernel twice
                 "gpu_launches": args.steps * world * ((dop.op.launches_per_vmult() if not dop.n_iface_groups else dop.op.launches_per_vmult()) + 2),

@@ -22,8 +22,18 @@ def rank_coords(rank, world, dim=3):
     return (rank % g[0], (rank // g[0]) % g[1], rank // (g[0] * g[1])), g
 
 
-def box_for_rank(rank, world, dim, r, left=-1.0, right=1.0):
-    """Local box descriptor (mfg_box_desc) of a rank: a 2^r cube of cells of edge h = (right-left)/2^r."""
+def local_log2(world, dim, r, strong=False):
+    """log2 of the cells per direction of one rank's box: weak scaling = a 2^r cube per rank (the domain grows with the
+    ranks), strong scaling = the refine_global(r) cube [left,right]^dim cut into the rank grid"""
+    _, g = rank_coords(0, world, dim)
+    lg = [r - (int(np.log2(g[d])) if strong else 0) for d in range(dim)]
+    assert min(lg) >= 0, "more ranks than cells in a direction"
+    return lg
+
+
+def box_for_rank(rank, world, dim, r, left=-1.0, right=1.0, strong=False):
+    """Local box descriptor (mfg_box_desc) of a rank: weak scaling: a 2^r cube of cells of edge h = (right-left)/2^r;
+    strong scaling: this rank's part of the refine_global(r) mesh of [left,right]^dim."""
     (ix, iy, iz), g = rank_coords(rank, world, dim)
     me = (ix, iy, iz)
     faces = 0
@@ -33,15 +43,17 @@ def box_for_rank(rank, world, dim, r, left=-1.0, right=1.0):
         if me[d] == g[d] - 1:
             faces |= 1 << (2 * d + 1)
     h = (right - left) / (1 << r)
-    return dict(log2_cells=[r] * dim + [0] * (3 - dim), origin=[left + me[d] * (right - left) for d in range(dim)] + [0.0] * (3 - dim),
+    lg = local_log2(world, dim, r, strong)
+    return dict(log2_cells=lg + [0] * (3 - dim), origin=[left + me[d] * h * (1 << lg[d]) for d in range(dim)] + [0.0] * (3 - dim),
                 h=h, dirichlet_faces=faces), me, g
 
 
-def global_n_dofs(world, dim, degree, r):
+def global_n_dofs(world, dim, degree, r, strong=False):
     _, g = rank_coords(0, world, dim)
+    lg = local_log2(world, dim, r, strong)
     n = 1
     for d in range(dim):
-        n *= degree * (1 << r) * g[d] + 1
+        n *= degree * (1 << lg[d]) * g[d] + 1
     return n
 
 
@@ -83,11 +95,12 @@ class ExchangePlan:
         self.owned_mask = owned
 
 
-def build_exchange_plan(rank, world, dim, degree, r, lattice_to_dof, n_local):
-    """lattice_to_dof: callable mapping an (m,3) uint32 array of LOCAL lattice points (0..p*2^r per direction)
+def build_exchange_plan(rank, world, dim, degree, r, lattice_to_dof, n_local, strong=False):
+    """lattice_to_dof: callable mapping an (m,3) uint32 array of LOCAL lattice points (0..p*2^r_d per direction)
     to local DoF indices (HyperCubeMesh.lattice_to_dof on the GPU; an oracle-based map in the CPU tests)."""
     me, g = rank_coords(rank, world, dim)
-    M = degree * (1 << r)  # last lattice index per direction of the local box
+    lg = local_log2(world, dim, r, strong)
+    Md = [degree * (1 << lg[d]) for d in range(dim)]  # last lattice index per direction of the local box
     lists, replicated = {}, {}
     for delta in itertools.product((-1, 0, 1), repeat=dim):
         if not any(delta):
@@ -99,6 +112,7 @@ def build_exchange_plan(rank, world, dim, degree, r, lattice_to_dof, n_local):
         def points(drop_dirichlet):
             ranges = []
             for d in range(dim):
+                M = Md[d]
                 if delta[d] == 1:
                     ranges.append(np.array([M]))
                 elif delta[d] == -1:

@@ -21,6 +21,7 @@ def main():
     from test_partition import global_box, local_to_global_map
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dim, p, r = 3, int(sys.argv[1]), int(sys.argv[2])
+    strong = len(sys.argv) > 3 and sys.argv[3] == "strong"
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     main_stream = torch.cuda.Stream()
@@ -28,12 +29,12 @@ def main():
     ctx = mf.Context(local_rank, main_stream.cuda_stream)
     worst = 0.0
     for dtype, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
-        dop = mfd.DistributedLaplaceOperator(ctx, rank, world, dim, p, r, dtype)
-        gbox, _ = global_box(world, dim, r)
+        dop = mfd.DistributedLaplaceOperator(ctx, rank, world, dim, p, r, dtype, strong=strong)
+        gbox, _ = global_box(world, dim, r, strong=strong)
         og = OracleMesh(dim, p, box=gbox)
-        ol = OracleMesh(dim, p, box=mfd.box_for_rank(rank, world, dim, r)[0])
+        ol = OracleMesh(dim, p, box=mfd.box_for_rank(rank, world, dim, r, strong=strong)[0])
         assert np.array_equal(dop.mesh.loc2glob(), ol.loc2glob), "local DoF map differs from the oracle"
-        l2g = local_to_global_map(ol, og, dop.me, p, r, dim)
+        l2g = local_to_global_map(ol, og, dop.me, p, r, dim, world, strong)
         u_g = sm64(21, og.n_dofs).astype(dtype)
         want = og.vmult(u_g.astype(np.float64))[l2g]
         src = mf.GpuVector.from_numpy(ctx, u_g[l2g])

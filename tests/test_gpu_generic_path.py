@@ -142,37 +142,3 @@ def test_user_written_laplace_general_geometry(ctx, gen):
     ov.n_cells, ov.n_dofs, ov.constrained, ov.loc2glob = o.n_cells, o.n_dofs, np.zeros(0, np.uint32), np.asarray(o.loc2glob)
     ov.shape_values, ov.shape_gradients = o.shape_values, o.shape_gradients
     assert rel_err(dst.toVector(), reference_apply(ov, dim, p, K, JxW, coef, q_idx, u)) <= 1e-12
-
-
-@pytest.mark.parametrize("dim,p,r", [(2, 2, 2), (3, 2, 1), (3, 4, 1)])
-def test_dst_only_cell_loop_and_evaluate_on_cells(ctx, gen, dim, p, r):
-    """MatrixFreeGpu::cell_loop(dst, loc_op) (matrix_free_gpu.h:382-393) and evaluate_on_cells<LocalCoeffOp> (:415-435,
-    laplace_operator_gpu.h:191-211): the dst-only loop gives the same right-hand side as the loop with a source vector, the
-    evaluated coefficient is 1 / (0.05 + 2 |x_q|^2) at the oracle's quadrature points"""
-    import dealii_cuda_b200 as mf
-    o = OracleMesh(dim, p, r)
-    m = mf.HyperCubeMesh(ctx, dim, p, r)
-    mfree = mf.MatrixFreeGpu(ctx, np.float64)
-    mfree.reinit(m)
-    dummy = mf.GpuVector(ctx, o.n_dofs)
-    a, b = mf.GpuVector(ctx, o.n_dofs), mf.GpuVector(ctx, o.n_dofs)
-    a.fill(0.0); b.fill(0.0)
-    gen(mfree, 2, dim, p, np.float64, a, dummy)
-    gen(mfree, 3, dim, p, np.float64, b, dummy)
-    assert rel_err(b.toVector(), a.toVector()) <= 1e-14
-    coef = mf.GpuVector(ctx, o.n_cells * (p + 1) ** dim)
-    gen(mfree, 4, dim, p, np.float64, coef, dummy)
-    assert rel_err(coef.toVector(), np.asarray(o.coefficient).ravel()) <= 1e-14
-
-
-def test_generic_path_refuses_hanging_node_meshes(ctx, gen):
-    """the generic FEEvaluationGpu path does not interpolate hanging nodes: it must say so instead of skipping cells"""
-    import dealii_cuda_b200 as mf
-    from oracle.adaptive import AdaptiveMesh
-    am = AdaptiveMesh(2, 2, 2, [lambda c, h: np.linalg.norm(c) < 0.5])
-    assert am.mask.max() > 0
-    mfree = mf.MatrixFreeGpu(ctx, np.float64)
-    mfree.reinit(dict(dim=2, degree=2, n_dofs=am.n_dofs, loc2glob=am.l2g, inv_jac=am.inv_jac, constraint_mask=am.mask))
-    a, b = mf.GpuVector(ctx, am.n_dofs), mf.GpuVector(ctx, am.n_dofs)
-    with pytest.raises(AssertionError, match="hanging"):
-        gen(mfree, 0, 2, 2, np.float64, a, b)

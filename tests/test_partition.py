@@ -15,17 +15,18 @@ if ROOT not in sys.path:
 from oracle.oracle import OracleMesh, sm64  # noqa: E402
 
 
-def global_box(world, dim, r, left=-1.0, right=1.0):
+def global_box(world, dim, r, left=-1.0, right=1.0, strong=False):
     from dealii_cuda_b200.partition import rank_coords
     _, g = rank_coords(0, world, dim)
-    lg = [r + int(np.log2(g[d])) for d in range(dim)]
+    lg = [r + (0 if strong else int(np.log2(g[d]))) for d in range(dim)]
     return dict(log2_cells=lg, origin=[left] * dim, h=(right - left) / (1 << r), dirichlet_faces=0x3f), g
 
 
-def local_to_global_map(olocal, oglobal, me, p, r, dim):
+def local_to_global_map(olocal, oglobal, me, p, r, dim, world=None, strong=False):
     """global DoF index of every local DoF, via lattice coordinates"""
-    M = p * (1 << r)
-    lat = olocal.dof_lattice.astype(np.int64) + np.array([me[d] * M if d < dim else 0 for d in range(3)])
+    from dealii_cuda_b200.partition import local_log2
+    lg = local_log2(world, dim, r, strong) if world is not None else [r] * dim
+    lat = olocal.dof_lattice.astype(np.int64) + np.array([me[d] * p * (1 << lg[d]) if d < dim else 0 for d in range(3)])
     glat = oglobal.dof_lattice.astype(np.int64)
     dims = glat.max(axis=0) + 1
     key = lambda a: a[:, 0] + dims[0] * (a[:, 1] + dims[1] * a[:, 2])
@@ -59,7 +60,7 @@ def numpy_accumulate(plan, vec, recv):
     return out
 
 
-def _gloo_worker(rank, world, port, dim, p, r, q):
+def _gloo_worker(rank, world, port, dim, p, r, q, strong=False):
     import torch
     import torch.distributed as dist
     from dealii_cuda_b200.partition import box_for_rank, build_exchange_plan, global_n_dofs
@@ -67,13 +68,13 @@ def _gloo_worker(rank, world, port, dim, p, r, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        gbox, _ = global_box(world, dim, r)
+        gbox, _ = global_box(world, dim, r, strong=strong)
         og = OracleMesh(dim, p, box=gbox)
-        assert og.n_dofs == global_n_dofs(world, dim, p, r)
-        box, me, g = box_for_rank(rank, world, dim, r)
+        assert og.n_dofs == global_n_dofs(world, dim, p, r, strong)
+        box, me, g = box_for_rank(rank, world, dim, r, strong=strong)
         ol = OracleMesh(dim, p, box=box)
-        l2gmap = local_to_global_map(ol, og, me, p, r, dim)
-        plan = build_exchange_plan(rank, world, dim, p, r, oracle_lattice_to_dof(ol), ol.n_dofs)
+        l2gmap = local_to_global_map(ol, og, me, p, r, dim, world, strong)
+        plan = build_exchange_plan(rank, world, dim, p, r, oracle_lattice_to_dof(ol), ol.n_dofs, strong)
         u_g = sm64(11, og.n_dofs)
         want = og.vmult(u_g)
         # local cell loop (oracle as the stand-in for the CUDA kernel), then the exchange
@@ -112,13 +113,14 @@ def _gloo_worker(rank, world, port, dim, p, r, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,dim,p,r", [(2, 3, 2, 1), (2, 3, 4, 1), (2, 2, 3, 2)])
-def test_partition_exchange_gloo(world, dim, p, r):
+@pytest.mark.parametrize("world,dim,p,r,strong", [(2, 3, 2, 1, False), (2, 3, 4, 1, False), (2, 2, 3, 2, False), (2, 3, 3, 2, True)])
+def test_partition_exchange_gloo(world, dim, p, r, strong):
+    """weak scaling (one 2^r cube per rank) and strong scaling (the refine_global(r) cube cut into the rank grid)"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_gloo_worker, args=(rk, world, port, dim, p, r, q)) for rk in range(world)]
+    procs = [ctx.Process(target=_gloo_worker, args=(rk, world, port, dim, p, r, q, strong)) for rk in range(world)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=120) for _ in procs]
