@@ -27,12 +27,15 @@ static void launch_gen(bool atomic, const uint32_t *idx, const Number *gsym, con
   const uint32_t blocks = (cell_end - cell_begin + CPB - 1) / CPB;
   auto ka = laplace_cell_general<dim, n, Number, true>;
   auto kc = laplace_cell_general<dim, n, Number, false>;
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024)
+  static bool attr_set[64] = {false};  // (function attributes are per device)
+  int dev = 0;
+  MFG_CUDA(cudaGetDevice(&dev));
+  MFG_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  if (!attr_set[dev] && smem > 48 * 1024)
     {
       MFG_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       MFG_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      attr_set[dev] = true;
     }
   if (atomic) ka<<<blocks, threads, smem, stream>>>(idx, gsym, src, dst, cell_begin, cell_end, sh);
   else kc<<<blocks, threads, smem, stream>>>(idx, gsym, src, dst, cell_begin, cell_end, sh);

@@ -31,13 +31,16 @@ static void launch_n(bool atomic, const uint32_t *idx, const Number *cw, const N
   auto             ka      = laplace_cell_v0<dim, n, Number, true, false>;
   auto             kc      = laplace_cell_v0<dim, n, Number, false, false>;
   auto             kh      = laplace_cell_v0<dim, n, Number, true, true>;
-  static bool      attr_set = false;
-  if (!attr_set && smem > 48 * 1024)
+  static bool      attr_set[64] = {false};  // (function attributes are per device)
+  int dev = 0;
+  MFG_CUDA(cudaGetDevice(&dev));
+  MFG_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  if (!attr_set[dev] && smem > 48 * 1024)
     {
       MFG_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       MFG_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       MFG_CUDA(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      attr_set[dev] = true;
     }
   if (hn_mask)
     {

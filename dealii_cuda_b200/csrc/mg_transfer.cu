@@ -154,6 +154,15 @@ int mfg_mgt_build(mfg_ctx *ctx, const mfg_mesh *coarse, const mfg_mesh *fine, mf
           }
       }
     cudaStream_t s = ctx->stream;
+    // 3D degree 7, 8: the two staged tensors of (2p+1)^dim doubles exceed the 48 KB a kernel gets without opting in
+    const size_t smem_needed = 2 * (size_t)ipow(nf, t->dim) * sizeof(double);
+    if (smem_needed > 48 * 1024)
+      {
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+      }
     const size_t nC = (size_t)coarse->n_cells * coarse->npc;
     t->coarse_idx.alloc(nC);
     mark_coarse<<<(unsigned)((nC + 255) / 256), 256, 0, s>>>(coarse->l2g.p, coarse->cflag.p, nC, t->coarse_idx.p);

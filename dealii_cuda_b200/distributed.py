@@ -368,7 +368,9 @@ def bench_main(args, metric):
     # Clock samples (20 ms period) start before the timed region, under the same load.  The number of lead-in applies must be
     # THE SAME ON EVERY RANK (an apply synchronises with its neighbours through the exchange barriers: a rank that runs one
     # more apply than its peers waits for ever), so it is a fixed count, not a time: about 0.3 s at the r = 6 rate.
-    apply_steps(1000 if n <= 20000000 else 150)
+    n_max = torch.tensor([n], dtype=torch.int64, device="cuda")
+    dist.all_reduce(n_max, op=dist.ReduceOp.MAX)     # (the count below is derived from a value every rank agrees on)
+    apply_steps(1000 if int(n_max.item()) <= 20000000 else 150)
     torch.cuda.synchronize()
     ta.fill_(0.1); tb.fill_(0.1)
     dist.barrier()
