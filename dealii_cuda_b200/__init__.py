@@ -21,7 +21,7 @@ import numpy as np
 from . import _capi
 from ._capi import F32, F64, SCATTER_ATOMIC, SCATTER_COLOR, MfgError, check, lib
 
-__all__ = ["Context", "GpuVector", "HyperCubeMesh", "MatrixFreeGpu", "ConstraintHandlerGpu", "LaplaceOperatorGpu",
+__all__ = ["Context", "GpuVector", "HyperCubeMesh", "AdaptiveMesh", "MatrixFreeGpu", "ConstraintHandlerGpu", "LaplaceOperatorGpu",
            "shape_info", "solver_cg", "hanging_node_weights", "F32", "F64", "SCATTER_ATOMIC", "SCATTER_COLOR", "MfgError"]
 
 _NP = {F32: np.float32, F64: np.float64}
@@ -380,6 +380,96 @@ class ConstraintHandlerGpu:
         check(lib.mfg_ch_copy_edge_values(self.h, dst.h, src.h))
 
 
+class AdaptiveMesh:
+    """Triangulation + DoFHandler + HangingNodes on hyper_cube(left, right) with local refinement (mfg_amesh_*, host code of
+    the library): what the reference takes from deal.II for its adaptive-grid runs (bmop_common.h:9-120,
+    matrix_free_gpu/hanging_nodes.cuh:209-454).  Needs no device; LaplaceOperatorGpu.reinit(adaptive_mesh) builds the
+    device objects."""
+
+    def __init__(self, dim, degree, left=-1.0, right=1.0):
+        h = C.c_void_p()
+        check(lib.mfg_amesh_create(int(dim), int(degree), float(left), float(right), C.byref(h)))
+        self.h, self.dim, self.degree, self.left, self.right = h, dim, degree, left, right
+        self.dofs_per_cell = (degree + 1) ** dim
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.mfg_amesh_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def refine_global(self, times=1):
+        check(lib.mfg_amesh_refine_global(self.h, int(times)))
+        return self
+
+    def set_refine_flags(self, flags):
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        assert f.size == self.n_cells
+        check(lib.mfg_amesh_set_refine_flags(self.h, f.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def _center(self, center):
+        if center is None:
+            return None
+        c = np.zeros(3)
+        c[:self.dim] = np.asarray(center, dtype=np.float64)[:self.dim]
+        return c
+
+    def mark_cells_in_annulus(self, R, r=0.0, center=None):
+        c = self._center(center)
+        check(lib.mfg_amesh_mark_cells_in_annulus(self.h, float(R), float(r), _dp(c) if c is not None else None))
+
+    def mark_cells_on_shell(self, R, center=None):
+        c = self._center(center)
+        check(lib.mfg_amesh_mark_cells_on_shell(self.h, float(R), _dp(c) if c is not None else None))
+
+    def mark_octant(self):
+        check(lib.mfg_amesh_mark_octant(self.h))
+
+    def execute_coarsening_and_refinement(self):
+        check(lib.mfg_amesh_execute_refinement(self.h))
+        return self
+
+    def pseudo_adaptive_refinement(self, n_ref):
+        """bmop_common.h:49-105 (domain CUBE) on the unrefined hyper_cube"""
+        check(lib.mfg_amesh_pseudo_adaptive_refinement(self.h, int(n_ref)))
+        return self
+
+    @property
+    def n_cells(self):
+        return lib.mfg_amesh_n_active_cells(self.h)
+
+    @property
+    def n_levels(self):
+        return lib.mfg_amesh_n_levels(self.h)
+
+    def active_cells(self):
+        """[n_cells][1 + dim]: level and integer coordinates of the active cells in iteration order"""
+        out = np.zeros((self.n_cells, 4), dtype=np.uint32)
+        check(lib.mfg_amesh_get_active_cells(self.h, _u32p(out)))
+        return out[:, :1 + self.dim]
+
+    def distribute_dofs(self):
+        check(lib.mfg_amesh_distribute_dofs(self.h))
+        self.n_dofs = lib.mfg_amesh_n_dofs(self.h)
+        return self
+
+    def arrays(self, quadrature_points=False):
+        """dict: loc2glob (rewritten), loc2glob_unconstrained, constraint_mask, constrained, hanging, inv_jac, coefficient"""
+        nc, npc = self.n_cells, self.dofs_per_cell
+        a = dict(loc2glob=np.zeros((nc, npc), np.uint32), loc2glob_unconstrained=np.zeros((nc, npc), np.uint32),
+                 constraint_mask=np.zeros(nc, np.uint32), constrained=np.zeros(lib.mfg_amesh_n_constrained(self.h), np.uint32),
+                 hanging=np.zeros(lib.mfg_amesh_n_hanging(self.h), np.uint32), inv_jac=np.zeros(nc), coefficient=np.zeros((nc, npc)))
+        qp = np.zeros((nc, npc, self.dim)) if quadrature_points else None
+        check(lib.mfg_amesh_get_arrays(self.h, _u32p(a["loc2glob"]), _u32p(a["loc2glob_unconstrained"]), _u32p(a["constraint_mask"]),
+                                       _u32p(a["constrained"]), _u32p(a["hanging"]), _dp(a["inv_jac"]), _dp(a["coefficient"]),
+                                       _dp(qp) if qp is not None else None))
+        if qp is not None:
+            a["quadrature_points"] = qp
+        return a
+
+
 class MatrixFreeGpu:
     """MatrixFreeGpu<dim,Number> (matrix_free_gpu.h:81-229): reinit / counters / free."""
 
@@ -463,6 +553,10 @@ class LaplaceOperatorGpu:
         if isinstance(mesh, HyperCubeMesh):
             scatter = SCATTER_COLOR if self.use_coloring else SCATTER_ATOMIC
             check(lib.mfg_laplace_create(self.ctx.h, mesh.h, self.code, scatter, C.byref(h)))
+            self._keep = mesh
+        elif isinstance(mesh, AdaptiveMesh):
+            assert not self.use_coloring, "hanging nodes need the atomic scatter"
+            check(lib.mfg_laplace_create_from_amesh(self.ctx.h, mesh.h, self.code, C.byref(h)))
             self._keep = mesh
         else:
             coef = np.ascontiguousarray(coefficient, dtype=np.float64)

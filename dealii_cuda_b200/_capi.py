@@ -176,6 +176,24 @@ def _load():
         "mfg_exchange_push_stream": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_int, vp]),
         "mfg_vec_dot_masked": (C.c_int, [vp, vp, vp, dp]),
         "mfg_laplace_bmop": (C.c_int, [vp, vp, vp, C.c_int, C.c_double, C.POINTER(C.c_float)]),
+        "mfg_amesh_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, pp]),
+        "mfg_amesh_destroy": (C.c_int, [vp]),
+        "mfg_amesh_refine_global": (C.c_int, [vp, C.c_int]),
+        "mfg_amesh_set_refine_flags": (C.c_int, [vp, C.POINTER(C.c_uint8)]),
+        "mfg_amesh_mark_cells_in_annulus": (C.c_int, [vp, C.c_double, C.c_double, dp]),
+        "mfg_amesh_mark_cells_on_shell": (C.c_int, [vp, C.c_double, dp]),
+        "mfg_amesh_mark_octant": (C.c_int, [vp]),
+        "mfg_amesh_execute_refinement": (C.c_int, [vp]),
+        "mfg_amesh_pseudo_adaptive_refinement": (C.c_int, [vp, C.c_int]),
+        "mfg_amesh_n_active_cells": (C.c_uint32, [vp]),
+        "mfg_amesh_n_levels": (C.c_uint32, [vp]),
+        "mfg_amesh_get_active_cells": (C.c_int, [vp, u32p]),
+        "mfg_amesh_distribute_dofs": (C.c_int, [vp]),
+        "mfg_amesh_n_dofs": (C.c_uint32, [vp]),
+        "mfg_amesh_n_constrained": (C.c_uint32, [vp]),
+        "mfg_amesh_n_hanging": (C.c_uint32, [vp]),
+        "mfg_amesh_get_arrays": (C.c_int, [vp, u32p, u32p, u32p, u32p, u32p, dp, dp, dp]),
+        "mfg_laplace_create_from_amesh": (C.c_int, [vp, vp, C.c_int, pp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError if a declared symbol is missing

@@ -134,6 +134,39 @@ int mfg_mesh_color_cells(const mfg_mesh *m, uint32_t *color_of_cell, uint32_t *n
 int mfg_graph_coloring(uint32_t n_cells, uint32_t dofs_per_cell, const uint32_t *conflict_indices_host, uint32_t n_indices,
                        uint32_t *color_of_cell, uint32_t *n_colors);
 
+/* ---- adaptively refined meshes with hanging nodes: host substrate ------------------------------------------------------
+ * What the reference takes from deal.II on such meshes (bmop.cu / poisson.cu with an adaptive grid), restated on the host:
+ * a Triangulation on hyper_cube(left, right) with refine_global / set_refine_flag / execute_coarsening_and_refinement
+ * (refinement flags are closed under deal.II's one-level rule across faces and, in 3D, edges; cells are kept per level in
+ * creation order, so the active cells iterate like deal.II's), the reference's flagging helpers (bmop_common.h:9-105,
+ * poisson_common.h:29-35), DoFHandler::distribute_dofs for FE_Q(p) and HangingNodes::setup_constraints
+ * (matrix_free_gpu/hanging_nodes.cuh:209-454): the 9-bit mask per cell and loc2glob with the coarse neighbour's DoFs on
+ * constrained faces / edges.  Pure host code, no device needed; mfg_laplace_create_from_amesh builds the device objects
+ * through mfg_mf_reinit (constraint_mask) + mfg_ch_create + mfg_laplace_create_from_arrays. */
+typedef struct mfg_amesh mfg_amesh;
+int mfg_amesh_create(int dim, int degree, double left, double right, mfg_amesh **out);     /* GridGenerator::hyper_cube, one cell */
+int mfg_amesh_destroy(mfg_amesh *am);
+int mfg_amesh_refine_global(mfg_amesh *am, int times);                                     /* Triangulation::refine_global */
+int mfg_amesh_set_refine_flags(mfg_amesh *am, const uint8_t *flags /* [n_active_cells] */); /* cell->set_refine_flag() */
+int mfg_amesh_mark_cells_in_annulus(mfg_amesh *am, double R, double r, const double *center /* [dim] or NULL = origin */); /* bmop_common.h:9-24 */
+int mfg_amesh_mark_cells_on_shell(mfg_amesh *am, double R, const double *center);          /* bmop_common.h:27-47 */
+int mfg_amesh_mark_octant(mfg_amesh *am);                                                  /* mark_cells(octant_criterion) poisson_common.h:29-35, 43-56 */
+int mfg_amesh_execute_refinement(mfg_amesh *am);                                           /* execute_coarsening_and_refinement */
+int mfg_amesh_pseudo_adaptive_refinement(mfg_amesh *am, int n_ref);                        /* bmop_common.h:49-105, domain CUBE */
+uint32_t mfg_amesh_n_active_cells(const mfg_amesh *am);
+uint32_t mfg_amesh_n_levels(const mfg_amesh *am);
+int mfg_amesh_get_active_cells(const mfg_amesh *am, uint32_t *level_xyz /* [n_active_cells][4]: level, x, y, z */);
+/* DoFHandler::distribute_dofs + HangingNodes::setup_constraints + the ConstraintHandlerGpu list (hanging and boundary DoFs) */
+int mfg_amesh_distribute_dofs(mfg_amesh *am);
+uint32_t mfg_amesh_n_dofs(const mfg_amesh *am);
+uint32_t mfg_amesh_n_constrained(const mfg_amesh *am);
+uint32_t mfg_amesh_n_hanging(const mfg_amesh *am);
+/* any pointer may be NULL.  loc2glob: [n_cells][(p+1)^dim] after the rewrite; loc2glob_unconstrained: the DoFHandler's own map;
+ * constraint_mask [n_cells]; constrained [n_constrained] ascending; hanging [n_hanging]; inv_jac [n_cells];
+ * coefficient [n_cells][(p+1)^dim] = 1/(0.05+2|x_q|^2) (poisson_common.h:146-158); quadrature_points [n_cells][(p+1)^dim][dim] */
+int mfg_amesh_get_arrays(const mfg_amesh *am, uint32_t *loc2glob, uint32_t *loc2glob_unconstrained, uint32_t *constraint_mask, uint32_t *constrained,
+                         uint32_t *hanging, double *inv_jac, double *coefficient, double *quadrature_points);
+
 /* ---- MatrixFreeGpu ------------------------------------------------------- */
 /* Explicit-array description: what ReinitHelper extracts from deal.II
  * (matrix_free_gpu.cu:283-339) -- this is the call a deal.II-based caller makes. */
@@ -217,6 +250,9 @@ int mfg_laplace_create(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_sca
  * values at quadrature points [n_cells][(p+1)^dim] (host, double). The operator
  * takes ownership of neither mf nor ch. */
 int mfg_laplace_create_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const double *coefficient_host, mfg_laplace **out);
+/* LaplaceOperatorGpu::reinit on an adaptively refined mesh (-DMATRIX_FREE_HANGING_NODES): MatrixFreeGpu with the masks,
+ * ConstraintHandlerGpu with hanging + boundary DoFs, the reference coefficient; the operator owns both. */
+int mfg_laplace_create_from_amesh(mfg_ctx *ctx, const mfg_amesh *am, mfg_dtype dt, mfg_laplace **out);
 /* replace the coefficient: a(x_q) at quadrature points, host, [n_cells][(p+1)^dim], cells in mesh / descriptor order */
 int mfg_laplace_set_coefficient(mfg_laplace *op, const double *coefficient_host);
 int mfg_laplace_destroy(mfg_laplace *op);                                            /* clear() :110-117 */

@@ -84,17 +84,25 @@ def resolve_hanging_nodes(values, mask, p, dim, transpose=False):
 class AdaptiveMesh:
     """2:1-balanced tree mesh with FE_Q(p) DoFs and the reference's hanging-node data."""
 
-    def __init__(self, dim, p, base_refine, refine_steps, left=-1.0, right=1.0):
-        """refine_steps: list of callables f(center ndarray, half-size) -> bool (refine this active cell)."""
+    def __init__(self, dim, p, base_refine, refine_steps, left=-1.0, right=1.0, balance="vertex", cells=None):
+        """refine_steps: list of callables f(center ndarray, half-size) -> bool (refine this active cell).
+        balance: "vertex" keeps neighbours across faces, edges AND vertices within one level; "dealii" is deal.II's rule
+        (faces, in 3D also edges).  cells: an explicit list of active cells (level, x, y[, z]) IN THE ORDER TO USE (e.g. the
+        creation order of a deal.II-like triangulation); base_refine / refine_steps are then ignored."""
         self.dim, self.p, self.n, self.left, self.right = dim, p, p + 1, left, right
-        cells = {(0,) + (0,) * dim}
-        for _ in range(base_refine):
-            cells = set(ch for c in cells for ch in self._children(c))
-        for crit in refine_steps:
-            flagged = [c for c in cells if crit(*self._center(c))]
-            for c in flagged:
-                cells = self._refine(cells, c)
-        self.cells = sorted(cells, key=lambda c: (c[0], self._morton(c)))   # active cells, level-major
+        self.max_nonzero = dim if balance == "vertex" else (2 if dim == 3 else 1)
+        if cells is not None:
+            self.cells = [tuple(int(v) for v in c[:1 + dim]) for c in cells]
+            assert len(set(self.cells)) == len(self.cells)
+        else:
+            cells = {(0,) + (0,) * dim}
+            for _ in range(base_refine):
+                cells = set(ch for c in cells for ch in self._children(c))
+            for crit in refine_steps:
+                flagged = [c for c in cells if crit(*self._center(c))]
+                for c in flagged:
+                    cells = self._refine(cells, c)
+            self.cells = sorted(cells, key=lambda c: (c[0], self._morton(c)))   # active cells, level-major
         self.n_cells = len(self.cells)
         self.lmax = max(c[0] for c in self.cells)
         self._build_lookup()
@@ -133,7 +141,7 @@ class AdaptiveMesh:
             return cells
         # 2:1 balance across faces, edges and vertices: every neighbour must be at least as fine as c
         for delta in itertools.product((-1, 0, 1), repeat=self.dim):
-            if not any(delta):
+            if not any(delta) or sum(1 for d in delta if d) > self.max_nonzero:
                 continue
             nb = self._find_active(cells, c[0], tuple(x + d for x, d in zip(c[1:], delta)))
             while nb not in (None, "finer") and nb[0] < c[0]:

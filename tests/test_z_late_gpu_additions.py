@@ -71,3 +71,26 @@ def test_operator_with_restated_dealii_coloring(ctx, dim, p, r):
     op.vmult(dst, src)
     want = o.vmult(u)
     assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("dim,p", [(2, 3), (3, 2), (3, 4)])
+def test_operator_on_library_built_adaptive_mesh(ctx, dim, p):
+    """LaplaceOperatorGpu::reinit on an adaptive mesh built by the LIBRARY's host substrate (mfg_amesh_*, tests/test_adaptive_mesh.py
+    pins its arrays to the oracle on the CPU): vmult, the Jacobi diagonal and a CG solve against oracle/adaptive.py on the same cells"""
+    import dealii_cuda_b200 as mf
+    from oracle.adaptive import AdaptiveMesh
+    am = mf.AdaptiveMesh(dim, p).refine_global(2)
+    am.mark_cells_in_annulus(0.8, 0.0, None); am.execute_coarsening_and_refinement()
+    am.mark_cells_in_annulus(0.45, 0.1, (-0.1, -0.2, -0.3)); am.execute_coarsening_and_refinement()
+    am.distribute_dofs()
+    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())
+    assert o.mask.max() > 0 and am.n_dofs == o.n_dofs
+    op = mf.LaplaceOperatorGpu(ctx, np.float64)
+    op.reinit(am)
+    u = sm64(11, o.n_dofs)
+    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs)
+    op.vmult(dst, src)
+    want = o.vmult(u)
+    assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * np.linalg.norm(want)
+    op.compute_diagonal()
+    assert rel_err(op.get_diagonal_inverse().toVector(), o.inverse_diagonal()) <= 1e-12
