@@ -1,5 +1,6 @@
 // bmop.cc -- the reference's benchmark driver (bmop.cu:66-230) on the C++ facade: host code is plain C++
 // (g++), all device work happens inside libmfgpu.so.   usage: bmop <max_refinement> [min_refinement]
+// -DADAPTIVE_GRID: the reference's pseudo-adaptive mesh with hanging nodes (BASELINE configs[3]); -DDEGREE_FE, -DDIMENSION, -DBMOP_USE_FLOATS as there
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +24,13 @@ typedef double number;
 
 template <int dim, int fe_degree> void run(int n_ref)
 {
+#ifdef ADAPTIVE_GRID
+  AdaptiveMesh<dim> mesh(fe_degree);           // bmop_setup_mesh(..., pseudo_adaptive_grid = true, n_ref) (bmop.cu:170-181)
+  mesh.pseudo_adaptive_refinement(n_ref);      // bmop_common.h:49-105
+  mesh.distribute_dofs();                      // + make_hanging_node_constraints (bmop.cu:116-126)
+#else
   HyperCubeMesh<dim> mesh(fe_degree, n_ref);  // bmop_setup_mesh + setup_system (bmop.cu:111-132)
+#endif
   LaplaceOperatorGpu<dim, fe_degree, number> system_matrix;
   system_matrix.reinit(mesh);
   GpuVector<number> src(system_matrix.n()), dst(system_matrix.n());

@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 #include "../mfgpu.h"
 
@@ -42,7 +43,11 @@ public:
   GpuVector(const GpuVector &o) : GpuVector() { check(mfg_vec_copy(v_, o.v_)); }
   template <typename Other> GpuVector(const GpuVector<Other> &o) : GpuVector() { check(mfg_vec_copy(v_, o.handle())); }
   explicit GpuVector(const std::vector<Number> &h) : GpuVector((unsigned int)h.size()) { fromHost(h.data(), (unsigned int)h.size()); }
-  ~GpuVector() { if (v_) mfg_vec_destroy(v_); }
+  // non-owning view of a vector that lives inside a library object (e.g. the operator's inverse diagonal): same interface,
+  // the handle is not destroyed with the view
+  static GpuVector borrowed(mfg_vec *v) { return GpuVector(v, false); }
+  GpuVector(GpuVector &&o) noexcept : v_(o.v_), owned_(o.owned_) { o.v_ = nullptr; }
+  ~GpuVector() { if (v_ && owned_) mfg_vec_destroy(v_); }
 
   GpuVector &operator=(const GpuVector &o) { check(mfg_vec_copy(v_, o.v_)); return *this; }
   template <typename Other> GpuVector &operator=(const GpuVector<Other> &o) { check(mfg_vec_copy(v_, o.handle())); return *this; }
@@ -84,7 +89,23 @@ public:
   void       compress() const {}  // gpu_vec.h:175
 
 private:
+  GpuVector(mfg_vec *v, bool owned) : v_(v), owned_(owned) {}
   mfg_vec *v_ = nullptr;
+  bool     owned_ = true;
+};
+
+// DiagonalMatrix<GpuVector<Number>> as the reference hands it to PreconditionChebyshev (laplace_operator_gpu.h:79, 423-429):
+// vmult = pointwise product with the stored vector
+template <typename Number> class DiagonalMatrix
+{
+public:
+  explicit DiagonalMatrix(GpuVector<Number> &&diag) : diag_(std::move(diag)) {}
+  const GpuVector<Number> &get_vector() const { return diag_; }
+  void vmult(GpuVector<Number> &dst, const GpuVector<Number> &src) const { dst = src; dst.scale(diag_); }
+  unsigned int m() const { return diag_.size(); }
+
+private:
+  GpuVector<Number> diag_;
 };
 
 // GpuList<T>: immutable device index array.  Only what the facade needs: the index lists live inside the

@@ -40,6 +40,33 @@ private:
   mfg_mesh *m_ = nullptr;
 };
 
+// Triangulation with local refinement + DoFHandler + HangingNodes (the reference's adaptive-grid runs: bmop_common.h:9-120,
+// matrix_free_gpu/hanging_nodes.cuh:209-454), host substrate of the library (mfg_amesh_*).  Usage mirrors deal.II:
+//   AdaptiveMesh<3> mesh(4); mesh.pseudo_adaptive_refinement(6); mesh.distribute_dofs(); op.reinit(mesh);
+template <int dim> class AdaptiveMesh
+{
+public:
+  explicit AdaptiveMesh(unsigned int fe_degree, double left = -1., double right = 1.) { check(mfg_amesh_create(dim, (int)fe_degree, left, right, &m_)); }
+  ~AdaptiveMesh() { if (m_) mfg_amesh_destroy(m_); }
+  AdaptiveMesh(const AdaptiveMesh &) = delete;
+  void refine_global(unsigned int times = 1) { check(mfg_amesh_refine_global(m_, (int)times)); }
+  void set_refine_flags(const std::vector<unsigned char> &flags) { check(mfg_amesh_set_refine_flags(m_, flags.data())); }
+  void mark_cells_in_annulus(double R, double r = 0.0, const double *center = nullptr) { check(mfg_amesh_mark_cells_in_annulus(m_, R, r, center)); }
+  void mark_cells_on_shell(double R, const double *center = nullptr) { check(mfg_amesh_mark_cells_on_shell(m_, R, center)); }
+  void mark_octant() { check(mfg_amesh_mark_octant(m_)); }
+  void execute_coarsening_and_refinement() { check(mfg_amesh_execute_refinement(m_)); }
+  void pseudo_adaptive_refinement(int n_ref) { check(mfg_amesh_pseudo_adaptive_refinement(m_, n_ref)); }
+  void distribute_dofs() { check(mfg_amesh_distribute_dofs(m_)); }
+  unsigned int n_active_cells() const { return mfg_amesh_n_active_cells(m_); }
+  unsigned int n_levels() const { return mfg_amesh_n_levels(m_); }
+  unsigned int n_dofs() const { return mfg_amesh_n_dofs(m_); }
+  unsigned int n_constraints() const { return mfg_amesh_n_constrained(m_); }
+  mfg_amesh *handle() const { return m_; }
+
+private:
+  mfg_amesh *m_ = nullptr;
+};
+
 template <typename Number> class ConstraintHandlerGpu
 {
 public:
@@ -132,15 +159,35 @@ public:
     clear();
     check(mfg_laplace_create_from_arrays(default_context(), data.handle(), ch.handle(), coefficient.data(), &op_));
   }
+  // adaptively refined mesh with hanging nodes (-DMATRIX_FREE_HANGING_NODES): masks, rewritten loc2glob, hanging + boundary
+  // constraints and the coefficient come from the mesh object
+  void reinit(const AdaptiveMesh<dim> &mesh)
+  {
+    clear();
+    check(mfg_laplace_create_from_amesh(default_context(), mesh.handle(), dtype_of<Number>(), &op_));
+  }
   unsigned int m() const { return mfg_laplace_m(op_); }
   unsigned int n() const { return mfg_laplace_m(op_); }
+  // "we cannot access matrix elements of a matrix free operator directly" (laplace_operator_gpu.h:69-74)
+  Number el(const unsigned int, const unsigned int) const { throw std::runtime_error("LaplaceOperatorGpu::el: not implemented (matrix-free operator)"); }
+  // edge matrices of the level operators (laplace_operator_gpu.h:306-352): they couple a level to the refinement edge of an
+  // adaptively refined hierarchy.  The level operators of this library live on globally refined meshes, which have no
+  // refinement edges: both products are zero.
+  void vmult_interface_down(VectorType &dst, const VectorType &) const { dst = Number(0); }
+  void vmult_interface_up(VectorType &dst, const VectorType &) const { dst = Number(0); }
   void vmult(VectorType &dst, const VectorType &src) const { check(mfg_laplace_vmult(op_, dst.handle(), src.handle())); }
   void Tvmult(VectorType &dst, const VectorType &src) const { vmult(dst, src); }
   void vmult_add(VectorType &dst, const VectorType &src) const { check(mfg_laplace_vmult_add(op_, dst.handle(), src.handle())); }
   void Tvmult_add(VectorType &dst, const VectorType &src) const { vmult_add(dst, src); }
   void compute_diagonal() { check(mfg_laplace_compute_diagonal(op_)); }
-  // borrowed handle to the inverse diagonal (DiagonalMatrix<VectorType>::get_vector in the reference)
-  mfg_vec *get_diagonal_inverse() const { mfg_vec *v = nullptr; check(mfg_laplace_get_diagonal_inverse(op_, &v)); return v; }
+  // get_diagonal_inverse (laplace_operator_gpu.h:423-429): DiagonalMatrix over a view of the operator's inverse diagonal
+  // (valid while the operator lives); Assert(diagonal_is_available) -> throws before compute_diagonal()
+  std::shared_ptr<DiagonalMatrix<VectorType>> get_diagonal_inverse() const
+  {
+    mfg_vec *v = nullptr;
+    check(mfg_laplace_get_diagonal_inverse(op_, &v));
+    return std::make_shared<DiagonalMatrix<VectorType>>(VectorType::borrowed(v));
+  }
   std::size_t  memory_consumption() const { return mfg_laplace_memory_consumption(op_); }
   mfg_laplace *handle() const { return op_; }
 

@@ -94,3 +94,17 @@ def test_operator_on_library_built_adaptive_mesh(ctx, dim, p):
     assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * np.linalg.norm(want)
     op.compute_diagonal()
     assert rel_err(op.get_diagonal_inverse().toVector(), o.inverse_diagonal()) <= 1e-12
+
+
+def test_bmop_driver_on_the_pseudo_adaptive_mesh():
+    """examples/bmop.cc built with -DADAPTIVE_GRID (bmop.cu:170-181): pseudo_adaptive_refinement + hanging-node operator through
+    the C++ facade; the DoF counts are those of the library's host substrate (checked on the CPU in tests/test_adaptive_mesh.py)"""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "_build", "bmop_adaptive")
+    assert os.path.exists(exe), "examples/_build/bmop_adaptive is missing: run __graft_entry__.build()"
+    out = subprocess.run([exe, "4", "3"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert [int(r[2]) for r in rows] == [729, 57142]
+    assert all(float(r[3]) > 0 for r in rows)
