@@ -114,6 +114,84 @@ def cpu_reference_run(args, steps, warmup):
             "sample": "%d applies of 3D Q%d FP64 r=%d (%d DoFs); sum-factorised, 8-cell SIMD batches, OpenMP over 8 colors (restatement of deal.II MatrixFree, not its binary)" % (steps, args.degree, r, m.n_dofs)}, dt / steps
 
 
+def adaptive_main(args, ctx, metric):
+    """BASELINE.json configs[3]: apply and CG solve on the reference's pseudo-adaptive mesh (bmop.cu -DADAPTIVE_GRID,
+    bmop_common.h:49-105).  The mesh, its DoFs, the hanging-node masks and the constraint list come from the library's host
+    substrate (mfg_amesh_*); cells without constraints run on the fast kernel, cells with a mask on the column kernel with the
+    interpolation fused into gather / scatter.  Same JSON layout as the headline line (no e2e / cpu_baseline legs)."""
+    import torch
+    import dealii_cuda_b200 as mf
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    s = 8 if args.dtype == "f64" else 4
+    t0 = time.perf_counter()
+    am = mf.AdaptiveMesh(args.dim, args.degree).pseudo_adaptive_refinement(args.refine).distribute_dofs()
+    setup_host_s = time.perf_counter() - t0
+    masks = am.arrays()["constraint_mask"]
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(am)
+    n = am.n_dofs
+    ta = torch.full((n,), 0.1, dtype=tdtype, device="cuda")
+    tb = torch.zeros((n,), dtype=tdtype, device="cuda")
+    pa, pb = ta.data_ptr(), tb.data_ptr()
+
+    def apply_steps(k):
+        nonlocal pa, pb
+        for _ in range(k):
+            pa, pb = pb, pa
+            op.vmult_ptr(pa, pb)
+
+    apply_steps(max(args.warmup, 3))
+    torch.cuda.synchronize()
+    ta.fill_(0.1); tb.fill_(0.1)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    t_lead = time.perf_counter()
+    while time.perf_counter() - t_lead < 0.3:
+        apply_steps(20)
+        torch.cuda.synchronize()
+    ta.fill_(0.1); tb.fill_(0.1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    apply_steps(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    cg = None
+    if not args.no_cg:
+        ue = mf.GpuVector.wrap(ctx, torch.rand((n,), dtype=tdtype, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
+        vb_, vx_ = mf.GpuVector(ctx, n, dtype), mf.GpuVector(ctx, n, dtype)
+        op.vmult(vb_, ue)
+        op.compute_diagonal()
+        mf.solver_cg(op, vx_, vb_, 0.0, 3)
+        vx_.fill(0.0)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        its, res = mf.solver_cg(op, vx_, vb_, (1e-12 if args.dtype == "f64" else 1e-5) * vb_.l2_norm(), 20000)
+        ctx.synchronize()
+        cg_s = time.perf_counter() - t0
+        cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "last_residual": res, "n_dofs": n,
+              "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|"}
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes: two vectors + per cell DoF the index (4 B) and the merged weight (s B); the mask is 4 B per cell
+    alg_bytes = 2.0 * s * n + float(am.n_cells) * (am.dofs_per_cell * (4 + s) + 4)
+    line = {"metric": metric, "value": n * args.steps / (ms * 1e-3), "unit": "DoFs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "bmop -DADAPTIVE_GRID: %dD hyper_cube(-1,1), pseudo_adaptive_refinement(%d) (bmop_common.h:49-105), FE_Q(%d): %d active cells on "
+                                   "%d levels, %d DoFs, %d cells with hanging-node constraints, atomic scatter"
+                                   % (args.dim, args.refine, args.degree, am.n_cells, am.n_levels, n, int((masks != 0).sum())),
+                       "l2": "inputs larger than L2" if alg_bytes > 126e6 else "L2-resident"},
+            "clocks": clocks, "e2e": None, "gpu_launches": args.steps * op.launches_per_vmult(),
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "whole vmult (fast kernel on plain cells + "
+                         "column kernel with fused hanging-node interpolation)", "peak_source": peak_src},
+            "cpu_baseline": None, "cg_solve": cg, "mesh_setup_host_seconds": setup_host_s}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -134,6 +212,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="N > 1 only: skip the host-buffer end-to-end leg (extra lines at sizes whose pinned buffers would not fit)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one refine_global(R) cube per GPU (default), strong = the refine_global(R) cube split over the GPUs")
+    ap.add_argument("--adaptive", action="store_true",
+                    help="BASELINE configs[3] instead of the headline: the reference's pseudo_adaptive_refinement(R) mesh with hanging nodes "
+                         "(bmop_common.h:49-105), apply + CG solve, N = 1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -168,6 +249,8 @@ def main():
     ctx = mf.Context(local_rank, stream)
     dtype = np.float64 if args.dtype == "f64" else np.float32
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    if args.adaptive:
+        return adaptive_main(args, ctx, metric)
     mesh = mf.HyperCubeMesh(ctx, args.dim, args.degree, args.refine)
     op = mf.LaplaceOperatorGpu(ctx, dtype, use_coloring=args.coloring)
     op.reinit(mesh)
