@@ -176,6 +176,16 @@ def _load():
         "mfg_exchange_push_stream": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_int, vp]),
         "mfg_vec_dot_masked": (C.c_int, [vp, vp, vp, dp]),
         "mfg_laplace_bmop": (C.c_int, [vp, vp, vp, C.c_int, C.c_double, C.POINTER(C.c_float)]),
+        "mfg_partition_rank_coords": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "mfg_partition_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(BoxDesc)]),
+        "mfg_partition_global_n_dofs": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+        "mfg_partition_interface_points": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                                     C.POINTER(C.c_int), C.POINTER(sz), u32p]),
+        "mfg_partition_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(sz), u32p,
+                                                C.c_int, C.POINTER(C.c_int), C.POINTER(sz), u32p, pp]),
+        "mfg_partition_plan_destroy": (C.c_int, [vp]),
+        "mfg_partition_plan_sizes": (C.c_int, [vp, C.POINTER(sz)]),
+        "mfg_partition_plan_get": (C.c_int, [vp, C.POINTER(C.c_int), u32p, u32p, u32p, u32p, u32p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]),
         "mfg_amesh_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, pp]),
         "mfg_amesh_destroy": (C.c_int, [vp]),
         "mfg_amesh_refine_global": (C.c_int, [vp, C.c_int]),

@@ -364,6 +364,27 @@ int mfg_mg_solve_cg(mfg_mg *mg, mfg_vec *x, const mfg_vec *b, double abs_tol, in
  *   shared_dofs[n_shared]       local DoFs that receive contributions
  *   offsets[n_shared+1], slots  CSR: contributions of shared DoF u in ascending rank order; slot >= 0 is an
  *                               index into the receive buffer, slot == -1 is this rank's own partial sum */
+/* Box partition and exchange plan on the host (csrc/partition.cu; pure host code, no device needed).  Ranks sit on the grid
+ * 1 -> 1x1x1, 2 -> 1x1x2, 4 -> 1x2x2, 8 -> 2x2x2 (2D: 2 -> 1x2, 4 -> 2x2), x fastest.  weak scaling (strong = 0): a 2^r cube of
+ * cells per rank; strong = 1: the refine_global(r) cube [left,right]^dim cut into the rank grid. */
+typedef struct mfg_partition_plan mfg_partition_plan;
+int mfg_partition_rank_coords(int rank, int world, int dim, int coords[3], int grid[3]);
+int mfg_partition_box(int rank, int world, int dim, int degree, int r, double left, double right, int strong, mfg_box_desc *out);
+int mfg_partition_global_n_dofs(int world, int dim, int degree, int r, int strong, uint64_t *out);
+/* lattice points (local coordinates 0 .. degree*2^lg_d, lexicographic, x fastest: the same order on both sides) this rank shares
+ * with the neighbour at grid offset delta[d] in {-1,0,1}; drop_dirichlet leaves out points on the global boundary (constrained on
+ * every replica, not exchanged).  xyz NULL: count only.  *neighbor_rank = -1 when there is no rank at that offset. */
+int mfg_partition_interface_points(int rank, int world, int dim, int degree, int r, int strong, const int delta[3], int drop_dirichlet,
+                                   int *neighbor_rank, size_t *n_points, uint32_t *xyz);
+/* the plan of mfg_exchange_create from the DoF lists (mfg_mesh_lattice_to_dof of the points above): list i holds
+ * dofs[list_start[i] .. list_start[i+1]) shared with rank list_rank[i]; the `repl` lists (all shared points incl. Dirichlet
+ * ones) only decide ownership: owner = lowest rank that touches a DoF */
+int mfg_partition_plan_create(int rank, int world, uint32_t n_local, int n_lists, const int *list_rank, const size_t *list_start, const uint32_t *dofs,
+                              int n_repl, const int *repl_rank, const size_t *repl_start, const uint32_t *repl_dofs, mfg_partition_plan **out);
+int mfg_partition_plan_destroy(mfg_partition_plan *p);
+int mfg_partition_plan_sizes(const mfg_partition_plan *p, size_t out[5]); /* n_send, n_shared, n_slots, n_neighbors, n_local */
+int mfg_partition_plan_get(const mfg_partition_plan *p, int *neighbors, uint32_t *splits /* [world] */, uint32_t *recv_off /* [world] */,
+                           uint32_t *pack_idx, uint32_t *shared_dofs, uint32_t *offsets, int32_t *slots, uint8_t *owned_mask);
 typedef struct mfg_exchange mfg_exchange;
 int mfg_exchange_create(mfg_ctx *ctx, mfg_dtype dt, const uint32_t *pack_idx_host, size_t n_send, const uint32_t *shared_dofs_host,
                         size_t n_shared, const uint32_t *offsets_host, const int32_t *slots_host, size_t n_slots, mfg_exchange **out);

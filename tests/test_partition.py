@@ -235,3 +235,29 @@ def test_partitions_emulated_on_one_gpu(ctx, world, p, r, dtype, split):
         seen = ~np.isnan(ref[pa["map"]])
         assert np.array_equal(ref[pa["map"]][seen], full[a].astype(np.float64)[seen])
         ref[pa["map"]] = full[a]
+
+
+@pytest.mark.parametrize("strong", [False, True])
+@pytest.mark.parametrize("dim,world", [(3, 1), (3, 2), (3, 4), (3, 8), (2, 2), (2, 4)])
+def test_library_partition_equals_numpy_statement(dim, world, strong):
+    """the library's C++ host code (csrc/partition.cu, mfg_partition_*) against the numpy statement of the same partition
+    (tests/partition_numpy_reference.py), array by array, for every rank of every grid"""
+    import partition_numpy_reference as ref
+    from dealii_cuda_b200 import partition as lib
+    p, r = 2, 2
+    assert lib.global_n_dofs(world, dim, p, r, strong) == ref.global_n_dofs(world, dim, p, r, strong)
+    assert lib.local_log2(world, dim, r, strong) == ref.local_log2(world, dim, r, strong)
+    for rank in range(world):
+        assert lib.rank_coords(rank, world, dim) == ref.rank_coords(rank, world, dim)
+        bl, mel, gl = lib.box_for_rank(rank, world, dim, r, -1.0, 1.0, strong)
+        br, mer, gr = ref.box_for_rank(rank, world, dim, r, -1.0, 1.0, strong)
+        assert bl == br and tuple(mel) == tuple(mer) and tuple(gl) == tuple(gr)
+        o = OracleMesh(dim, p, box=bl)
+        l2d = oracle_lattice_to_dof(o)
+        a = lib.build_exchange_plan(rank, world, dim, p, r, l2d, o.n_dofs, strong)
+        b = ref.build_exchange_plan(rank, world, dim, p, r, l2d, o.n_dofs, strong)
+        assert a.neighbors == b.neighbors and a.splits == b.splits and a.n_send == b.n_send and a.recv_off == b.recv_off
+        for name in ("pack_idx", "shared_dofs", "offsets", "slots", "owned_mask"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+            assert getattr(a, name).dtype == getattr(b, name).dtype, name
+        assert all(np.array_equal(a.lists[q], b.lists[q]) for q in a.neighbors)
