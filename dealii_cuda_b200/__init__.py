@@ -386,10 +386,12 @@ class AdaptiveMesh:
     matrix_free_gpu/hanging_nodes.cuh:209-454).  Needs no device; LaplaceOperatorGpu.reinit(adaptive_mesh) builds the
     device objects."""
 
-    def __init__(self, dim, degree, left=-1.0, right=1.0):
+    def __init__(self, dim, degree, left=-1.0, right=1.0, limit_level_difference_at_vertices=False):
         h = C.c_void_p()
         check(lib.mfg_amesh_create(int(dim), int(degree), float(left), float(right), C.byref(h)))
         self.h, self.dim, self.degree, self.left, self.right = h, dim, degree, left, right
+        if limit_level_difference_at_vertices:   # Triangulation::MeshSmoothing of the reference's MG drivers (poisson_mg.cu:132)
+            check(lib.mfg_amesh_set_limit_level_difference_at_vertices(h, 1))
         self.dofs_per_cell = (degree + 1) ** dim
 
     def __del__(self):
@@ -449,6 +451,13 @@ class AdaptiveMesh:
         out = np.zeros((self.n_cells, 4), dtype=np.uint32)
         check(lib.mfg_amesh_get_active_cells(self.h, _u32p(out)))
         return out[:, :1 + self.dim]
+
+    def level_cells(self, level):
+        """[n][dim + 1]: integer coordinates of ALL cells of a level in storage order and 1 where the cell has children"""
+        out = np.zeros((lib.mfg_amesh_n_level_cells(self.h, int(level)), 4), dtype=np.uint32)
+        if out.shape[0]:
+            check(lib.mfg_amesh_get_level_cells(self.h, int(level), _u32p(out)))
+        return np.concatenate([out[:, :self.dim], out[:, 3:]], axis=1)
 
     def distribute_dofs(self):
         check(lib.mfg_amesh_distribute_dofs(self.h))

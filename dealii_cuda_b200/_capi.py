@@ -188,6 +188,7 @@ def _load():
         "mfg_partition_plan_get": (C.c_int, [vp, C.POINTER(C.c_int), u32p, u32p, u32p, u32p, u32p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]),
         "mfg_amesh_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, pp]),
         "mfg_amesh_destroy": (C.c_int, [vp]),
+        "mfg_amesh_set_limit_level_difference_at_vertices": (C.c_int, [vp, C.c_int]),
         "mfg_amesh_refine_global": (C.c_int, [vp, C.c_int]),
         "mfg_amesh_set_refine_flags": (C.c_int, [vp, C.POINTER(C.c_uint8)]),
         "mfg_amesh_mark_cells_in_annulus": (C.c_int, [vp, C.c_double, C.c_double, dp]),
@@ -198,6 +199,8 @@ def _load():
         "mfg_amesh_n_active_cells": (C.c_uint32, [vp]),
         "mfg_amesh_n_levels": (C.c_uint32, [vp]),
         "mfg_amesh_get_active_cells": (C.c_int, [vp, u32p]),
+        "mfg_amesh_n_level_cells": (C.c_uint32, [vp, C.c_int]),
+        "mfg_amesh_get_level_cells": (C.c_int, [vp, C.c_int, u32p]),
         "mfg_amesh_distribute_dofs": (C.c_int, [vp]),
         "mfg_amesh_n_dofs": (C.c_uint32, [vp]),
         "mfg_amesh_n_constrained": (C.c_uint32, [vp]),

@@ -67,6 +67,7 @@ struct mfg_amesh
 {
   int    dim = 0, p = 0, n = 0;
   double left = 0, right = 0;
+  bool   limit_level_difference_at_vertices = false;  // Triangulation::MeshSmoothing flag of the MG drivers (poisson_mg.cu:132)
   std::vector<std::vector<ACell>>                        levels;
   std::vector<std::unordered_map<uint64_t, uint32_t>>    index;  // per level: packed coordinates -> position in the level
   // active cells in deal.II's iteration order (rebuilt after every refinement)
@@ -136,7 +137,7 @@ struct mfg_amesh
     for (uint32_t l = 0; l < levels.size(); ++l)
       for (uint32_t i = 0; i < levels[l].size(); ++i)
         if (levels[l][i].child0 < 0 && levels[l][i].flag) stack.emplace_back(l, i);
-    const int max_nonzero = dim == 3 ? 2 : 1;  // faces; in 3D also edges
+    const int max_nonzero = limit_level_difference_at_vertices ? dim : (dim == 3 ? 2 : 1);  // faces; in 3D also edges; with the flag also vertices
     while (!stack.empty())
       {
         const auto [l, i] = stack.back();
@@ -464,6 +465,10 @@ int mfg_amesh_create(int dim, int degree, double left, double right, mfg_amesh *
     *out = am.release();
   });
 }
+int mfg_amesh_set_limit_level_difference_at_vertices(mfg_amesh *am, int on)
+{
+  return guarded([&] { MFG_REQUIRE(am, "null argument"); am->limit_level_difference_at_vertices = on != 0; });
+}
 int mfg_amesh_destroy(mfg_amesh *am) { return guarded([&] { delete am; }); }
 int mfg_amesh_refine_global(mfg_amesh *am, int times)
 {
@@ -527,6 +532,19 @@ int mfg_amesh_get_active_cells(const mfg_amesh *am, uint32_t *level_xyz)
         const ACell &c = am->cell(a);
         level_xyz[4 * a] = am->act_level[a];
         for (int d = 0; d < 3; ++d) level_xyz[4 * a + 1 + d] = c.x[d];
+      }
+  });
+}
+uint32_t mfg_amesh_n_level_cells(const mfg_amesh *am, int level) { return am && level >= 0 && level < (int)am->levels.size() ? (uint32_t)am->levels[level].size() : 0; }
+int mfg_amesh_get_level_cells(const mfg_amesh *am, int level, uint32_t *xyz_children)
+{
+  return guarded([&] {
+    MFG_REQUIRE(am && xyz_children && level >= 0 && level < (int)am->levels.size(), "bad argument");
+    const auto &L = am->levels[level];
+    for (size_t i = 0; i < L.size(); ++i)
+      {
+        for (int d = 0; d < 3; ++d) xyz_children[4 * i + d] = L[i].x[d];
+        xyz_children[4 * i + 3] = L[i].child0 >= 0 ? 1u : 0u;
       }
   });
 }

@@ -46,7 +46,12 @@ private:
 template <int dim> class AdaptiveMesh
 {
 public:
-  explicit AdaptiveMesh(unsigned int fe_degree, double left = -1., double right = 1.) { check(mfg_amesh_create(dim, (int)fe_degree, left, right, &m_)); }
+  enum MeshSmoothing { none = 0, limit_level_difference_at_vertices = 1 };  // Triangulation::MeshSmoothing (poisson_mg.cu:132)
+  explicit AdaptiveMesh(unsigned int fe_degree, MeshSmoothing smoothing = none, double left = -1., double right = 1.)
+  {
+    check(mfg_amesh_create(dim, (int)fe_degree, left, right, &m_));
+    if (smoothing == limit_level_difference_at_vertices) check(mfg_amesh_set_limit_level_difference_at_vertices(m_, 1));
+  }
   ~AdaptiveMesh() { if (m_) mfg_amesh_destroy(m_); }
   AdaptiveMesh(const AdaptiveMesh &) = delete;
   void refine_global(unsigned int times = 1) { check(mfg_amesh_refine_global(m_, (int)times)); }

@@ -146,6 +146,9 @@ int mfg_graph_coloring(uint32_t n_cells, uint32_t dofs_per_cell, const uint32_t 
 typedef struct mfg_amesh mfg_amesh;
 int mfg_amesh_create(int dim, int degree, double left, double right, mfg_amesh **out);     /* GridGenerator::hyper_cube, one cell */
 int mfg_amesh_destroy(mfg_amesh *am);
+/* Triangulation::limit_level_difference_at_vertices (the MeshSmoothing flag of the reference's multigrid drivers, poisson_mg.cu:132,
+ * bmop_mg.cu:130): cells that share only a vertex also differ by at most one level; required by the multigrid hierarchy */
+int mfg_amesh_set_limit_level_difference_at_vertices(mfg_amesh *am, int on);
 int mfg_amesh_refine_global(mfg_amesh *am, int times);                                     /* Triangulation::refine_global */
 int mfg_amesh_set_refine_flags(mfg_amesh *am, const uint8_t *flags /* [n_active_cells] */); /* cell->set_refine_flag() */
 int mfg_amesh_mark_cells_in_annulus(mfg_amesh *am, double R, double r, const double *center /* [dim] or NULL = origin */); /* bmop_common.h:9-24 */
@@ -156,6 +159,9 @@ int mfg_amesh_pseudo_adaptive_refinement(mfg_amesh *am, int n_ref);             
 uint32_t mfg_amesh_n_active_cells(const mfg_amesh *am);
 uint32_t mfg_amesh_n_levels(const mfg_amesh *am);
 int mfg_amesh_get_active_cells(const mfg_amesh *am, uint32_t *level_xyz /* [n_active_cells][4]: level, x, y, z */);
+/* all cells of a level (active or refined) in storage order = the level mesh of the multigrid hierarchy */
+uint32_t mfg_amesh_n_level_cells(const mfg_amesh *am, int level);
+int mfg_amesh_get_level_cells(const mfg_amesh *am, int level, uint32_t *xyz_children /* [n][4]: x, y, z, 1 if the cell has children */);
 /* DoFHandler::distribute_dofs + HangingNodes::setup_constraints + the ConstraintHandlerGpu list (hanging and boundary DoFs) */
 int mfg_amesh_distribute_dofs(mfg_amesh *am);
 uint32_t mfg_amesh_n_dofs(const mfg_amesh *am);
