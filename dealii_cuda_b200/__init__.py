@@ -464,6 +464,25 @@ class AdaptiveMesh:
         self.n_dofs = lib.mfg_amesh_n_dofs(self.h)
         return self
 
+    def build_mg(self, min_level=0):
+        """level meshes, level DoFs, MGConstrainedDoFs sets, transfer blocks and copy indices of the multigrid hierarchy"""
+        check(lib.mfg_amesh_build_mg(self.h, int(min_level)))
+        self.mg_min_level = int(min_level)
+        return self
+
+    def mg_level(self, level):
+        """dict of the host arrays of one level of the hierarchy (mfg_amesh_mg_level_get)"""
+        sz = np.zeros(6, np.uint32)
+        check(lib.mfg_amesh_mg_level_sizes(self.h, int(level), _u32p(sz)))
+        nc, nd, nb, ne, npar, ncp = (int(v) for v in sz)
+        npc, nF, n3 = self.dofs_per_cell, (2 * self.degree + 1) ** self.dim, 3 ** self.dim
+        a = dict(n_dofs=nd, loc2glob=np.zeros((nc, npc), np.uint32), boundary=np.zeros(nb, np.uint32), edge=np.zeros(ne, np.uint32),
+                 coefficient=np.zeros((nc, npc)), copy_global=np.zeros(ncp, np.uint32), copy_level=np.zeros(ncp, np.uint32),
+                 coarse_idx=np.zeros((npar, npc), np.uint32), fine_idx=np.zeros((npar, nF), np.uint32), weights=np.zeros((npar, n3)))
+        check(lib.mfg_amesh_mg_level_get(self.h, int(level), _u32p(a["loc2glob"]), _u32p(a["boundary"]), _u32p(a["edge"]), _dp(a["coefficient"]),
+                                         _u32p(a["copy_global"]), _u32p(a["copy_level"]), _u32p(a["coarse_idx"]), _u32p(a["fine_idx"]), _dp(a["weights"])))
+        return a
+
     def arrays(self, quadrature_points=False):
         """dict: loc2glob (rewritten), loc2glob_unconstrained, constraint_mask, constrained, hanging, inv_jac, coefficient"""
         nc, npc = self.n_cells, self.dofs_per_cell

@@ -78,6 +78,19 @@ struct mfg_amesh
   std::vector<uint32_t> l2g_own, l2g, mask, hanging, boundary, constrained;
   std::vector<double>   inv_jac;
   FEData1D              fe;
+  // multigrid hierarchy (build_mg): level meshes = ALL cells of a level, level DoFs, MGConstrainedDoFs sets, transfer blocks
+  struct MgLevel
+  {
+    uint32_t              n_cells = 0, n_dofs = 0, n_parents = 0;
+    std::vector<uint32_t> l2g;                     // [n_cells][npc] lexicographic, level numbering
+    std::vector<uint32_t> boundary, edge;          // ascending: boundary_indices / refinement_edge_indices of the level
+    std::vector<uint32_t> coarse_idx, fine_idx;    // transfer INTO this level: [n_parents][npc] (bit 31: boundary DoF of level-1), [n_parents][(2p+1)^dim]
+    std::vector<double>   weights;                 // [n_parents][3^dim]: 1 / number of refined parents that hold the fine DoF
+    std::vector<uint32_t> copy_global, copy_level; // copy_to_mg / copy_from_mg pairs (active DoF, level DoF)
+  };
+  bool                 mg_ready = false;
+  int                  mg_min_level = 0;
+  std::vector<MgLevel> mg;                         // [level - mg_min_level]
 
   uint32_t n_active() const { return (uint32_t)act_level.size(); }
   ACell       &cell(uint32_t a) { return levels[act_level[a]][act_pos[a]]; }
@@ -89,7 +102,7 @@ struct mfg_amesh
     for (uint32_t l = 0; l < levels.size(); ++l)
       for (uint32_t i = 0; i < levels[l].size(); ++i)
         if (levels[l][i].child0 < 0) { act_level.push_back(l); act_pos.push_back(i); }
-    dofs_ready = false;
+    dofs_ready = false; mg_ready = false;
   }
 
   // the active cell covering position xs of level `level`: 1 = found (level / position returned), 0 = outside the domain,
@@ -250,30 +263,25 @@ void pseudo_adaptive_refinement(mfg_amesh *am, int n_ref)
       }
 }
 
-void distribute_dofs(mfg_amesh *am)
+// DoFHandler::distribute_dofs / distribute_mg_dofs for FE_Q(p): first touch over the given cells in order, hierarchic order
+// inside a cell.  The DoFs of one mesh entity (vertex, line, quad, hex) are consecutive in the hierarchic order and every
+// cell meets them in the same order, so an entity gets a block of numbers when its first cell arrives.  sizes[c] = edge length
+// of cell c in the units of the entity keys, S = edge length of the domain in those units.  Returns the number of DoFs.
+uint32_t number_cells(int dim, int p, const std::vector<const ACell *> &cells, const std::vector<uint32_t> &sizes, uint32_t S,
+                      std::vector<uint32_t> &l2g, std::vector<uint8_t> &on_boundary)
 {
-  const int      dim = am->dim, p = am->p, n = am->n;
-  const uint32_t npc = ipow(n, dim), nact = am->n_active();
-  MFG_REQUIRE((uint64_t)nact * npc < (1ull << 32), "too many cells for 32-bit local-to-global offsets");
-  am->npc = npc;
-  am->lmax = 0;
-  for (uint32_t a = 0; a < nact; ++a) am->lmax = std::max(am->lmax, am->act_level[a]);
+  const int      n = p + 1;
+  const uint32_t npc = ipow(n, dim), nc = (uint32_t)cells.size();
   const std::vector<uint32_t> h2l = hierarchic_to_lexicographic(dim, p);
-  auto size_of = [&](uint32_t a) { return 1u << (am->lmax - am->act_level[a]); };
-
-  // ---- DoFHandler::distribute_dofs: first touch over the active cells, hierarchic order inside a cell.  The DoFs of one
-  // mesh entity (vertex, line, quad, hex) are consecutive in the hierarchic order and every cell meets them in the same
-  // order, so an entity gets a block of numbers when its first cell arrives.
   std::unordered_map<EntityKey, uint32_t, EntityHash> first_dof;
-  first_dof.reserve((size_t)nact * (dim == 3 ? 8 : 4));
-  am->l2g_own.assign((size_t)nact * npc, 0);
-  std::vector<uint8_t> on_boundary;
-  uint32_t             nxt = 0;
-  const uint32_t       S = 1u << am->lmax;
-  for (uint32_t a = 0; a < nact; ++a)
+  first_dof.reserve((size_t)nc * (dim == 3 ? 8 : 4));
+  l2g.assign((size_t)nc * npc, 0);
+  on_boundary.clear();
+  uint32_t nxt = 0;
+  for (uint32_t a = 0; a < nc; ++a)
     {
-      const ACell   &c = am->cell(a);
-      const uint32_t s = size_of(a);
+      const ACell   &c = *cells[a];
+      const uint32_t s = sizes[a];
       EntityKey      prev{{0, 0, 0}, 0xffffffffu};
       uint32_t       base_no = 0, rank = 0;
       for (uint32_t hI = 0; hI < npc; ++hI)
@@ -314,11 +322,29 @@ void distribute_dofs(mfg_amesh *am)
               else base_no = it->second;
             }
           const uint32_t g = base_no + rank;
-          am->l2g_own[(size_t)a * npc + li] = g;
+          l2g[(size_t)a * npc + li] = g;
           if (bnd) on_boundary[g] = 1;
         }
     }
-  am->n_dofs = nxt;
+  return nxt;
+}
+
+void distribute_dofs(mfg_amesh *am)
+{
+  const int      dim = am->dim, p = am->p, n = am->n;
+  const uint32_t npc = ipow(n, dim), nact = am->n_active();
+  MFG_REQUIRE((uint64_t)nact * npc < (1ull << 32), "too many cells for 32-bit local-to-global offsets");
+  am->npc = npc;
+  am->lmax = 0;
+  for (uint32_t a = 0; a < nact; ++a) am->lmax = std::max(am->lmax, am->act_level[a]);
+  const std::vector<uint32_t> h2l = hierarchic_to_lexicographic(dim, p);
+  auto size_of = [&](uint32_t a) { return 1u << (am->lmax - am->act_level[a]); };
+
+  std::vector<const ACell *> cells(nact);
+  std::vector<uint32_t>      sizes(nact);
+  for (uint32_t a = 0; a < nact; ++a) { cells[a] = &am->cell(a); sizes[a] = size_of(a); }
+  std::vector<uint8_t> on_boundary;
+  am->n_dofs = number_cells(dim, p, cells, sizes, 1u << am->lmax, am->l2g_own, on_boundary);
 
   // ---- HangingNodes::setup_constraints (hanging_nodes.cuh:209-454): masks and the loc2glob rewrite
   am->l2g = am->l2g_own;
@@ -417,6 +443,160 @@ void distribute_dofs(mfg_amesh *am)
   am->inv_jac.resize(nact);
   for (uint32_t a = 0; a < nact; ++a) am->inv_jac[a] = 1.0 / am->cell_h(am->act_level[a]);
   am->dofs_ready = true;
+}
+
+// The multigrid hierarchy of the reference's poisson_mg.cu / bmop_mg.cu on an adaptively refined mesh, as deal.II hands it to
+// MGTransferMatrixFreeGpu, LaplaceOperatorGpu::reinit(dof_handler, mg_constrained_dofs, level) and ConstraintHandlerGpu::reinit
+// (mg_constrained_dofs, level):
+//   * DoFHandler::distribute_mg_dofs: first touch over ALL cells of a level in storage order;
+//   * MGConstrainedDoFs: boundary_indices(level) and refinement_edge_indices(level) = the DoFs on faces of level cells whose
+//     neighbour inside the domain is not refined to that level (MGTools::extract_inner_interface_dofs);
+//   * the transfer blocks of internal::MGTransfer::setup_transfer (mg_transfer_matrix_free_gpu.cu:173-257): per refined
+//     cell of level l-1 its level DoFs and the (2p+1)^dim level-l DoFs of its children, weights = 1 / multiplicity;
+//   * the copy indices of MGTransfer::fill_copy_indices (.cu:109-146): (active DoF, level DoF) on the active cells of a level,
+//     without the level's refinement-edge DoFs.
+void build_mg(mfg_amesh *am, int min_level)
+{
+  MFG_REQUIRE(am->dofs_ready, "call mfg_amesh_distribute_dofs first");
+  const int      dim = am->dim, p = am->p, n = am->n;
+  const uint32_t npc = am->npc, nact = am->n_active();
+  uint32_t       min_active = 0xffffffffu;
+  for (uint32_t a = 0; a < nact; ++a) min_active = std::min(min_active, am->act_level[a]);
+  MFG_REQUIRE(min_level >= 0 && (uint32_t)min_level <= min_active, "min_level must not exceed the coarsest active level");
+  const int n_levels = (int)am->levels.size();
+  am->mg.clear();
+  am->mg.resize(n_levels - min_level);
+  am->mg_min_level = min_level;
+  auto lat = [&](const uint32_t i[3]) { return i[0] + n * (i[1] + n * i[2]); };
+  std::vector<std::vector<uint8_t>> is_edge(n_levels - min_level);
+  for (int l = min_level; l < n_levels; ++l)
+    {
+      mfg_amesh::MgLevel &L = am->mg[l - min_level];
+      const auto         &C = am->levels[l];
+      L.n_cells = (uint32_t)C.size();
+      MFG_REQUIRE((uint64_t)L.n_cells * npc < (1ull << 32), "too many cells on a level");
+      std::vector<const ACell *> cells(C.size());
+      std::vector<uint32_t>      sizes(C.size(), 1u);
+      for (size_t i = 0; i < C.size(); ++i) cells[i] = &C[i];
+      std::vector<uint8_t> on_boundary;
+      L.n_dofs = number_cells(dim, p, cells, sizes, 1u << l, L.l2g, on_boundary);
+      for (uint32_t g = 0; g < L.n_dofs; ++g)
+        if (on_boundary[g]) L.boundary.push_back(g);
+      std::vector<uint8_t> &E = is_edge[l - min_level];
+      E.assign(L.n_dofs, 0);
+      for (size_t ci = 0; ci < C.size(); ++ci)
+        for (int d = 0; d < dim; ++d)
+          for (int side = 0; side < 2; ++side)
+            {
+              int64_t nb = (int64_t)C[ci].x[d] + (side == 0 ? -1 : 1);
+              if (nb < 0 || nb >= ((int64_t)1 << l)) continue;  // domain boundary
+              uint32_t x[3] = {C[ci].x[0], C[ci].x[1], C[ci].x[2]};
+              x[d] = (uint32_t)nb;
+              if (am->index[l].count(pack(x))) continue;       // the neighbour is refined to this level as well
+              const uint32_t nt = ipow(n, dim - 1);
+              for (uint32_t t = 0; t < nt; ++t)
+                {
+                  uint32_t idx[3] = {0, 0, 0}, tt = t;
+                  idx[d] = side == 0 ? 0 : p;
+                  for (int e = 0; e < dim; ++e)
+                    if (e != d) { idx[e] = tt % n; tt /= n; }
+                  E[L.l2g[ci * npc + lat(idx)]] = 1;
+                }
+            }
+      for (uint32_t g = 0; g < L.n_dofs; ++g)
+        if (E[g]) L.edge.push_back(g);
+    }
+  // transfer blocks into level l from level l-1
+  const int      nf = 2 * p + 1;
+  const uint32_t nF = ipow(nf, dim), n3 = ipow(3, dim);
+  for (int l = min_level + 1; l < n_levels; ++l)
+    {
+      mfg_amesh::MgLevel       &L = am->mg[l - min_level];
+      const mfg_amesh::MgLevel &Lc = am->mg[l - 1 - min_level];
+      const auto               &P = am->levels[l - 1];
+      std::vector<uint8_t>      cb(Lc.n_dofs, 0);
+      for (uint32_t g : Lc.boundary) cb[g] = 1;
+      std::vector<uint32_t> count(L.n_dofs, 0);
+      for (size_t pi = 0; pi < P.size(); ++pi)
+        {
+          if (P[pi].child0 < 0) continue;
+          ++L.n_parents;
+          for (uint32_t i = 0; i < npc; ++i)
+            {
+              const uint32_t g = Lc.l2g[pi * npc + i];
+              L.coarse_idx.push_back(g | (cb[g] ? 0x80000000u : 0u));
+            }
+          for (uint32_t f = 0; f < nF; ++f)
+            {
+              uint32_t a[3] = {0, 0, 0}, t = f, k = 0, li[3] = {0, 0, 0};
+              for (int d = 0; d < dim; ++d)
+                {
+                  a[d] = t % nf; t /= nf;
+                  const uint32_t kd = a[d] > (uint32_t)p ? 1u : 0u;   // the children share the points a_d == p: take the lower one
+                  k |= kd << d;
+                  li[d] = a[d] - kd * p;
+                }
+              const uint32_t g = L.l2g[((size_t)P[pi].child0 + k) * npc + lat(li)];
+              L.fine_idx.push_back(g);
+              ++count[g];
+            }
+        }
+      L.weights.resize((size_t)L.n_parents * n3);
+      for (uint32_t q = 0; q < L.n_parents; ++q)
+        for (uint32_t r = 0; r < n3; ++r)
+          {
+            uint32_t t = r, f = 0, stride = 1;
+            for (int d = 0; d < dim; ++d)
+              {
+                const uint32_t rd = t % 3; t /= 3;
+                f += (rd == 0 ? 0u : rd == 1 ? 1u : (uint32_t)(2 * p)) * stride;   // a representative point of the region
+                stride *= nf;
+              }
+            L.weights[(size_t)q * n3 + r] = 1.0 / (double)count[L.fine_idx[(size_t)q * nF + f]];
+          }
+    }
+  // copy indices
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> pairs(n_levels - min_level);
+  for (uint32_t a = 0; a < nact; ++a)
+    {
+      const uint32_t            l = am->act_level[a], pos = am->act_pos[a];
+      const mfg_amesh::MgLevel &L = am->mg[l - min_level];
+      for (uint32_t i = 0; i < npc; ++i)
+        {
+          const uint32_t lv = L.l2g[(size_t)pos * npc + i];
+          if (!is_edge[l - min_level][lv]) pairs[l - min_level].push_back({am->l2g_own[(size_t)a * npc + i], lv});
+        }
+    }
+  for (int l = min_level; l < n_levels; ++l)
+    {
+      auto &pr = pairs[l - min_level];
+      std::sort(pr.begin(), pr.end());
+      pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+      mfg_amesh::MgLevel &L = am->mg[l - min_level];
+      for (auto &q : pr) { L.copy_global.push_back(q.first); L.copy_level.push_back(q.second); }
+    }
+  am->mg_ready = true;
+}
+
+// inverse Jacobian and Coefficient::value at the Gauss points of ALL cells of a level (the level operator's data)
+void level_coefficient(const mfg_amesh *am, int level, double *coef)
+{
+  const int    dim = am->dim, n = am->n;
+  const auto  &C = am->levels[level];
+  const double h = am->cell_h(level);
+  for (size_t ci = 0; ci < C.size(); ++ci)
+    for (uint32_t q = 0; q < am->npc; ++q)
+      {
+        uint32_t t = q;
+        double   r2 = 0;
+        for (int d = 0; d < dim; ++d)
+          {
+            const double x = am->left + h * ((double)C[ci].x[d] + am->fe.qpts[t % n]);
+            t /= n;
+            r2 += x * x;
+          }
+        coef[ci * am->npc + q] = 1.0 / (0.05 + 2.0 * r2);
+      }
 }
 
 // Coefficient::value = 1 / (0.05 + 2 |x|^2) (poisson_common.h:146-158) at the Gauss points of every active cell
@@ -564,6 +744,38 @@ int mfg_amesh_get_arrays(const mfg_amesh *am, uint32_t *loc2glob, uint32_t *loc2
     if (hanging) std::copy(am->hanging.begin(), am->hanging.end(), hanging);
     if (inv_jac) std::copy(am->inv_jac.begin(), am->inv_jac.end(), inv_jac);
     if (coefficient || quadrature_points) coefficient_at_qpoints(am, coefficient, quadrature_points);
+  });
+}
+
+int mfg_amesh_build_mg(mfg_amesh *am, int min_level) { return guarded([&] { MFG_REQUIRE(am, "null argument"); build_mg(am, min_level); }); }
+// sizes of a level of the hierarchy: out[0..5] = cells, DoFs, boundary indices, refinement-edge indices, refined cells of level-1
+// (transfer blocks into this level), copy-index pairs
+int mfg_amesh_mg_level_sizes(const mfg_amesh *am, int level, uint32_t out[6])
+{
+  return guarded([&] {
+    MFG_REQUIRE(am && out && am->mg_ready, "call mfg_amesh_build_mg first");
+    MFG_REQUIRE(level >= am->mg_min_level && level < (int)am->levels.size(), "bad level");
+    const mfg_amesh::MgLevel &L = am->mg[level - am->mg_min_level];
+    out[0] = L.n_cells; out[1] = L.n_dofs; out[2] = (uint32_t)L.boundary.size(); out[3] = (uint32_t)L.edge.size(); out[4] = L.n_parents;
+    out[5] = (uint32_t)L.copy_global.size();
+  });
+}
+int mfg_amesh_mg_level_get(const mfg_amesh *am, int level, uint32_t *loc2glob, uint32_t *boundary, uint32_t *edge, double *coefficient, uint32_t *copy_global,
+                           uint32_t *copy_level, uint32_t *coarse_idx, uint32_t *fine_idx, double *weights)
+{
+  return guarded([&] {
+    MFG_REQUIRE(am && am->mg_ready, "call mfg_amesh_build_mg first");
+    MFG_REQUIRE(level >= am->mg_min_level && level < (int)am->levels.size(), "bad level");
+    const mfg_amesh::MgLevel &L = am->mg[level - am->mg_min_level];
+    if (loc2glob) std::copy(L.l2g.begin(), L.l2g.end(), loc2glob);
+    if (boundary) std::copy(L.boundary.begin(), L.boundary.end(), boundary);
+    if (edge) std::copy(L.edge.begin(), L.edge.end(), edge);
+    if (coefficient) level_coefficient(am, level, coefficient);
+    if (copy_global) std::copy(L.copy_global.begin(), L.copy_global.end(), copy_global);
+    if (copy_level) std::copy(L.copy_level.begin(), L.copy_level.end(), copy_level);
+    if (coarse_idx) std::copy(L.coarse_idx.begin(), L.coarse_idx.end(), coarse_idx);
+    if (fine_idx) std::copy(L.fine_idx.begin(), L.fine_idx.end(), fine_idx);
+    if (weights) std::copy(L.weights.begin(), L.weights.end(), weights);
   });
 }
 

@@ -173,6 +173,22 @@ uint32_t mfg_amesh_n_hanging(const mfg_amesh *am);
 int mfg_amesh_get_arrays(const mfg_amesh *am, uint32_t *loc2glob, uint32_t *loc2glob_unconstrained, uint32_t *constraint_mask, uint32_t *constrained,
                          uint32_t *hanging, double *inv_jac, double *coefficient, double *quadrature_points);
 
+/* The multigrid hierarchy on an adaptively refined mesh (local smoothing, poisson_mg.cu / bmop_mg.cu with an adaptive grid; the mesh
+ * needs mfg_amesh_set_limit_level_difference_at_vertices like the reference's Triangulation): level meshes = all cells of a level,
+ * DoFHandler::distribute_mg_dofs, MGConstrainedDoFs (boundary and refinement-edge indices), the transfer blocks of
+ * MGTransferMatrixFreeGpu::build (mg_transfer_matrix_free_gpu.cu:173-257) and the copy indices of copy_to_mg / copy_from_mg
+ * (.cu:109-146, 688-757).  Host code; min_level <= the coarsest active level. */
+int mfg_amesh_build_mg(mfg_amesh *am, int min_level);
+/* out[0..5] = cells, DoFs, boundary indices, refinement-edge indices, transfer blocks into this level (= refined cells of level-1),
+ * copy-index pairs */
+int mfg_amesh_mg_level_sizes(const mfg_amesh *am, int level, uint32_t out[6]);
+/* any pointer may be NULL.  loc2glob [cells][(p+1)^dim] (level numbering, lexicographic); boundary / edge ascending; coefficient
+ * [cells][(p+1)^dim]; copy_global / copy_level [pairs]: active DoF <-> level DoF; coarse_idx [blocks][(p+1)^dim] level-1 DoFs of the
+ * refined cell (bit 31 = boundary DoF of level-1), fine_idx [blocks][(2p+1)^dim] level DoFs of its children (lexicographic lattice),
+ * weights [blocks][3^dim] = 1 / multiplicity of the fine DoFs of a block region (low face, interior, high face per direction) */
+int mfg_amesh_mg_level_get(const mfg_amesh *am, int level, uint32_t *loc2glob, uint32_t *boundary, uint32_t *edge, double *coefficient, uint32_t *copy_global,
+                           uint32_t *copy_level, uint32_t *coarse_idx, uint32_t *fine_idx, double *weights);
+
 /* ---- MatrixFreeGpu ------------------------------------------------------- */
 /* Explicit-array description: what ReinitHelper extracts from deal.II
  * (matrix_free_gpu.cu:283-339) -- this is the call a deal.II-based caller makes. */
