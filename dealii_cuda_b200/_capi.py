@@ -186,6 +186,21 @@ def _load():
         "mfg_partition_plan_destroy": (C.c_int, [vp]),
         "mfg_partition_plan_sizes": (C.c_int, [vp, C.POINTER(sz)]),
         "mfg_partition_plan_get": (C.c_int, [vp, C.POINTER(C.c_int), u32p, u32p, u32p, u32p, u32p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]),
+        "mfg_amesh_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "mfg_mgt_build_from_blocks": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_uint32, u32p, u32p, dp, C.c_uint32, C.c_uint32, pp]),
+        "mfg_amg_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, pp]),
+        "mfg_amg_destroy": (C.c_int, [vp]),
+        "mfg_amg_vcycle": (C.c_int, [vp, vp, vp]),
+        "mfg_amg_active_operator": (C.c_int, [vp, pp]),
+        "mfg_amg_level_operator": (C.c_int, [vp, C.c_int, pp]),
+        "mfg_amg_vmult_interface_down": (C.c_int, [vp, C.c_int, vp, vp]),
+        "mfg_amg_vmult_interface_up": (C.c_int, [vp, C.c_int, vp, vp]),
+        "mfg_amg_prolongate": (C.c_int, [vp, C.c_int, vp, vp]),
+        "mfg_amg_restrict_and_add": (C.c_int, [vp, C.c_int, vp, vp]),
+        "mfg_amg_copy_to_level": (C.c_int, [vp, C.c_int, vp, vp]),
+        "mfg_amg_copy_from_level": (C.c_int, [vp, C.c_int, vp, vp]),
+        "mfg_amg_info": (C.c_int, [vp, C.c_int, dp, C.POINTER(C.c_long), C.POINTER(sz), C.POINTER(sz)]),
+        "mfg_amg_solve_cg": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(C.c_int), dp, dp]),
         "mfg_amesh_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, pp]),
         "mfg_amesh_destroy": (C.c_int, [vp]),
         "mfg_amesh_set_limit_level_difference_at_vertices": (C.c_int, [vp, C.c_int]),

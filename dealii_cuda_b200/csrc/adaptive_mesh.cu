@@ -701,6 +701,23 @@ int mfg_amesh_pseudo_adaptive_refinement(mfg_amesh *am, int n_ref)
     pseudo_adaptive_refinement(am, n_ref);
   });
 }
+int mfg_amesh_info(const mfg_amesh *am, int *dim, int *degree, double *left, double *right, int *n_levels, int *coarsest_active_level)
+{
+  return guarded([&] {
+    MFG_REQUIRE(am, "null argument");
+    if (dim) *dim = am->dim;
+    if (degree) *degree = am->p;
+    if (left) *left = am->left;
+    if (right) *right = am->right;
+    if (n_levels) *n_levels = (int)am->levels.size();
+    if (coarsest_active_level)
+      {
+        uint32_t m = 0xffffffffu;
+        for (uint32_t a = 0; a < am->n_active(); ++a) m = std::min(m, am->act_level[a]);
+        *coarsest_active_level = (int)m;
+      }
+  });
+}
 uint32_t mfg_amesh_n_active_cells(const mfg_amesh *am) { return am ? am->n_active() : 0; }
 uint32_t mfg_amesh_n_levels(const mfg_amesh *am) { return am ? (uint32_t)am->levels.size() : 0; }
 int mfg_amesh_get_active_cells(const mfg_amesh *am, uint32_t *level_xyz)

@@ -17,6 +17,7 @@ struct mfg_mgt
   mfg::DevBuf<uint32_t> coarse_idx;  // [n_coarse_cells][(p+1)^dim], bit 31 = coarse Dirichlet DoF
   mfg::DevBuf<uint32_t> fine_idx;    // [n_coarse_cells][(2p+1)^dim] lexicographic
   mfg::DevBuf<uint32_t> cell_xyz;    // [n_coarse_cells][3] (valence weights)
+  mfg::DevBuf<double>   wtab;        // adaptive hierarchies: [n_coarse_cells][3^dim] weights per block region (empty: closed-form valence)
   double P[17 * 9];                  // P[f*(p+1)+i]
 };
 
@@ -67,7 +68,18 @@ __device__ inline double valence_weight(int dim, int p, const uint32_t *cx, cons
   return w;
 }
 
-struct MgArgs { int dim, p; uint32_t n_cells; uint32_t nc[3]; const uint32_t *coarse_idx, *fine_idx, *cxyz; };
+struct MgArgs { int dim, p; uint32_t n_cells; uint32_t nc[3]; const uint32_t *coarse_idx, *fine_idx, *cxyz; const double *wtab; };
+
+// weight of lattice point a of a block: closed-form valence on globally refined meshes, else the block's table of 3^dim
+// regions (low face / interior / high face per direction; weights_on_refined, mg_transfer_matrix_free_gpu.cu:357-387)
+__device__ inline double block_weight(const MgArgs &A, uint32_t cell, const uint32_t *cx, const int *a)
+{
+  if (A.wtab == nullptr) return valence_weight(A.dim, A.p, cx, A.nc, a);
+  int r = 0, s = 1;
+  for (int d = 0; d < A.dim; ++d) { r += (a[d] == 0 ? 0 : a[d] == 2 * A.p ? 2 : 1) * s; s *= 3; }
+  const int n3 = A.dim == 3 ? 27 : 9;
+  return A.wtab[(size_t)cell * n3 + r];
+}
 
 template <typename Number, bool PROLONG>
 __global__ void mg_kernel(MgArgs A, PMat pm, Number *__restrict__ dst, const Number *__restrict__ src)
@@ -90,7 +102,7 @@ __global__ void mg_kernel(MgArgs A, PMat pm, Number *__restrict__ dst, const Num
     for (int f = threadIdx.x; f < nF; f += blockDim.x)
       {
         const int a[3] = {f % nfine, (f / nfine) % nfine, dim == 3 ? f / (nfine * nfine) : 0};
-        b0[f] = (double)src[fidx[f]] * valence_weight(dim, p, cx, A.nc, a);   // weigh_values
+        b0[f] = (double)src[fidx[f]] * block_weight(A, cell, cx, a);   // weigh_values
       }
   __syncthreads();
   double *in = b0, *out = b1;
@@ -107,7 +119,7 @@ __global__ void mg_kernel(MgArgs A, PMat pm, Number *__restrict__ dst, const Num
     for (int f = threadIdx.x; f < nF; f += blockDim.x)
       {
         const int a[3] = {f % nfine, (f / nfine) % nfine, dim == 3 ? f / (nfine * nfine) : 0};
-        atomicAdd(dst + fidx[f], (Number)(in[f] * valence_weight(dim, p, cx, A.nc, a)));
+        atomicAdd(dst + fidx[f], (Number)(in[f] * block_weight(A, cell, cx, a)));
       }
   else
     for (int i = threadIdx.x; i < nC; i += blockDim.x)
@@ -180,6 +192,54 @@ int mfg_mgt_build(mfg_ctx *ctx, const mfg_mesh *coarse, const mfg_mesh *fine, mf
     *out = t.release();
   });
 }
+// transfer between two levels of an ADAPTIVE hierarchy from explicit blocks (mfg_amesh_mg_level_get): one block per refined
+// cell of the coarse level
+int mfg_mgt_build_from_blocks(mfg_ctx *ctx, mfg_dtype dt, int dim, int degree, uint32_t n_blocks, const uint32_t *coarse_idx_host, const uint32_t *fine_idx_host,
+                              const double *weights_host, uint32_t n_coarse_dofs, uint32_t n_fine_dofs, mfg_mgt **out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && out, "null argument");
+    MFG_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
+    MFG_REQUIRE(degree >= 1 && degree <= 8, "degree must be in 1..8");
+    MFG_REQUIRE(n_blocks == 0 || (coarse_idx_host && fine_idx_host && weights_host), "null block arrays");
+    std::unique_ptr<mfg_mgt> t(new mfg_mgt);
+    t->ctx = ctx; t->dt = dt; t->dim = dim; t->p = degree;
+    t->n_coarse_cells = n_blocks; t->n_coarse_dofs = n_coarse_dofs; t->n_fine_dofs = n_fine_dofs;
+    const int p = degree, n = p + 1, nf = 2 * p + 1;
+    const size_t nC = ipow(n, dim), nF = ipow(nf, dim), n3 = ipow(3, dim);
+    for (size_t i = 0; i < (size_t)n_blocks * nC; ++i) MFG_REQUIRE((coarse_idx_host[i] & 0x7fffffffu) < n_coarse_dofs, "coarse index out of range");
+    for (size_t i = 0; i < (size_t)n_blocks * nF; ++i) MFG_REQUIRE(fine_idx_host[i] < n_fine_dofs, "fine index out of range");
+    const FEData1D fe = make_fe_data(degree);
+    for (int f = 0; f < nf; ++f)
+      {
+        const long double x = f <= p ? (long double)fe.nodes[f] / 2 : 0.5L + (long double)fe.nodes[f - p] / 2;
+        for (int i = 0; i < n; ++i)
+          {
+            long double v = 1;
+            for (int m = 0; m < n; ++m) if (m != i) v *= (x - fe.nodes[m]) / ((long double)fe.nodes[i] - fe.nodes[m]);
+            t->P[f * n + i] = (double)v;
+          }
+      }
+    cudaStream_t s = ctx->stream;
+    const size_t smem_needed = 2 * nF * sizeof(double);
+    if (smem_needed > 48 * 1024)
+      {
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+        MFG_CUDA(cudaFuncSetAttribute(mg_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_needed));
+      }
+    if (n_blocks)
+      {
+        t->coarse_idx.upload(coarse_idx_host, (size_t)n_blocks * nC, s);
+        t->fine_idx.upload(fine_idx_host, (size_t)n_blocks * nF, s);
+        t->wtab.upload(weights_host, (size_t)n_blocks * n3, s);
+        std::vector<uint32_t> zero((size_t)n_blocks * 3, 0u);
+        t->cell_xyz.upload(zero.data(), zero.size(), s);
+      }
+    *out = t.release();
+  });
+}
 int mfg_mgt_destroy(mfg_mgt *t) { return guarded([&] { delete t; }); }
 
 static void mgt_run(mfg_mgt *t, mfg_vec *dst, const mfg_vec *src, bool prolong)
@@ -189,7 +249,8 @@ static void mgt_run(mfg_mgt *t, mfg_vec *dst, const mfg_vec *src, bool prolong)
   MFG_REQUIRE(dst->n == (prolong ? t->n_fine_dofs : t->n_coarse_dofs) && src->n == (prolong ? t->n_coarse_dofs : t->n_fine_dofs), "vector sizes do not match the levels");
   MgArgs A; A.dim = t->dim; A.p = t->p; A.n_cells = t->n_coarse_cells;
   for (int d = 0; d < 3; ++d) A.nc[d] = t->nc[d];
-  A.coarse_idx = t->coarse_idx.p; A.fine_idx = t->fine_idx.p; A.cxyz = t->cell_xyz.p;
+  A.coarse_idx = t->coarse_idx.p; A.fine_idx = t->fine_idx.p; A.cxyz = t->cell_xyz.p; A.wtab = t->wtab.n ? t->wtab.p : nullptr;
+  if (t->n_coarse_cells == 0) { if (prolong) vec_fill(dst, 0.0); return; }
   PMat pm; std::memcpy(pm.P, t->P, sizeof(pm.P));
   const size_t nF = ipow(2 * t->p + 1, t->dim), smem = 2 * nF * sizeof(double);
   cudaStream_t s = t->ctx->stream;

@@ -18,6 +18,7 @@
 //     recurse, prolongate, x += t, post-smooth (step); coarsest level: unpreconditioned CG to 1e-10 |b|.
 // Globally refined meshes: there are no refinement edges, so the edge matrices (vmult_interface_down / up,
 // laplace_operator_gpu.h:306-352) are the zero operator and are not called.
+#include <algorithm>
 #include <cmath>
 #include <memory>
 #include <vector>
@@ -91,6 +92,42 @@ double tridiag_eigenvalue(const std::vector<double> &a, const std::vector<double
       if (sturm_count(a, b, mid) > k) hi = mid; else lo = mid;
     }
   return 0.5 * (lo + hi);
+}
+
+// SolverCG control flow (poisson.cu:233-260) with a preconditioner given as a callable h = M^-1 g
+template <typename Precond>
+void solve_cg_preconditioned(mfg_ctx *ctx, mfg_dtype dt, mfg_laplace *op, Precond &&precond, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter,
+                             int *iters, double *last_residual, double *history)
+{
+  const size_t n = op->mf->n_dofs;
+  Vec g(ctx, dt, n), h(ctx, dt, n), d(ctx, dt, n);
+  if (vec_all_zero(x)) vec_equ(g.v, -1.0, b);
+  else { laplace_vmult(op, g.v->p, x->p, false); vec_sadd(g.v, 1.0, -1.0, b); }
+  double res = std::sqrt(vec_dot(g.v, g.v));
+  int it = 0;
+  if (history) history[0] = res;
+  if (res > abs_tol)
+    {
+      precond(h.v, g.v);
+      vec_equ(d.v, -1.0, h.v);
+      double gh = vec_dot(g.v, h.v);
+      for (it = 1; it <= max_iter; ++it)
+        {
+          laplace_vmult(op, h.v->p, d.v->p, false);
+          const double alpha = gh / vec_dot(d.v, h.v);
+          vec_sadd(x, 1.0, alpha, d.v);
+          res = std::sqrt(vec_add_and_dot(g.v, alpha, h.v, g.v));
+          if (history) history[it] = res;
+          if (res <= abs_tol) break;
+          precond(h.v, g.v);
+          const double gh_new = vec_dot(g.v, h.v), beta = gh_new / gh;
+          gh = gh_new;
+          vec_sadd(d.v, beta, -1.0, h.v);
+        }
+      if (it > max_iter) it = max_iter;
+    }
+  if (iters) *iters = it;
+  if (last_residual) *last_residual = res;
 }
 
 }  // namespace
@@ -222,6 +259,105 @@ struct mfg_mg
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Multigrid with local smoothing on an adaptively refined mesh.  Host hierarchy: csrc/adaptive_mesh.cu (mfg_amesh_build_mg);
+// checker: oracle/adaptive_mg.py.  Every device operation below is a kernel the globally refined path already uses
+// (level operators from explicit arrays, the transfer kernel with a weight table, indexed copies, BLAS-1).
+// ---------------------------------------------------------------------------------------------------------------------
+struct mfg_amg
+{
+  mfg_ctx *ctx = nullptr;
+  mfg_dtype dt = MFG_F64;
+  int min_level = 0, max_level = 0;
+  mfg_laplace *active_op = nullptr;
+  struct Level
+  {
+    mfg_laplace *op = nullptr, *raw = nullptr;   // level operator (boundary + edge constrained); the same cell loop without constraints
+    mfg_ch      *ch = nullptr;                   // borrowed from op: constrained + edge lists
+    mfg_mgt     *transfer = nullptr;             // level-1 -> level
+    std::unique_ptr<mfg_cheb> smoother;
+    Vec          x, b, t, w1, w2, w3;
+    DevBuf<uint32_t> copy_global, copy_level;
+    size_t       n = 0, n_edge = 0;
+  };
+  std::vector<Level> lv;
+  long coarse_iterations = 0;
+  Level &L(int level) { return lv[level - min_level]; }
+  ~mfg_amg()
+  {
+    for (auto &l : lv)
+      {
+        l.smoother.reset();
+        if (l.transfer) mfg_mgt_destroy(l.transfer);
+        if (l.raw) mfg_laplace_destroy(l.raw);
+        if (l.op) mfg_laplace_destroy(l.op);
+      }
+    if (active_op) mfg_laplace_destroy(active_op);
+  }
+  // dst = edge rows of A_raw (src with the constrained entries zeroed), zero elsewhere  (laplace_operator_gpu.h:306-331)
+  void interface_down(Level &l, mfg_vec *dst, const mfg_vec *src)
+  {
+    vec_fill(dst, 0.0);
+    if (!l.n_edge) return;
+    MG_CHECK(mfg_vec_copy(l.w1.v, src));
+    ch_set(l.ch, l.w1.v, 0.0);
+    laplace_vmult(l.raw, l.w2.v->p, l.w1.v->p, false);
+    vec_copy_with_indices(dst, l.w2.v, l.ch->edge.p, l.ch->edge.p, l.ch->edge.n);
+  }
+  // dst = A_raw (src restricted to the edge DoFs), constrained rows zeroed  (laplace_operator_gpu.h:333-352)
+  void interface_up(Level &l, mfg_vec *dst, const mfg_vec *src)
+  {
+    if (!l.n_edge) { vec_fill(dst, 0.0); return; }
+    vec_fill(l.w1.v, 0.0);
+    vec_copy_with_indices(l.w1.v, src, l.ch->edge.p, l.ch->edge.p, l.ch->edge.n);
+    laplace_vmult(l.raw, dst->p, l.w1.v->p, false);
+    ch_set(l.ch, dst, 0.0);
+  }
+  void cycle(int level)  // Multigrid::level_v_step with edge_out = edge_in = the interface operators
+  {
+    Level &l = L(level);
+    if (level == min_level)
+      {
+        vec_fill(l.x.v, 0.0);
+        const double bn = std::sqrt(vec_dot(l.b.v, l.b.v));
+        int its = 0;
+        MG_CHECK(mfg_solver_cg(l.op, l.x.v, l.b.v, 1e-10 * std::max(bn, 1e-300), 10000, 0, &its, nullptr, nullptr));
+        coarse_iterations += its;
+        return;
+      }
+    Level &lc = L(level - 1);
+    l.smoother->apply(l.x.v, l.b.v, true);                          // pre-smoothing from a zero guess
+    laplace_vmult(l.op, l.t.v->p, l.x.v->p, false);                 // t = A x
+    if (l.n_edge)
+      {
+        interface_down(l, l.w3.v, l.x.v);                           // edge_out->vmult_add
+        vec_sadd(l.t.v, 1.0, 1.0, l.w3.v);
+      }
+    vec_sadd(l.t.v, -1.0, 1.0, l.b.v);                              // t = b - t
+    MG_CHECK(mfg_mgt_restrict_and_add(l.transfer, lc.b.v, l.t.v));  // the coarse defect already holds copy_to_mg's part
+    cycle(level - 1);
+    MG_CHECK(mfg_mgt_prolongate(l.transfer, l.t.v, lc.x.v));
+    vec_sadd(l.x.v, 1.0, 1.0, l.t.v);
+    if (l.n_edge)
+      {
+        interface_up(l, l.t.v, l.x.v);                              // edge_in->Tvmult
+        vec_sadd(l.b.v, 1.0, -1.0, l.t.v);                          // defect -= t
+      }
+    l.smoother->apply(l.x.v, l.b.v, false);                         // post-smoothing
+  }
+  void vmult(mfg_vec *dst, const mfg_vec *src)  // PreconditionMG::vmult
+  {
+    for (auto &l : lv)                                              // copy_to_mg (mg_transfer_matrix_free_gpu.cu:688-727)
+      {
+        vec_fill(l.b.v, 0.0);
+        vec_copy_with_indices(l.b.v, src, l.copy_level.p, l.copy_global.p, l.copy_global.n);
+      }
+    cycle(max_level);
+    vec_fill(dst, 0.0);                                             // copy_from_mg (.cu:731-757)
+    for (auto &l : lv) vec_copy_with_indices(dst, l.x.v, l.copy_global.p, l.copy_level.p, l.copy_global.n);
+  }
+};
+
 extern "C" {
 
 int mfg_chebyshev_create(mfg_laplace *op, int degree, double smoothing_range, int eig_cg_n_iterations, mfg_cheb **out)
@@ -334,34 +470,175 @@ int mfg_mg_solve_cg(mfg_mg *mg, mfg_vec *x, const mfg_vec *b, double abs_tol, in
     mfg_laplace *op = mg->ops.back();
     const size_t n = op->mf->n_dofs;
     MFG_REQUIRE(x->n == n && b->n == n && x->dt == mg->dt && b->dt == mg->dt, "vector does not fit the finest level");
-    Vec g(mg->ctx, mg->dt, n), h(mg->ctx, mg->dt, n), d(mg->ctx, mg->dt, n);
-    if (vec_all_zero(x)) vec_equ(g.v, -1.0, b);
-    else { laplace_vmult(op, g.v->p, x->p, false); vec_sadd(g.v, 1.0, -1.0, b); }
-    double res = std::sqrt(vec_dot(g.v, g.v));
-    int it = 0;
-    if (history) history[0] = res;
-    if (res > abs_tol)
+    solve_cg_preconditioned(mg->ctx, mg->dt, op, [&](mfg_vec *h, const mfg_vec *g) { mg->vmult(h, g); }, x, b, abs_tol, max_iter, iters, last_residual, history);
+  });
+}
+
+// ---- multigrid on adaptively refined meshes ------------------------------------------------------------------------------
+int mfg_amg_create(mfg_ctx *ctx, mfg_amesh *am, int min_level, mfg_dtype dt, int smoother_degree, double smoothing_range, int eig_cg_n_iterations,
+                   mfg_amg **out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && am && out, "null argument");
+    int dim = 0, degree = 0, n_levels = 0;
+    double left = 0, right = 0;
+    MG_CHECK(mfg_amesh_info(am, &dim, &degree, &left, &right, &n_levels, nullptr));
+    MG_CHECK(mfg_amesh_build_mg(am, min_level));
+    std::unique_ptr<mfg_amg> mg(new mfg_amg);
+    mg->ctx = ctx; mg->dt = dt; mg->min_level = min_level; mg->max_level = n_levels - 1;
+    MG_CHECK(mfg_laplace_create_from_amesh(ctx, am, dt, &mg->active_op));
+    mg->lv.resize(n_levels - min_level);
+    const uint32_t npc = ipow(degree + 1, dim), nF = ipow(2 * degree + 1, dim), n3 = ipow(3, dim);
+    uint32_t n_dofs_below = 0;
+    for (int level = min_level; level < n_levels; ++level)
       {
-        mg->vmult(h.v, g.v);
-        vec_equ(d.v, -1.0, h.v);
-        double gh = vec_dot(g.v, h.v);
-        for (it = 1; it <= max_iter; ++it)
+        mfg_amg::Level &l = mg->L(level);
+        uint32_t sz[6];
+        MG_CHECK(mfg_amesh_mg_level_sizes(am, level, sz));
+        const uint32_t nc = sz[0], nd = sz[1], nb = sz[2], ne = sz[3], nblk = sz[4], ncp = sz[5];
+        std::vector<uint32_t> l2g((size_t)nc * npc), boundary(nb), edge(ne), cg(ncp), cl(ncp), cidx((size_t)nblk * npc), fidx((size_t)nblk * nF);
+        std::vector<double>   coef((size_t)nc * npc), w((size_t)nblk * n3);
+        MG_CHECK(mfg_amesh_mg_level_get(am, level, l2g.data(), boundary.data(), edge.data(), coef.data(), cg.data(), cl.data(), cidx.data(), fidx.data(), w.data()));
+        l.n = nd; l.n_edge = ne;
+        // LaplaceOperatorGpu::reinit(dof_handler, mg_constrained_dofs, level): the level's cells, no hanging nodes; constraints =
+        // boundary + refinement-edge DoFs, edge list = the refinement-edge DoFs (constraint_handler_gpu.cu:99-123)
+        std::vector<double> inv_jac(nc, (double)((uint64_t)1 << level) / (right - left));
+        std::vector<uint32_t> constrained(nb + ne);
+        std::merge(boundary.begin(), boundary.end(), edge.begin(), edge.end(), constrained.begin());
+        constrained.erase(std::unique(constrained.begin(), constrained.end()), constrained.end());
+        mfg_mf_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.dim = dim; d.degree = degree; d.dtype = dt; d.n_cells = nc; d.n_dofs = nd; d.loc2glob = l2g.data();
+        d.geometry = MFG_GEOM_UNIFORM; d.inv_jac = inv_jac.data(); d.scatter = MFG_SCATTER_ATOMIC;
+        {
+          std::unique_ptr<mfg_mf> mf(mf_from_desc(ctx, d));
+          std::unique_ptr<mfg_ch> ch(ch_create(ctx, dt, constrained.data(), constrained.size(), edge.data(), edge.size()));
+          l.op = laplace_from_arrays(ctx, mf.get(), ch.get(), coef.data());
+          l.op->owns_mf = true; l.op->owns_ch = true;
+          l.ch = ch.get();
+          mf.release(); ch.release();
+        }
+        if (ne)
           {
-            laplace_vmult(op, h.v->p, d.v->p, false);
-            const double alpha = gh / vec_dot(d.v, h.v);
-            vec_sadd(x, 1.0, alpha, d.v);
-            res = std::sqrt(vec_add_and_dot(g.v, alpha, h.v, g.v));
-            if (history) history[it] = res;
-            if (res <= abs_tol) break;
-            mg->vmult(h.v, g.v);
-            const double gh_new = vec_dot(g.v, h.v), beta = gh_new / gh;
-            gh = gh_new;
-            vec_sadd(d.v, beta, -1.0, h.v);
+            // the cell loop without the constraint handler, for the interface operators (they read and write edge rows)
+            std::unique_ptr<mfg_mf> mf(mf_from_desc(ctx, d));
+            std::unique_ptr<mfg_ch> ch(ch_create(ctx, dt, nullptr, 0, nullptr, 0));
+            l.raw = laplace_from_arrays(ctx, mf.get(), ch.get(), coef.data());
+            l.raw->owns_mf = true; l.raw->owns_ch = true;
+            l.raw->variant = 1;  // column kernel: no second copy of the index map in consumption order
+            mf.release(); ch.release();
           }
-        if (it > max_iter) it = max_iter;
+        l.x = Vec(ctx, dt, nd); l.b = Vec(ctx, dt, nd); l.t = Vec(ctx, dt, nd);
+        if (ne) { l.w1 = Vec(ctx, dt, nd); l.w2 = Vec(ctx, dt, nd); l.w3 = Vec(ctx, dt, nd); }
+        l.copy_global.upload(cg.data(), cg.size(), ctx->stream);
+        l.copy_level.upload(cl.data(), cl.size(), ctx->stream);
+        if (level > min_level)
+          {
+            MG_CHECK(mfg_mgt_build_from_blocks(ctx, dt, dim, degree, nblk, cidx.data(), fidx.data(), w.data(), n_dofs_below, nd, &l.transfer));
+            mfg_cheb *c = nullptr;
+            MG_CHECK(mfg_chebyshev_create(l.op, smoother_degree, smoothing_range, eig_cg_n_iterations, &c));
+            l.smoother.reset(c);
+          }
+        n_dofs_below = nd;
       }
-    if (iters) *iters = it;
-    if (last_residual) *last_residual = res;
+    *out = mg.release();
+  });
+}
+int mfg_amg_destroy(mfg_amg *mg) { return guarded([&] { delete mg; }); }
+static void amg_check_active(const mfg_amg *mg, const mfg_vec *a, const mfg_vec *b)
+{
+  const size_t n = mg->active_op->mf->n_dofs;
+  MFG_REQUIRE(a && b && a != b && a->n == n && b->n == n && a->dt == mg->dt && b->dt == mg->dt, "vector does not fit the active mesh");
+}
+static mfg_amg::Level &amg_level(mfg_amg *mg, int level)
+{
+  MFG_REQUIRE(mg && level >= mg->min_level && level <= mg->max_level, "bad level");
+  return mg->L(level);
+}
+static void amg_check_level(const mfg_amg *mg, const mfg_amg::Level &l, const mfg_vec *v)
+{
+  MFG_REQUIRE(v && v->n == l.n && v->dt == mg->dt, "vector does not fit the level");
+}
+int mfg_amg_vcycle(mfg_amg *mg, mfg_vec *dst, const mfg_vec *src)
+{
+  return guarded([&] { MFG_REQUIRE(mg, "null argument"); amg_check_active(mg, dst, src); mg->vmult(dst, src); });
+}
+int mfg_amg_active_operator(mfg_amg *mg, mfg_laplace **op) { return guarded([&] { MFG_REQUIRE(mg && op, "null argument"); *op = mg->active_op; }); }
+int mfg_amg_level_operator(mfg_amg *mg, int level, mfg_laplace **op)
+{
+  return guarded([&] { MFG_REQUIRE(op, "null argument"); *op = amg_level(mg, level).op; });
+}
+int mfg_amg_vmult_interface_down(mfg_amg *mg, int level, mfg_vec *dst, const mfg_vec *src)
+{
+  return guarded([&] {
+    mfg_amg::Level &l = amg_level(mg, level);
+    amg_check_level(mg, l, dst); amg_check_level(mg, l, src);
+    MFG_REQUIRE(dst != src, "aliased arguments");
+    mg->interface_down(l, dst, src);
+  });
+}
+int mfg_amg_vmult_interface_up(mfg_amg *mg, int level, mfg_vec *dst, const mfg_vec *src)
+{
+  return guarded([&] {
+    mfg_amg::Level &l = amg_level(mg, level);
+    amg_check_level(mg, l, dst); amg_check_level(mg, l, src);
+    MFG_REQUIRE(dst != src, "aliased arguments");
+    mg->interface_up(l, dst, src);
+  });
+}
+int mfg_amg_prolongate(mfg_amg *mg, int level, mfg_vec *dst_fine, const mfg_vec *src_coarse)
+{
+  return guarded([&] {
+    mfg_amg::Level &l = amg_level(mg, level);
+    MFG_REQUIRE(level > mg->min_level, "no transfer into the coarsest level");
+    MG_CHECK(mfg_mgt_prolongate(l.transfer, dst_fine, src_coarse));
+  });
+}
+int mfg_amg_restrict_and_add(mfg_amg *mg, int level, mfg_vec *dst_coarse, const mfg_vec *src_fine)
+{
+  return guarded([&] {
+    mfg_amg::Level &l = amg_level(mg, level);
+    MFG_REQUIRE(level > mg->min_level, "no transfer into the coarsest level");
+    MG_CHECK(mfg_mgt_restrict_and_add(l.transfer, dst_coarse, src_fine));
+  });
+}
+int mfg_amg_copy_to_level(mfg_amg *mg, int level, mfg_vec *dst_level, const mfg_vec *src_active)
+{
+  return guarded([&] {
+    mfg_amg::Level &l = amg_level(mg, level);
+    amg_check_level(mg, l, dst_level);
+    MFG_REQUIRE(src_active && src_active->n == mg->active_op->mf->n_dofs, "source does not fit the active mesh");
+    vec_fill(dst_level, 0.0);
+    vec_copy_with_indices(dst_level, src_active, l.copy_level.p, l.copy_global.p, l.copy_global.n);
+  });
+}
+int mfg_amg_copy_from_level(mfg_amg *mg, int level, mfg_vec *dst_active, const mfg_vec *src_level)
+{
+  return guarded([&] {
+    mfg_amg::Level &l = amg_level(mg, level);
+    amg_check_level(mg, l, src_level);
+    MFG_REQUIRE(dst_active && dst_active->n == mg->active_op->mf->n_dofs, "destination does not fit the active mesh");
+    vec_copy_with_indices(dst_active, src_level, l.copy_global.p, l.copy_level.p, l.copy_global.n);
+  });
+}
+int mfg_amg_info(const mfg_amg *mg, int level, double *lambda_max, long *coarse_iterations, size_t *n_dofs, size_t *n_edge)
+{
+  return guarded([&] {
+    MFG_REQUIRE(mg && level >= mg->min_level && level <= mg->max_level, "bad level");
+    const mfg_amg::Level &l = mg->lv[level - mg->min_level];
+    if (lambda_max) *lambda_max = l.smoother ? l.smoother->lambda_max : 0.0;
+    if (coarse_iterations) *coarse_iterations = mg->coarse_iterations;
+    if (n_dofs) *n_dofs = l.n;
+    if (n_edge) *n_edge = l.n_edge;
+  });
+}
+int mfg_amg_solve_cg(mfg_amg *mg, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter, int *iters, double *last_residual, double *history)
+{
+  return guarded([&] {
+    MFG_REQUIRE(mg, "null argument");
+    amg_check_active(mg, x, b);
+    solve_cg_preconditioned(mg->ctx, mg->dt, mg->active_op, [&](mfg_vec *h, const mfg_vec *g) { mg->vmult(h, g); }, x, b, abs_tol, max_iter, iters,
+                            last_residual, history);
   });
 }
 

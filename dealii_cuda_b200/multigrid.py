@@ -145,6 +145,73 @@ class GeometricMultigrid:
         return (its.value, res.value, list(hist[:its.value + 1])) if history else (its.value, res.value)
 
 
+class AdaptiveMultigrid:
+    """Multigrid with local smoothing on an adaptively refined mesh (poisson_mg.cu / bmop_mg.cu with an adaptive grid): binding of
+    mfg_amg_* (csrc/multigrid.cu) over the host hierarchy of AdaptiveMesh.build_mg (csrc/adaptive_mesh.cu).  The mesh must have
+    been created with limit_level_difference_at_vertices=True like the reference's Triangulation (poisson_mg.cu:132)."""
+
+    def __init__(self, ctx, amesh, min_level=0, dtype=np.float64, smoother_degree=5, smoothing_range=15.0, eig_iterations=15):
+        self.ctx, self.dtype, self.amesh = ctx, dtype, amesh
+        code = _capi.F64 if np.dtype(dtype) == np.float64 else _capi.F32
+        h = C.c_void_p()
+        check(lib.mfg_amg_create(ctx.h, amesh.h, int(min_level), code, int(smoother_degree), float(smoothing_range), int(eig_iterations), C.byref(h)))
+        self.h = h
+        self.levels = list(range(min_level, amesh.n_levels))
+        oh = C.c_void_p()
+        check(lib.mfg_amg_active_operator(h, C.byref(oh)))
+        self.op = _LevelOperator(ctx, oh, amesh.n_dofs, dtype)          # the operator on the active mesh (hanging nodes resolved)
+        self.ops, self.lambda_max, self.n_dofs, self.n_edge = {}, {}, {}, {}
+        for l in self.levels:
+            oh, lm, ci, nd, ne = C.c_void_p(), C.c_double(), C.c_long(), C.c_size_t(), C.c_size_t()
+            check(lib.mfg_amg_level_operator(h, l, C.byref(oh)))
+            check(lib.mfg_amg_info(h, l, C.byref(lm), C.byref(ci), C.byref(nd), C.byref(ne)))
+            self.ops[l] = _LevelOperator(ctx, oh, nd.value, dtype)
+            self.lambda_max[l], self.n_dofs[l], self.n_edge[l] = lm.value, nd.value, ne.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.mfg_amg_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def coarse_iterations(self):
+        ci = C.c_long()
+        check(lib.mfg_amg_info(self.h, self.levels[0], None, C.byref(ci), None, None))
+        return ci.value
+
+    def vmult(self, dst, src):
+        """PreconditionMG::vmult on vectors of the active mesh: copy_to_mg, one V-cycle with the edge matrices, copy_from_mg"""
+        check(lib.mfg_amg_vcycle(self.h, dst.h, src.h))
+
+    def vmult_interface_down(self, level, dst, src):
+        check(lib.mfg_amg_vmult_interface_down(self.h, int(level), dst.h, src.h))
+
+    def vmult_interface_up(self, level, dst, src):
+        check(lib.mfg_amg_vmult_interface_up(self.h, int(level), dst.h, src.h))
+
+    def prolongate(self, to_level, dst, src):
+        check(lib.mfg_amg_prolongate(self.h, int(to_level), dst.h, src.h))
+
+    def restrict_and_add(self, from_level, dst, src):
+        check(lib.mfg_amg_restrict_and_add(self.h, int(from_level), dst.h, src.h))
+
+    def copy_to_level(self, level, dst, src):
+        check(lib.mfg_amg_copy_to_level(self.h, int(level), dst.h, src.h))
+
+    def copy_from_level(self, level, dst, src):
+        check(lib.mfg_amg_copy_from_level(self.h, int(level), dst.h, src.h))
+
+    def solve_cg(self, x, b, abs_tol, max_iter=1000, history=False):
+        """SolverCG on the active operator preconditioned by the V-cycle (poisson_mg.cu:504-518)"""
+        its, res = C.c_int(), C.c_double()
+        hist = (C.c_double * (max_iter + 1))() if history else None
+        check(lib.mfg_amg_solve_cg(self.h, x.h, b.h, float(abs_tol), int(max_iter), C.byref(its), C.byref(res), hist))
+        return (its.value, res.value, list(hist[:its.value + 1])) if history else (its.value, res.value)
+
+
 def solver_cg_preconditioned(ctx, op, x, b, precond, abs_tol, max_iter=1000):
     """SolverCG control flow with an arbitrary preconditioner object (vmult(dst, src)); host-side
     variant for preconditioners written in Python (the library's own is GeometricMultigrid.solve_cg)."""

@@ -156,6 +156,7 @@ int mfg_amesh_mark_cells_on_shell(mfg_amesh *am, double R, const double *center)
 int mfg_amesh_mark_octant(mfg_amesh *am);                                                  /* mark_cells(octant_criterion) poisson_common.h:29-35, 43-56 */
 int mfg_amesh_execute_refinement(mfg_amesh *am);                                           /* execute_coarsening_and_refinement */
 int mfg_amesh_pseudo_adaptive_refinement(mfg_amesh *am, int n_ref);                        /* bmop_common.h:49-105, domain CUBE */
+int mfg_amesh_info(const mfg_amesh *am, int *dim, int *degree, double *left, double *right, int *n_levels, int *coarsest_active_level); /* any pointer may be NULL */
 uint32_t mfg_amesh_n_active_cells(const mfg_amesh *am);
 uint32_t mfg_amesh_n_levels(const mfg_amesh *am);
 int mfg_amesh_get_active_cells(const mfg_amesh *am, uint32_t *level_xyz /* [n_active_cells][4]: level, x, y, z */);
@@ -341,6 +342,11 @@ int mfg_mgt_destroy(mfg_mgt *t);
 int mfg_mgt_prolongate(mfg_mgt *t, mfg_vec *dst_fine, const mfg_vec *src_coarse);
 int mfg_mgt_restrict_and_add(mfg_mgt *t, mfg_vec *dst_coarse, const mfg_vec *src_fine);
 
+/* transfer between two levels of an ADAPTIVE hierarchy from explicit blocks (mfg_amesh_mg_level_get: coarse_idx, fine_idx, weights):
+ * one block per refined cell of the coarse level (internal::MGTransfer::setup_transfer, mg_transfer_matrix_free_gpu.cu:173-257) */
+int mfg_mgt_build_from_blocks(mfg_ctx *ctx, mfg_dtype dt, int dim, int degree, uint32_t n_blocks, const uint32_t *coarse_idx_host, const uint32_t *fine_idx_host,
+                              const double *weights_host, uint32_t n_coarse_dofs, uint32_t n_fine_dofs, mfg_mgt **out);
+
 /* ---- solver ----------------------------------------------------------------------------------------------
  * Conjugate gradients with the control flow of deal.II's SolverCG as instantiated on GpuVector by the reference
  * (poisson.cu:233-260): stops when |r| <= abs_tol (the reference uses 1e-12*|b|) or after max_iter iterations.
@@ -444,6 +450,32 @@ int mfg_cgd_alpha(mfg_ctx *ctx, double *scal_dev);                 /* alpha = g.
 int mfg_cgd_residual(mfg_ctx *ctx, mfg_dtype dt, void *g, void *h, const void *minv, const uint8_t *owned_dev, size_t n, double *scal_dev, int first);
 int mfg_cgd_beta(mfg_ctx *ctx, double *scal_dev, double tol, int it);  /* |g|, convergence flag, beta */
 int mfg_cgd_advance(mfg_ctx *ctx, mfg_dtype dt, void *x, void *d, const void *z, size_t n, const double *scal_dev, int it);
+
+/* ---- multigrid with local smoothing on an adaptively refined mesh (poisson_mg.cu / bmop_mg.cu with an adaptive grid) -------------
+ * Built from the host hierarchy of mfg_amesh_build_mg: per level a LaplaceOperatorGpu::reinit(dof_handler, mg_constrained_dofs, level)
+ * (laplace_operator_gpu.h:153-186; constraint handler = boundary + refinement-edge DoFs, constraint_handler_gpu.cu:99-123), its
+ * interface operators vmult_interface_down / vmult_interface_up (:306-352), MGTransferMatrixFreeGpu with copy_to_mg / copy_from_mg
+ * through index pairs (mg_transfer_matrix_free_gpu.cu:688-757), Chebyshev smoothers, Multigrid::level_v_step with
+ * set_edge_matrices(interface, interface) (poisson_mg.cu:365-375), coarse solve = CG to a 1e-10 reduction.
+ * mfg_amg_vcycle = PreconditionMG::vmult on vectors of the ACTIVE mesh; mfg_amg_solve_cg = SolverCG on the active operator
+ * (hanging nodes resolved in its gather / scatter) preconditioned by it. */
+typedef struct mfg_amg mfg_amg;
+int mfg_amg_create(mfg_ctx *ctx, mfg_amesh *am, int min_level, mfg_dtype dt, int smoother_degree, double smoothing_range, int eig_cg_n_iterations,
+                   mfg_amg **out);
+int mfg_amg_destroy(mfg_amg *mg);
+int mfg_amg_vcycle(mfg_amg *mg, mfg_vec *dst, const mfg_vec *src);
+int mfg_amg_active_operator(mfg_amg *mg, mfg_laplace **op);             /* borrowed: the operator on the active mesh */
+int mfg_amg_level_operator(mfg_amg *mg, int level, mfg_laplace **op);   /* borrowed */
+/* interface operators of a level (laplace_operator_gpu.h:306-352) on level vectors */
+int mfg_amg_vmult_interface_down(mfg_amg *mg, int level, mfg_vec *dst, const mfg_vec *src);
+int mfg_amg_vmult_interface_up(mfg_amg *mg, int level, mfg_vec *dst, const mfg_vec *src);
+/* level transfer and copies, for tests and drivers: prolongate to `level` from level-1, restrict_and_add from `level` into level-1 */
+int mfg_amg_prolongate(mfg_amg *mg, int level, mfg_vec *dst_fine, const mfg_vec *src_coarse);
+int mfg_amg_restrict_and_add(mfg_amg *mg, int level, mfg_vec *dst_coarse, const mfg_vec *src_fine);
+int mfg_amg_copy_to_level(mfg_amg *mg, int level, mfg_vec *dst_level, const mfg_vec *src_active);     /* one level of copy_to_mg (dst zeroed first) */
+int mfg_amg_copy_from_level(mfg_amg *mg, int level, mfg_vec *dst_active, const mfg_vec *src_level);   /* one level of copy_from_mg (dst not zeroed) */
+int mfg_amg_info(const mfg_amg *mg, int level, double *lambda_max, long *coarse_iterations, size_t *n_dofs, size_t *n_edge);
+int mfg_amg_solve_cg(mfg_amg *mg, mfg_vec *x, const mfg_vec *b, double abs_tol, int max_iter, int *iters, double *last_residual, double *history);
 
 #ifdef __cplusplus
 }

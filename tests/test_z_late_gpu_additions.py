@@ -108,3 +108,93 @@ def test_bmop_driver_on_the_pseudo_adaptive_mesh():
     rows = [l.split() for l in out.stdout.strip().splitlines()]
     assert [int(r[2]) for r in rows] == [729, 57142]
     assert all(float(r[3]) > 0 for r in rows)
+
+
+def _adaptive_mg_case(ctx, dim, p, base, steps, min_level):
+    import dealii_cuda_b200 as mf
+    from dealii_cuda_b200.multigrid import AdaptiveMultigrid
+    from oracle.adaptive import AdaptiveMesh
+    from oracle.adaptive_mg import AdaptiveMultigridOracle
+    am = mf.AdaptiveMesh(dim, p, limit_level_difference_at_vertices=True).refine_global(base)
+    for R, r, c in steps:
+        am.mark_cells_in_annulus(R, r, c)
+        am.execute_coarsening_and_refinement()
+    am.distribute_dofs()
+    mg = AdaptiveMultigrid(ctx, am, min_level=min_level)
+    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())
+    lc = {l: [tuple(int(v) for v in row) for row in am.level_cells(l)] for l in range(am.n_levels)}
+    return am, mg, o, AdaptiveMultigridOracle(dim, p, lc, o, min_level=min_level)
+
+
+AMG_CASES = [(2, 2, 2, [(0.6, 0.0, None), (0.4, 0.1, (-0.1, -0.2))], 1), (2, 3, 1, [(0.9, 0.0, None), (0.5, 0.0, None)], 1),
+             (3, 2, 1, [(0.9, 0.0, None), (0.5, 0.0, (-0.1, -0.2, -0.3))], 1)]
+
+
+@pytest.mark.parametrize("dim,p,base,steps,min_level", AMG_CASES)
+def test_adaptive_multigrid_building_blocks(ctx, dim, p, base, steps, min_level):
+    """mfg_amg_* (csrc/multigrid.cu) piece by piece against oracle/adaptive_mg.py: level operators with boundary + refinement-edge
+    constraints (laplace_operator_gpu.h:153-186), vmult_interface_down / up (:306-352), prolongate / restrict_and_add on the
+    adaptive blocks (mg_transfer_matrix_free_gpu.cu:592-654), copy_to_mg / copy_from_mg (.cu:688-757), Chebyshev eigenvalues"""
+    import dealii_cuda_b200 as mf
+    am, mg, o, omg = _adaptive_mg_case(ctx, dim, p, base, steps, min_level)
+    assert any(mg.n_edge[l] for l in mg.levels)
+    V = lambda a: mf.GpuVector.from_numpy(ctx, np.ascontiguousarray(a, dtype=np.float64))
+    for l in mg.levels:
+        lm = omg.levels[l]
+        assert mg.n_dofs[l] == lm.n_dofs and mg.n_edge[l] == lm.edge.size
+        u = sm64(20 + l, lm.n_dofs)
+        src, dst = V(u), mf.GpuVector(ctx, lm.n_dofs)
+        mg.ops[l].vmult(dst, src)
+        assert rel_err(dst.toVector(), lm.vmult(u)) <= 1e-12
+        mg.vmult_interface_down(l, dst, src)
+        want = lm.vmult_interface_down(u)
+        assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * max(np.linalg.norm(want), 1e-300) and (np.linalg.norm(want) > 0) == (lm.edge.size > 0)
+        mg.vmult_interface_up(l, dst, src)
+        want = lm.vmult_interface_up(u)
+        assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * max(np.linalg.norm(want), 1e-300)
+        # copies between the active mesh and the level
+        ua = sm64(40 + l, o.n_dofs)
+        vl = mf.GpuVector(ctx, lm.n_dofs); vl.fill(3.0)
+        mg.copy_to_level(l, vl, V(ua))
+        assert np.array_equal(vl.toVector(), omg.copy_to_mg(ua)[l])
+        va = mf.GpuVector(ctx, o.n_dofs); va.fill(0.0)
+        mg.copy_from_level(l, va, src)
+        g, lv = omg.copy[l]
+        want = np.zeros(o.n_dofs); want[g] = u[lv]
+        assert np.array_equal(va.toVector(), want)
+        if l > mg.levels[0]:
+            lc = omg.levels[l - 1]
+            uc = sm64(60 + l, lc.n_dofs)
+            fine = mf.GpuVector(ctx, lm.n_dofs); fine.fill(7.0)
+            mg.prolongate(l, fine, V(uc))
+            assert rel_err(fine.toVector(), omg.P[l] @ uc) <= 1e-13
+            d0 = sm64(80 + l, lc.n_dofs)
+            coarse = V(d0)
+            mg.restrict_and_add(l, coarse, src)
+            assert rel_err(coarse.toVector(), d0 + omg.P[l].T @ u) <= 1e-13
+            assert abs(mg.lambda_max[l] - omg.smoothers[l][0]) <= 1e-8 * omg.smoothers[l][0]
+
+
+@pytest.mark.parametrize("dim,p,base,steps,min_level", AMG_CASES)
+def test_adaptive_multigrid_vcycle_and_cg(ctx, dim, p, base, steps, min_level):
+    """PreconditionMG::vmult (Multigrid::level_v_step with the edge matrices, poisson_mg.cu:365-375) and the V-cycle-preconditioned
+    SolverCG on the active operator (:504-518) against the numpy oracle: the same V-cycle output, the same iteration count"""
+    import dealii_cuda_b200 as mf
+    from oracle.adaptive_mg import cg_preconditioned
+    am, mg, o, omg = _adaptive_mg_case(ctx, dim, p, base, steps, min_level)
+    r = sm64(7, o.n_dofs); r[o.constrained] = 0.0
+    src, dst = mf.GpuVector.from_numpy(ctx, r), mf.GpuVector(ctx, o.n_dofs)
+    mg.vmult(dst, src)
+    want = omg.vmult(r)
+    assert np.linalg.norm(dst.toVector() - want) <= 1e-7 * np.linalg.norm(want)      # (coarse solve: CG to 1e-10 vs a direct solve)
+    ue = sm64(5, o.n_dofs); ue[o.constrained] = 0.0
+    b = o.vmult(ue)
+    tol = 1e-10 * np.linalg.norm(b)
+    _, it_ref, hist_ref = cg_preconditioned(o.vmult, omg.vmult, b, tol)
+    vb, vx = mf.GpuVector.from_numpy(ctx, b), mf.GpuVector(ctx, o.n_dofs)
+    it, res, hist = mg.solve_cg(vx, vb, tol, 100, history=True)
+    assert abs(it - it_ref) <= 1 and it <= 12, (it, it_ref)
+    k = min(it, it_ref)
+    assert np.allclose(hist[:k // 2 + 1], hist_ref[:k // 2 + 1], rtol=1e-5)
+    assert np.linalg.norm(vx.toVector() - ue) <= 1e-8 * np.linalg.norm(ue)
+    assert mg.coarse_iterations > 0
