@@ -63,13 +63,43 @@ template <int dim, int fe_degree> void mg_transfer_smoke()
   std::printf("mg transfer adjointness: <Pu,v> = %.12g, <u,Rv> = %.12g\n", a, b);
 }
 
+#ifdef ADAPTIVE_GRID
+// poisson_mg.cu on the pseudo-adaptive grid: SolverCG preconditioned by the multigrid V-cycle with local smoothing
+// (Triangulation::limit_level_difference_at_vertices like poisson_mg.cu:132); right-hand side b = A u for u = 1 on the free DoFs
+template <int dim, int fe_degree> void adaptive_mg_solve(int n_ref)
+{
+  AdaptiveMesh<dim> mesh(fe_degree, AdaptiveMesh<dim>::limit_level_difference_at_vertices);
+  mesh.pseudo_adaptive_refinement(n_ref);
+  mesh.distribute_dofs();
+  AdaptiveMultigrid<dim, number> mg(mesh);
+  GpuVector<number> u(mg.m()), b(mg.m()), x(mg.m()), zero(mg.m());
+  u = number(1);
+  mg.vmult_active(b, u);            // constrained rows: b = u
+  mg.vmult_active(zero, x);         // (x = 0)
+  // keep only the free part of b: A maps constrained entries to themselves, the solve then returns u there as well
+  const double bnorm = (double)b.l2_norm();
+  check(mfg_ctx_synchronize(default_context()));
+  const auto t0 = std::chrono::steady_clock::now();
+  const int its = mg.solve_cg(x, b, 1e-10 * bnorm, 100);
+  check(mfg_ctx_synchronize(default_context()));
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  x -= u;
+  std::printf("adaptive mg: %d\t%d\t%u cells\t%u dofs\t%u levels\t%d iterations\t%g s\terror %.3e\n", dim, fe_degree, mesh.n_active_cells(), mesh.n_dofs(),
+              mesh.n_levels(), its, sec, (double)x.l2_norm() / (double)u.l2_norm());
+}
+#endif
+
 int main(int argc, char **argv)
 {
   try
     {
       const int max_refinement = argc > 1 ? std::atoi(argv[1]) : 1;
       const int min_refinement = argc > 2 ? std::atoi(argv[2]) : 0;
+#ifdef ADAPTIVE_GRID
+      if (argc > 3 && std::string(argv[3]) == "mg") { adaptive_mg_solve<DIMENSION, DEGREE_FE>(max_refinement); return 0; }
+#else
       if (argc > 3 && std::string(argv[3]) == "mg") { mg_transfer_smoke<DIMENSION, DEGREE_FE>(); return 0; }
+#endif
       for (int r = min_refinement; r <= max_refinement; ++r) run<DIMENSION, DEGREE_FE>(r);
     }
   catch (std::exception &exc)

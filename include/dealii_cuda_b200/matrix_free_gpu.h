@@ -243,4 +243,47 @@ private:
   unsigned int           min_level_ = 0;
 };
 
+// Multigrid + PreconditionMG + MGTransferMatrixFreeGpu + level LaplaceOperatorGpu objects of the reference's poisson_mg.cu /
+// bmop_mg.cu on an ADAPTIVELY refined mesh (local smoothing: level operators with MGConstrainedDoFs, edge matrices
+// vmult_interface_down / up, index-based copy_to_mg / copy_from_mg), owned by the library (mfg_amg_*).  The mesh must be built
+// with AdaptiveMesh<dim>::limit_level_difference_at_vertices like the reference's Triangulation (poisson_mg.cu:132).
+//   AdaptiveMesh<3> mesh(4, AdaptiveMesh<3>::limit_level_difference_at_vertices); ...refine...; mesh.distribute_dofs();
+//   AdaptiveMultigrid<3, double> mg(mesh);  mg.vmult(dst, src) /* PreconditionMG::vmult */;  mg.solve_cg(x, b, tol);
+template <int dim, typename Number> class AdaptiveMultigrid
+{
+public:
+  explicit AdaptiveMultigrid(const AdaptiveMesh<dim> &mesh, unsigned int min_level = 0, unsigned int smoother_degree = 5, double smoothing_range = 15.,
+                             unsigned int eig_cg_n_iterations = 15)
+  {
+    check(mfg_amg_create(default_context(), mesh.handle(), (int)min_level, dtype_of<Number>(), (int)smoother_degree, smoothing_range,
+                         (int)eig_cg_n_iterations, &mg_));
+  }
+  ~AdaptiveMultigrid() { if (mg_) mfg_amg_destroy(mg_); }
+  AdaptiveMultigrid(const AdaptiveMultigrid &) = delete;
+  unsigned int m() const { mfg_laplace *op = nullptr; check(mfg_amg_active_operator(mg_, &op)); return mfg_laplace_m(op); }
+  // the operator on the active mesh (hanging nodes resolved in gather / scatter)
+  void vmult_active(GpuVector<Number> &dst, const GpuVector<Number> &src) const
+  {
+    mfg_laplace *op = nullptr;
+    check(mfg_amg_active_operator(mg_, &op));
+    check(mfg_laplace_vmult(op, dst.handle(), src.handle()));
+  }
+  void vmult(GpuVector<Number> &dst, const GpuVector<Number> &src) const { check(mfg_amg_vcycle(mg_, dst.handle(), src.handle())); }  // PreconditionMG::vmult
+  void vmult_interface_down(unsigned int level, GpuVector<Number> &dst, const GpuVector<Number> &src) const { check(mfg_amg_vmult_interface_down(mg_, (int)level, dst.handle(), src.handle())); }
+  void vmult_interface_up(unsigned int level, GpuVector<Number> &dst, const GpuVector<Number> &src) const { check(mfg_amg_vmult_interface_up(mg_, (int)level, dst.handle(), src.handle())); }
+  void prolongate(unsigned int to_level, GpuVector<Number> &dst, const GpuVector<Number> &src) const { check(mfg_amg_prolongate(mg_, (int)to_level, dst.handle(), src.handle())); }
+  void restrict_and_add(unsigned int from_level, GpuVector<Number> &dst, const GpuVector<Number> &src) const { check(mfg_amg_restrict_and_add(mg_, (int)from_level, dst.handle(), src.handle())); }
+  // SolverCG + PreconditionMG (poisson_mg.cu:504-518); returns the number of iterations
+  int solve_cg(GpuVector<Number> &x, const GpuVector<Number> &b, double abs_tol, int max_iter = 1000) const
+  {
+    int its = 0;
+    check(mfg_amg_solve_cg(mg_, x.handle(), b.handle(), abs_tol, max_iter, &its, nullptr, nullptr));
+    return its;
+  }
+  mfg_amg *handle() const { return mg_; }
+
+private:
+  mfg_amg *mg_ = nullptr;
+};
+
 }  // namespace dealii_cuda_b200

@@ -198,3 +198,17 @@ def test_adaptive_multigrid_vcycle_and_cg(ctx, dim, p, base, steps, min_level):
     assert np.allclose(hist[:k // 2 + 1], hist_ref[:k // 2 + 1], rtol=1e-5)
     assert np.linalg.norm(vx.toVector() - ue) <= 1e-8 * np.linalg.norm(ue)
     assert mg.coarse_iterations > 0
+
+
+def test_adaptive_multigrid_through_the_cxx_facade():
+    """examples/bmop.cc -DADAPTIVE_GRID, mode `mg`: AdaptiveMesh<3>(limit_level_difference_at_vertices) + pseudo_adaptive_refinement +
+    AdaptiveMultigrid<3,double>::solve_cg through the header-only facade (poisson_mg.cu:430-552 on the adaptive grid)"""
+    import os
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "_build", "bmop_adaptive")
+    out = subprocess.run([exe, "4", "4", "mg"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out.stdout)
+    assert m, out.stdout
+    assert int(m.group(1)) <= 20 and float(m.group(2)) <= 1e-7, out.stdout
