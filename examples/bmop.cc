@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 #include "../include/dealii_cuda_b200/matrix_free_gpu.h"
 
 using namespace dealii_cuda_b200;
@@ -72,11 +73,12 @@ template <int dim, int fe_degree> void adaptive_mg_solve(int n_ref)
   mesh.pseudo_adaptive_refinement(n_ref);
   mesh.distribute_dofs();
   AdaptiveMultigrid<dim, number> mg(mesh);
-  GpuVector<number> u(mg.m()), b(mg.m()), x(mg.m()), zero(mg.m());
-  u = number(1);
-  mg.vmult_active(b, u);            // constrained rows: b = u
-  mg.vmult_active(zero, x);         // (x = 0)
-  // keep only the free part of b: A maps constrained entries to themselves, the solve then returns u there as well
+  // u = 1 on the free DoFs, 0 on the constrained ones (hanging + boundary): b = A u is then zero on the constrained rows, as the
+  // reference's right-hand sides are after ConstraintMatrix::condense (the V-cycle returns 0 on hanging DoFs)
+  std::vector<number> uh(mg.m(), number(1));
+  for (unsigned int c : mesh.constrained_dofs()) uh[c] = number(0);
+  GpuVector<number> u(uh), b(mg.m()), x(mg.m());
+  mg.vmult_active(b, u);
   const double bnorm = (double)b.l2_norm();
   check(mfg_ctx_synchronize(default_context()));
   const auto t0 = std::chrono::steady_clock::now();

@@ -66,6 +66,13 @@ public:
   unsigned int n_levels() const { return mfg_amesh_n_levels(m_); }
   unsigned int n_dofs() const { return mfg_amesh_n_dofs(m_); }
   unsigned int n_constraints() const { return mfg_amesh_n_constrained(m_); }
+  // hanging + Dirichlet boundary DoFs, ascending (the ConstraintHandlerGpu list, constraint_handler_gpu.cu:77-83)
+  std::vector<unsigned int> constrained_dofs() const
+  {
+    std::vector<unsigned int> c(mfg_amesh_n_constrained(m_));
+    check(mfg_amesh_get_arrays(m_, nullptr, nullptr, nullptr, c.data(), nullptr, nullptr, nullptr, nullptr));
+    return c;
+  }
   mfg_amesh *handle() const { return m_; }
 
 private:
