@@ -174,6 +174,37 @@ def adaptive_main(args, ctx, metric):
         cg_s = time.perf_counter() - t0
         cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "last_residual": res, "n_dofs": n,
               "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|"}
+    # the same system solved by CG preconditioned with the multigrid V-cycle (local smoothing on the adaptive hierarchy,
+    # poisson_mg.cu:430-552); needs the vertex-balanced mesh of the reference's MG drivers, so it is built separately
+    mg_solve = None
+    if not args.no_cg:
+        try:
+            from dealii_cuda_b200.multigrid import AdaptiveMultigrid
+            t0 = time.perf_counter()
+            am2 = mf.AdaptiveMesh(args.dim, args.degree, limit_level_difference_at_vertices=True).pseudo_adaptive_refinement(args.refine).distribute_dofs()
+            amg = AdaptiveMultigrid(ctx, am2, 0, dtype)
+            ctx.synchronize()
+            mg_setup_s = time.perf_counter() - t0
+            n2 = am2.n_dofs
+            con = torch.from_numpy(am2.arrays()["constrained"].astype(np.int64)).cuda()
+            tu = torch.rand((n2,), dtype=tdtype, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+            tu[con] = 0                                   # right-hand sides are zero on hanging / boundary rows (ConstraintMatrix::condense)
+            ue2 = mf.GpuVector.wrap(ctx, tu)
+            b2, x2 = mf.GpuVector(ctx, n2, dtype), mf.GpuVector(ctx, n2, dtype)
+            amg.op.vmult(b2, ue2)
+            amg.solve_cg(x2, b2, 0.0, 1)                  # warm-up
+            x2.fill(0.0)
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            its2, res2 = amg.solve_cg(x2, b2, (1e-10 if args.dtype == "f64" else 1e-5) * b2.l2_norm(), 200)
+            ctx.synchronize()
+            mg_s = time.perf_counter() - t0
+            x2.add(-1.0, ue2)
+            mg_solve = {"seconds": mg_s, "iterations": its2, "rel_error": x2.l2_norm() / ue2.l2_norm(), "n_dofs": n2, "n_cells": am2.n_cells,
+                        "levels": am2.n_levels, "setup_seconds": mg_setup_s, "tolerance": "1e-10*|b|" if args.dtype == "f64" else "1e-5*|b|",
+                        "preconditioner": "V-cycle, local smoothing, Chebyshev(5), edge matrices; mesh with limit_level_difference_at_vertices"}
+        except Exception as e:  # the apply / CG figures above stand on their own
+            mg_solve = {"error": "%s: %s" % (type(e).__name__, e)}
     peak, peak_src = measured_peaks()
     # algorithmic bytes: two vectors + per cell DoF the index (4 B) and the merged weight (s B); the mask is 4 B per cell
     alg_bytes = 2.0 * s * n + float(am.n_cells) * (am.dofs_per_cell * (4 + s) + 4)
@@ -187,7 +218,7 @@ def adaptive_main(args, ctx, metric):
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "whole vmult (fast kernel on plain cells + "
                          "column kernel with fused hanging-node interpolation)", "peak_source": peak_src},
-            "cpu_baseline": None, "cg_solve": cg, "mesh_setup_host_seconds": setup_host_s}
+            "cpu_baseline": None, "cg_solve": cg, "mg_solve": mg_solve, "mesh_setup_host_seconds": setup_host_s}
     print(json.dumps(line))
     return 0
 
