@@ -301,6 +301,64 @@ def graph_coloring(loc2glob, n_indices):
     return col, nc.value
 
 
+def assemble_laplace_csr(dim, degree, loc2glob, n_dofs, inv_jac, coefficient, constrained):
+    """host assembly of the operator as CSR (bmop_spm.cu:150-201 restated in the library, mfg_csr_assemble_laplace):
+    returns (row_ptr, col, val) numpy arrays"""
+    l2g = np.ascontiguousarray(loc2glob, dtype=np.uint32)
+    ij = np.ascontiguousarray(inv_jac, dtype=np.float64)
+    cf = np.ascontiguousarray(coefficient, dtype=np.float64)
+    con = np.ascontiguousarray(constrained, dtype=np.uint32)
+    h = C.c_void_p()
+    check(lib.mfg_csr_assemble_laplace(int(dim), int(degree), l2g.shape[0], int(n_dofs), _u32p(l2g), _dp(ij), _dp(cf), _u32p(con), con.size, C.byref(h)))
+    try:
+        n, nnz = C.c_uint32(), C.c_size_t()
+        check(lib.mfg_csr_sizes(h, C.byref(n), C.byref(nnz)))
+        rp, col, val = np.zeros(n.value + 1, np.uint32), np.zeros(nnz.value, np.uint32), np.zeros(nnz.value)
+        check(lib.mfg_csr_get(h, _u32p(rp), _u32p(col), _dp(val)))
+    finally:
+        lib.mfg_csr_destroy(h)
+    return rp, col, val
+
+
+class SparseMatrixGpu:
+    """CUDAWrappers::SparseMatrix<Number> (matrix_free_gpu/cuda_sparse_matrix.h): the assembled competitor of the matrix-free
+    operator (bmop_spm.cu), here for the Laplace operator of a uniform mesh: reinit(mesh), vmult, m, n_nonzero_elements"""
+
+    def __init__(self, ctx, dtype=np.float64):
+        self.ctx, self.code, self.h = ctx, _dtype_code(dtype), None
+
+    def reinit(self, mesh):
+        self.clear()
+        h = C.c_void_p()
+        check(lib.mfg_spm_create_from_mesh(self.ctx.h, mesh.h, self.code, C.byref(h)))
+        self.h = h
+
+    def clear(self):
+        if self.h:
+            lib.mfg_spm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.clear()
+        except Exception:
+            pass
+
+    def m(self):
+        return lib.mfg_spm_m(self.h)
+
+    n = m
+
+    def n_nonzero_elements(self):
+        return lib.mfg_spm_n_nonzero_elements(self.h)
+
+    def memory_consumption(self):
+        return lib.mfg_spm_memory_consumption(self.h)
+
+    def vmult(self, dst, src):
+        check(lib.mfg_spm_vmult(self.h, dst.h, src.h))
+
+
 def hanging_node_weights(degree):
     """W[k][i] = phi_i(xi_k/2) (setup_constraint_weights, hanging_nodes.cuh:580-598)."""
     n = degree + 1

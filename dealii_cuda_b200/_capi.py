@@ -186,6 +186,17 @@ def _load():
         "mfg_partition_plan_destroy": (C.c_int, [vp]),
         "mfg_partition_plan_sizes": (C.c_int, [vp, C.POINTER(sz)]),
         "mfg_partition_plan_get": (C.c_int, [vp, C.POINTER(C.c_int), u32p, u32p, u32p, u32p, u32p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]),
+        "mfg_csr_assemble_laplace": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, u32p, dp, dp, u32p, sz, pp]),
+        "mfg_csr_destroy": (C.c_int, [vp]),
+        "mfg_csr_sizes": (C.c_int, [vp, u32p, C.POINTER(sz)]),
+        "mfg_csr_get": (C.c_int, [vp, u32p, u32p, dp]),
+        "mfg_spm_create": (C.c_int, [vp, C.c_int, vp, pp]),
+        "mfg_spm_create_from_mesh": (C.c_int, [vp, vp, C.c_int, pp]),
+        "mfg_spm_destroy": (C.c_int, [vp]),
+        "mfg_spm_m": (C.c_uint32, [vp]),
+        "mfg_spm_n_nonzero_elements": (sz, [vp]),
+        "mfg_spm_memory_consumption": (sz, [vp]),
+        "mfg_spm_vmult": (C.c_int, [vp, vp, vp]),
         "mfg_amesh_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "mfg_mgt_build_from_blocks": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_uint32, u32p, u32p, dp, C.c_uint32, C.c_uint32, pp]),
         "mfg_amg_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, pp]),

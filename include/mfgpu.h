@@ -347,6 +347,26 @@ int mfg_mgt_restrict_and_add(mfg_mgt *t, mfg_vec *dst_coarse, const mfg_vec *src
 int mfg_mgt_build_from_blocks(mfg_ctx *ctx, mfg_dtype dt, int dim, int degree, uint32_t n_blocks, const uint32_t *coarse_idx_host, const uint32_t *fine_idx_host,
                               const double *weights_host, uint32_t n_coarse_dofs, uint32_t n_fine_dofs, mfg_mgt **out);
 
+/* ---- assembled sparse matrix: the competitor row of the reference (CUDAWrappers::SparseMatrix, matrix_free_gpu/cuda_sparse_matrix.{h,cu};
+ * bmop_spm.cu, poisson_spm.cu, test_spm.cu) ------------------------------------------------------------------------------
+ * mfg_csr_assemble_laplace: host assembly (bmop_spm.cu:150-201) of the same operator the matrix-free path applies, from the same
+ * arrays (uniform geometry, no hanging nodes): constrained rows / columns eliminated, diagonal 1.  mfg_spm_*: the device matrix
+ * (reinit = upload, cuda_sparse_matrix.cu:60-120) and vmult (:414-429; here a hand-written CSR kernel, one warp per row). */
+typedef struct mfg_csr mfg_csr;
+typedef struct mfg_spm mfg_spm;
+int mfg_csr_assemble_laplace(int dim, int degree, uint32_t n_cells, uint32_t n_dofs, const uint32_t *loc2glob_host, const double *inv_jac_host,
+                             const double *coefficient_host, const uint32_t *constrained_host, size_t n_constrained, mfg_csr **out);
+int mfg_csr_destroy(mfg_csr *A);
+int mfg_csr_sizes(const mfg_csr *A, uint32_t *n_rows, size_t *nnz);
+int mfg_csr_get(const mfg_csr *A, uint32_t *row_ptr, uint32_t *col, double *val);
+int mfg_spm_create(mfg_ctx *ctx, mfg_dtype dt, const mfg_csr *A, mfg_spm **out);
+int mfg_spm_create_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_spm **out);
+int mfg_spm_destroy(mfg_spm *S);
+uint32_t mfg_spm_m(const mfg_spm *S);
+size_t mfg_spm_n_nonzero_elements(const mfg_spm *S);
+size_t mfg_spm_memory_consumption(const mfg_spm *S);
+int mfg_spm_vmult(mfg_spm *S, mfg_vec *dst, const mfg_vec *src);
+
 /* ---- solver ----------------------------------------------------------------------------------------------
  * Conjugate gradients with the control flow of deal.II's SolverCG as instantiated on GpuVector by the reference
  * (poisson.cu:233-260): stops when |r| <= abs_tol (the reference uses 1e-12*|b|) or after max_iter iterations.

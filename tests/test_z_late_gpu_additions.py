@@ -212,3 +212,21 @@ def test_adaptive_multigrid_through_the_cxx_facade():
     m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out.stdout)
     assert m, out.stdout
     assert int(m.group(1)) <= 20 and float(m.group(2)) <= 1e-7, out.stdout
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
+def test_sparse_matrix_vmult(ctx, dim, p, r, dtype):
+    """SparseMatrix::vmult (cuda_sparse_matrix.cu:414-429) against the oracle and against the matrix-free operator"""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(dim, p, r)
+    mesh = mf.HyperCubeMesh(ctx, dim, p, r)
+    S = mf.SparseMatrixGpu(ctx, dtype)
+    S.reinit(mesh)
+    assert S.m() == o.n_dofs and S.n_nonzero_elements() > o.n_dofs
+    u = sm64(3, o.n_dofs); u[o.constrained] = 0.0
+    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, o.n_dofs, dtype)
+    S.vmult(dst, src)
+    want = o.vmult(u)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    assert np.linalg.norm(dst.toVector().astype(np.float64) - want) <= tol * np.linalg.norm(want)
