@@ -223,6 +223,56 @@ def adaptive_main(args, ctx, metric):
     return 0
 
 
+def spmv_main(args, ctx, metric):
+    """bmop_spm.cu: the assembled CSR matrix of the operator (CUDAWrappers::SparseMatrix::vmult) against the matrix-free apply on the
+    same mesh, bmop loop, DoFs/s.  Algorithmic bytes of a CSR product: (s + 4) per entry + 4 per row + 2 s per row."""
+    import torch
+    import dealii_cuda_b200 as mf
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    s = 8 if args.dtype == "f64" else 4
+    mesh = mf.HyperCubeMesh(ctx, args.dim, args.degree, args.refine)
+    t0 = time.perf_counter()
+    S = mf.SparseMatrixGpu(ctx, dtype)
+    S.reinit(mesh)
+    assembly_s = time.perf_counter() - t0
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(mesh)
+    n = mesh.n_dofs
+    va, vb = mf.GpuVector(ctx, n, dtype), mf.GpuVector(ctx, n, dtype)
+
+    def timed(apply):
+        va.fill(0.0); vb.fill(0.1)
+        for _ in range(max(args.warmup, 3)):
+            apply(va, vb)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            apply(va, vb)     # (same input every step: the loop is not renormalised; values do not influence the timing)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    ms_spm = timed(S.vmult)
+    ms_mf = timed(op.vmult)
+    peak, peak_src = measured_peaks()
+    nnz = S.n_nonzero_elements()
+    bytes_spm = nnz * (s + 4) + n * (4 + 2 * s)
+    line = {"metric": metric.replace("Laplace apply", "Laplace apply, assembled CSR matrix"), "value": n / (ms_spm * 1e-3), "unit": "DoFs/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_spm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "bmop_spm: %dD FE_Q(%d) refine_global(%d), %d DoFs, %d matrix entries (%.1f per row), CSR kernel with one warp per row"
+                                   % (args.dim, args.degree, args.refine, n, nnz, nnz / max(1, n)),
+                       "l2": "matrix %.0f MB" % (bytes_spm / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": bytes_spm / (ms_spm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_spm / (ms_spm * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "csr_vmult_warp_per_row", "peak_source": peak_src},
+            "matrix_free": {"value": n / (ms_mf * 1e-3), "unit": "DoFs/s", "ms_per_step": ms_mf, "speedup_over_assembled": ms_spm / ms_mf},
+            "assembly_host_seconds": assembly_s, "matrix_bytes": S.memory_consumption(), "gpu_launches": args.steps}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +296,9 @@ def main():
     ap.add_argument("--adaptive", action="store_true",
                     help="BASELINE configs[3] instead of the headline: the reference's pseudo_adaptive_refinement(R) mesh with hanging nodes "
                          "(bmop_common.h:49-105), apply + CG solve, N = 1")
+    ap.add_argument("--spmv", action="store_true",
+                    help="the reference's competitor row instead of the headline (bmop_spm.cu): the ASSEMBLED sparse matrix of the same operator "
+                         "applied with a CSR kernel, next to the matrix-free apply on the same mesh (use --refine <= 4 in 3D: the matrix of r=4 holds 1e8 entries)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -282,6 +335,8 @@ def main():
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
     if args.adaptive:
         return adaptive_main(args, ctx, metric)
+    if args.spmv:
+        return spmv_main(args, ctx, metric)
     mesh = mf.HyperCubeMesh(ctx, args.dim, args.degree, args.refine)
     op = mf.LaplaceOperatorGpu(ctx, dtype, use_coloring=args.coloring)
     op.reinit(mesh)
