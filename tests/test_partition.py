@@ -261,3 +261,30 @@ def test_library_partition_equals_numpy_statement(dim, world, strong):
             assert np.array_equal(getattr(a, name), getattr(b, name)), name
             assert getattr(a, name).dtype == getattr(b, name).dtype, name
         assert all(np.array_equal(a.lists[q], b.lists[q]) for q in a.neighbors)
+
+
+@pytest.mark.parametrize("world,dim,p,r,strong", [(8, 3, 2, 2, 0), (4, 3, 1, 2, 1), (2, 3, 3, 1, 0), (4, 2, 3, 3, 1), (1, 3, 2, 1, 0)])
+def test_cxx_facade_partition_plan(world, dim, p, r, strong):
+    """include/dealii_cuda_b200/distributed.h (BoxPartition, ExchangePlan) through the host-only example: the same plans as the Python
+    binding for the same lattice -> DoF map, and every global DoF owned exactly once"""
+    import re
+    import subprocess
+    from dealii_cuda_b200 import partition as lib
+    exe = os.path.join(ROOT, "examples", "_build", "partition_plan")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples"), "-s", "_build/partition_plan"])
+    out = subprocess.run([exe, str(world), str(dim), str(p), str(r), str(strong)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert len(out.stdout.strip().splitlines()) == world
+    total_owned = 0
+    for rank, line in enumerate(out.stdout.strip().splitlines()):
+        f = {k: int(v) for k, v in re.findall(r"(n_local|neighbors|n_send|shared|slots|owned|global) (\d+)", line)}
+        lg = lib.local_log2(world, dim, r, bool(strong))
+        M = [p * (1 << lg[d]) + 1 if d < dim else 1 for d in range(3)]
+        l2d = lambda pts: (pts[:, 0] + M[0] * (pts[:, 1] + M[1] * pts[:, 2])).astype(np.uint32)
+        plan = lib.build_exchange_plan(rank, world, dim, p, r, l2d, M[0] * M[1] * M[2], bool(strong))
+        assert f["n_local"] == M[0] * M[1] * M[2] and f["neighbors"] == len(plan.neighbors) and f["n_send"] == plan.n_send
+        assert f["shared"] == plan.shared_dofs.size and f["slots"] == plan.slots.size and f["owned"] == int(plan.owned_mask.sum())
+        assert f["global"] == lib.global_n_dofs(world, dim, p, r, bool(strong))
+        total_owned += f["owned"]
+    assert total_owned == lib.global_n_dofs(world, dim, p, r, bool(strong))
