@@ -321,7 +321,8 @@ struct mfg_amg
         vec_fill(l.x.v, 0.0);
         const double bn = std::sqrt(vec_dot(l.b.v, l.b.v));
         int its = 0;
-        MG_CHECK(mfg_solver_cg(l.op, l.x.v, l.b.v, 1e-10 * std::max(bn, 1e-300), 10000, 0, &its, nullptr, nullptr));
+        // (poisson_mg.cu:73-80: reduction 1e-10; single precision cannot resolve that, so 1e-5 there)
+        MG_CHECK(mfg_solver_cg(l.op, l.x.v, l.b.v, (dt == MFG_F64 ? 1e-10 : 1e-5) * std::max(bn, 1e-300), 10000, 0, &its, nullptr, nullptr));
         coarse_iterations += its;
         return;
       }
