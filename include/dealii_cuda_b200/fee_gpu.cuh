@@ -23,7 +23,8 @@
 // Thread layout: one thread per local DoF / quadrature point (the reference's "parallel in element" scheme), several
 // cells per CTA, values / gradients / two scratch planes of a cell in shared memory.  Every method is called by all
 // threads of the CTA (they contain barriers).  No constraint handling here, as in the reference's cell_loop
-// (ConstraintHandlerGpu is applied around it).
+// (ConstraintHandlerGpu is applied around it); on meshes with hanging nodes read_dof_values / distribute_local_to_global
+// interpolate on the cells that carry a constraint mask, like the reference's resolve_hanging_nodes_shmem (fee_gpu.cuh:333-351).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -54,6 +55,9 @@ template <int dim, typename Number> struct GpuData
   const Number   *shape_gradients;    // [i*n+q] phi_i'(x_q)
   uint32_t        n_cells;            // cells below this bound are valid in the current launch
   int             general, use_coloring;
+  // hanging nodes (-DMATRIX_FREE_HANGING_NODES): non-null only in the launch over the cells that carry a constraint mask
+  const uint32_t *constraint_mask;    // [n_cells] 9-bit masks of HangingNodes::setup_constraints (hanging_nodes.cuh:38-50)
+  const Number   *hanging_weights;    // [k*n+i] = phi_i(xi_k / 2) (setup_constraint_weights, hanging_nodes.cuh:580-598)
 };
 
 template <int dim, typename Number> struct SharedData
@@ -63,7 +67,7 @@ template <int dim, typename Number> struct SharedData
   Number *scratch[2];
 };
 
-template <typename Number, int n> struct ShapeTables { Number val[n * n], grad[n * n]; };
+template <typename Number, int n> struct ShapeTables { Number val[n * n], grad[n * n], hang[n * n]; };
 
 template <int dim, int fe_degree, typename Number> class FEEvaluationGpu
 {
@@ -91,10 +95,12 @@ public:
   {
     values[t] = src[d->loc2glob[(size_t)cell * n_local_dofs + t] & 0x7fffffffu];
     __syncthreads();
+    if (d->constraint_mask != nullptr) resolve_hanging_nodes(false);   // resolve_hanging_nodes_shmem (fee_gpu.cuh:333-335)
   }
   // dst[loc2glob[cell][i]] += values[i]: plain if the cells of a launch are conflict free (coloring), else atomic (:346-365)
   __device__ void distribute_local_to_global(Number *dst)
   {
+    if (d->constraint_mask != nullptr) resolve_hanging_nodes(true);    // the transposed interpolation (fee_gpu.cuh:349-351)
     if (!valid) return;
     const uint32_t g = d->loc2glob[(size_t)cell * n_local_dofs + t] & 0x7fffffffu;
     if (d->use_coloring) dst[g] += values[t];
@@ -225,6 +231,51 @@ public:
   }
 
 private:
+  // resolve_hanging_nodes_shmem (hanging_nodes.cuh:617-778) on the cell's nodal values, one thread per local DoF: a sweep along
+  // every direction replaces the values on constrained faces / edges by the interpolation of the coarse neighbour's values
+  // (which loc2glob put there), W[k][i] = phi_i(xi_k / 2) for a child on the lower side of the direction, the mirrored table for
+  // the upper one; transpose = the adjoint, applied before the scatter.  Called by all threads of the CTA (barriers).
+  __device__ void resolve_hanging_nodes(const bool transpose)
+  {
+    constexpr int      n = fe_degree + 1, p = fe_degree;
+    const unsigned int mask = d->constraint_mask[cell];
+    const Number      *W = d->hanging_weights;
+    int                idx[3] = {(int)(t % n), (int)((t / n) % n), dim == 3 ? (int)(t / (n * n)) : 0};
+    for (int dir = 0; dir < dim; ++dir)
+      {
+        bool flag;
+        if (dim == 2)
+          {
+            const int  a = 1 - dir;
+            const bool on = (mask & (1u << a)) ? idx[a] == 0 : idx[a] == p;
+            flag = (mask & (8u << a)) && on;
+          }
+        else
+          {
+            const int      f1 = (dir + 1) % 3, f2 = (dir + 2) % 3;
+            const bool     on1 = (mask & (1u << f1)) ? idx[f1] == 0 : idx[f1] == p, on2 = (mask & (1u << f2)) ? idx[f2] == 0 : idx[f2] == p;
+            const unsigned edge_bit = dir == 0 ? (1u << 7) : dir == 1 ? (1u << 8) : (1u << 6);   // edge along x: YZ, y: ZX, z: XY (:48-50)
+            flag = ((mask & (8u << f1)) && on1) || ((mask & (8u << f2)) && on2) || ((mask & edge_bit) && on1 && on2);
+          }
+        Number val = values[t];
+        if (flag)
+          {
+            const int  stride = dir == 0 ? 1 : dir == 1 ? n : n * n, k = idx[dir], base = (int)t - k * stride;
+            const bool lower = (mask & (1u << dir)) != 0;
+            Number     acc = 0;
+            for (int i = 0; i < n; ++i)
+              {
+                const Number w = lower ? (transpose ? W[i * n + k] : W[k * n + i]) : (transpose ? W[(p - i) * n + (p - k)] : W[(p - k) * n + (p - i)]);
+                acc += w * values[base + i * stride];
+              }
+            val = acc;
+          }
+        __syncthreads();
+        values[t] = val;
+        __syncthreads();
+      }
+  }
+
   // out(.., a, ..) = sum_b M[b*n+a] in(.., b, ..) along direction dir   (tr: M[a*n+b])
   __device__ Number contract(const Number *M, const Number *in, const int dir, const bool tr) const
   {
@@ -261,6 +312,7 @@ __global__ void apply_kernel_shmem(Number *dst, const Number *src, const LocOp l
   GpuData<dim, Number> gd = gpu_data;
   gd.shape_values = tab.val;
   gd.shape_gradients = tab.grad;
+  gd.hanging_weights = tab.hang;
   const unsigned int cell = cell_begin + blockIdx.x * (blockDim.x / npc) + threadIdx.x / npc;
   loc_op.cell_apply(dst, src, &gd, cell, &sh);
 }
@@ -282,6 +334,7 @@ __global__ void apply_kernel_shmem_dst(Number *dst, const LocOp loc_op, const Gp
   GpuData<dim, Number> gd = gpu_data;
   gd.shape_values = tab.val;
   gd.shape_gradients = tab.grad;
+  gd.hanging_weights = tab.hang;
   const unsigned int cell = cell_begin + blockIdx.x * (blockDim.x / npc) + threadIdx.x / npc;
   loc_op.cell_apply(dst, &gd, cell, &sh);
 }
@@ -305,6 +358,19 @@ inline void fee_check_cuda(cudaError_t e, const char *what)
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// the kernel's parameter block of 1-D tables: shape values / gradients of the MatrixFreeGpu object, hanging-node weights of its degree
+template <typename Number, int n> void fill_shape_tables(const mfg_gpu_data &g, ShapeTables<Number, n> &tab)
+{
+  double W[n * n];
+  fee_check(mfg_hanging_node_weights(n - 1, W), "mfg_hanging_node_weights");
+  for (int i = 0; i < n * n; ++i)
+    {
+      tab.val[i] = (Number)g.shape_values[i];
+      tab.grad[i] = (Number)g.shape_gradients[i];
+      tab.hang[i] = (Number)W[i];
+    }
+}
+
 // MatrixFreeGpu::cell_loop(dst, src, loc_op) (matrix_free_gpu.h:369-380) on the raw handle and device pointers: one launch
 // per color.  `Number` must be the operator's dtype.
 template <int dim, int fe_degree, typename Number, typename LocOp>
@@ -314,11 +380,7 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const Number *src_dev, const LocOp &
   fee_check(mfg_mf_get_gpu_data(mf, &g), "mfg_mf_get_gpu_data");
   if (g.dim != dim || g.degree != fe_degree) throw std::runtime_error("cell_loop: dim / fe_degree differ from the MatrixFreeGpu object");
   if ((g.dtype == MFG_F64) != (sizeof(Number) == 8)) throw std::runtime_error("cell_loop: Number differs from the MatrixFreeGpu dtype");
-  // read_dof_values / distribute_local_to_global of this path do not apply resolve_hanging_nodes_shmem (fee_gpu.cuh:333-335,
-  // 349-351): on a mesh with hanging-node cells the result would silently miss them, so refuse instead
-  if (g.constraint_mask != nullptr)
-    throw std::runtime_error("cell_loop: the MatrixFreeGpu object holds cells with hanging-node constraints, which the generic "
-                             "FEEvaluationGpu path does not interpolate; use LaplaceOperatorGpu or a mesh without hanging nodes");
+  if (g.constraint_mask != nullptr && g.use_coloring) throw std::runtime_error("cell_loop: hanging nodes need the atomic scatter");
   constexpr unsigned int n = fe_degree + 1, npc = dim == 2 ? n * n : n * n * n;
   static_assert(npc <= 1024, "one thread per local DoF");
   GpuData<dim, Number> gd;
@@ -329,8 +391,10 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const Number *src_dev, const LocOp &
   gd.shape_values = gd.shape_gradients = nullptr;
   gd.general = g.general;
   gd.use_coloring = g.use_coloring;
+  gd.constraint_mask = nullptr;
+  gd.hanging_weights = nullptr;
   ShapeTables<Number, n> tab;
-  for (unsigned int i = 0; i < n * n; ++i) { tab.val[i] = (Number)g.shape_values[i]; tab.grad[i] = (Number)g.shape_gradients[i]; }
+  fill_shape_tables<Number, n>(g, tab);
   const unsigned int cpb = npc >= 128 ? 1 : 128 / npc;
   const size_t       smem = (size_t)cpb * (3 + dim) * npc * sizeof(Number);
   auto kern = apply_kernel_shmem<LocOp, dim, fe_degree, Number>;
@@ -344,6 +408,14 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const Number *src_dev, const LocOp &
       kern<<<(c1 - c0 + cpb - 1) / cpb, cpb * npc, smem, st>>>(dst_dev, src_dev, loc_op, gd, tab, c0);
       fee_check_cuda(cudaGetLastError(), "cell_loop launch");
     }
+  // cells with hanging-node constraints (sorted behind the plain ones): read_dof_values / distribute_local_to_global interpolate
+  if (g.constraint_mask != nullptr && g.n_plain_cells < g.n_cells)
+    {
+      gd.constraint_mask = g.constraint_mask;
+      gd.n_cells = g.n_cells;
+      kern<<<(g.n_cells - g.n_plain_cells + cpb - 1) / cpb, cpb * npc, smem, st>>>(dst_dev, src_dev, loc_op, gd, tab, g.n_plain_cells);
+      fee_check_cuda(cudaGetLastError(), "cell_loop launch (hanging-node cells)");
+    }
 }
 
 // MatrixFreeGpu::cell_loop(dst, loc_op) (matrix_free_gpu.h:382-393): no source vector, loc_op.cell_apply(dst, gpu_data, cell, shdata)
@@ -354,7 +426,7 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const LocOp &loc_op)
   fee_check(mfg_mf_get_gpu_data(mf, &g), "mfg_mf_get_gpu_data");
   if (g.dim != dim || g.degree != fe_degree) throw std::runtime_error("cell_loop: dim / fe_degree differ from the MatrixFreeGpu object");
   if ((g.dtype == MFG_F64) != (sizeof(Number) == 8)) throw std::runtime_error("cell_loop: Number differs from the MatrixFreeGpu dtype");
-  if (g.constraint_mask != nullptr) throw std::runtime_error("cell_loop: hanging-node cells are not supported by the generic FEEvaluationGpu path");
+  if (g.constraint_mask != nullptr && g.use_coloring) throw std::runtime_error("cell_loop: hanging nodes need the atomic scatter");
   constexpr unsigned int n = fe_degree + 1, npc = dim == 2 ? n * n : n * n * n;
   GpuData<dim, Number> gd;
   gd.loc2glob = g.loc2glob;
@@ -364,8 +436,10 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const LocOp &loc_op)
   gd.shape_values = gd.shape_gradients = nullptr;
   gd.general = g.general;
   gd.use_coloring = g.use_coloring;
+  gd.constraint_mask = nullptr;
+  gd.hanging_weights = nullptr;
   ShapeTables<Number, n> tab;
-  for (unsigned int i = 0; i < n * n; ++i) { tab.val[i] = (Number)g.shape_values[i]; tab.grad[i] = (Number)g.shape_gradients[i]; }
+  fill_shape_tables<Number, n>(g, tab);
   const unsigned int cpb = npc >= 128 ? 1 : 128 / npc;
   const size_t       smem = (size_t)cpb * (3 + dim) * npc * sizeof(Number);
   auto kern = apply_kernel_shmem_dst<LocOp, dim, fe_degree, Number>;
@@ -378,6 +452,13 @@ void cell_loop(mfg_mf *mf, Number *dst_dev, const LocOp &loc_op)
       gd.n_cells = c1;
       kern<<<(c1 - c0 + cpb - 1) / cpb, cpb * npc, smem, st>>>(dst_dev, loc_op, gd, tab, c0);
       fee_check_cuda(cudaGetLastError(), "cell_loop launch");
+    }
+  if (g.constraint_mask != nullptr && g.n_plain_cells < g.n_cells)
+    {
+      gd.constraint_mask = g.constraint_mask;
+      gd.n_cells = g.n_cells;
+      kern<<<(g.n_cells - g.n_plain_cells + cpb - 1) / cpb, cpb * npc, smem, st>>>(dst_dev, loc_op, gd, tab, g.n_plain_cells);
+      fee_check_cuda(cudaGetLastError(), "cell_loop launch (hanging-node cells)");
     }
 }
 
@@ -401,6 +482,8 @@ void evaluate_on_cells(mfg_mf *mf, Number *vec_dev)
   gd.shape_values = gd.shape_gradients = nullptr;
   gd.general = g.general;
   gd.use_coloring = g.use_coloring;
+  gd.constraint_mask = nullptr;
+  gd.hanging_weights = nullptr;
   gd.n_cells = g.n_cells;
   if (g.n_cells == 0) return;
   cell_eval_kernel<dim, Number, Op><<<(g.n_cells + 127) / 128, 128, 0, static_cast<cudaStream_t>(g.cuda_stream)>>>(vec_dev, gd, nq);

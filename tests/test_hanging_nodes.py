@@ -196,3 +196,54 @@ def test_gpu_cg_solve_on_adaptive_mesh(ctx, dim, p, base, kind):
     got = vx.toVector()
     assert np.linalg.norm(m.vmult(got) - b) <= 2 * tol
     assert np.linalg.norm(got - ue) <= 1e-6 * np.linalg.norm(ue)
+
+
+def _generic_path_resolve(values, mask, p, dim, transpose):
+    """line-by-line transliteration of FEEvaluationGpu::resolve_hanging_nodes (include/dealii_cuda_b200/fee_gpu.cuh): one thread per
+    local DoF t, sweep per direction, stride / base index arithmetic and weight-table indexing as in the device code"""
+    n = p + 1
+    W = constraint_weights(p).ravel()                 # W[k*n+i]
+    vals = values.copy().ravel()                      # lexicographic, x fastest
+    for d in range(dim):
+        new = vals.copy()
+        for t in range(n ** dim):
+            idx = [t % n, (t // n) % n, (t // (n * n)) if dim == 3 else 0]
+            if dim == 2:
+                a = 1 - d
+                on = (idx[a] == 0) if (mask & (1 << a)) else (idx[a] == p)
+                flag = bool(mask & (8 << a)) and on
+            else:
+                f1, f2 = (d + 1) % 3, (d + 2) % 3
+                on1 = (idx[f1] == 0) if (mask & (1 << f1)) else (idx[f1] == p)
+                on2 = (idx[f2] == 0) if (mask & (1 << f2)) else (idx[f2] == p)
+                edge_bit = (1 << 7) if d == 0 else (1 << 8) if d == 1 else (1 << 6)
+                flag = (bool(mask & (8 << f1)) and on1) or (bool(mask & (8 << f2)) and on2) or (bool(mask & edge_bit) and on1 and on2)
+            if not flag:
+                continue
+            stride = 1 if d == 0 else n if d == 1 else n * n
+            k = idx[d]
+            base = t - k * stride
+            lower = (mask & (1 << d)) != 0
+            acc = 0.0
+            for i in range(n):
+                if lower:
+                    w = W[i * n + k] if transpose else W[k * n + i]
+                else:
+                    w = W[(p - i) * n + (p - k)] if transpose else W[(p - k) * n + (p - i)]
+                acc += w * vals[base + i * stride]
+            new[t] = acc
+        vals = new
+    return vals
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 3), (3, 1), (3, 2)])
+def test_generic_path_resolve_index_arithmetic(dim, p):
+    """the index arithmetic of the generic path's device function, transliterated, equals resolve_hanging_nodes for every mask"""
+    rng = np.random.default_rng(0)
+    n = p + 1
+    for mask in range(1 << (6 if dim == 2 else 9)):
+        if dim == 2 and (mask & 0b100100):
+            continue
+        v = rng.random((n,) * dim)
+        for tr in (False, True):
+            assert np.array_equal(resolve_hanging_nodes(v, mask, p, dim, transpose=tr).ravel(), _generic_path_resolve(v, mask, p, dim, tr))

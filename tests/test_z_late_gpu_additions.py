@@ -2,7 +2,7 @@
 logic is covered on the CPU, but they have not run on hardware yet.  The file sorts last so that, with `pytest -x`, nothing
 here can mask the hardware-verified suite in front of it.
   * generic FEEvaluationGpu path: MatrixFreeGpu::cell_loop(dst, loc_op) (matrix_free_gpu.h:382-393), evaluate_on_cells<Op>
-    (:415-435), refusal of meshes with hanging nodes (fee_gpu.cuh:333-335 is not applied on that path);
+    (:415-435), hanging-node interpolation in read_dof_values / distribute_local_to_global (fee_gpu.cuh:333-351);
   * the restated deal.II graph coloring (coloring.cc:8-33) driving the atomics-free scatter."""
 import numpy as np
 import pytest
@@ -34,17 +34,44 @@ def test_dst_only_cell_loop_and_evaluate_on_cells(ctx, gen, dim, p, r):
     assert rel_err(coef.toVector(), np.asarray(o.coefficient).ravel()) <= 1e-14
 
 
-def test_generic_path_refuses_hanging_node_meshes(ctx, gen):
-    """the generic FEEvaluationGpu path does not interpolate hanging nodes: it must say so instead of skipping cells"""
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,p", [(2, 2), (2, 4), (3, 1), (3, 2), (3, 3)])
+def test_generic_path_interpolates_hanging_nodes(ctx, gen, dim, p, dtype):
+    """read_dof_values / distribute_local_to_global of the generic FEEvaluationGpu path apply resolve_hanging_nodes_shmem
+    (fee_gpu.cuh:333-335, 349-351) on the cells that carry a constraint mask: a user-written MASS operator on an adaptive mesh
+    against numpy (gather through the rewritten map, interpolate, local mass matrix, transposed interpolation, scatter)"""
     import dealii_cuda_b200 as mf
-    from oracle.adaptive import AdaptiveMesh
-    am = AdaptiveMesh(2, 2, 2, [lambda c, h: np.linalg.norm(c) < 0.5])
-    assert am.mask.max() > 0
-    mfree = mf.MatrixFreeGpu(ctx, np.float64)
-    mfree.reinit(dict(dim=2, degree=2, n_dofs=am.n_dofs, loc2glob=am.l2g, inv_jac=am.inv_jac, constraint_mask=am.mask))
-    a, b = mf.GpuVector(ctx, am.n_dofs), mf.GpuVector(ctx, am.n_dofs)
-    with pytest.raises(AssertionError, match="hanging"):
-        gen(mfree, 0, 2, 2, np.float64, a, b)
+    from oracle.adaptive import AdaptiveMesh, resolve_hanging_nodes
+    am = mf.AdaptiveMesh(dim, p).refine_global(2 if dim == 2 else 1)
+    am.mark_cells_in_annulus(0.9, 0.0, None); am.execute_coarsening_and_refinement()
+    am.mark_cells_in_annulus(0.5, 0.0, (-0.1, -0.2, -0.3)); am.execute_coarsening_and_refinement()
+    am.distribute_dofs()
+    a = am.arrays()
+    assert a["constraint_mask"].max() > 0
+    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())     # (resolve_hanging_nodes needs no mesh; o gives h per cell)
+    n = p + 1
+    _, _, xq, wq = mf.shape_info(p)
+    N = np.asarray(mf.shape_info(p)[0])                                    # [i][q]
+    q = np.arange(n ** dim)
+    q_idx = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
+    Nq = np.ones((n ** dim, n ** dim))
+    for e in range(dim):
+        Nq *= N[q_idx[None, :, e], q_idx[:, None, e]]                      # [q][i]
+    wref = np.prod(wq[q_idx], axis=1)
+    u = sm64(31, am.n_dofs)
+    want = np.zeros(am.n_dofs)
+    for ci in range(am.n_cells):
+        row, mask = a["loc2glob"][ci].astype(np.int64), int(a["constraint_mask"][ci])
+        ul = resolve_hanging_nodes(u[row].reshape((n,) * dim), mask, p, dim, transpose=False).ravel()
+        v = Nq.T @ ((o.h[ci] ** dim * wref) * (Nq @ ul))
+        v = resolve_hanging_nodes(v.reshape((n,) * dim), mask, p, dim, transpose=True).ravel()
+        np.add.at(want, row, v)
+    mfree = mf.MatrixFreeGpu(ctx, dtype)
+    mfree.reinit(dict(dim=dim, degree=p, n_dofs=am.n_dofs, loc2glob=a["loc2glob"], inv_jac=a["inv_jac"], constraint_mask=a["constraint_mask"]))
+    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, am.n_dofs, dtype)
+    dst.fill(0.0)
+    gen(mfree, 0, dim, p, dtype, dst, src)
+    assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
 
 
 @pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
