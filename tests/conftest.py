@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# tests/late_gpu/ holds GPU tests that have not run on hardware yet; tests/test_z_late_gpu_additions.py runs them in child processes
+collect_ignore = [] if os.environ.get("MFG_RUN_LATE_GPU") else ["late_gpu"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -1,259 +1,37 @@
-"""GPU tests added late in round 2, AFTER the round's GPU budget was spent: they exercise code that compiles and whose host
-logic is covered on the CPU, but they have not run on hardware yet.  The file sorts last so that, with `pytest -x`, nothing
-here can mask the hardware-verified suite in front of it.
-  * generic FEEvaluationGpu path: MatrixFreeGpu::cell_loop(dst, loc_op) (matrix_free_gpu.h:382-393), evaluate_on_cells<Op>
-    (:415-435), hanging-node interpolation in read_dof_values / distribute_local_to_global (fee_gpu.cuh:333-351);
-  * the restated deal.II graph coloring (coloring.cc:8-33) driving the atomics-free scatter."""
-import numpy as np
+"""Runs the GPU tests of tests/late_gpu/ -- written after the round's GPU budget was spent, never run on hardware -- one test
+function per CHILD pytest process.  A failure, a hang (timeout) or a crash of the process in there is one failed test here and
+cannot mask or take down the hardware-verified suite in front of it (this file sorts last)."""
+import ast
+import os
+import subprocess
+import sys
+
 import pytest
 
-pytestmark = pytest.mark.gpu
-
-from oracle.oracle import OracleMesh, sm64  # noqa: E402  (checker)
-from test_gpu_generic_path import gen, rel_err  # noqa: E402,F401  (fixture: the compiled example functors)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LATE = os.path.join(ROOT, "tests", "late_gpu", "test_late_gpu_additions.py")
 
 
-@pytest.mark.parametrize("dim,p,r", [(2, 2, 2), (3, 2, 1), (3, 4, 1)])
-def test_dst_only_cell_loop_and_evaluate_on_cells(ctx, gen, dim, p, r):
-    """MatrixFreeGpu::cell_loop(dst, loc_op) (matrix_free_gpu.h:382-393) and evaluate_on_cells<LocalCoeffOp> (:415-435,
-    laplace_operator_gpu.h:191-211): the dst-only loop gives the same right-hand side as the loop with a source vector, the
-    evaluated coefficient is 1 / (0.05 + 2 |x_q|^2) at the oracle's quadrature points"""
-    import dealii_cuda_b200 as mf
-    o = OracleMesh(dim, p, r)
-    m = mf.HyperCubeMesh(ctx, dim, p, r)
-    mfree = mf.MatrixFreeGpu(ctx, np.float64)
-    mfree.reinit(m)
-    dummy = mf.GpuVector(ctx, o.n_dofs)
-    a, b = mf.GpuVector(ctx, o.n_dofs), mf.GpuVector(ctx, o.n_dofs)
-    a.fill(0.0); b.fill(0.0)
-    gen(mfree, 2, dim, p, np.float64, a, dummy)
-    gen(mfree, 3, dim, p, np.float64, b, dummy)
-    assert rel_err(b.toVector(), a.toVector()) <= 1e-14
-    coef = mf.GpuVector(ctx, o.n_cells * (p + 1) ** dim)
-    gen(mfree, 4, dim, p, np.float64, coef, dummy)
-    assert rel_err(coef.toVector(), np.asarray(o.coefficient).ravel()) <= 1e-14
+def late_test_names():
+    tree = ast.parse(open(LATE).read())
+    return [n.name for n in tree.body if isinstance(n, ast.FunctionDef) and n.name.startswith("test_")]
 
 
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("dim,p", [(2, 2), (2, 4), (3, 1), (3, 2), (3, 3)])
-def test_generic_path_interpolates_hanging_nodes(ctx, gen, dim, p, dtype):
-    """read_dof_values / distribute_local_to_global of the generic FEEvaluationGpu path apply resolve_hanging_nodes_shmem
-    (fee_gpu.cuh:333-335, 349-351) on the cells that carry a constraint mask: a user-written MASS operator on an adaptive mesh
-    against numpy (gather through the rewritten map, interpolate, local mass matrix, transposed interpolation, scatter)"""
-    import dealii_cuda_b200 as mf
-    from oracle.adaptive import AdaptiveMesh, resolve_hanging_nodes
-    am = mf.AdaptiveMesh(dim, p).refine_global(2 if dim == 2 else 1)
-    am.mark_cells_in_annulus(0.9, 0.0, None); am.execute_coarsening_and_refinement()
-    am.mark_cells_in_annulus(0.5, 0.0, (-0.1, -0.2, -0.3)); am.execute_coarsening_and_refinement()
-    am.distribute_dofs()
-    a = am.arrays()
-    assert a["constraint_mask"].max() > 0
-    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())     # (resolve_hanging_nodes needs no mesh; o gives h per cell)
-    n = p + 1
-    _, _, xq, wq = mf.shape_info(p)
-    N = np.asarray(mf.shape_info(p)[0])                                    # [i][q]
-    q = np.arange(n ** dim)
-    q_idx = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
-    Nq = np.ones((n ** dim, n ** dim))
-    for e in range(dim):
-        Nq *= N[q_idx[None, :, e], q_idx[:, None, e]]                      # [q][i]
-    wref = np.prod(wq[q_idx], axis=1)
-    u = sm64(31, am.n_dofs)
-    want = np.zeros(am.n_dofs)
-    for ci in range(am.n_cells):
-        row, mask = a["loc2glob"][ci].astype(np.int64), int(a["constraint_mask"][ci])
-        ul = resolve_hanging_nodes(u[row].reshape((n,) * dim), mask, p, dim, transpose=False).ravel()
-        v = Nq.T @ ((o.h[ci] ** dim * wref) * (Nq @ ul))
-        v = resolve_hanging_nodes(v.reshape((n,) * dim), mask, p, dim, transpose=True).ravel()
-        np.add.at(want, row, v)
-    mfree = mf.MatrixFreeGpu(ctx, dtype)
-    mfree.reinit(dict(dim=dim, degree=p, n_dofs=am.n_dofs, loc2glob=a["loc2glob"], inv_jac=a["inv_jac"], constraint_mask=a["constraint_mask"]))
-    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, am.n_dofs, dtype)
-    dst.fill(0.0)
-    gen(mfree, 0, dim, p, dtype, dst, src)
-    assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
+def run_child(args, timeout):
+    env = dict(os.environ, MFG_RUN_LATE_GPU="1")
+    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider"] + args, cwd=ROOT, env=env, capture_output=True, text=True,
+                          timeout=timeout)
 
 
-@pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
-def test_operator_with_restated_dealii_coloring(ctx, dim, p, r):
-    """cells sorted by the restated deal.II colors, atomics-free scatter (use_coloring): same operator as the oracle"""
-    import dealii_cuda_b200 as mf
-    o = OracleMesh(dim, p, r)
-    l2g = np.asarray(o.loc2glob)
-    color, nc = mf.graph_coloring(l2g, o.n_dofs)
-    perm = np.argsort(color, kind="stable")
-    offsets = np.concatenate([[0], np.cumsum(np.bincount(color, minlength=nc))]).astype(np.uint32)
-    n = p + 1
-    h = 2.0 / round(o.n_cells ** (1.0 / dim))
-    data = mf.MatrixFreeGpu(ctx, np.float64)
-    data.reinit(dict(dim=dim, degree=p, n_dofs=o.n_dofs, loc2glob=l2g[perm], inv_jac=np.full(o.n_cells, 1.0 / h), color_offsets=offsets),
-                use_coloring=True)
-    assert data.num_colors == nc
-    ch = mf.ConstraintHandlerGpu(ctx, np.float64)
-    ch.reinit(np.asarray(o.constrained), o.n_dofs)
-    op = mf.LaplaceOperatorGpu(ctx, np.float64, use_coloring=True)
-    op.reinit(data, ch, coefficient=np.asarray(o.coefficient)[perm])
-    u = sm64(5, o.n_dofs)
-    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs)
-    op.vmult(dst, src)
-    want = o.vmult(u)
-    assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * np.linalg.norm(want)
+def test_late_gpu_tests_are_collectable():
+    """(CPU) the late file imports and collects: syntax, fixtures and parametrisations are in order"""
+    r = run_child([LATE, "--collect-only"], 600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert len(late_test_names()) >= 8 and "test_adaptive_multigrid_vcycle_and_cg" in r.stdout
 
 
-@pytest.mark.parametrize("dim,p", [(2, 3), (3, 2), (3, 4)])
-def test_operator_on_library_built_adaptive_mesh(ctx, dim, p):
-    """LaplaceOperatorGpu::reinit on an adaptive mesh built by the LIBRARY's host substrate (mfg_amesh_*, tests/test_adaptive_mesh.py
-    pins its arrays to the oracle on the CPU): vmult, the Jacobi diagonal and a CG solve against oracle/adaptive.py on the same cells"""
-    import dealii_cuda_b200 as mf
-    from oracle.adaptive import AdaptiveMesh
-    am = mf.AdaptiveMesh(dim, p).refine_global(2)
-    am.mark_cells_in_annulus(0.8, 0.0, None); am.execute_coarsening_and_refinement()
-    am.mark_cells_in_annulus(0.45, 0.1, (-0.1, -0.2, -0.3)); am.execute_coarsening_and_refinement()
-    am.distribute_dofs()
-    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())
-    assert o.mask.max() > 0 and am.n_dofs == o.n_dofs
-    op = mf.LaplaceOperatorGpu(ctx, np.float64)
-    op.reinit(am)
-    u = sm64(11, o.n_dofs)
-    src, dst = mf.GpuVector.from_numpy(ctx, u), mf.GpuVector(ctx, o.n_dofs)
-    op.vmult(dst, src)
-    want = o.vmult(u)
-    assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * np.linalg.norm(want)
-    op.compute_diagonal()
-    assert rel_err(op.get_diagonal_inverse().toVector(), o.inverse_diagonal()) <= 1e-12
-
-
-def test_bmop_driver_on_the_pseudo_adaptive_mesh():
-    """examples/bmop.cc built with -DADAPTIVE_GRID (bmop.cu:170-181): pseudo_adaptive_refinement + hanging-node operator through
-    the C++ facade; the DoF counts are those of the library's host substrate (checked on the CPU in tests/test_adaptive_mesh.py)"""
-    import os
-    import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "_build", "bmop_adaptive")
-    assert os.path.exists(exe), "examples/_build/bmop_adaptive is missing: run __graft_entry__.build()"
-    out = subprocess.run([exe, "4", "3"], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    rows = [l.split() for l in out.stdout.strip().splitlines()]
-    assert [int(r[2]) for r in rows] == [729, 57142]
-    assert all(float(r[3]) > 0 for r in rows)
-
-
-def _adaptive_mg_case(ctx, dim, p, base, steps, min_level):
-    import dealii_cuda_b200 as mf
-    from dealii_cuda_b200.multigrid import AdaptiveMultigrid
-    from oracle.adaptive import AdaptiveMesh
-    from oracle.adaptive_mg import AdaptiveMultigridOracle
-    am = mf.AdaptiveMesh(dim, p, limit_level_difference_at_vertices=True).refine_global(base)
-    for R, r, c in steps:
-        am.mark_cells_in_annulus(R, r, c)
-        am.execute_coarsening_and_refinement()
-    am.distribute_dofs()
-    mg = AdaptiveMultigrid(ctx, am, min_level=min_level)
-    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())
-    lc = {l: [tuple(int(v) for v in row) for row in am.level_cells(l)] for l in range(am.n_levels)}
-    return am, mg, o, AdaptiveMultigridOracle(dim, p, lc, o, min_level=min_level)
-
-
-AMG_CASES = [(2, 2, 2, [(0.6, 0.0, None), (0.4, 0.1, (-0.1, -0.2))], 1), (2, 3, 1, [(0.9, 0.0, None), (0.5, 0.0, None)], 1),
-             (3, 2, 1, [(0.9, 0.0, None), (0.5, 0.0, (-0.1, -0.2, -0.3))], 1)]
-
-
-@pytest.mark.parametrize("dim,p,base,steps,min_level", AMG_CASES)
-def test_adaptive_multigrid_building_blocks(ctx, dim, p, base, steps, min_level):
-    """mfg_amg_* (csrc/multigrid.cu) piece by piece against oracle/adaptive_mg.py: level operators with boundary + refinement-edge
-    constraints (laplace_operator_gpu.h:153-186), vmult_interface_down / up (:306-352), prolongate / restrict_and_add on the
-    adaptive blocks (mg_transfer_matrix_free_gpu.cu:592-654), copy_to_mg / copy_from_mg (.cu:688-757), Chebyshev eigenvalues"""
-    import dealii_cuda_b200 as mf
-    am, mg, o, omg = _adaptive_mg_case(ctx, dim, p, base, steps, min_level)
-    assert any(mg.n_edge[l] for l in mg.levels)
-    V = lambda a: mf.GpuVector.from_numpy(ctx, np.ascontiguousarray(a, dtype=np.float64))
-    for l in mg.levels:
-        lm = omg.levels[l]
-        assert mg.n_dofs[l] == lm.n_dofs and mg.n_edge[l] == lm.edge.size
-        u = sm64(20 + l, lm.n_dofs)
-        src, dst = V(u), mf.GpuVector(ctx, lm.n_dofs)
-        mg.ops[l].vmult(dst, src)
-        assert rel_err(dst.toVector(), lm.vmult(u)) <= 1e-12
-        mg.vmult_interface_down(l, dst, src)
-        want = lm.vmult_interface_down(u)
-        assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * max(np.linalg.norm(want), 1e-300) and (np.linalg.norm(want) > 0) == (lm.edge.size > 0)
-        mg.vmult_interface_up(l, dst, src)
-        want = lm.vmult_interface_up(u)
-        assert np.linalg.norm(dst.toVector() - want) <= 1e-12 * max(np.linalg.norm(want), 1e-300)
-        # copies between the active mesh and the level
-        ua = sm64(40 + l, o.n_dofs)
-        vl = mf.GpuVector(ctx, lm.n_dofs); vl.fill(3.0)
-        mg.copy_to_level(l, vl, V(ua))
-        assert np.array_equal(vl.toVector(), omg.copy_to_mg(ua)[l])
-        va = mf.GpuVector(ctx, o.n_dofs); va.fill(0.0)
-        mg.copy_from_level(l, va, src)
-        g, lv = omg.copy[l]
-        want = np.zeros(o.n_dofs); want[g] = u[lv]
-        assert np.array_equal(va.toVector(), want)
-        if l > mg.levels[0]:
-            lc = omg.levels[l - 1]
-            uc = sm64(60 + l, lc.n_dofs)
-            fine = mf.GpuVector(ctx, lm.n_dofs); fine.fill(7.0)
-            mg.prolongate(l, fine, V(uc))
-            assert rel_err(fine.toVector(), omg.P[l] @ uc) <= 1e-13
-            d0 = sm64(80 + l, lc.n_dofs)
-            coarse = V(d0)
-            mg.restrict_and_add(l, coarse, src)
-            assert rel_err(coarse.toVector(), d0 + omg.P[l].T @ u) <= 1e-13
-            assert abs(mg.lambda_max[l] - omg.smoothers[l][0]) <= 1e-8 * omg.smoothers[l][0]
-
-
-@pytest.mark.parametrize("dim,p,base,steps,min_level", AMG_CASES)
-def test_adaptive_multigrid_vcycle_and_cg(ctx, dim, p, base, steps, min_level):
-    """PreconditionMG::vmult (Multigrid::level_v_step with the edge matrices, poisson_mg.cu:365-375) and the V-cycle-preconditioned
-    SolverCG on the active operator (:504-518) against the numpy oracle: the same V-cycle output, the same iteration count"""
-    import dealii_cuda_b200 as mf
-    from oracle.adaptive_mg import cg_preconditioned
-    am, mg, o, omg = _adaptive_mg_case(ctx, dim, p, base, steps, min_level)
-    r = sm64(7, o.n_dofs); r[o.constrained] = 0.0
-    src, dst = mf.GpuVector.from_numpy(ctx, r), mf.GpuVector(ctx, o.n_dofs)
-    mg.vmult(dst, src)
-    want = omg.vmult(r)
-    assert np.linalg.norm(dst.toVector() - want) <= 1e-7 * np.linalg.norm(want)      # (coarse solve: CG to 1e-10 vs a direct solve)
-    ue = sm64(5, o.n_dofs); ue[o.constrained] = 0.0
-    b = o.vmult(ue)
-    tol = 1e-10 * np.linalg.norm(b)
-    _, it_ref, hist_ref = cg_preconditioned(o.vmult, omg.vmult, b, tol)
-    vb, vx = mf.GpuVector.from_numpy(ctx, b), mf.GpuVector(ctx, o.n_dofs)
-    it, res, hist = mg.solve_cg(vx, vb, tol, 100, history=True)
-    assert abs(it - it_ref) <= 1 and it <= 12, (it, it_ref)
-    k = min(it, it_ref)
-    assert np.allclose(hist[:k // 2 + 1], hist_ref[:k // 2 + 1], rtol=1e-5)
-    assert np.linalg.norm(vx.toVector() - ue) <= 1e-8 * np.linalg.norm(ue)
-    assert mg.coarse_iterations > 0
-
-
-def test_adaptive_multigrid_through_the_cxx_facade():
-    """examples/bmop.cc -DADAPTIVE_GRID, mode `mg`: AdaptiveMesh<3>(limit_level_difference_at_vertices) + pseudo_adaptive_refinement +
-    AdaptiveMultigrid<3,double>::solve_cg through the header-only facade (poisson_mg.cu:430-552 on the adaptive grid)"""
-    import os
-    import re
-    import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "_build", "bmop_adaptive")
-    out = subprocess.run([exe, "4", "4", "mg"], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr
-    m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out.stdout)
-    assert m, out.stdout
-    assert int(m.group(1)) <= 20 and float(m.group(2)) <= 1e-7, out.stdout
-
-
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
-def test_sparse_matrix_vmult(ctx, dim, p, r, dtype):
-    """SparseMatrix::vmult (cuda_sparse_matrix.cu:414-429) against the oracle and against the matrix-free operator"""
-    import dealii_cuda_b200 as mf
-    o = OracleMesh(dim, p, r)
-    mesh = mf.HyperCubeMesh(ctx, dim, p, r)
-    S = mf.SparseMatrixGpu(ctx, dtype)
-    S.reinit(mesh)
-    assert S.m() == o.n_dofs and S.n_nonzero_elements() > o.n_dofs
-    u = sm64(3, o.n_dofs); u[o.constrained] = 0.0
-    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, o.n_dofs, dtype)
-    S.vmult(dst, src)
-    want = o.vmult(u)
-    tol = 1e-12 if dtype == np.float64 else 1e-5
-    assert np.linalg.norm(dst.toVector().astype(np.float64) - want) <= tol * np.linalg.norm(want)
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", late_test_names())
+def test_late(name):
+    r = run_child([LATE + "::" + name, "-x", "-m", "gpu"], 1500)
+    assert r.returncode == 0, "late GPU test %s (first run on hardware) failed:\n%s" % (name, (r.stdout + r.stderr)[-4000:])
