@@ -522,6 +522,17 @@ class AdaptiveMesh:
         self.n_dofs = lib.mfg_amesh_n_dofs(self.h)
         return self
 
+    def boundary_dofs(self):
+        out = np.zeros(lib.mfg_amesh_n_boundary(self.h), np.uint32)
+        check(lib.mfg_amesh_get_boundary(self.h, _u32p(out)))
+        return out
+
+    def support_points(self):
+        """DoFTools::map_dofs_to_support_points: [n_dofs][dim]"""
+        out = np.zeros((self.n_dofs, self.dim))
+        check(lib.mfg_amesh_get_support_points(self.h, _dp(out)))
+        return out
+
     def build_mg(self, min_level=0):
         """level meshes, level DoFs, MGConstrainedDoFs sets, transfer blocks and copy indices of the multigrid hierarchy"""
         check(lib.mfg_amesh_build_mg(self.h, int(min_level)))
@@ -569,6 +580,10 @@ class MatrixFreeGpu:
         scatter = SCATTER_COLOR if use_coloring else SCATTER_ATOMIC
         if isinstance(mesh_or_arrays, HyperCubeMesh):
             check(lib.mfg_mf_reinit_from_mesh(self.ctx.h, mesh_or_arrays.h, self.code, scatter, C.byref(h)))
+            self._keep = mesh_or_arrays
+        elif isinstance(mesh_or_arrays, AdaptiveMesh):
+            assert not use_coloring, "hanging nodes need the atomic scatter"
+            check(lib.mfg_mf_reinit_from_amesh(self.ctx.h, mesh_or_arrays.h, self.code, C.byref(h)))
             self._keep = mesh_or_arrays
         else:
             a = mesh_or_arrays

@@ -228,6 +228,10 @@ def _load():
         "mfg_amesh_n_level_cells": (C.c_uint32, [vp, C.c_int]),
         "mfg_amesh_get_level_cells": (C.c_int, [vp, C.c_int, u32p]),
         "mfg_amesh_distribute_dofs": (C.c_int, [vp]),
+        "mfg_amesh_n_boundary": (C.c_uint32, [vp]),
+        "mfg_amesh_get_boundary": (C.c_int, [vp, u32p]),
+        "mfg_amesh_get_support_points": (C.c_int, [vp, dp]),
+        "mfg_mf_reinit_from_amesh": (C.c_int, [vp, vp, C.c_int, pp]),
         "mfg_amesh_build_mg": (C.c_int, [vp, C.c_int]),
         "mfg_amesh_mg_level_sizes": (C.c_int, [vp, C.c_int, u32p]),
         "mfg_amesh_mg_level_get": (C.c_int, [vp, C.c_int, u32p, u32p, u32p, dp, u32p, u32p, u32p, u32p, dp]),

@@ -796,6 +796,57 @@ int mfg_amesh_mg_level_get(const mfg_amesh *am, int level, uint32_t *loc2glob, u
   });
 }
 
+uint32_t mfg_amesh_n_boundary(const mfg_amesh *am) { return am && am->dofs_ready ? (uint32_t)am->boundary.size() : 0; }
+// DoFs on the boundary of the domain, ascending (VectorTools::interpolate_boundary_values visits these, poisson.cu:155-158)
+int mfg_amesh_get_boundary(const mfg_amesh *am, uint32_t *out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(am && am->dofs_ready && (out || am->boundary.empty()), "call mfg_amesh_distribute_dofs first");
+    std::copy(am->boundary.begin(), am->boundary.end(), out);
+  });
+}
+// DoFTools::map_dofs_to_support_points: [n_dofs][dim]
+int mfg_amesh_get_support_points(const mfg_amesh *am, double *out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(am && am->dofs_ready && out, "call mfg_amesh_distribute_dofs first");
+    const int dim = am->dim, n = am->n;
+    for (uint32_t a = 0; a < am->n_active(); ++a)
+      {
+        const ACell &c = am->cell(a);
+        const double h = am->cell_h(am->act_level[a]);
+        for (uint32_t i = 0; i < am->npc; ++i)
+          {
+            uint32_t t = i;
+            const uint32_t g = am->l2g_own[(size_t)a * am->npc + i];
+            for (int d = 0; d < dim; ++d) { out[(size_t)g * dim + d] = am->left + h * ((double)c.x[d] + am->fe.nodes[t % n]); t /= n; }
+          }
+      }
+  });
+}
+// MatrixFreeGpu::reinit on the adaptive mesh for user-written cell loops (generic FEEvaluationGpu path): masks, rewritten
+// loc2glob, J^-1 per cell and the quadrature points
+int mfg_mf_reinit_from_amesh(mfg_ctx *ctx, const mfg_amesh *am, mfg_dtype dt, mfg_mf **out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && am && out, "null argument");
+    MFG_REQUIRE(am->dofs_ready, "call mfg_amesh_distribute_dofs first");
+    const uint32_t nact = am->n_active();
+    mfg_mf_desc    d;
+    std::memset(&d, 0, sizeof(d));
+    d.dim = am->dim; d.degree = am->p; d.dtype = dt; d.n_cells = nact; d.n_dofs = am->n_dofs;
+    d.loc2glob = am->l2g.data(); d.geometry = MFG_GEOM_UNIFORM; d.inv_jac = am->inv_jac.data();
+    d.scatter = MFG_SCATTER_ATOMIC;
+    bool any = false;
+    for (uint32_t m : am->mask) any = any || m != 0;
+    d.constraint_mask = any ? am->mask.data() : nullptr;
+    std::vector<double> qp((size_t)nact * am->npc * am->dim);
+    coefficient_at_qpoints(am, nullptr, qp.data());
+    d.quadrature_points = qp.data();
+    *out = mf_from_desc(ctx, d);
+  });
+}
+
 int mfg_laplace_create_from_amesh(mfg_ctx *ctx, const mfg_amesh *am, mfg_dtype dt, mfg_laplace **out)
 {
   return guarded([&] {

@@ -7,12 +7,15 @@
 //   vector g~, submit_value(f), submit_gradient(-a grad g~), integrate(true, true))
 // * solver: SolverCG with the inverse diagonal as preconditioner (mfg_solver_cg; poisson.cu:233-260)
 // * error: || u_h - u_exact ||_L2 through a second functor (sum of (phi_i, e^2) over i = integral of e^2)
-// usage: poisson <dim> <degree> <min_refinement> <max_refinement>     prints one line per refinement:
+// usage: poisson <dim> <degree> <min_refinement> <max_refinement> [nonuniform]     prints one line per refinement
+// (nonuniform: the reference's grid_refinement = NONUNIFORM -- locally refined mesh with hanging nodes, poisson_common.h:76-92):
 //        dim degree refinement n_dofs cg_iterations l2_error setup_seconds solve_seconds
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
+#include <string>
 #include <vector>
 
 #include "../include/dealii_cuda_b200/fee_gpu.cuh"
@@ -111,34 +114,59 @@ template <int dim, int fe_degree> struct SquaredError
 
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-template <int dim, int fe_degree> void run(int min_ref, int max_ref)
+template <int dim, int fe_degree> void run(int min_ref, int max_ref, bool nonuniform)
 {
   for (int r = min_ref; r <= max_ref; ++r)
     {
       const double t0 = now();
-      HyperCubeMesh<dim> mesh(fe_degree, r);                       // make_grid + setup_system (poisson.cu:96-148)
+      // make_grid + setup_system (poisson.cu:96-148); the mesh outlives the operator objects (they keep a pointer to it)
+      std::unique_ptr<HyperCubeMesh<dim>> mesh;
+      std::unique_ptr<AdaptiveMesh<dim>>  amesh;
       LaplaceOperatorGpu<dim, fe_degree, number> system_matrix;
-      system_matrix.reinit(mesh);
       MatrixFreeGpu<dim, number> data;                             // for the user-written cell loops
-      data.reinit(mesh);
-      const unsigned int n = mesh.n_dofs();
-      // interpolate_boundary_values(Solution): g~ = u_exact at the constrained DoFs, 0 elsewhere (poisson.cu:155-158)
-      std::vector<double> pts((size_t)n * dim);
-      check(mfg_mesh_get_support_points(mesh.handle(), pts.data()));
+      ConstraintHandlerGpu<number> ch;
+      std::vector<double> pts;
+      std::vector<unsigned int> boundary;
+      unsigned int n = 0;
+      if (!nonuniform)
+        {
+          mesh.reset(new HyperCubeMesh<dim>(fe_degree, r));
+          system_matrix.reinit(*mesh);
+          data.reinit(*mesh);
+          n = mesh->n_dofs();
+          pts.resize((size_t)n * dim);
+          check(mfg_mesh_get_support_points(mesh->handle(), pts.data()));
+          boundary = mesh->constrained_dofs();
+          ch.reinit(*mesh);
+        }
+      else
+        {
+          // grid_refinement = NONUNIFORM (poisson_common.h:76-92): refine_global(r), then twice the cells of the octant x_d > 0.2;
+          // hanging-node constraints join the Dirichlet ones (poisson.cu:139-146)
+          amesh.reset(new AdaptiveMesh<dim>(fe_degree));
+          amesh->refine_global(r);
+          for (int k = 0; k < 2; ++k) { amesh->mark_octant(); amesh->execute_coarsening_and_refinement(); }
+          amesh->distribute_dofs();
+          system_matrix.reinit(*amesh);
+          data.reinit(*amesh);
+          n = amesh->n_dofs();
+          pts = amesh->support_points();
+          boundary = amesh->boundary_dofs();
+          ch.reinit(amesh->constrained_dofs(), n);
+        }
+      // interpolate_boundary_values(Solution): g~ = u_exact at the boundary DoFs, 0 elsewhere (poisson.cu:155-158)
       std::vector<number> lift_host(n, 0.0);
-      for (unsigned int c : mesh.constrained_dofs())
+      for (unsigned int c : boundary)
         {
           double u, gu[dim], lu;
           solution<dim>(&pts[(size_t)c * dim], u, gu, lu);
           lift_host[c] = u;
         }
       GpuVector<number> lift(lift_host), rhs(n), x(n), err(n);
-      // assemble_system (poisson.cu:153-229)
+      // assemble_system (poisson.cu:153-229); on the adaptive mesh read_dof_values / distribute_local_to_global interpolate
       rhs = number(0);
       cell_loop<dim, fe_degree>(data, rhs, lift, RhsWithLifting<dim, fe_degree>());
-      // constrained rows of the operator are the identity: their right-hand side is the boundary value
-      ConstraintHandlerGpu<number> ch;
-      ch.reinit(mesh);
+      // constrained rows of the operator are the identity: their right-hand side is the boundary value (hanging rows: 0)
       ch.set_constrained_values(rhs, 0);
       rhs += lift;  // lift is zero away from the boundary
       system_matrix.compute_diagonal();
@@ -166,15 +194,16 @@ int main(int argc, char **argv)
 {
   const int dim = argc > 1 ? std::atoi(argv[1]) : 3, degree = argc > 2 ? std::atoi(argv[2]) : 4;
   const int min_ref = argc > 3 ? std::atoi(argv[3]) : 2, max_ref = argc > 4 ? std::atoi(argv[4]) : 4;
+  const bool nonuniform = argc > 5 && std::string(argv[5]) == "nonuniform";
   try
     {
-      if (dim == 2 && degree == 1) run<2, 1>(min_ref, max_ref);
-      else if (dim == 2 && degree == 2) run<2, 2>(min_ref, max_ref);
-      else if (dim == 2 && degree == 4) run<2, 4>(min_ref, max_ref);
-      else if (dim == 3 && degree == 1) run<3, 1>(min_ref, max_ref);
-      else if (dim == 3 && degree == 2) run<3, 2>(min_ref, max_ref);
-      else if (dim == 3 && degree == 3) run<3, 3>(min_ref, max_ref);
-      else if (dim == 3 && degree == 4) run<3, 4>(min_ref, max_ref);
+      if (dim == 2 && degree == 1) run<2, 1>(min_ref, max_ref, nonuniform);
+      else if (dim == 2 && degree == 2) run<2, 2>(min_ref, max_ref, nonuniform);
+      else if (dim == 2 && degree == 4) run<2, 4>(min_ref, max_ref, nonuniform);
+      else if (dim == 3 && degree == 1) run<3, 1>(min_ref, max_ref, nonuniform);
+      else if (dim == 3 && degree == 2) run<3, 2>(min_ref, max_ref, nonuniform);
+      else if (dim == 3 && degree == 3) run<3, 3>(min_ref, max_ref, nonuniform);
+      else if (dim == 3 && degree == 4) run<3, 4>(min_ref, max_ref, nonuniform);
       else { std::fprintf(stderr, "poisson: (dim, degree) not instantiated\n"); return 2; }
     }
   catch (const std::exception &e)

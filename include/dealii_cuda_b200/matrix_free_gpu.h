@@ -73,6 +73,20 @@ public:
     check(mfg_amesh_get_arrays(m_, nullptr, nullptr, nullptr, c.data(), nullptr, nullptr, nullptr, nullptr));
     return c;
   }
+  // DoFs on the boundary of the domain, ascending (what VectorTools::interpolate_boundary_values visits, poisson.cu:155-158)
+  std::vector<unsigned int> boundary_dofs() const
+  {
+    std::vector<unsigned int> b(mfg_amesh_n_boundary(m_));
+    check(mfg_amesh_get_boundary(m_, b.data()));
+    return b;
+  }
+  // DoFTools::map_dofs_to_support_points: [n_dofs][dim]
+  std::vector<double> support_points() const
+  {
+    std::vector<double> x((size_t)mfg_amesh_n_dofs(m_) * dim);
+    check(mfg_amesh_get_support_points(m_, x.data()));
+    return x;
+  }
   mfg_amesh *handle() const { return m_; }
 
 private:
@@ -129,6 +143,13 @@ public:
     free();
     check(mfg_mf_reinit_from_mesh(default_context(), mesh.handle(), dtype_of<Number>(), ad.use_coloring ? MFG_SCATTER_COLOR : MFG_SCATTER_ATOMIC, &mf_));
     fill_counters(ad.use_coloring);
+  }
+  // adaptively refined mesh of the library: constraint masks, rewritten loc2glob, quadrature points (atomic scatter)
+  void reinit(const AdaptiveMesh<dim> &mesh)
+  {
+    free();
+    check(mfg_mf_reinit_from_amesh(default_context(), mesh.handle(), dtype_of<Number>(), &mf_));
+    fill_counters(false);
   }
   // explicit arrays, as ReinitHelper extracts them from deal.II (matrix_free_gpu.cu:283-339)
   void reinit(const mfg_mf_desc &desc)

@@ -168,6 +168,9 @@ int mfg_amesh_distribute_dofs(mfg_amesh *am);
 uint32_t mfg_amesh_n_dofs(const mfg_amesh *am);
 uint32_t mfg_amesh_n_constrained(const mfg_amesh *am);
 uint32_t mfg_amesh_n_hanging(const mfg_amesh *am);
+uint32_t mfg_amesh_n_boundary(const mfg_amesh *am);
+int mfg_amesh_get_boundary(const mfg_amesh *am, uint32_t *out);          /* DoFs on the domain boundary, ascending */
+int mfg_amesh_get_support_points(const mfg_amesh *am, double *out);      /* DoFTools::map_dofs_to_support_points: [n_dofs][dim] */
 /* any pointer may be NULL.  loc2glob: [n_cells][(p+1)^dim] after the rewrite; loc2glob_unconstrained: the DoFHandler's own map;
  * constraint_mask [n_cells]; constrained [n_constrained] ascending; hanging [n_hanging]; inv_jac [n_cells];
  * coefficient [n_cells][(p+1)^dim] = 1/(0.05+2|x_q|^2) (poisson_common.h:146-158); quadrature_points [n_cells][(p+1)^dim][dim] */
@@ -221,6 +224,8 @@ typedef struct mfg_mf_desc
 
 int mfg_mf_reinit(mfg_ctx *ctx, const mfg_mf_desc *desc, mfg_mf **out);              /* MatrixFreeGpu::reinit matrix_free_gpu.cu:448-563 */
 int mfg_mf_reinit_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter, mfg_mf **out);
+/* the same on an adaptively refined mesh of the library (masks, rewritten loc2glob, quadrature points), for user-written cell loops */
+int mfg_mf_reinit_from_amesh(mfg_ctx *ctx, const mfg_amesh *am, mfg_dtype dt, mfg_mf **out);
 int mfg_mf_destroy(mfg_mf *mf);                                                       /* MatrixFreeGpu::free matrix_free_gpu.cu:566-596 */
 uint32_t mfg_mf_n_dofs(const mfg_mf *mf);
 uint32_t mfg_mf_n_cells(const mfg_mf *mf);

@@ -265,3 +265,21 @@ def test_sparse_matrix_vmult(ctx, dim, p, r, dtype):
     want = o.vmult(u)
     tol = 1e-12 if dtype == np.float64 else 1e-5
     assert np.linalg.norm(dst.toVector().astype(np.float64) - want) <= tol * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("dim,p,rmin,rmax", [(2, 2, 3, 6), (2, 4, 2, 5), (3, 2, 2, 4), (3, 4, 2, 4)])
+def test_poisson_on_a_locally_refined_mesh_converges_at_the_optimal_rate(dim, p, rmin, rmax):
+    """examples/poisson.cu with grid_refinement = NONUNIFORM (poisson_common.h:76-92): hanging-node constraints in the precompiled
+    operator, in the user-written right-hand-side / error functors of the generic path and in the constraint handler at once.
+    Against the ANALYTIC solution of poisson_common.cc the L2 error must still fall like h^(p+1) per refinement of the family."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "poisson")
+    assert os.path.exists(exe), "examples/_build/poisson is missing: run __graft_entry__.build()"
+    out = subprocess.run([exe, str(dim), str(p), str(rmin), str(rmax), "nonuniform"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert len(rows) == rmax - rmin + 1
+    errs = [float(r[5]) for r in rows]
+    for a, b in zip(errs[:-1], errs[1:]):
+        assert 0.5 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), (errs, "expected a factor 2^(p+1) per refinement")
+    assert all(int(r[4]) > 0 for r in rows)
