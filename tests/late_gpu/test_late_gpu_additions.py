@@ -1,7 +1,7 @@
 """GPU tests added late in round 2, AFTER the round's GPU budget was spent: they exercise code that compiles and whose host
 logic is covered on the CPU, but they have not run on hardware yet.  They are not collected by the main suite: the wrapper
-tests/test_z_late_gpu_additions.py (last in the suite) runs every test function of this file in a CHILD pytest process, so that
-nothing here -- not even a crash of the process -- can mask or take down the hardware-verified tests in front of it.
+tests/test_z_late_gpu_additions.py (last in the suite) runs this file in a CHILD pytest process and reports every test function,
+so that nothing here -- not even a crash of the process -- can mask or take down the hardware-verified tests in front of it.
   * generic FEEvaluationGpu path: MatrixFreeGpu::cell_loop(dst, loc_op) (matrix_free_gpu.h:382-393), evaluate_on_cells<Op>
     (:415-435), hanging-node interpolation in read_dof_values / distribute_local_to_global (fee_gpu.cuh:333-351);
   * the restated deal.II graph coloring (coloring.cc:8-33) driving the atomics-free scatter;
