@@ -466,8 +466,7 @@ class AdaptiveMesh:
 
     def set_refine_flags(self, flags):
         f = np.ascontiguousarray(flags, dtype=np.uint8)
-        assert f.size == self.n_cells
-        check(lib.mfg_amesh_set_refine_flags(self.h, f.ctypes.data_as(C.POINTER(C.c_uint8))))
+        check(lib.mfg_amesh_set_refine_flags(self.h, f.ctypes.data_as(C.POINTER(C.c_uint8)), f.size))
 
     def _center(self, center):
         if center is None:

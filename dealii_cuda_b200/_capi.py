@@ -216,7 +216,7 @@ def _load():
         "mfg_amesh_destroy": (C.c_int, [vp]),
         "mfg_amesh_set_limit_level_difference_at_vertices": (C.c_int, [vp, C.c_int]),
         "mfg_amesh_refine_global": (C.c_int, [vp, C.c_int]),
-        "mfg_amesh_set_refine_flags": (C.c_int, [vp, C.POINTER(C.c_uint8)]),
+        "mfg_amesh_set_refine_flags": (C.c_int, [vp, C.POINTER(C.c_uint8), sz]),
         "mfg_amesh_mark_cells_in_annulus": (C.c_int, [vp, C.c_double, C.c_double, dp]),
         "mfg_amesh_mark_cells_on_shell": (C.c_int, [vp, C.c_double, dp]),
         "mfg_amesh_mark_octant": (C.c_int, [vp]),

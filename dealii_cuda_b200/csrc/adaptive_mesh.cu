@@ -654,10 +654,11 @@ int mfg_amesh_refine_global(mfg_amesh *am, int times)
 {
   return guarded([&] { MFG_REQUIRE(am && times >= 0, "bad argument"); refine_global(am, times); });
 }
-int mfg_amesh_set_refine_flags(mfg_amesh *am, const uint8_t *flags)
+int mfg_amesh_set_refine_flags(mfg_amesh *am, const uint8_t *flags, size_t n_flags)
 {
   return guarded([&] {
     MFG_REQUIRE(am && flags, "null argument");
+    MFG_REQUIRE(n_flags == am->n_active(), "one flag per active cell");
     for (uint32_t a = 0; a < am->n_active(); ++a)
       if (flags[a]) am->cell(a).flag = 1;
   });

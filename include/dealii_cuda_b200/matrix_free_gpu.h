@@ -55,7 +55,7 @@ public:
   ~AdaptiveMesh() { if (m_) mfg_amesh_destroy(m_); }
   AdaptiveMesh(const AdaptiveMesh &) = delete;
   void refine_global(unsigned int times = 1) { check(mfg_amesh_refine_global(m_, (int)times)); }
-  void set_refine_flags(const std::vector<unsigned char> &flags) { check(mfg_amesh_set_refine_flags(m_, flags.data())); }
+  void set_refine_flags(const std::vector<unsigned char> &flags) { check(mfg_amesh_set_refine_flags(m_, flags.data(), flags.size())); }
   void mark_cells_in_annulus(double R, double r = 0.0, const double *center = nullptr) { check(mfg_amesh_mark_cells_in_annulus(m_, R, r, center)); }
   void mark_cells_on_shell(double R, const double *center = nullptr) { check(mfg_amesh_mark_cells_on_shell(m_, R, center)); }
   void mark_octant() { check(mfg_amesh_mark_octant(m_)); }

@@ -150,7 +150,7 @@ int mfg_amesh_destroy(mfg_amesh *am);
  * bmop_mg.cu:130): cells that share only a vertex also differ by at most one level; required by the multigrid hierarchy */
 int mfg_amesh_set_limit_level_difference_at_vertices(mfg_amesh *am, int on);
 int mfg_amesh_refine_global(mfg_amesh *am, int times);                                     /* Triangulation::refine_global */
-int mfg_amesh_set_refine_flags(mfg_amesh *am, const uint8_t *flags /* [n_active_cells] */); /* cell->set_refine_flag() */
+int mfg_amesh_set_refine_flags(mfg_amesh *am, const uint8_t *flags, size_t n_flags /* = n_active_cells */); /* cell->set_refine_flag() */
 int mfg_amesh_mark_cells_in_annulus(mfg_amesh *am, double R, double r, const double *center /* [dim] or NULL = origin */); /* bmop_common.h:9-24 */
 int mfg_amesh_mark_cells_on_shell(mfg_amesh *am, double R, const double *center);          /* bmop_common.h:27-47 */
 int mfg_amesh_mark_octant(mfg_amesh *am);                                                  /* mark_cells(octant_criterion) poisson_common.h:29-35, 43-56 */
