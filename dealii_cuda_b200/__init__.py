@@ -21,7 +21,7 @@ import numpy as np
 from . import _capi
 from ._capi import F32, F64, SCATTER_ATOMIC, SCATTER_COLOR, MfgError, check, lib
 
-__all__ = ["Context", "GpuVector", "HyperCubeMesh", "AdaptiveMesh", "MatrixFreeGpu", "ConstraintHandlerGpu", "LaplaceOperatorGpu",
+__all__ = ["Context", "GpuVector", "HyperCubeMesh", "AdaptiveMesh", "BallMesh", "MatrixFreeGpu", "ConstraintHandlerGpu", "LaplaceOperatorGpu",
            "shape_info", "solver_cg", "hanging_node_weights", "F32", "F64", "SCATTER_ATOMIC", "SCATTER_COLOR", "MfgError"]
 
 _NP = {F32: np.float32, F64: np.float64}
@@ -566,6 +566,58 @@ class AdaptiveMesh:
         return a
 
 
+class BallMesh:
+    """GridGenerator::hyper_ball + SphericalManifold on the boundary + refine_global (the reference's BALL_GRID,
+    poisson_common.h:59-72) with FE_Q DoFs and MappingQ1 geometry: host substrate of the library (mfg_umesh_*).  Needs no device;
+    LaplaceOperatorGpu.reinit(ball_mesh) builds the operator on the general-geometry path."""
+
+    def __init__(self, dim, degree, n_refine=0, radius=1.0):
+        h = C.c_void_p()
+        check(lib.mfg_umesh_hyper_ball(int(dim), int(degree), float(radius), C.byref(h)))
+        self.h, self.dim, self.degree, self.radius = h, dim, degree, radius
+        self.dofs_per_cell = (degree + 1) ** dim
+        if n_refine:
+            self.refine_global(n_refine)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.mfg_umesh_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def refine_global(self, times=1):
+        check(lib.mfg_umesh_refine_global(self.h, int(times)))
+        return self
+
+    def distribute_dofs(self):
+        check(lib.mfg_umesh_distribute_dofs(self.h))
+        self.n_dofs = lib.mfg_umesh_n_dofs(self.h)
+        return self
+
+    @property
+    def n_cells(self):
+        return lib.mfg_umesh_n_cells(self.h)
+
+    def mesh(self):
+        """(vertices [n_vertices][dim], cell_vertices [n_cells][2^dim] in local lexicographic order)"""
+        v = np.zeros((lib.mfg_umesh_n_vertices(self.h), self.dim))
+        c = np.zeros((self.n_cells, 1 << self.dim), np.uint32)
+        check(lib.mfg_umesh_get_mesh(self.h, _dp(v), _u32p(c)))
+        return v, c
+
+    def arrays(self):
+        """dict: loc2glob, boundary (Dirichlet DoFs), inv_jac [cell][q][d1][d2], JxW, quadrature_points, coefficient"""
+        nc, npc, dim = self.n_cells, self.dofs_per_cell, self.dim
+        a = dict(loc2glob=np.zeros((nc, npc), np.uint32), boundary=np.zeros(lib.mfg_umesh_n_boundary(self.h), np.uint32),
+                 inv_jac=np.zeros((nc, npc, dim, dim)), JxW=np.zeros((nc, npc)), quadrature_points=np.zeros((nc, npc, dim)),
+                 coefficient=np.zeros((nc, npc)))
+        check(lib.mfg_umesh_get_arrays(self.h, _u32p(a["loc2glob"]), _u32p(a["boundary"]), _dp(a["inv_jac"]), _dp(a["JxW"]),
+                                       _dp(a["quadrature_points"]), _dp(a["coefficient"])))
+        return a
+
+
 class MatrixFreeGpu:
     """MatrixFreeGpu<dim,Number> (matrix_free_gpu.h:81-229): reinit / counters / free."""
 
@@ -657,6 +709,10 @@ class LaplaceOperatorGpu:
         elif isinstance(mesh, AdaptiveMesh):
             assert not self.use_coloring, "hanging nodes need the atomic scatter"
             check(lib.mfg_laplace_create_from_amesh(self.ctx.h, mesh.h, self.code, C.byref(h)))
+            self._keep = mesh
+        elif isinstance(mesh, BallMesh):
+            assert not self.use_coloring
+            check(lib.mfg_laplace_create_from_umesh(self.ctx.h, mesh.h, self.code, C.byref(h)))
             self._keep = mesh
         else:
             coef = np.ascontiguousarray(coefficient, dtype=np.float64)

@@ -197,6 +197,17 @@ def _load():
         "mfg_spm_n_nonzero_elements": (sz, [vp]),
         "mfg_spm_memory_consumption": (sz, [vp]),
         "mfg_spm_vmult": (C.c_int, [vp, vp, vp]),
+        "mfg_umesh_hyper_ball": (C.c_int, [C.c_int, C.c_int, C.c_double, pp]),
+        "mfg_umesh_destroy": (C.c_int, [vp]),
+        "mfg_umesh_refine_global": (C.c_int, [vp, C.c_int]),
+        "mfg_umesh_distribute_dofs": (C.c_int, [vp]),
+        "mfg_umesh_n_cells": (C.c_uint32, [vp]),
+        "mfg_umesh_n_vertices": (C.c_uint32, [vp]),
+        "mfg_umesh_n_dofs": (C.c_uint32, [vp]),
+        "mfg_umesh_n_boundary": (C.c_uint32, [vp]),
+        "mfg_umesh_get_mesh": (C.c_int, [vp, dp, u32p]),
+        "mfg_umesh_get_arrays": (C.c_int, [vp, u32p, u32p, dp, dp, dp, dp]),
+        "mfg_laplace_create_from_umesh": (C.c_int, [vp, vp, C.c_int, pp]),
         "mfg_amesh_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "mfg_mgt_build_from_blocks": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_uint32, u32p, u32p, dp, C.c_uint32, C.c_uint32, pp]),
         "mfg_amg_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, pp]),

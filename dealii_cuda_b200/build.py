@@ -19,7 +19,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/us
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 # (source, object suffix, extra defines)
-UNITS = [("capi.cu", "", []), ("mesh.cu", "", []), ("vector.cu", "", []), ("operators.cu", "", []), ("exchange.cu", "", []), ("solver.cu", "", []), ("mg_transfer.cu", "", []), ("stage_plan.cu", "", []), ("multigrid.cu", "", []), ("coloring.cu", "", []), ("adaptive_mesh.cu", "", []), ("partition.cu", "", []), ("sparse_matrix.cu", "", [])]
+UNITS = [("capi.cu", "", []), ("mesh.cu", "", []), ("vector.cu", "", []), ("operators.cu", "", []), ("exchange.cu", "", []), ("solver.cu", "", []), ("mg_transfer.cu", "", []), ("stage_plan.cu", "", []), ("multigrid.cu", "", []), ("coloring.cu", "", []), ("adaptive_mesh.cu", "", []), ("partition.cu", "", []), ("sparse_matrix.cu", "", []), ("ball_mesh.cu", "", [])]
 for dim in (2, 3):
     for f64 in (0, 1):
         UNITS.append(("kernels_v0_inst.cu", f"_d{dim}_f{f64}", [f"-DMFG_INST_DIM={dim}", f"-DMFG_INST_F64={f64}"]))

@@ -1,6 +1,7 @@
 // bmop.cc -- the reference's benchmark driver (bmop.cu:66-230) on the C++ facade: host code is plain C++
 // (g++), all device work happens inside libmfgpu.so.   usage: bmop <max_refinement> [min_refinement]
-// -DADAPTIVE_GRID: the reference's pseudo-adaptive mesh with hanging nodes (BASELINE configs[3]); -DDEGREE_FE, -DDIMENSION, -DBMOP_USE_FLOATS as there
+// -DADAPTIVE_GRID: the reference's pseudo-adaptive mesh with hanging nodes (BASELINE configs[3]); -DBALL_GRID: hyper_ball with non-affine
+// cells; -DDEGREE_FE, -DDIMENSION, -DBMOP_USE_FLOATS as there
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,7 +26,9 @@ typedef double number;
 
 template <int dim, int fe_degree> void run(int n_ref)
 {
-#ifdef ADAPTIVE_GRID
+#if defined(BALL_GRID)
+  BallMesh<dim> mesh(fe_degree, n_ref);        // bmop_setup_mesh(domain = BALL) (bmop.cu:164-168): hyper_ball + SphericalManifold + refine_global
+#elif defined(ADAPTIVE_GRID)
   AdaptiveMesh<dim> mesh(fe_degree);           // bmop_setup_mesh(..., pseudo_adaptive_grid = true, n_ref) (bmop.cu:170-181)
   mesh.pseudo_adaptive_refinement(n_ref);      // bmop_common.h:49-105
   mesh.distribute_dofs();                      // + make_hanging_node_constraints (bmop.cu:116-126)

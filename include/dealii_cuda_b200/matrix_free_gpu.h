@@ -93,6 +93,28 @@ private:
   mfg_amesh *m_ = nullptr;
 };
 
+// GridGenerator::hyper_ball + SphericalManifold on the boundary + refine_global (the reference's -DBALL_GRID, poisson_common.h:59-72):
+// unstructured mesh with FE_Q DoFs and MappingQ1 geometry, host substrate of the library (mfg_umesh_*)
+template <int dim> class BallMesh
+{
+public:
+  BallMesh(unsigned int fe_degree, unsigned int n_refine, double radius = 1.)
+  {
+    check(mfg_umesh_hyper_ball(dim, (int)fe_degree, radius, &m_));
+    check(mfg_umesh_refine_global(m_, (int)n_refine));
+    check(mfg_umesh_distribute_dofs(m_));
+  }
+  ~BallMesh() { if (m_) mfg_umesh_destroy(m_); }
+  BallMesh(const BallMesh &) = delete;
+  unsigned int n_dofs() const { return mfg_umesh_n_dofs(m_); }
+  unsigned int n_active_cells() const { return mfg_umesh_n_cells(m_); }
+  unsigned int n_constraints() const { return mfg_umesh_n_boundary(m_); }
+  mfg_umesh *handle() const { return m_; }
+
+private:
+  mfg_umesh *m_ = nullptr;
+};
+
 template <typename Number> class ConstraintHandlerGpu
 {
 public:
@@ -198,6 +220,12 @@ public:
   {
     clear();
     check(mfg_laplace_create_from_amesh(default_context(), mesh.handle(), dtype_of<Number>(), &op_));
+  }
+  // the ball mesh (-DBALL_GRID): non-affine cells, full J^-1 per quadrature point (fee_gpu.cuh:236-240, 276-280)
+  void reinit(const BallMesh<dim> &mesh)
+  {
+    clear();
+    check(mfg_laplace_create_from_umesh(default_context(), mesh.handle(), dtype_of<Number>(), &op_));
   }
   unsigned int m() const { return mfg_laplace_m(op_); }
   unsigned int n() const { return mfg_laplace_m(op_); }

@@ -193,6 +193,25 @@ int mfg_amesh_mg_level_sizes(const mfg_amesh *am, int level, uint32_t out[6]);
 int mfg_amesh_mg_level_get(const mfg_amesh *am, int level, uint32_t *loc2glob, uint32_t *boundary, uint32_t *edge, double *coefficient, uint32_t *copy_global,
                            uint32_t *copy_level, uint32_t *coarse_idx, uint32_t *fine_idx, double *weights);
 
+/* ---- the reference's BALL_GRID (poisson_common.h:59-72: GridGenerator::hyper_ball + SphericalManifold on the boundary + refine_global)
+ * as an unstructured quad / hex mesh with FE_Q DoFs and the tri-linear (MappingQ1) geometry per quadrature point (host code,
+ * csrc/ball_mesh.cu).  The operator on it runs on the general-geometry path (MFG_GEOM_GENERAL). */
+typedef struct mfg_umesh mfg_umesh;
+int mfg_umesh_hyper_ball(int dim, int degree, double radius, mfg_umesh **out);
+int mfg_umesh_destroy(mfg_umesh *um);
+int mfg_umesh_refine_global(mfg_umesh *um, int times);
+int mfg_umesh_distribute_dofs(mfg_umesh *um);               /* DoFHandler::distribute_dofs + the Dirichlet boundary DoFs */
+uint32_t mfg_umesh_n_cells(const mfg_umesh *um);
+uint32_t mfg_umesh_n_vertices(const mfg_umesh *um);
+uint32_t mfg_umesh_n_dofs(const mfg_umesh *um);
+uint32_t mfg_umesh_n_boundary(const mfg_umesh *um);
+int mfg_umesh_get_mesh(const mfg_umesh *um, double *vertices /* [n_vertices][dim] */, uint32_t *cell_vertices /* [n_cells][2^dim], lexicographic */);
+/* any pointer may be NULL.  loc2glob [n_cells][(p+1)^dim]; boundary [n_boundary] ascending; inv_jac [n_cells][(p+1)^dim][dim][dim]
+ * (K[d1][d2] = d xi_d1 / d x_d2, FEValues::get_inverse_jacobians order); JxW, coefficient [n_cells][(p+1)^dim];
+ * quadrature_points [n_cells][(p+1)^dim][dim] */
+int mfg_umesh_get_arrays(const mfg_umesh *um, uint32_t *loc2glob, uint32_t *boundary, double *inv_jac, double *JxW, double *quadrature_points,
+                         double *coefficient);
+
 /* ---- MatrixFreeGpu ------------------------------------------------------- */
 /* Explicit-array description: what ReinitHelper extracts from deal.II
  * (matrix_free_gpu.cu:283-339) -- this is the call a deal.II-based caller makes. */
@@ -281,6 +300,8 @@ int mfg_laplace_create_from_arrays(mfg_ctx *ctx, mfg_mf *mf, mfg_ch *ch, const d
 /* LaplaceOperatorGpu::reinit on an adaptively refined mesh (-DMATRIX_FREE_HANGING_NODES): MatrixFreeGpu with the masks,
  * ConstraintHandlerGpu with hanging + boundary DoFs, the reference coefficient; the operator owns both. */
 int mfg_laplace_create_from_amesh(mfg_ctx *ctx, const mfg_amesh *am, mfg_dtype dt, mfg_laplace **out);
+/* LaplaceOperatorGpu::reinit on the ball mesh (-DBALL_GRID): general geometry, Dirichlet boundary, the reference coefficient */
+int mfg_laplace_create_from_umesh(mfg_ctx *ctx, const mfg_umesh *um, mfg_dtype dt, mfg_laplace **out);
 /* replace the coefficient: a(x_q) at quadrature points, host, [n_cells][(p+1)^dim], cells in mesh / descriptor order */
 int mfg_laplace_set_coefficient(mfg_laplace *op, const double *coefficient_host);
 int mfg_laplace_destroy(mfg_laplace *op);                                            /* clear() :110-117 */

@@ -283,3 +283,53 @@ def test_poisson_on_a_locally_refined_mesh_converges_at_the_optimal_rate(dim, p,
     for a, b in zip(errs[:-1], errs[1:]):
         assert 0.5 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), (errs, "expected a factor 2^(p+1) per refinement")
     assert all(int(r[4]) > 0 for r in rows)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,p,r", [(2, 2, 1), (2, 4, 1), (3, 1, 1), (3, 2, 1), (3, 4, 0)])
+def test_operator_on_the_ball_mesh(ctx, dim, p, r, dtype):
+    """LaplaceOperatorGpu::reinit on the library's BALL_GRID substrate (mfg_umesh_*: hyper_ball + SphericalManifold + refine_global,
+    poisson_common.h:59-72; tests/test_ball_mesh.py pins its arrays on the CPU): general geometry, against the dense numpy operator
+    built from the same loc2glob / K / JxW / coefficient (fee_gpu.cuh:236-240, 276-280), identity on the Dirichlet rows"""
+    import dealii_cuda_b200 as mf
+    bm = mf.BallMesh(dim, p, r).distribute_dofs()
+    a = bm.arrays()
+    n, npc = p + 1, (p + 1) ** dim
+    val, grad, _, _ = (np.asarray(t) for t in mf.shape_info(p))
+    q = np.arange(npc)
+    qi = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
+    B = np.zeros((dim, npc, npc))                        # [d][q][i]
+    for d in range(dim):
+        t = np.ones((npc, npc))
+        for e in range(dim):
+            t *= (grad if e == d else val)[qi[None, :, e], qi[:, None, e]]
+        B[d] = t
+    A = np.zeros((bm.n_dofs, bm.n_dofs))
+    for c in range(bm.n_cells):
+        gx = np.einsum("qed,eqi->qdi", a["inv_jac"][c], B)             # grad_x phi_i at q = K^T grad_xi phi_i
+        row = a["loc2glob"][c].astype(np.int64)
+        A[np.ix_(row, row)] += np.einsum("qdi,q,qdj->ij", gx, a["coefficient"][c] * a["JxW"][c], gx)
+    con = a["boundary"].astype(np.int64)
+    A[con, :] = 0.0; A[:, con] = 0.0; A[con, con] = 1.0
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(bm)
+    u = sm64(13, bm.n_dofs)
+    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, bm.n_dofs, dtype)
+    op.vmult(dst, src)
+    want = A @ u
+    assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
+    assert np.array_equal(dst.toVector()[con], u.astype(dtype)[con])
+    if dtype == np.float64:
+        op.compute_diagonal()
+        assert rel_err(op.get_diagonal_inverse().toVector(), 1.0 / np.diag(A)) <= 1e-12
+
+
+def test_bmop_driver_on_the_ball_mesh():
+    """examples/bmop.cc built with -DBALL_GRID (bmop.cu:164-168) through the C++ facade"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "bmop_ball")
+    assert os.path.exists(exe), "examples/_build/bmop_ball is missing: run __graft_entry__.build()"
+    out = subprocess.run([exe, "2", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert [int(r[2]) for r in rows] == [3817, 29521] and all(float(r[3]) > 0 for r in rows)

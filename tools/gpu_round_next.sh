@@ -11,6 +11,7 @@ python bench.py --adaptive --refine 6 --degree 3 --steps 200 --warmup 5 > gpurun
 # the assembled-matrix competitor row (bmop_spm.cu)
 python bench.py --spmv --refine 4 --steps 50 --warmup 3 > gpurun_out/bench_spmv_q4_r4.json 2> gpurun_out/bench_spmv.err
 python bench.py --spmv --refine 5 --degree 2 --steps 50 --warmup 3 > gpurun_out/bench_spmv_q2_r5.json 2>> gpurun_out/bench_spmv.err
+examples/_build/bmop_ball 4 2 > gpurun_out/bmop_ball.txt 2>&1
 examples/_build/bmop_adaptive 6 5 > gpurun_out/bmop_adaptive.txt 2>&1
 examples/_build/bmop_adaptive 6 6 mg >> gpurun_out/bmop_adaptive.txt 2>&1
 cat gpurun_out/bench_adaptive_q4.json gpurun_out/bench_spmv_q4_r4.json gpurun_out/bmop_adaptive.txt
