@@ -607,6 +607,12 @@ class BallMesh:
         check(lib.mfg_umesh_get_mesh(self.h, _dp(v), _u32p(c)))
         return v, c
 
+    def support_points(self):
+        """DoFTools::map_dofs_to_support_points (MappingQ1): [n_dofs][dim]"""
+        out = np.zeros((self.n_dofs, self.dim))
+        check(lib.mfg_umesh_get_support_points(self.h, _dp(out)))
+        return out
+
     def arrays(self):
         """dict: loc2glob, boundary (Dirichlet DoFs), inv_jac [cell][q][d1][d2], JxW, quadrature_points, coefficient"""
         nc, npc, dim = self.n_cells, self.dofs_per_cell, self.dim
@@ -635,6 +641,10 @@ class MatrixFreeGpu:
         elif isinstance(mesh_or_arrays, AdaptiveMesh):
             assert not use_coloring, "hanging nodes need the atomic scatter"
             check(lib.mfg_mf_reinit_from_amesh(self.ctx.h, mesh_or_arrays.h, self.code, C.byref(h)))
+            self._keep = mesh_or_arrays
+        elif isinstance(mesh_or_arrays, BallMesh):
+            assert not use_coloring
+            check(lib.mfg_mf_reinit_from_umesh(self.ctx.h, mesh_or_arrays.h, self.code, C.byref(h)))
             self._keep = mesh_or_arrays
         else:
             a = mesh_or_arrays

@@ -206,6 +206,8 @@ def _load():
         "mfg_umesh_n_dofs": (C.c_uint32, [vp]),
         "mfg_umesh_n_boundary": (C.c_uint32, [vp]),
         "mfg_umesh_get_mesh": (C.c_int, [vp, dp, u32p]),
+        "mfg_umesh_get_support_points": (C.c_int, [vp, dp]),
+        "mfg_mf_reinit_from_umesh": (C.c_int, [vp, vp, C.c_int, pp]),
         "mfg_umesh_get_arrays": (C.c_int, [vp, u32p, u32p, dp, dp, dp, dp]),
         "mfg_laplace_create_from_umesh": (C.c_int, [vp, vp, C.c_int, pp]),
         "mfg_amesh_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -431,6 +431,40 @@ int mfg_umesh_get_arrays(const mfg_umesh *um, uint32_t *loc2glob, uint32_t *boun
     if (inv_jac || JxW || quadrature_points || coefficient) geometry(um, inv_jac, JxW, quadrature_points, coefficient);
   });
 }
+// DoFTools::map_dofs_to_support_points with MappingQ1: [n_dofs][dim]
+int mfg_umesh_get_support_points(const mfg_umesh *um, double *out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(um && um->dofs_ready && out, "call mfg_umesh_distribute_dofs first");
+    const int dim = um->dim, n = um->n;
+    for (size_t ci = 0; ci < um->cells.size(); ++ci)
+      for (uint32_t i = 0; i < um->npc; ++i)
+        {
+          double   xi[3] = {0, 0, 0}, x[3], J[9];
+          uint32_t t = i;
+          for (int d = 0; d < dim; ++d) { xi[d] = um->fe.nodes[t % n]; t /= n; }
+          map_point(um, um->cells[ci], xi, x, J);
+          std::copy(x, x + dim, out + (size_t)um->l2g[ci * um->npc + i] * dim);
+        }
+  });
+}
+// MatrixFreeGpu::reinit on the ball for user-written cell loops (generic FEEvaluationGpu path, general geometry)
+int mfg_mf_reinit_from_umesh(mfg_ctx *ctx, const mfg_umesh *um, mfg_dtype dt, mfg_mf **out)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && um && out, "null argument");
+    MFG_REQUIRE(um->dofs_ready, "call mfg_umesh_distribute_dofs first");
+    const size_t        total = um->cells.size() * um->npc;
+    std::vector<double> K(total * um->dim * um->dim), jxw(total), qp(total * um->dim);
+    geometry(um, K.data(), jxw.data(), qp.data(), nullptr);
+    mfg_mf_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.dim = um->dim; d.degree = um->p; d.dtype = dt; d.n_cells = (uint32_t)um->cells.size(); d.n_dofs = um->n_dofs;
+    d.loc2glob = um->l2g.data(); d.geometry = MFG_GEOM_GENERAL; d.inv_jac = K.data(); d.JxW = jxw.data(); d.quadrature_points = qp.data();
+    d.scatter = MFG_SCATTER_ATOMIC;
+    *out = mf_from_desc(ctx, d);
+  });
+}
 // LaplaceOperatorGpu::reinit on the ball: general geometry (full J^-1 per quadrature point), Dirichlet boundary, reference coefficient
 int mfg_laplace_create_from_umesh(mfg_ctx *ctx, const mfg_umesh *um, mfg_dtype dt, mfg_laplace **out)
 {

@@ -7,8 +7,9 @@
 //   vector g~, submit_value(f), submit_gradient(-a grad g~), integrate(true, true))
 // * solver: SolverCG with the inverse diagonal as preconditioner (mfg_solver_cg; poisson.cu:233-260)
 // * error: || u_h - u_exact ||_L2 through a second functor (sum of (phi_i, e^2) over i = integral of e^2)
-// usage: poisson <dim> <degree> <min_refinement> <max_refinement> [nonuniform]     prints one line per refinement
-// (nonuniform: the reference's grid_refinement = NONUNIFORM -- locally refined mesh with hanging nodes, poisson_common.h:76-92):
+// usage: poisson <dim> <degree> <min_refinement> <max_refinement> [nonuniform | ball]     prints one line per refinement
+// (nonuniform: the reference's grid_refinement = NONUNIFORM -- locally refined mesh with hanging nodes, poisson_common.h:76-92;
+//  ball: domain = BALL -- hyper_ball with non-affine cells, poisson_common.h:65-70):
 //        dim degree refinement n_dofs cg_iterations l2_error setup_seconds solve_seconds
 #include <chrono>
 #include <cmath>
@@ -114,21 +115,36 @@ template <int dim, int fe_degree> struct SquaredError
 
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-template <int dim, int fe_degree> void run(int min_ref, int max_ref, bool nonuniform)
+enum GridCase { UNIFORM, NONUNIFORM, BALL };
+
+template <int dim, int fe_degree> void run(int min_ref, int max_ref, GridCase grid)
 {
+  const bool nonuniform = grid == NONUNIFORM;
   for (int r = min_ref; r <= max_ref; ++r)
     {
       const double t0 = now();
       // make_grid + setup_system (poisson.cu:96-148); the mesh outlives the operator objects (they keep a pointer to it)
       std::unique_ptr<HyperCubeMesh<dim>> mesh;
       std::unique_ptr<AdaptiveMesh<dim>>  amesh;
+      std::unique_ptr<BallMesh<dim>>      ball;
       LaplaceOperatorGpu<dim, fe_degree, number> system_matrix;
       MatrixFreeGpu<dim, number> data;                             // for the user-written cell loops
       ConstraintHandlerGpu<number> ch;
       std::vector<double> pts;
       std::vector<unsigned int> boundary;
       unsigned int n = 0;
-      if (!nonuniform)
+      if (grid == BALL)
+        {
+          // domain = BALL (poisson_common.h:65-70): hyper_ball + SphericalManifold on the boundary, refine_global(r); non-affine cells
+          ball.reset(new BallMesh<dim>(fe_degree, r));
+          system_matrix.reinit(*ball);
+          data.reinit(*ball);
+          n = ball->n_dofs();
+          pts = ball->support_points();
+          boundary = ball->boundary_dofs();
+          ch.reinit(boundary, n);
+        }
+      else if (!nonuniform)
         {
           mesh.reset(new HyperCubeMesh<dim>(fe_degree, r));
           system_matrix.reinit(*mesh);
@@ -194,16 +210,16 @@ int main(int argc, char **argv)
 {
   const int dim = argc > 1 ? std::atoi(argv[1]) : 3, degree = argc > 2 ? std::atoi(argv[2]) : 4;
   const int min_ref = argc > 3 ? std::atoi(argv[3]) : 2, max_ref = argc > 4 ? std::atoi(argv[4]) : 4;
-  const bool nonuniform = argc > 5 && std::string(argv[5]) == "nonuniform";
+  const GridCase grid = argc > 5 && std::string(argv[5]) == "nonuniform" ? NONUNIFORM : argc > 5 && std::string(argv[5]) == "ball" ? BALL : UNIFORM;
   try
     {
-      if (dim == 2 && degree == 1) run<2, 1>(min_ref, max_ref, nonuniform);
-      else if (dim == 2 && degree == 2) run<2, 2>(min_ref, max_ref, nonuniform);
-      else if (dim == 2 && degree == 4) run<2, 4>(min_ref, max_ref, nonuniform);
-      else if (dim == 3 && degree == 1) run<3, 1>(min_ref, max_ref, nonuniform);
-      else if (dim == 3 && degree == 2) run<3, 2>(min_ref, max_ref, nonuniform);
-      else if (dim == 3 && degree == 3) run<3, 3>(min_ref, max_ref, nonuniform);
-      else if (dim == 3 && degree == 4) run<3, 4>(min_ref, max_ref, nonuniform);
+      if (dim == 2 && degree == 1) run<2, 1>(min_ref, max_ref, grid);
+      else if (dim == 2 && degree == 2) run<2, 2>(min_ref, max_ref, grid);
+      else if (dim == 2 && degree == 4) run<2, 4>(min_ref, max_ref, grid);
+      else if (dim == 3 && degree == 1) run<3, 1>(min_ref, max_ref, grid);
+      else if (dim == 3 && degree == 2) run<3, 2>(min_ref, max_ref, grid);
+      else if (dim == 3 && degree == 3) run<3, 3>(min_ref, max_ref, grid);
+      else if (dim == 3 && degree == 4) run<3, 4>(min_ref, max_ref, grid);
       else { std::fprintf(stderr, "poisson: (dim, degree) not instantiated\n"); return 2; }
     }
   catch (const std::exception &e)

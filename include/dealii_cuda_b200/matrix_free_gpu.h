@@ -109,6 +109,18 @@ public:
   unsigned int n_dofs() const { return mfg_umesh_n_dofs(m_); }
   unsigned int n_active_cells() const { return mfg_umesh_n_cells(m_); }
   unsigned int n_constraints() const { return mfg_umesh_n_boundary(m_); }
+  std::vector<unsigned int> boundary_dofs() const
+  {
+    std::vector<unsigned int> b(mfg_umesh_n_boundary(m_));
+    check(mfg_umesh_get_arrays(m_, nullptr, b.data(), nullptr, nullptr, nullptr, nullptr));
+    return b;
+  }
+  std::vector<double> support_points() const   // DoFTools::map_dofs_to_support_points: [n_dofs][dim]
+  {
+    std::vector<double> x((size_t)mfg_umesh_n_dofs(m_) * dim);
+    check(mfg_umesh_get_support_points(m_, x.data()));
+    return x;
+  }
   mfg_umesh *handle() const { return m_; }
 
 private:
@@ -165,6 +177,13 @@ public:
     free();
     check(mfg_mf_reinit_from_mesh(default_context(), mesh.handle(), dtype_of<Number>(), ad.use_coloring ? MFG_SCATTER_COLOR : MFG_SCATTER_ATOMIC, &mf_));
     fill_counters(ad.use_coloring);
+  }
+  // the ball mesh: full J^-1 and JxW per quadrature point (general geometry), quadrature points
+  void reinit(const BallMesh<dim> &mesh)
+  {
+    free();
+    check(mfg_mf_reinit_from_umesh(default_context(), mesh.handle(), dtype_of<Number>(), &mf_));
+    fill_counters(false);
   }
   // adaptively refined mesh of the library: constraint masks, rewritten loc2glob, quadrature points (atomic scatter)
   void reinit(const AdaptiveMesh<dim> &mesh)

@@ -205,6 +205,7 @@ uint32_t mfg_umesh_n_cells(const mfg_umesh *um);
 uint32_t mfg_umesh_n_vertices(const mfg_umesh *um);
 uint32_t mfg_umesh_n_dofs(const mfg_umesh *um);
 uint32_t mfg_umesh_n_boundary(const mfg_umesh *um);
+int mfg_umesh_get_support_points(const mfg_umesh *um, double *out);   /* DoFTools::map_dofs_to_support_points (MappingQ1): [n_dofs][dim] */
 int mfg_umesh_get_mesh(const mfg_umesh *um, double *vertices /* [n_vertices][dim] */, uint32_t *cell_vertices /* [n_cells][2^dim], lexicographic */);
 /* any pointer may be NULL.  loc2glob [n_cells][(p+1)^dim]; boundary [n_boundary] ascending; inv_jac [n_cells][(p+1)^dim][dim][dim]
  * (K[d1][d2] = d xi_d1 / d x_d2, FEValues::get_inverse_jacobians order); JxW, coefficient [n_cells][(p+1)^dim];
@@ -245,6 +246,7 @@ int mfg_mf_reinit(mfg_ctx *ctx, const mfg_mf_desc *desc, mfg_mf **out);         
 int mfg_mf_reinit_from_mesh(mfg_ctx *ctx, const mfg_mesh *mesh, mfg_dtype dt, mfg_scatter scatter, mfg_mf **out);
 /* the same on an adaptively refined mesh of the library (masks, rewritten loc2glob, quadrature points), for user-written cell loops */
 int mfg_mf_reinit_from_amesh(mfg_ctx *ctx, const mfg_amesh *am, mfg_dtype dt, mfg_mf **out);
+int mfg_mf_reinit_from_umesh(mfg_ctx *ctx, const mfg_umesh *um, mfg_dtype dt, mfg_mf **out);   /* the ball mesh: general geometry */
 int mfg_mf_destroy(mfg_mf *mf);                                                       /* MatrixFreeGpu::free matrix_free_gpu.cu:566-596 */
 uint32_t mfg_mf_n_dofs(const mfg_mf *mf);
 uint32_t mfg_mf_n_cells(const mfg_mf *mf);

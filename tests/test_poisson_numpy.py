@@ -111,3 +111,55 @@ def test_l2_error_on_locally_refined_meshes_falls_at_the_optimal_rate(dim, p, rs
         errs.append(err)
     ratio = errs[0] / errs[1]
     assert 0.6 * 2 ** (p + 1) <= ratio <= 1.6 * 2 ** (p + 1), (errs, ratio)
+
+
+def solve_poisson_on_ball(dim, p, r):
+    """(n_dofs, L2 error) on the library's BALL_GRID substrate (hyper_ball + SphericalManifold + refine_global(r), MappingQ1): the
+    same problem with the non-affine geometry arrays (K, JxW per quadrature point), Dirichlet data on the polygonal boundary,
+    sparse direct solve"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    bm = mf.BallMesh(dim, p, r).distribute_dofs()
+    a = bm.arrays()
+    n, npc = p + 1, (p + 1) ** dim
+    val, grad, _, _ = (np.asarray(t) for t in mf.shape_info(p))
+    q = np.arange(npc)
+    qi = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
+    Nq = np.ones((npc, npc))
+    for e in range(dim):
+        Nq *= val[qi[None, :, e], qi[:, None, e]]
+    B = np.zeros((dim, npc, npc))
+    for d in range(dim):
+        t = np.ones((npc, npc))
+        for e in range(dim):
+            t *= (grad if e == d else val)[qi[None, :, e], qi[:, None, e]]
+        B[d] = t
+    nd, bnd = bm.n_dofs, a["boundary"].astype(np.int64)
+    lift = np.zeros(nd)
+    lift[bnd] = solution(bm.support_points()[bnd])[0]
+    rows, cols, vals, rhs = [], [], [], np.zeros(nd)
+    for c in range(bm.n_cells):
+        row, X, coef, jxw = a["loc2glob"][c].astype(np.int64), a["quadrature_points"][c], a["coefficient"][c], a["JxW"][c]
+        gx = np.einsum("qed,eqi->qdi", a["inv_jac"][c], B)                 # grad_x phi_i = K^T grad_xi phi_i
+        Ac = np.einsum("qdi,q,qdj->ij", gx, coef * jxw, gx)
+        rows.append(np.repeat(row, npc)); cols.append(np.tile(row, npc)); vals.append(Ac.ravel())
+        _, gu, lu = solution(X)
+        f = -coef * lu - ((-4.0 * X * (coef ** 2)[:, None]) * gu).sum(-1)
+        rhs[row] += Nq.T @ (f * jxw) - Ac @ lift[row]
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nd, nd))
+    free = np.ones(nd, bool)
+    free[bnd] = False
+    x = lift.copy()
+    x[free] = spl.spsolve(A[free][:, free].tocsc(), rhs[free])
+    err2 = 0.0
+    for c in range(bm.n_cells):
+        e = Nq @ x[a["loc2glob"][c].astype(np.int64)] - solution(a["quadrature_points"][c])[0]
+        err2 += (e * e * a["JxW"][c]).sum()
+    return nd, np.sqrt(err2)
+
+
+@pytest.mark.parametrize("dim,p,rs", [(2, 2, (2, 3)), (2, 4, (2, 3)), (3, 2, (1, 2))])
+def test_l2_error_on_the_ball_mesh_falls_at_the_optimal_rate(dim, p, rs):
+    errs = [solve_poisson_on_ball(dim, p, r)[1] for r in rs]
+    ratio = errs[0] / errs[1]
+    assert 0.6 * 2 ** (p + 1) <= ratio <= 1.6 * 2 ** (p + 1), (errs, ratio)
