@@ -13,7 +13,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LATE = os.path.join(ROOT, "tests", "late_gpu", "test_late_gpu_additions.py")
-CHILD_TIMEOUT_S = 600      # all late tests together run for two to three minutes
+CHILD_TIMEOUT_S = 480      # all late tests together run for two to three minutes
 MAX_CHILDREN = 3           # one, plus one per crash / hang
 _results = None
 
