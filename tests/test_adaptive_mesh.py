@@ -152,3 +152,32 @@ def test_pseudo_adaptive_refinement_counts():
     assert np.isin(a["hanging"], a["constrained"]).all()
     am3 = mf.AdaptiveMesh(3, 1).pseudo_adaptive_refinement(5).distribute_dofs()
     assert am3.n_cells > 512 and am3.arrays()["constraint_mask"].max() > 0
+
+
+@pytest.mark.parametrize("dim,p,n_ref", [(3, 2, 4), (2, 3, 5)])
+def test_cxx_facade_on_the_host_substrates(dim, p, n_ref):
+    """include/dealii_cuda_b200/matrix_free_gpu.h (AdaptiveMesh<dim>, BallMesh<dim>) through a host-only example: the same meshes,
+    DoF counts and multigrid hierarchy as the Python binding"""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "_build", "host_substrates")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "examples"), "-s", "_build/host_substrates"])
+    out = subprocess.run([exe, str(dim), str(p), str(n_ref)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    num = lambda line: {k: int(v) for k, v in re.findall(r"([a-z]+) (\d+)", line)}
+    am = mf.AdaptiveMesh(dim, p, limit_level_difference_at_vertices=True).pseudo_adaptive_refinement(n_ref).distribute_dofs().build_mg(0)
+    a = am.arrays()
+    f = num(lines[0])
+    assert (f["cells"], f["levels"], f["dofs"], f["constrained"], f["boundary"]) == (am.n_cells, am.n_levels, am.n_dofs, a["constrained"].size,
+                                                                                  am.boundary_dofs().size)
+    for l in range(am.n_levels):
+        f, lv = num(lines[1 + l]), am.mg_level(l)
+        assert (f["cells"], f["dofs"], f["boundary"], f["edge"], f["blocks"], f["copy"]) == (
+            lv["loc2glob"].shape[0], lv["n_dofs"], lv["boundary"].size, lv["edge"].size, lv["coarse_idx"].shape[0], lv["copy_global"].size)
+    bm = mf.BallMesh(dim, p, max(n_ref - 2, 0)).distribute_dofs()
+    f = num(lines[-1])
+    assert (f["cells"], f["dofs"], f["boundary"]) == (bm.n_cells, bm.n_dofs, bm.arrays()["boundary"].size)
