@@ -80,6 +80,16 @@ def test_generic_path_interpolates_hanging_nodes(ctx, gen, dim, p, dtype):
     dst.fill(0.0)
     gen(mfree, 0, dim, p, dtype, dst, src)
     assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
+    # the reference's own Laplace LocalOperator on the same path: the free rows of the oracle's hanging-node operator.  Per-point user
+    # arrays are indexed in kernel cell order = cells without a mask first (stable), get_global_q
+    perm = np.concatenate([np.nonzero(a["constraint_mask"] == 0)[0], np.nonzero(a["constraint_mask"] != 0)[0]])
+    u0 = u.copy(); u0[o.constrained] = 0.0
+    cdev = mf.GpuVector.from_numpy(ctx, a["coefficient"][perm].reshape(-1).astype(dtype))
+    src0 = mf.GpuVector.from_numpy(ctx, u0.astype(dtype))
+    dst.fill(0.0)
+    gen(mfree, 1, dim, p, dtype, dst, src0, cdev)
+    free = np.ones(am.n_dofs, bool); free[o.constrained] = False
+    assert rel_err(dst.toVector()[free], o.vmult(u0)[free]) <= (1e-12 if dtype == np.float64 else 2e-5)
 
 
 @pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
