@@ -181,3 +181,32 @@ def test_cxx_facade_on_the_host_substrates(dim, p, n_ref):
     bm = mf.BallMesh(dim, p, max(n_ref - 2, 0)).distribute_dofs()
     f = num(lines[-1])
     assert (f["cells"], f["dofs"], f["boundary"]) == (bm.n_cells, bm.n_dofs, bm.arrays()["boundary"].size)
+
+
+@pytest.mark.parametrize("dim,p,seed,smooth", [(2, 2, 1, False), (2, 3, 2, True), (2, 4, 6, False), (3, 1, 3, False), (3, 1, 7, True), (3, 2, 4, True)])
+def test_random_refinement_matches_oracle(dim, p, seed, smooth):
+    """three passes of pseudo-random flags (the reference's RANDOM grid case, poisson_common.h:37-40, with a reproducible
+    generator): the same cell set as the oracle's refinement under the same one-level rule, and the same arrays bit for bit"""
+    def flagged(center, h):       # a deterministic function of the cell: both sides flag the same cells
+        key = np.floor((np.asarray(center) + 1.0) * 4096).astype(np.int64)
+        return int((key * np.array([73856093, 19349663, 83492791])[:dim]).sum() * (seed * 2 + 1) + int(h * 65536)) % 100 < 35
+    am = mf.AdaptiveMesh(dim, p, limit_level_difference_at_vertices=smooth).refine_global(1)
+    for _ in range(3):
+        cells = am.active_cells()
+        hs = 2.0 / (1 << cells[:, 0].astype(np.int64))
+        centers = -1.0 + hs[:, None] * (cells[:, 1:] + 0.5)
+        am.set_refine_flags([flagged(c, h / 2) for c, h in zip(centers, hs)])
+        am.execute_coarsening_and_refinement()
+    am.distribute_dofs()
+    o_own = OracleAdaptive(dim, p, 1, [flagged] * 3, balance="vertex" if smooth else "dealii")
+    cells = am.active_cells()
+    assert set(map(tuple, cells.tolist())) == set(o_own.cells)
+    o = OracleAdaptive(dim, p, 0, [], cells=cells.tolist())
+    a = am.arrays()
+    assert np.array_equal(a["loc2glob_unconstrained"], o.l2g_own) and np.array_equal(a["loc2glob"], o.l2g)
+    assert np.array_equal(a["constraint_mask"], o.mask) and np.array_equal(a["constrained"], o.constrained)
+    assert np.array_equal(a["hanging"], o.hanging)
+    # and the masks / maps mean the right thing: matrix-free apply == C^T A C from geometry alone
+    u = np.random.default_rng(seed).standard_normal(o.n_dofs)
+    want = o.assembled_vmult(u)
+    assert np.linalg.norm(o.vmult(u) - want) <= 1e-12 * np.linalg.norm(want)
