@@ -3,7 +3,6 @@ CPU part: the library's host substrate (csrc/adaptive_mesh.cu: mfg_amesh_build_m
 (oracle/adaptive_mg.py) -- level DoF maps, MGConstrainedDoFs sets and copy indices bit for bit, the transfer blocks + weights
 (what the transfer kernel consumes) against the GEOMETRIC prolongation matrix; and the oracle itself: its V-cycle is a symmetric
 positive definite preconditioner with bounded CG iteration counts."""
-import itertools
 
 import numpy as np
 import pytest
@@ -121,3 +120,34 @@ def test_min_level_above_zero_and_its_limit():
     assert it <= 12
     with pytest.raises(mf.MfgError):
         am.build_mg(3)       # level-2 cells are active: the hierarchy cannot start above them
+
+
+@pytest.mark.parametrize("dim,p,seed", [(2, 2, 1), (3, 1, 2)])
+def test_hierarchy_of_randomly_refined_meshes(dim, p, seed):
+    """the same comparison on meshes refined by pseudo-random flags (vertex-balanced): level maps, index sets, copy pairs, transfer
+    blocks -- and the V-cycle on them is symmetric"""
+    def flagged(center, h):
+        key = np.floor((np.asarray(center) + 1.0) * 4096).astype(np.int64)
+        return int((key * np.array([73856093, 19349663, 83492791])[:dim]).sum() * (seed * 2 + 1) + int(h * 65536)) % 100 < 30
+    am = mf.AdaptiveMesh(dim, p, limit_level_difference_at_vertices=True).refine_global(1)
+    for _ in range(3):
+        cells = am.active_cells()
+        hs = 2.0 / (1 << cells[:, 0].astype(np.int64))
+        centers = -1.0 + hs[:, None] * (cells[:, 1:] + 0.5)
+        am.set_refine_flags([flagged(c, h / 2) for c, h in zip(centers, hs)])
+        am.execute_coarsening_and_refinement()
+    am.distribute_dofs().build_mg(0)
+    o = OracleAdaptive(dim, p, 0, [], cells=am.active_cells().tolist())
+    lc = {l: [tuple(int(v) for v in row) for row in am.level_cells(l)] for l in range(am.n_levels)}
+    mg = AdaptiveMultigridOracle(dim, p, lc, o)
+    for l in range(am.n_levels):
+        lv, lm = am.mg_level(l), mg.levels[l]
+        assert np.array_equal(lv["loc2glob"], lm.l2g) and np.array_equal(lv["boundary"], lm.boundary) and np.array_equal(lv["edge"], lm.edge)
+        g, lvl = mg.copy[l]
+        assert np.array_equal(lv["copy_global"], g) and np.array_equal(lv["copy_level"], lvl)
+        if l > 0:
+            assert np.abs(block_prolongation(dim, p, lv, mg.levels[l - 1].n_dofs) - mg.P[l]).max() <= 1e-13
+    M = mg.matrix()
+    free = np.setdiff1d(np.arange(o.n_dofs), o.constrained)
+    Mf = M[np.ix_(free, free)]
+    assert np.abs(Mf - Mf.T).max() <= 1e-12 * np.abs(Mf).max() and np.linalg.eigvalsh(0.5 * (Mf + Mf.T)).min() > 0
