@@ -27,8 +27,9 @@ def run_child(args, timeout, log=None):
     env = dict(os.environ, MFG_RUN_LATE_GPU="1")
     if log:
         env["MFG_LATE_LOG"] = log
-    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider"] + args, cwd=ROOT, env=env, capture_output=True, text=True,
-                          timeout=timeout)
+    # (--rootdir: tests/conftest.py with the `ctx` fixture and the gpu marker must be found whatever file is named)
+    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", ROOT] + args, cwd=ROOT, env=env,
+                          capture_output=True, text=True, timeout=timeout)
 
 
 def late_results(late=None, extra_args=("-m", "gpu")):
