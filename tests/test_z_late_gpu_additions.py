@@ -110,5 +110,8 @@ def test_wrapper_survives_failures_and_crashes(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", late_test_names())
 def test_late(name):
-    ok, msg = late_results()[name]
-    assert ok, "late GPU test %s (first run on hardware) failed:\n%s" % (name, msg)
+    res = late_results()
+    ok, msg = res[name]
+    # (`pytest -x` stops at the first failure: the message carries the outcome of every late test, so that nothing is lost)
+    table = "\n".join("  %s  %s" % ("PASS" if res[n][0] else "FAIL", n) for n in late_test_names())
+    assert ok, "late GPU test %s (first run on hardware) failed:\n%s\noutcome of all late GPU tests:\n%s" % (name, msg, table)
