@@ -42,56 +42,6 @@ def test_dst_only_cell_loop_and_evaluate_on_cells(ctx, gen, dim, p, r):
     assert rel_err(coef.toVector(), np.asarray(o.coefficient).ravel()) <= 1e-14
 
 
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("dim,p", [(2, 2), (2, 4), (3, 1), (3, 2), (3, 3)])
-def test_generic_path_interpolates_hanging_nodes(ctx, gen, dim, p, dtype):
-    """read_dof_values / distribute_local_to_global of the generic FEEvaluationGpu path apply resolve_hanging_nodes_shmem
-    (fee_gpu.cuh:333-335, 349-351) on the cells that carry a constraint mask: a user-written MASS operator on an adaptive mesh
-    against numpy (gather through the rewritten map, interpolate, local mass matrix, transposed interpolation, scatter)"""
-    import dealii_cuda_b200 as mf
-    from oracle.adaptive import AdaptiveMesh, resolve_hanging_nodes
-    am = mf.AdaptiveMesh(dim, p).refine_global(2 if dim == 2 else 1)
-    am.mark_cells_in_annulus(0.9, 0.0, None); am.execute_coarsening_and_refinement()
-    am.mark_cells_in_annulus(0.5, 0.0, (-0.1, -0.2, -0.3)); am.execute_coarsening_and_refinement()
-    am.distribute_dofs()
-    a = am.arrays()
-    assert a["constraint_mask"].max() > 0
-    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())     # (resolve_hanging_nodes needs no mesh; o gives h per cell)
-    n = p + 1
-    _, _, xq, wq = mf.shape_info(p)
-    N = np.asarray(mf.shape_info(p)[0])                                    # [i][q]
-    q = np.arange(n ** dim)
-    q_idx = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
-    Nq = np.ones((n ** dim, n ** dim))
-    for e in range(dim):
-        Nq *= N[q_idx[None, :, e], q_idx[:, None, e]]                      # [q][i]
-    wref = np.prod(wq[q_idx], axis=1)
-    u = sm64(31, am.n_dofs)
-    want = np.zeros(am.n_dofs)
-    for ci in range(am.n_cells):
-        row, mask = a["loc2glob"][ci].astype(np.int64), int(a["constraint_mask"][ci])
-        ul = resolve_hanging_nodes(u[row].reshape((n,) * dim), mask, p, dim, transpose=False).ravel()
-        v = Nq.T @ ((o.h[ci] ** dim * wref) * (Nq @ ul))
-        v = resolve_hanging_nodes(v.reshape((n,) * dim), mask, p, dim, transpose=True).ravel()
-        np.add.at(want, row, v)
-    mfree = mf.MatrixFreeGpu(ctx, dtype)
-    mfree.reinit(dict(dim=dim, degree=p, n_dofs=am.n_dofs, loc2glob=a["loc2glob"], inv_jac=a["inv_jac"], constraint_mask=a["constraint_mask"]))
-    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, am.n_dofs, dtype)
-    dst.fill(0.0)
-    gen(mfree, 0, dim, p, dtype, dst, src)
-    assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
-    # the reference's own Laplace LocalOperator on the same path: the free rows of the oracle's hanging-node operator.  Per-point user
-    # arrays are indexed in kernel cell order = cells without a mask first (stable), get_global_q
-    perm = np.concatenate([np.nonzero(a["constraint_mask"] == 0)[0], np.nonzero(a["constraint_mask"] != 0)[0]])
-    u0 = u.copy(); u0[o.constrained] = 0.0
-    cdev = mf.GpuVector.from_numpy(ctx, a["coefficient"][perm].reshape(-1).astype(dtype))
-    src0 = mf.GpuVector.from_numpy(ctx, u0.astype(dtype))
-    dst.fill(0.0)
-    gen(mfree, 1, dim, p, dtype, dst, src0, cdev)
-    free = np.ones(am.n_dofs, bool); free[o.constrained] = False
-    assert rel_err(dst.toVector()[free], o.vmult(u0)[free]) <= (1e-12 if dtype == np.float64 else 2e-5)
-
-
 @pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
 def test_operator_with_restated_dealii_coloring(ctx, dim, p, r):
     """cells sorted by the restated deal.II colors, atomics-free scatter (use_coloring): same operator as the oracle"""
@@ -153,6 +103,158 @@ def test_bmop_driver_on_the_pseudo_adaptive_mesh():
     rows = [l.split() for l in out.stdout.strip().splitlines()]
     assert [int(r[2]) for r in rows] == [729, 57142]
     assert all(float(r[3]) > 0 for r in rows)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
+def test_sparse_matrix_vmult(ctx, dim, p, r, dtype):
+    """SparseMatrix::vmult (cuda_sparse_matrix.cu:414-429) against the oracle and against the matrix-free operator"""
+    import dealii_cuda_b200 as mf
+    o = OracleMesh(dim, p, r)
+    mesh = mf.HyperCubeMesh(ctx, dim, p, r)
+    S = mf.SparseMatrixGpu(ctx, dtype)
+    S.reinit(mesh)
+    assert S.m() == o.n_dofs and S.n_nonzero_elements() > o.n_dofs
+    u = sm64(3, o.n_dofs); u[o.constrained] = 0.0
+    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, o.n_dofs, dtype)
+    S.vmult(dst, src)
+    want = o.vmult(u)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    assert np.linalg.norm(dst.toVector().astype(np.float64) - want) <= tol * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,p,r", [(2, 2, 1), (2, 4, 1), (3, 1, 1), (3, 2, 1), (3, 4, 0)])
+def test_operator_on_the_ball_mesh(ctx, dim, p, r, dtype):
+    """LaplaceOperatorGpu::reinit on the library's BALL_GRID substrate (mfg_umesh_*: hyper_ball + SphericalManifold + refine_global,
+    poisson_common.h:59-72; tests/test_ball_mesh.py pins its arrays on the CPU): general geometry, against the dense numpy operator
+    built from the same loc2glob / K / JxW / coefficient (fee_gpu.cuh:236-240, 276-280), identity on the Dirichlet rows"""
+    import dealii_cuda_b200 as mf
+    bm = mf.BallMesh(dim, p, r).distribute_dofs()
+    a = bm.arrays()
+    n, npc = p + 1, (p + 1) ** dim
+    val, grad, _, _ = (np.asarray(t) for t in mf.shape_info(p))
+    q = np.arange(npc)
+    qi = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
+    B = np.zeros((dim, npc, npc))                        # [d][q][i]
+    for d in range(dim):
+        t = np.ones((npc, npc))
+        for e in range(dim):
+            t *= (grad if e == d else val)[qi[None, :, e], qi[:, None, e]]
+        B[d] = t
+    A = np.zeros((bm.n_dofs, bm.n_dofs))
+    for c in range(bm.n_cells):
+        gx = np.einsum("qed,eqi->qdi", a["inv_jac"][c], B)             # grad_x phi_i at q = K^T grad_xi phi_i
+        row = a["loc2glob"][c].astype(np.int64)
+        A[np.ix_(row, row)] += np.einsum("qdi,q,qdj->ij", gx, a["coefficient"][c] * a["JxW"][c], gx)
+    con = a["boundary"].astype(np.int64)
+    A[con, :] = 0.0; A[:, con] = 0.0; A[con, con] = 1.0
+    op = mf.LaplaceOperatorGpu(ctx, dtype)
+    op.reinit(bm)
+    u = sm64(13, bm.n_dofs)
+    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, bm.n_dofs, dtype)
+    op.vmult(dst, src)
+    want = A @ u
+    assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
+    assert np.array_equal(dst.toVector()[con], u.astype(dtype)[con])
+    if dtype == np.float64:
+        op.compute_diagonal()
+        assert rel_err(op.get_diagonal_inverse().toVector(), 1.0 / np.diag(A)) <= 1e-12
+
+
+def test_bmop_driver_on_the_ball_mesh():
+    """examples/bmop.cc built with -DBALL_GRID (bmop.cu:164-168) through the C++ facade"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "bmop_ball")
+    assert os.path.exists(exe), "examples/_build/bmop_ball is missing: run __graft_entry__.build()"
+    out = subprocess.run([exe, "2", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert [int(r[2]) for r in rows] == [3817, 29521] and all(float(r[3]) > 0 for r in rows)
+
+
+@pytest.mark.parametrize("dim,p,rmin,rmax", [(2, 2, 2, 4), (2, 4, 1, 3), (3, 2, 1, 3), (3, 4, 1, 2)])
+def test_poisson_on_the_ball_converges(dim, p, rmin, rmax):
+    """examples/poisson.cu with domain = BALL (poisson_common.h:65-70): non-affine cells in the precompiled operator (general
+    geometry) and in the user-written functors of the generic path.  The numpy restatement on the same mesh arrays gives L2 error
+    ratios 7.5 / 7.7 (2D Q2), 21 / 36 (2D Q4), 6.6 / 6.9 (3D Q2), 19 (3D Q4, still pre-asymptotic) per refinement."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "poisson")
+    out = subprocess.run([exe, str(dim), str(p), str(rmin), str(rmax), "ball"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert len(rows) == rmax - rmin + 1
+    errs = [float(r[5]) for r in rows]
+    for a, b in zip(errs[:-1], errs[1:]):
+        assert 0.4 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), (errs, "expected about a factor 2^(p+1) per refinement")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dim,p", [(2, 2), (2, 4), (3, 1), (3, 2), (3, 3)])
+def test_generic_path_interpolates_hanging_nodes(ctx, gen, dim, p, dtype):
+    """read_dof_values / distribute_local_to_global of the generic FEEvaluationGpu path apply resolve_hanging_nodes_shmem
+    (fee_gpu.cuh:333-335, 349-351) on the cells that carry a constraint mask: a user-written MASS operator on an adaptive mesh
+    against numpy (gather through the rewritten map, interpolate, local mass matrix, transposed interpolation, scatter)"""
+    import dealii_cuda_b200 as mf
+    from oracle.adaptive import AdaptiveMesh, resolve_hanging_nodes
+    am = mf.AdaptiveMesh(dim, p).refine_global(2 if dim == 2 else 1)
+    am.mark_cells_in_annulus(0.9, 0.0, None); am.execute_coarsening_and_refinement()
+    am.mark_cells_in_annulus(0.5, 0.0, (-0.1, -0.2, -0.3)); am.execute_coarsening_and_refinement()
+    am.distribute_dofs()
+    a = am.arrays()
+    assert a["constraint_mask"].max() > 0
+    o = AdaptiveMesh(dim, p, 0, [], cells=am.active_cells().tolist())     # (resolve_hanging_nodes needs no mesh; o gives h per cell)
+    n = p + 1
+    _, _, xq, wq = mf.shape_info(p)
+    N = np.asarray(mf.shape_info(p)[0])                                    # [i][q]
+    q = np.arange(n ** dim)
+    q_idx = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
+    Nq = np.ones((n ** dim, n ** dim))
+    for e in range(dim):
+        Nq *= N[q_idx[None, :, e], q_idx[:, None, e]]                      # [q][i]
+    wref = np.prod(wq[q_idx], axis=1)
+    u = sm64(31, am.n_dofs)
+    want = np.zeros(am.n_dofs)
+    for ci in range(am.n_cells):
+        row, mask = a["loc2glob"][ci].astype(np.int64), int(a["constraint_mask"][ci])
+        ul = resolve_hanging_nodes(u[row].reshape((n,) * dim), mask, p, dim, transpose=False).ravel()
+        v = Nq.T @ ((o.h[ci] ** dim * wref) * (Nq @ ul))
+        v = resolve_hanging_nodes(v.reshape((n,) * dim), mask, p, dim, transpose=True).ravel()
+        np.add.at(want, row, v)
+    mfree = mf.MatrixFreeGpu(ctx, dtype)
+    mfree.reinit(dict(dim=dim, degree=p, n_dofs=am.n_dofs, loc2glob=a["loc2glob"], inv_jac=a["inv_jac"], constraint_mask=a["constraint_mask"]))
+    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, am.n_dofs, dtype)
+    dst.fill(0.0)
+    gen(mfree, 0, dim, p, dtype, dst, src)
+    assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
+    # the reference's own Laplace LocalOperator on the same path: the free rows of the oracle's hanging-node operator.  Per-point user
+    # arrays are indexed in kernel cell order = cells without a mask first (stable), get_global_q
+    perm = np.concatenate([np.nonzero(a["constraint_mask"] == 0)[0], np.nonzero(a["constraint_mask"] != 0)[0]])
+    u0 = u.copy(); u0[o.constrained] = 0.0
+    cdev = mf.GpuVector.from_numpy(ctx, a["coefficient"][perm].reshape(-1).astype(dtype))
+    src0 = mf.GpuVector.from_numpy(ctx, u0.astype(dtype))
+    dst.fill(0.0)
+    gen(mfree, 1, dim, p, dtype, dst, src0, cdev)
+    free = np.ones(am.n_dofs, bool); free[o.constrained] = False
+    assert rel_err(dst.toVector()[free], o.vmult(u0)[free]) <= (1e-12 if dtype == np.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("dim,p,rmin,rmax", [(2, 2, 3, 6), (2, 4, 2, 5), (3, 2, 2, 4), (3, 4, 2, 4)])
+def test_poisson_on_a_locally_refined_mesh_converges_at_the_optimal_rate(dim, p, rmin, rmax):
+    """examples/poisson.cu with grid_refinement = NONUNIFORM (poisson_common.h:76-92): hanging-node constraints in the precompiled
+    operator, in the user-written right-hand-side / error functors of the generic path and in the constraint handler at once.
+    Against the ANALYTIC solution of poisson_common.cc the L2 error must still fall like h^(p+1) per refinement of the family."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "poisson")
+    assert os.path.exists(exe), "examples/_build/poisson is missing: run __graft_entry__.build()"
+    out = subprocess.run([exe, str(dim), str(p), str(rmin), str(rmax), "nonuniform"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert len(rows) == rmax - rmin + 1
+    errs = [float(r[5]) for r in rows]
+    for a, b in zip(errs[:-1], errs[1:]):
+        assert 0.5 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), (errs, "expected a factor 2^(p+1) per refinement")
+    assert all(int(r[4]) > 0 for r in rows)
 
 
 def _adaptive_mg_case(ctx, dim, p, base, steps, min_level):
@@ -257,105 +359,3 @@ def test_adaptive_multigrid_through_the_cxx_facade():
     m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out.stdout)
     assert m, out.stdout
     assert int(m.group(1)) <= 20 and float(m.group(2)) <= 1e-7, out.stdout
-
-
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("dim,p,r", [(2, 3, 3), (3, 2, 2), (3, 4, 2)])
-def test_sparse_matrix_vmult(ctx, dim, p, r, dtype):
-    """SparseMatrix::vmult (cuda_sparse_matrix.cu:414-429) against the oracle and against the matrix-free operator"""
-    import dealii_cuda_b200 as mf
-    o = OracleMesh(dim, p, r)
-    mesh = mf.HyperCubeMesh(ctx, dim, p, r)
-    S = mf.SparseMatrixGpu(ctx, dtype)
-    S.reinit(mesh)
-    assert S.m() == o.n_dofs and S.n_nonzero_elements() > o.n_dofs
-    u = sm64(3, o.n_dofs); u[o.constrained] = 0.0
-    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, o.n_dofs, dtype)
-    S.vmult(dst, src)
-    want = o.vmult(u)
-    tol = 1e-12 if dtype == np.float64 else 1e-5
-    assert np.linalg.norm(dst.toVector().astype(np.float64) - want) <= tol * np.linalg.norm(want)
-
-
-@pytest.mark.parametrize("dim,p,rmin,rmax", [(2, 2, 3, 6), (2, 4, 2, 5), (3, 2, 2, 4), (3, 4, 2, 4)])
-def test_poisson_on_a_locally_refined_mesh_converges_at_the_optimal_rate(dim, p, rmin, rmax):
-    """examples/poisson.cu with grid_refinement = NONUNIFORM (poisson_common.h:76-92): hanging-node constraints in the precompiled
-    operator, in the user-written right-hand-side / error functors of the generic path and in the constraint handler at once.
-    Against the ANALYTIC solution of poisson_common.cc the L2 error must still fall like h^(p+1) per refinement of the family."""
-    import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "poisson")
-    assert os.path.exists(exe), "examples/_build/poisson is missing: run __graft_entry__.build()"
-    out = subprocess.run([exe, str(dim), str(p), str(rmin), str(rmax), "nonuniform"], capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stderr
-    rows = [l.split() for l in out.stdout.strip().splitlines()]
-    assert len(rows) == rmax - rmin + 1
-    errs = [float(r[5]) for r in rows]
-    for a, b in zip(errs[:-1], errs[1:]):
-        assert 0.5 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), (errs, "expected a factor 2^(p+1) per refinement")
-    assert all(int(r[4]) > 0 for r in rows)
-
-
-@pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("dim,p,r", [(2, 2, 1), (2, 4, 1), (3, 1, 1), (3, 2, 1), (3, 4, 0)])
-def test_operator_on_the_ball_mesh(ctx, dim, p, r, dtype):
-    """LaplaceOperatorGpu::reinit on the library's BALL_GRID substrate (mfg_umesh_*: hyper_ball + SphericalManifold + refine_global,
-    poisson_common.h:59-72; tests/test_ball_mesh.py pins its arrays on the CPU): general geometry, against the dense numpy operator
-    built from the same loc2glob / K / JxW / coefficient (fee_gpu.cuh:236-240, 276-280), identity on the Dirichlet rows"""
-    import dealii_cuda_b200 as mf
-    bm = mf.BallMesh(dim, p, r).distribute_dofs()
-    a = bm.arrays()
-    n, npc = p + 1, (p + 1) ** dim
-    val, grad, _, _ = (np.asarray(t) for t in mf.shape_info(p))
-    q = np.arange(npc)
-    qi = np.stack([(q // n ** e) % n for e in range(dim)], axis=1)
-    B = np.zeros((dim, npc, npc))                        # [d][q][i]
-    for d in range(dim):
-        t = np.ones((npc, npc))
-        for e in range(dim):
-            t *= (grad if e == d else val)[qi[None, :, e], qi[:, None, e]]
-        B[d] = t
-    A = np.zeros((bm.n_dofs, bm.n_dofs))
-    for c in range(bm.n_cells):
-        gx = np.einsum("qed,eqi->qdi", a["inv_jac"][c], B)             # grad_x phi_i at q = K^T grad_xi phi_i
-        row = a["loc2glob"][c].astype(np.int64)
-        A[np.ix_(row, row)] += np.einsum("qdi,q,qdj->ij", gx, a["coefficient"][c] * a["JxW"][c], gx)
-    con = a["boundary"].astype(np.int64)
-    A[con, :] = 0.0; A[:, con] = 0.0; A[con, con] = 1.0
-    op = mf.LaplaceOperatorGpu(ctx, dtype)
-    op.reinit(bm)
-    u = sm64(13, bm.n_dofs)
-    src, dst = mf.GpuVector.from_numpy(ctx, u.astype(dtype)), mf.GpuVector(ctx, bm.n_dofs, dtype)
-    op.vmult(dst, src)
-    want = A @ u
-    assert rel_err(dst.toVector(), want) <= (1e-12 if dtype == np.float64 else 2e-5)
-    assert np.array_equal(dst.toVector()[con], u.astype(dtype)[con])
-    if dtype == np.float64:
-        op.compute_diagonal()
-        assert rel_err(op.get_diagonal_inverse().toVector(), 1.0 / np.diag(A)) <= 1e-12
-
-
-def test_bmop_driver_on_the_ball_mesh():
-    """examples/bmop.cc built with -DBALL_GRID (bmop.cu:164-168) through the C++ facade"""
-    import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "bmop_ball")
-    assert os.path.exists(exe), "examples/_build/bmop_ball is missing: run __graft_entry__.build()"
-    out = subprocess.run([exe, "2", "1"], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    rows = [l.split() for l in out.stdout.strip().splitlines()]
-    assert [int(r[2]) for r in rows] == [3817, 29521] and all(float(r[3]) > 0 for r in rows)
-
-
-@pytest.mark.parametrize("dim,p,rmin,rmax", [(2, 2, 2, 4), (2, 4, 1, 3), (3, 2, 1, 3), (3, 4, 1, 2)])
-def test_poisson_on_the_ball_converges(dim, p, rmin, rmax):
-    """examples/poisson.cu with domain = BALL (poisson_common.h:65-70): non-affine cells in the precompiled operator (general
-    geometry) and in the user-written functors of the generic path.  The numpy restatement on the same mesh arrays gives L2 error
-    ratios 7.5 / 7.7 (2D Q2), 21 / 36 (2D Q4), 6.6 / 6.9 (3D Q2), 19 (3D Q4, still pre-asymptotic) per refinement."""
-    import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "poisson")
-    out = subprocess.run([exe, str(dim), str(p), str(rmin), str(rmax), "ball"], capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stderr
-    rows = [l.split() for l in out.stdout.strip().splitlines()]
-    assert len(rows) == rmax - rmin + 1
-    errs = [float(r[5]) for r in rows]
-    for a, b in zip(errs[:-1], errs[1:]):
-        assert 0.4 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), (errs, "expected about a factor 2^(p+1) per refinement")
