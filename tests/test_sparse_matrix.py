@@ -32,3 +32,31 @@ def test_assembled_matrix_equals_matrix_free_operator(dim, p, r):
     A = sp.csr_matrix((val, col.astype(np.int64), rp.astype(np.int64)), shape=(o.n_dofs, o.n_dofs))
     assert abs(A - A.T).max() <= 1e-13 * abs(A).max()
     assert all(np.all(np.diff(col[rp[i]:rp[i + 1]].astype(np.int64)) > 0) for i in range(0, o.n_dofs, max(1, o.n_dofs // 50)))
+
+
+def test_csr_kernel_emulated():
+    """the device code of the CSR kernel (one warp per row, __shfl_down_sync reduction) on the CPU emulation of tests/emu: the
+    assembled matrix times u equals the oracle operator -- kernel and host assembly together, before their first run on hardware"""
+    import ctypes as C
+    import os
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "dealii_cuda_b200", "csrc", "sparse_matrix.cu")).read()
+    a, b = src.index("template <typename T>\n__global__ void csr_vmult_warp_per_row"), src.index("void assemble(int dim")
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "csr_kernel_device_part.h"), "w").write(src[a:b])
+        so = os.path.join(tmp, "libemu_csr.so")
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-I", tmp, "-I", os.path.join(root, "tests", "emu"), "-o", so,
+                               os.path.join(root, "tests", "emu", "emu_csr.cc")])
+        lib = C.CDLL(so)
+        u32, dp = C.POINTER(C.c_uint32), C.POINTER(C.c_double)
+        lib.emu_csr_vmult.argtypes = [C.c_uint32, u32, u32, dp, dp, dp]
+        for dim, p, r in [(2, 3, 2), (3, 2, 1)]:
+            o = OracleMesh(dim, p, r)
+            rp, col, val = mf.assemble_laplace_csr(dim, p, o.loc2glob, o.n_dofs, np.full(o.n_cells, (1 << r) / 2.0), o.coefficient, o.constrained)
+            u = sm64(3, o.n_dofs); u[o.constrained] = 0.0
+            y = np.zeros(o.n_dofs)
+            lib.emu_csr_vmult(o.n_dofs, rp.ctypes.data_as(u32), col.ctypes.data_as(u32), val.ctypes.data_as(dp), u.ctypes.data_as(dp), y.ctypes.data_as(dp))
+            want = o.vmult(u)
+            assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)
