@@ -396,6 +396,66 @@ def bench_main(args, metric):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, k_avg_ms = float(t[0]), float(t[1])
 
+    def make_line(e2e, cg, note):
+        ng = dop.n_global
+        peak, peak_src = measured_peaks()
+        alg_bytes = b_alg(args.degree, args.dim, s) * n
+        achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+        workload = ("bmop: 3D variable-coefficient Laplace apply, FE_Q(%d), " % args.degree
+                    + (("the refine_global(%d) cube cut into boxes of %d cells per GPU, " if strong else "one refine_global(%d) cube of %d cells per GPU, ")
+                       % (args.refine, dop.mesh.n_cells))
+                    + "%s grid of boxes, %d global DoFs (%d per GPU incl. interface replicas), atomic scatter, interface exchange: %s"
+                    % ("x".join(map(str, dop.grid)), ng, n,
+                       "NVLink P2P stores + device-side barriers" if dop.exchange.symm is not None else "NCCL all_to_all_single"))
+        line = {"metric": metric, "value": ng * args.steps / (ms * 1e-3), "unit": "DoFs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": workload,
+                           "l2": "inputs larger than L2"},
+                "clocks": clocks,
+                "e2e": e2e,
+                # per apply and rank: constraint pass + cell kernel(s) + push (or pack) + accumulate; the split apply zeroes
+                # dst with cudaMemsetAsync (no zero kernel) and launches the cell kernel twice
+                "gpu_launches": args.steps * world * ((dop.op.launches_per_vmult() if not dop.n_iface_groups else dop.op.launches_per_vmult()) + 2),
+                "launch_mode": "CUDA graph replay of one apply (cell kernels + pack + all_to_all + accumulate)" if use_graphs else "eager",
+                "selfcheck": selfcheck,
+                "exchange": ("NVLink P2P stores into the neighbours' symmetric-memory receive buffers + device-side barriers"
+                             if dop.exchange.symm is not None else "NCCL all_to_all_single"),
+                "overlap": "interface cell groups first (%d of the groups), exchange on a side stream during the interior groups" % dop.n_iface_groups
+                           if dop.n_iface_groups else "none",
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             # same kernel and per-GPU workload as the N = 1 line: the committed single-GPU ncu capture applies
+                             "traffic": PROFILED_TRAFFIC.get((args.dim, args.degree, args.dtype, args.refine, dop.op.active_variant())),
+                             "kernel": "laplace cell kernel (variant %d), per GPU and apply (%d launches), max over ranks"
+                                       % (dop.op.active_variant(), kernel_launches // n_k),
+                             "kernel_ms": k_avg_ms, "peak_source": peak_src},
+                "cpu_baseline": None, "cg_solve": cg}
+        if note:
+            line["note"] = note
+        return line
+
+
+    # What follows (host-buffer end-to-end steps, the CG solve) has run on 2 GPUs only: a watchdog on every rank makes sure that the
+    # apply line measured above is printed even if one of these sections hangs on a larger world (they are then reported as
+    # timed out instead of losing the line; all ranks leave).
+    section = {"name": "e2e"}
+    extra = {"e2e": None, "cg": None}
+
+    base_line = make_line(None, None, None)    # (built now: the watchdog thread only fills in what has finished)
+
+    def on_timeout():
+        if rank == 0:
+            base_line.update({"e2e": extra["e2e"], "cg_solve": extra["cg"] or {"error": "section '%s' exceeded the watchdog limit" % section["name"]},
+                              "note": "section '%s' did not finish within %d s: reported without it" % (section["name"], WATCHDOG_S)})
+            os.write(json_fd, (json.dumps(base_line) + "\n").encode())
+        os._exit(0)
+
+    WATCHDOG_S = int(os.environ.get("MFG_BENCH_WATCHDOG_S", "420"))
+    import threading
+    watchdog = threading.Timer(WATCHDOG_S, on_timeout)
+    watchdog.daemon = True
+    watchdog.start()
+
     e2e_s = e2e_block_s = float("nan")
     n_e2e = 0
     if not getattr(args, "no_e2e", False):
@@ -449,10 +509,13 @@ def bench_main(args, metric):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s, e2e_block_s = float(te[0]), float(te[1])
         del hs, hd, ds, dd
+        extra["e2e"] = {"value": dop.n_global / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
+                        "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3}
 
 
     # CG solve over all GPUs (BASELINE metric "CG time"): b = A u for a vector u whose interface replicas agree
     cg = None
+    section["name"] = "cg_solve"
     if not args.no_cg:
         from . import GpuVector as GV
         ta.fill_(1.0)
@@ -478,43 +541,10 @@ def bench_main(args, metric):
               "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|",
               "loop": "distributed.solver_cg_distributed: graph-replayed apply + mfg_cgd_* kernels, scalars all-reduced on the device (NCCL, "
                       "in stream order), one host read of the convergence flag every 8 iterations"}
+        extra["cg"] = cg
+    watchdog.cancel()
     if rank == 0:
-        ng = dop.n_global
-        peak, peak_src = measured_peaks()
-        alg_bytes = b_alg(args.degree, args.dim, s) * n
-        achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
-        workload = ("bmop: 3D variable-coefficient Laplace apply, FE_Q(%d), " % args.degree
-                    + (("the refine_global(%d) cube cut into boxes of %d cells per GPU, " if strong else "one refine_global(%d) cube of %d cells per GPU, ")
-                       % (args.refine, dop.mesh.n_cells))
-                    + "%s grid of boxes, %d global DoFs (%d per GPU incl. interface replicas), atomic scatter, interface exchange: %s"
-                    % ("x".join(map(str, dop.grid)), ng, n,
-                       "NVLink P2P stores + device-side barriers" if dop.exchange.symm is not None else "NCCL all_to_all_single"))
-        line = {"metric": metric, "value": ng * args.steps / (ms * 1e-3), "unit": "DoFs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-                "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": workload,
-                           "l2": "inputs larger than L2"},
-                "clocks": clocks,
-                "e2e": ({"value": ng / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
-                         "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3}
-                        if n_e2e else None),
-                # per apply and rank: constraint pass + cell kernel(s) + push (or pack) + accumulate; the split apply zeroes
-                # dst with cudaMemsetAsync (no zero kernel) and launches the cell kernel twice
-                "gpu_launches": args.steps * world * ((dop.op.launches_per_vmult() if not dop.n_iface_groups else dop.op.launches_per_vmult()) + 2),
-                "launch_mode": "CUDA graph replay of one apply (cell kernels + pack + all_to_all + accumulate)" if use_graphs else "eager",
-                "selfcheck": selfcheck,
-                "exchange": ("NVLink P2P stores into the neighbours' symmetric-memory receive buffers + device-side barriers"
-                             if dop.exchange.symm is not None else "NCCL all_to_all_single"),
-                "overlap": "interface cell groups first (%d of the groups), exchange on a side stream during the interior groups" % dop.n_iface_groups
-                           if dop.n_iface_groups else "none",
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             # same kernel and per-GPU workload as the N = 1 line: the committed single-GPU ncu capture applies
-                             "traffic": PROFILED_TRAFFIC.get((args.dim, args.degree, args.dtype, args.refine, dop.op.active_variant())),
-                             "kernel": "laplace cell kernel (variant %d), per GPU and apply (%d launches), max over ranks"
-                                       % (dop.op.active_variant(), kernel_launches // n_k),
-                             "kernel_ms": k_avg_ms, "peak_source": peak_src},
-                "cpu_baseline": None, "cg_solve": cg}
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        os.write(json_fd, (json.dumps(make_line(extra["e2e"], extra["cg"], None)) + "\n").encode())
     # Teardown: ncclCommDestroy hung on this stack (torch 2.11 / NCCL 2.28) after captured graphs that hold NCCL kernels had
     # run; the graphs are released first and the teardown gets 20 s on a watchdog thread before the ranks leave without it.
     graphs.clear()

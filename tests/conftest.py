@@ -16,7 +16,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# MFG_EMULATION=1 (set by tests/test_emulated_library.py for its child process): `dealii_cuda_b200` on sys.path is a copy of the
+# binding next to libmfgpu_emu.so, the library's own sources compiled for the CPU (tests/emu/): GPU tests of paths that need no
+# fast kernel then run without a device
+EMULATION = os.environ.get("MFG_EMULATION") == "1"
+
+
 def _has_cuda():
+    if EMULATION:
+        return True
     try:
         import torch
         return torch.cuda.is_available()
@@ -35,7 +43,8 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def ctx():
-    import torch
     import dealii_cuda_b200 as mf
-    torch.cuda.init()
+    if not EMULATION:
+        import torch
+        torch.cuda.init()
     return mf.Context(0, None)

@@ -6,6 +6,8 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -56,6 +58,68 @@ template <typename T> inline T atomicAdd(T *addr, T val)
   return old;
 }
 
+// dynamic shared memory of the running block for sources transformed by build_emu_lib.py (`extern __shared__ T x[]` becomes a pointer to it)
+alignas(16) inline unsigned char emu_dyn_smem[256 * 1024];
+
+// worker pool: OS threads are created once and reused by every launch (a CG solve launches thousands of small kernels)
+class emu_pool
+{
+public:
+  static emu_pool &get() { static emu_pool p; return p; }
+  // run fn(t) for t = 0 .. n-1 on n workers concurrently, return when all are done
+  void run(unsigned n, const std::function<void(unsigned)> &fn)
+  {
+    grow(n);
+    task_ = &fn;
+    remaining_.store((int)n);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      want_ = n; ++generation_;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [&] { return remaining_.load() == 0; });
+  }
+  ~emu_pool()
+  {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++generation_; }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+private:
+  void grow(unsigned n)
+  {
+    while (workers_.size() < n)
+      {
+        const unsigned id = (unsigned)workers_.size();
+        unsigned long   seen;
+        { std::lock_guard<std::mutex> lk(m_); seen = generation_; }
+        workers_.emplace_back([this, id, seen]() mutable {
+          for (;;)
+            {
+              std::unique_lock<std::mutex> lk(m_);
+              cv_.wait(lk, [&] { return generation_ != seen; });
+              seen = generation_;
+              if (stop_) return;
+              const bool mine = id < want_;
+              lk.unlock();
+              if (!mine) continue;
+              (*task_)(id);
+              if (remaining_.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m_); done_cv_.notify_all(); }
+            }
+        });
+      }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex               m_;
+  std::condition_variable  cv_, done_cv_;
+  unsigned long            generation_ = 0;
+  unsigned                 want_ = 0;
+  bool                     stop_ = false;
+  std::atomic<int>         remaining_{0};
+  const std::function<void(unsigned)> *task_ = nullptr;
+};
+
 // kernel<<<grid, block>>>(args...): blocks sequentially, the threads of a block concurrently
 template <typename Kernel, typename... Args> void emu_launch(unsigned grid, unsigned block, Kernel kernel, Args... args)
 {
@@ -64,15 +128,19 @@ template <typename Kernel, typename... Args> void emu_launch(unsigned grid, unsi
       std::barrier<>           bar((std::ptrdiff_t)block);
       std::vector<std::unique_ptr<emu_warp_ctx>> warps;
       for (unsigned w = 0; w * 32 < block; ++w) warps.emplace_back(new emu_warp_ctx((int)std::min(32u, block - w * 32)));
-      std::vector<std::thread> threads;
-      threads.reserve(block);
-      for (unsigned t = 0; t < block; ++t)
-        threads.emplace_back([&, t] {
-          threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
-          emu_block_barrier = &bar;
-          emu_warp = warps[t / 32].get();
-          kernel(args...);
-        });
-      for (auto &th : threads) th.join();
+      emu_pool::get().run(block, [&](unsigned t) {
+        threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+        emu_block_barrier = &bar;
+        emu_warp = warps[t / 32].get();
+        kernel(args...);
+        // a thread that has left the kernel no longer takes part in the barriers of its block / warp (as on the device)
+        emu_warp->bar.arrive_and_drop();
+        bar.arrive_and_drop();
+      });
     }
+}
+// the transformed form of kernel<<<grid, block, smem, stream>>>(args...)
+template <typename Kernel, typename... Args> void emu_launch4(unsigned grid, unsigned block, size_t, void *, Kernel kernel, Args... args)
+{
+  emu_launch(grid, block, kernel, args...);
 }

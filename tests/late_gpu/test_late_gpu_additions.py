@@ -18,6 +18,9 @@ pytestmark = pytest.mark.gpu
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests/ (the generic-path fixtures live there)
 from oracle.oracle import OracleMesh, sm64  # noqa: E402  (checker)
+# the compiled examples (examples/_build, built by __graft_entry__.build()); the emulation run points this at its own builds
+EXAMPLES_BUILD = os.environ.get("MFG_EXAMPLES_BUILD") or os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
+                                                                      "examples", "_build")
 from test_gpu_generic_path import gen, rel_err  # noqa: E402,F401  (fixture: the compiled example functors)
 
 
@@ -96,7 +99,7 @@ def test_bmop_driver_on_the_pseudo_adaptive_mesh():
     the C++ facade; the DoF counts are those of the library's host substrate (checked on the CPU in tests/test_adaptive_mesh.py)"""
     import os
     import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "bmop_adaptive")
+    exe = os.path.join(EXAMPLES_BUILD, "bmop_adaptive")
     assert os.path.exists(exe), "examples/_build/bmop_adaptive is missing: run __graft_entry__.build()"
     out = subprocess.run([exe, "4", "3"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
@@ -165,7 +168,7 @@ def test_operator_on_the_ball_mesh(ctx, dim, p, r, dtype):
 def test_bmop_driver_on_the_ball_mesh():
     """examples/bmop.cc built with -DBALL_GRID (bmop.cu:164-168) through the C++ facade"""
     import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "bmop_ball")
+    exe = os.path.join(EXAMPLES_BUILD, "bmop_ball")
     assert os.path.exists(exe), "examples/_build/bmop_ball is missing: run __graft_entry__.build()"
     out = subprocess.run([exe, "2", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
@@ -179,7 +182,7 @@ def test_poisson_on_the_ball_converges(dim, p, rmin, rmax):
     geometry) and in the user-written functors of the generic path.  The numpy restatement on the same mesh arrays gives L2 error
     ratios 7.5 / 7.7 (2D Q2), 21 / 36 (2D Q4), 6.6 / 6.9 (3D Q2), 19 (3D Q4, still pre-asymptotic) per refinement."""
     import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "poisson")
+    exe = os.path.join(EXAMPLES_BUILD, "poisson")
     out = subprocess.run([exe, str(dim), str(p), str(rmin), str(rmax), "ball"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr
     rows = [l.split() for l in out.stdout.strip().splitlines()]
@@ -245,7 +248,7 @@ def test_poisson_on_a_locally_refined_mesh_converges_at_the_optimal_rate(dim, p,
     operator, in the user-written right-hand-side / error functors of the generic path and in the constraint handler at once.
     Against the ANALYTIC solution of poisson_common.cc the L2 error must still fall like h^(p+1) per refinement of the family."""
     import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "poisson")
+    exe = os.path.join(EXAMPLES_BUILD, "poisson")
     assert os.path.exists(exe), "examples/_build/poisson is missing: run __graft_entry__.build()"
     out = subprocess.run([exe, str(dim), str(p), str(rmin), str(rmax), "nonuniform"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr
@@ -353,7 +356,7 @@ def test_adaptive_multigrid_through_the_cxx_facade():
     import os
     import re
     import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "examples", "_build", "bmop_adaptive")
+    exe = os.path.join(EXAMPLES_BUILD, "bmop_adaptive")
     out = subprocess.run([exe, "4", "4", "mg"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out.stdout)

@@ -22,7 +22,7 @@ def ctx():
 
 @pytest.fixture(scope="module")
 def gen():
-    path = os.path.join(ROOT, "examples", "_build", "libgeneric_ops.so")
+    path = os.path.join(os.environ.get("MFG_EXAMPLES_BUILD") or os.path.join(ROOT, "examples", "_build"), "libgeneric_ops.so")
     assert os.path.exists(path), "examples/_build/libgeneric_ops.so is missing: run __graft_entry__.build()"
     lib = C.CDLL(path)
     lib.generic_apply.restype = C.c_int
