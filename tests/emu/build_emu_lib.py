@@ -189,7 +189,10 @@ def build_examples(out_dir, so):
             (["-x", "c++", os.path.join(ex, "poisson.cu"), "-o", os.path.join(bld, "poisson")]),
             ([os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop")]),
             (["-DADAPTIVE_GRID", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_adaptive")]),
-            (["-DBALL_GRID", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_ball")])]
+            (["-DBALL_GRID", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_ball")]),
+            # (degree 2 builds: the emulation runs one OS thread per CUDA thread, the Q4 drivers take minutes at any useful size)
+            (["-DADAPTIVE_GRID", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_adaptive_q2")]),
+            (["-DBALL_GRID", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_ball_q2")])]
 
     def run(j):
         # (-x c++ applies to the files behind it: the link options go last, behind `-x none`)

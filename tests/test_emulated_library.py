@@ -1,0 +1,90 @@
+"""The LIBRARY'S OWN SOURCES on the CPU: tests/emu/build_emu_lib.py compiles dealii_cuda_b200/csrc (everything except the slab3 /
+staged cell kernels, which are inline PTX) and the examples with g++ against a small CUDA stand-in (one OS thread per CUDA thread,
+blocks one after the other), giving libmfgpu_emu.so with the same C ABI.  A child pytest process then runs the GPU tests of
+tests/late_gpu/ -- code written after the round's GPU budget was spent, never run on hardware -- against it: host orchestration,
+launch arithmetic, every kernel's index logic, barriers and atomics of the column / general / CSR / transfer / solver / multigrid
+kernels and of the header-only generic path run for real, only the hardware is missing.  The drivers (bmop -DADAPTIVE_GRID,
+-DBALL_GRID, poisson on the ball and on locally refined meshes) run at sizes the emulation finishes in seconds.
+
+The product package has no emulation switch: the child sees a COPY of the Python binding next to libmfgpu_emu.so in front of the
+repository on PYTHONPATH.  Nothing here counts as a parity claim for the GPU (the -m gpu tests do); it is a pre-flight check."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LATE = os.path.join(ROOT, "tests", "late_gpu", "test_late_gpu_additions.py")
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    import build_emu_lib
+    out = str(tmp_path_factory.mktemp("mfg_emu"))
+    so = build_emu_lib.build(out)
+    return {"so": so, "examples": build_emu_lib.build_examples(out, so), "pkg": build_emu_lib.build_package(out, so)}
+
+
+def _env(emu):
+    return dict(os.environ, MFG_EMULATION="1", MFG_RUN_LATE_GPU="1", MFG_EXAMPLES_BUILD=emu["examples"],
+                PYTHONPATH=os.pathsep.join([emu["pkg"], ROOT]))
+
+
+def test_emulated_library_exports_the_c_abi(emu):
+    """libmfgpu_emu.so is the same library: every symbol include/mfgpu.h declares is there"""
+    decl = set(re.findall(r"\b(mfg_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "include", "mfgpu.h")).read()))
+    out = subprocess.run(["nm", "-D", "--defined-only", emu["so"]], capture_output=True, text=True, check=True).stdout
+    have = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    assert decl and not (decl - have), sorted(decl - have)
+
+
+def test_late_gpu_tests_on_the_emulated_library(emu):
+    """the ctx-based tests of tests/late_gpu/ (generic path with hanging nodes, dst-only cell_loop, evaluate_on_cells, restated coloring,
+    adaptive-mesh operator, ball operator, CSR competitor, adaptive multigrid pieces and V-cycle CG) pass against the emulation;
+    the driver-based ones run below at smaller sizes"""
+    args = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", ROOT, LATE, "-m", "gpu", "-rA",
+            "-k", "not poisson and not bmop and not cxx_facade and not (vcycle_and_cg and (3-2-1 or 2-3-1))"]
+    # (cwd is the package copy: `python -m` puts the cwd in front of PYTHONPATH, the repository's package must not win)
+    r = subprocess.run(args, cwd=emu["pkg"], env=_env(emu), capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-6000:]
+    assert r.returncode == 0, tail
+    passed = re.findall(r"^PASSED (\S+)", r.stdout, flags=re.M)
+    fns = {p.split("::")[-1].split("[")[0] for p in passed}
+    assert len(passed) >= 35 and not re.search(r"^(FAILED|ERROR) ", r.stdout, flags=re.M), tail
+    assert {"test_dst_only_cell_loop_and_evaluate_on_cells", "test_operator_with_restated_dealii_coloring", "test_operator_on_library_built_adaptive_mesh",
+            "test_sparse_matrix_vmult", "test_operator_on_the_ball_mesh", "test_generic_path_interpolates_hanging_nodes",
+            "test_adaptive_multigrid_building_blocks", "test_adaptive_multigrid_vcycle_and_cg"} <= fns, fns
+
+
+def _run(emu, exe, *args, timeout=300):
+    r = subprocess.run([os.path.join(emu["examples"], exe)] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout, env=_env(emu))
+    assert r.returncode == 0, r.stderr[-3000:]
+    return r.stdout
+
+
+def test_bmop_drivers_on_the_emulated_library(emu):
+    """bmop -DADAPTIVE_GRID / -DBALL_GRID through the C++ facade (degree-2 builds): DoF counts equal the host substrates' (bound from
+    the real library, no device needed), the adaptive `mg` mode converges"""
+    import dealii_cuda_b200 as mf
+    rows = [l.split() for l in _run(emu, "bmop_adaptive_q2", 4, 3).strip().splitlines()]
+    want = [mf.AdaptiveMesh(3, 2).pseudo_adaptive_refinement(r).distribute_dofs().n_dofs for r in (3, 4)]
+    assert [int(r[2]) for r in rows] == want and all(float(r[3]) > 0 for r in rows)
+    rows = [l.split() for l in _run(emu, "bmop_ball_q2", 1, 0).strip().splitlines()]
+    assert [int(r[2]) for r in rows] == [mf.BallMesh(3, 2, r).distribute_dofs().n_dofs for r in (0, 1)]
+    out = _run(emu, "bmop_adaptive_q2", 3, 3, "mg")
+    m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out)
+    assert m and int(m.group(1)) <= 20 and float(m.group(2)) <= 1e-7, out
+
+
+@pytest.mark.parametrize("dim,p,rmin,rmax,domain", [(2, 2, 2, 3, "ball"), (2, 2, 3, 4, "nonuniform")])
+def test_poisson_driver_on_the_emulated_library(emu, dim, p, rmin, rmax, domain):
+    """examples/poisson.cu (precompiled operator + user-written right-hand-side / error functors of the generic path + CG) on the ball
+    and on a locally refined mesh: the L2 error against the analytic solution falls like h^(p+1)"""
+    rows = [l.split() for l in _run(emu, "poisson", dim, p, rmin, rmax, domain).strip().splitlines()]
+    errs = [float(r[5]) for r in rows]
+    assert len(errs) == rmax - rmin + 1
+    for a, b in zip(errs[:-1], errs[1:]):
+        assert 0.5 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), errs
