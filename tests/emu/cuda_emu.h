@@ -139,8 +139,18 @@ template <typename Kernel, typename... Args> void emu_launch(unsigned grid, unsi
       });
     }
 }
-// the transformed form of kernel<<<grid, block, smem, stream>>>(args...)
-template <typename Kernel, typename... Args> void emu_launch4(unsigned grid, unsigned block, size_t, void *, Kernel kernel, Args... args)
+// the transformed form of kernel<<<grid, block, smem, stream>>>(args...).  The launch limits of the device are enforced: at most
+// 1024 threads per block, dynamic shared memory above 48 KB only after an opt-in (cudaFuncSetAttribute records the largest value
+// asked for; the emulation cannot tell the kernels apart), never above 227 KB; a canary behind the `smem` bytes of the launch
+// catches a block that writes past what the host code reserved for it.
+inline size_t emu_max_dyn_smem_optin = 0;
+inline int    emu_launch_error = 0;   // sticky, read by cudaGetLastError of cuda_emu_runtime.h: 1 = invalid configuration, 2 = smem overrun
+template <typename Kernel, typename... Args> void emu_launch4(unsigned grid, unsigned block, size_t smem, void *, Kernel kernel, Args... args)
 {
+  if (block == 0 || block > 1024 || grid == 0 || smem > 227 * 1024 || (smem > 48 * 1024 && smem > emu_max_dyn_smem_optin)) { emu_launch_error = 1; return; }
+  const size_t guard = 4096;
+  std::memset(emu_dyn_smem + smem, 0xA5, std::min(guard, sizeof(emu_dyn_smem) - smem));
   emu_launch(grid, block, kernel, args...);
+  for (size_t i = 0; i < std::min(guard, sizeof(emu_dyn_smem) - smem); ++i)
+    if (emu_dyn_smem[smem + i] != 0xA5) { emu_launch_error = 2; break; }
 }

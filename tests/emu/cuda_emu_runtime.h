@@ -18,8 +18,18 @@ struct cudaDeviceProp { int multiProcessorCount, major, minor, l2CacheSize; char
 struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
-inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
-inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+enum { cudaErrorInvalidConfiguration = 9, cudaErrorIllegalAddress = 700 };
+inline const char *cudaGetErrorString(cudaError_t e)
+{
+  return e == cudaSuccess ? "no error" : e == cudaErrorInvalidConfiguration ? "emulation: invalid launch configuration (block size / dynamic shared memory without opt-in)" :
+         e == cudaErrorIllegalAddress ? "emulation: a block wrote behind its dynamic shared memory" : "emulated CUDA error";
+}
+inline cudaError_t cudaGetLastError()
+{
+  const int e = emu_launch_error;
+  emu_launch_error = 0;
+  return e == 1 ? cudaErrorInvalidConfiguration : e == 2 ? cudaErrorIllegalAddress : cudaSuccess;
+}
 inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <typename T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc(reinterpret_cast<void **>(p), n); }
 inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
@@ -30,8 +40,8 @@ inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) 
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { if (n) std::memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaGetLastError(); }   // (a failed launch surfaces at the next synchronisation, as on the device)
+inline cudaError_t cudaDeviceSynchronize() { return cudaGetLastError(); }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
@@ -52,7 +62,11 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
   std::strcpy(p->name, "CPU emulation");
   return cudaSuccess;
 }
-template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute a, int v)
+{
+  if (a == cudaFuncAttributeMaxDynamicSharedMemorySize) emu_max_dyn_smem_optin = std::max(emu_max_dyn_smem_optin, (size_t)v);
+  return cudaSuccess;
+}
 template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *b, F, int, size_t) { *b = 1; return cudaSuccess; }
 
 #define __launch_bounds__(...)
