@@ -407,8 +407,17 @@ def main():
     # end-to-end through the public host-buffer API: every step copies its input from pinned host memory (H2D),
     # applies, and copies its result back (D2H).  Two slots are pipelined so that step k's D2H overlaps step k+1's
     # H2D (mfg_laplace_vmult_host_async); the blocking single-call latency is reported next to it.
-    hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
-    hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
+    # (the pinned buffers are allocated while the thread runs on the GPU's NUMA node -- first touch puts them next to its PCIe root --
+    # and the affinity is restored afterwards: the CPU baseline below uses all host threads)
+    from dealii_cuda_b200.distributed import bind_to_gpu_numa_node
+    saved_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_node = bind_to_gpu_numa_node(local_rank)
+    try:
+        hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
+        hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
+    finally:
+        if numa_node is not None and saved_affinity:
+            os.sched_setaffinity(0, saved_affinity)
     op.vmult_host(hd[0].numpy(), hs[0].numpy())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -426,7 +435,8 @@ def main():
     op.host_sync()
     e2e_s = (time.perf_counter() - t0) / n_e2e
     e2e = {"value": n / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s, "d2h_bytes_per_step": n * s,
-           "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_blocking_s * 1e3}
+           "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_blocking_s * 1e3,
+           "host_buffers": "pinned, allocated on the GPU's NUMA node (node %d)" % numa_node if numa_node is not None else "pinned, no NUMA placement (topology not visible or a single node)"}
 
     # CG solve time on the same operator (BASELINE metric "CG time"; poisson.cu:233-260 control flow, Jacobi
     # preconditioner, |r| <= 1e-12 |b|, right-hand side b = A u for a seeded random u)

@@ -276,6 +276,38 @@ def solver_cg_distributed(dop, x, b, abs_tol, max_iter=10000, use_jacobi=True, c
     return its, float(state[3])
 
 
+def parse_cpulist(text):
+    """'0-3,8,10-11' (sysfs cpulist) -> set of CPU numbers"""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank, sysfs="/sys"):
+    """Run this rank's host threads on the CPUs of the NUMA node its GPU hangs on, so that the pinned host buffers of the end-to-end
+    leg (first touch) are local to the GPU's PCIe root: with one rank per GPU and 2 x 136 MB crossing PCIe per step and rank, buffers
+    on the other socket put every copy on the inter-socket link.  Returns the node, or None where the topology is not visible
+    (containers without sysfs NUMA information, a single node): nothing is changed then."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")).read())
+        if node < 0 or not os.path.isdir(os.path.join(sysfs, "devices/system/node/node1")):
+            return None
+        cpus = parse_cpulist(open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)).read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def bench_main(args, metric):
     """bench.py --gpus N (N > 1): weak scaling, one 2^r cube of cells per GPU."""
     import torch
@@ -291,6 +323,7 @@ def bench_main(args, metric):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
     # The exchange runs beside the persistent interior cell kernel, which leaves 4 CTA slots free (MFG_SLAB2_RESERVE):
     # NCCL's send/recv kernel must fit into them, so few and narrow channels (measured on 2 x B200: 0.281 ms per apply
     # against 0.287 with NCCL's defaults, profiles/r01_multigpu_overlap.txt)
@@ -510,7 +543,9 @@ def bench_main(args, metric):
         e2e_s, e2e_block_s = float(te[0]), float(te[1])
         del hs, hd, ds, dd
         extra["e2e"] = {"value": dop.n_global / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
-                        "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3}
+                        "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3,
+                        "host_buffers": "pinned, rank bound to the GPU's NUMA node (rank 0: node %d)" % numa_node if numa_node is not None
+                                        else "pinned, no NUMA binding (topology not visible or a single node)"}
 
 
     # CG solve over all GPUs (BASELINE metric "CG time"): b = A u for a vector u whose interface replicas agree

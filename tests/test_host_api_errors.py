@@ -68,3 +68,14 @@ def test_ball_mesh_and_sparse_matrix_arguments():
 def test_graph_coloring_and_stage_plan_reject_bad_input():
     with pytest.raises(mf.MfgError):
         mf.graph_coloring(np.array([[0, 1, 2, 99]], np.uint32), 4)   # conflict index beyond n_indices
+
+
+def test_numa_binding_helper_is_harmless_without_topology():
+    """bench's NUMA placement of pinned buffers: the cpulist parser, and no change of the affinity where the GPU / sysfs topology is
+    not visible (this container)"""
+    import os
+    from dealii_cuda_b200.distributed import bind_to_gpu_numa_node, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and parse_cpulist("5") == {5} and parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
