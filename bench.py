@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cg", action="store_true", help="skip the CG solve-time measurement (second part of BASELINE's metric)")
     ap.add_argument("--no-e2e", action="store_true", help="N > 1 only: skip the host-buffer end-to-end leg (extra lines at sizes whose pinned buffers would not fit)")
+    ap.add_argument("--no-mg", action="store_true", help="N > 1 only: skip the multigrid-preconditioned CG over the partition")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one refine_global(R) cube per GPU (default), strong = the refine_global(R) cube split over the GPUs")
     ap.add_argument("--adaptive", action="store_true",

@@ -472,13 +472,14 @@ def bench_main(args, metric):
     # apply line measured above is printed even if one of these sections hangs on a larger world (they are then reported as
     # timed out instead of losing the line; all ranks leave).
     section = {"name": "e2e"}
-    extra = {"e2e": None, "cg": None}
+    extra = {"e2e": None, "cg": None, "mg": None}
 
     base_line = make_line(None, None, None)    # (built now: the watchdog thread only fills in what has finished)
 
     def on_timeout():
         if rank == 0:
             base_line.update({"e2e": extra["e2e"], "cg_solve": extra["cg"] or {"error": "section '%s' exceeded the watchdog limit" % section["name"]},
+                              "mg_solve": extra["mg"],
                               "note": "section '%s' did not finish within %d s: reported without it" % (section["name"], WATCHDOG_S)})
             os.write(json_fd, (json.dumps(base_line) + "\n").encode())
         os._exit(0)
@@ -577,9 +578,41 @@ def bench_main(args, metric):
               "loop": "distributed.solver_cg_distributed: graph-replayed apply + mfg_cgd_* kernels, scalars all-reduced on the device (NCCL, "
                       "in stream order), one host read of the convergence flag every 8 iterations"}
         extra["cg"] = cg
+        # The same system by CG preconditioned with the multigrid V-cycle over the partition (partitioned_mg.py: every level partitioned
+        # like the finest, local transfers, Chebyshev(5) smoothers with exchanged diagonals, partitioned coarse CG).  First hardware run
+        # of this leg is the driver's: any failure is reported in place of the figures, a hang is the watchdog's.
+        section["name"] = "mg_solve"
+        if not getattr(args, "no_mg", False):
+            try:
+                from .partitioned_mg import DistributedLevel, PartitionedMultigrid
+                t0 = time.perf_counter()
+                pm = PartitionedMultigrid(lambda l: DistributedLevel(ctx, rank, world, args.dim, args.degree, l, dtype, strong,
+                                                                     dop=dop if l == args.refine else None), 1, args.refine)
+                torch.cuda.synchronize(); dist.barrier()
+                mg_setup_s = time.perf_counter() - t0
+                xf = [GV(ctx, n, dtype)]
+                xf[0].fill(0.0)
+                pm.solve_cg(xf, [vb], 0.0, 1)                  # warm-up: one iteration = one V-cycle
+                xf[0].fill(0.0)
+                pm.coarse_iterations = 0
+                torch.cuda.synchronize(); dist.barrier()
+                t0 = time.perf_counter()
+                its2, res2 = pm.solve_cg(xf, [vb], (1e-10 if args.dtype == "f64" else 1e-5) * bnorm, 100)
+                torch.cuda.synchronize(); dist.barrier()
+                mg_s = time.perf_counter() - t0
+                xf[0].add(-1.0, ue)
+                extra["mg"] = {"seconds": mg_s, "iterations": its2, "rel_error": dop.dot(xf[0], xf[0]) ** 0.5 / dop.dot(ue, ue) ** 0.5,
+                               "n_dofs": dop.n_global, "levels": args.refine, "coarse_cg_iterations": pm.coarse_iterations, "setup_seconds": mg_setup_s,
+                               "tolerance": "1e-10*|b|" if args.dtype == "f64" else "1e-5*|b|",
+                               "preconditioner": "V-cycle over the box partition, levels 1..%d, Chebyshev(5), local transfers, partitioned coarse CG; "
+                                                 "host-orchestrated (one host read per dot product)" % args.refine}
+            except Exception as e:
+                extra["mg"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     watchdog.cancel()
     if rank == 0:
-        os.write(json_fd, (json.dumps(make_line(extra["e2e"], extra["cg"], None)) + "\n").encode())
+        line = make_line(extra["e2e"], extra["cg"], None)
+        line["mg_solve"] = extra["mg"]
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     # Teardown: ncclCommDestroy hung on this stack (torch 2.11 / NCCL 2.28) after captured graphs that hold NCCL kernels had
     # run; the graphs are released first and the teardown gets 20 s on a watchdog thread before the ranks leave without it.
     graphs.clear()

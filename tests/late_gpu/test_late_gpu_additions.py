@@ -362,3 +362,95 @@ def test_adaptive_multigrid_through_the_cxx_facade():
     m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out.stdout)
     assert m, out.stdout
     assert int(m.group(1)) <= 20 and float(m.group(2)) <= 1e-7, out.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# multigrid over the box partition (dealii_cuda_b200/partitioned_mg.py): all boxes in this process (LocalWorldLevel: the exchange is
+# staged through the host), the same algorithm a torchrun job runs with one box per rank
+
+def _partitioned_mg(ctx, world, dim, p, r, strong=False):
+    from dealii_cuda_b200.partitioned_mg import LocalWorldLevel, PartitionedMultigrid
+    return PartitionedMultigrid(lambda l: LocalWorldLevel(ctx, world, dim, p, l, np.float64, strong), 1, r)
+
+
+@pytest.mark.parametrize("dim,p,r", [(2, 2, 3), (3, 2, 2)])
+def test_partitioned_multigrid_with_one_box_is_the_library_vcycle(ctx, dim, p, r):
+    """world = 1: the field algorithm of partitioned_mg.py (Chebyshev with the Lanczos estimate, level_v_step, coarse CG) gives the
+    V-cycle of the library's GeometricMultigrid (mfg_mg_*, hardware-verified) -- same eigenvalue estimates, same result"""
+    import dealii_cuda_b200 as mf
+    from dealii_cuda_b200.multigrid import GeometricMultigrid
+    pm = _partitioned_mg(ctx, 1, dim, p, r)
+    gm = GeometricMultigrid(ctx, dim, p, 1, r)
+    for l in range(2, r + 1):
+        assert abs(pm.smoothers[l].lambda_max - gm.lambda_max[l]) <= 1e-10 * gm.lambda_max[l]
+    n = pm.finest.parts[0].n
+    src = sm64(3, n)
+    src[pm.finest.parts[0].mesh.constrained_dofs()] = 0.0
+    a, b1, b2 = mf.GpuVector.from_numpy(ctx, src), mf.GpuVector(ctx, n), mf.GpuVector(ctx, n)
+    pm.vmult([b1], [a])
+    gm.vmult(b2, a)
+    want = b2.toVector()
+    assert np.linalg.norm(b1.toVector() - want) <= 1e-8 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("world,dim,p,r,strong", [(2, 2, 2, 3, False), (4, 2, 3, 2, False), (2, 3, 2, 2, False), (8, 3, 2, 1, False), (4, 2, 2, 3, True)])
+def test_partitioned_multigrid_solves_the_global_problem(ctx, world, dim, p, r, strong):
+    """several boxes: MG-preconditioned CG over the partition solves A u = b of the GLOBAL mesh (oracle operator on the global box) in a
+    handful of iterations, the V-cycle is symmetric in the global inner product, replicas of interface DoFs stay equal"""
+    import dealii_cuda_b200 as mf
+    from dealii_cuda_b200.partition import box_for_rank
+    from test_partition import global_box, local_to_global_map
+    pm = _partitioned_mg(ctx, world, dim, p, r, strong)
+    L = pm.finest
+    gbox, _ = global_box(world, dim, r, strong=strong)
+    og = OracleMesh(dim, p, box=gbox)
+    assert og.n_dofs == L.n_global
+    maps = []
+    for rank, part in enumerate(L.parts):
+        box, me, _ = box_for_rank(rank, world, dim, r, strong=strong)
+        maps.append(local_to_global_map(OracleMesh(dim, p, box=box), og, me, p, r, dim, world, strong))
+    u = sm64(11, og.n_dofs)
+    u[np.asarray(og.constrained)] = 0.0
+    b_g = og.vmult(u)
+    field = lambda g: [mf.GpuVector.from_numpy(ctx, np.ascontiguousarray(g[m])) for m in maps]
+    b, x = field(b_g), L.new_field()
+    for v in x:
+        v.fill(0.0)
+    # the partitioned operator is the global one
+    t = L.new_field()
+    L.vmult(t, field(u))
+    for v, m in zip(t, maps):
+        assert np.linalg.norm(v.toVector() - b_g[m]) <= 1e-12 * np.linalg.norm(b_g)
+    assert abs(L.dot(b, b) - b_g @ b_g) <= 1e-12 * (b_g @ b_g)
+    hist = []
+    its, res = pm.solve_cg(x, b, 1e-10 * np.sqrt(L.dot(b, b)), 50, history=hist)
+    assert its <= 12, (its, hist)
+    got = np.full(og.n_dofs, np.nan)
+    for v, m in zip(x, maps):
+        part = v.toVector()
+        seen = ~np.isnan(got[m])
+        assert np.allclose(got[m][seen], part[seen], rtol=0, atol=1e-12 * np.abs(u).max())      # replicas agree
+        got[m] = part
+    assert np.linalg.norm(got - u) <= 1e-8 * np.linalg.norm(u)
+    # symmetry of the preconditioner: <M r1, r2> = <r1, M r2>
+    r1_g, r2_g = sm64(12, og.n_dofs), sm64(13, og.n_dofs)
+    r1_g[np.asarray(og.constrained)] = 0.0; r2_g[np.asarray(og.constrained)] = 0.0
+    r1, r2, m1, m2 = field(r1_g), field(r2_g), L.new_field(), L.new_field()
+    pm.vmult(m1, r1); pm.vmult(m2, r2)
+    s12, s21 = L.dot(m1, r2), L.dot(r1, m2)
+    assert abs(s12 - s21) <= 1e-7 * abs(s12)
+
+
+@pytest.mark.parametrize("world,p,r,mode", [(2, 2, 3, "weak"), (8, 2, 2, "weak"), (4, 2, 3, "strong")])
+def test_partitioned_multigrid_on_real_ranks(world, p, r, mode):
+    """the same multigrid with ONE box per rank (torchrun, NCCL / NVLink exchange, all-reduced dots): tests/multirank_mg_worker.py"""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    port = 29900 + (os.getpid() % 300) + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "multirank_mg_worker.py"), str(p), str(r), mode]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root)
+    assert out.returncode == 0 and out.stdout.count("MULTIRANK_MG_OK") == world, out.stdout[-3000:] + out.stderr[-3000:]
