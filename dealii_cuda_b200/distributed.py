@@ -484,7 +484,7 @@ def bench_main(args, metric):
             os.write(json_fd, (json.dumps(base_line) + "\n").encode())
         os._exit(0)
 
-    WATCHDOG_S = int(os.environ.get("MFG_BENCH_WATCHDOG_S", "420"))
+    WATCHDOG_S = int(os.environ.get("MFG_BENCH_WATCHDOG_S", "240"))
     import threading
     watchdog = threading.Timer(WATCHDOG_S, on_timeout)
     watchdog.daemon = True

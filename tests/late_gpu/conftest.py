@@ -20,4 +20,4 @@ def pytest_runtest_logstart(nodeid, location):
 def pytest_runtest_logreport(report):
     if report.when == "call" or report.outcome != "passed":   # the call result, or a setup / teardown that failed or skipped
         _log({"id": report.nodeid, "when": report.when, "outcome": report.outcome,
-              "msg": str(report.longrepr)[-3000:] if report.outcome == "failed" else ""})
+              "msg": str(report.longrepr)[-3000:] if report.outcome in ("failed", "skipped") else ""})

@@ -13,7 +13,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LATE = os.path.join(ROOT, "tests", "late_gpu", "test_late_gpu_additions.py")
-CHILD_TIMEOUT_S = 480      # all late tests together run for two to three minutes
+CHILD_TIMEOUT_S = 720      # all late tests together run for three to five minutes (the torchrun ones only where there are GPUs for them)
 MAX_CHILDREN = 3           # one, plus one per crash / hang
 _results = None
 
@@ -77,7 +77,8 @@ def late_results(late=None, extra_args=("-m", "gpu")):
         elif bad:
             results[fn] = (False, "\n".join(bad))
         elif all(o[0] == "skipped" for o in mine.values()):
-            results[fn] = (False, "skipped in the child process (no CUDA device there?)")
+            # (a test that needs more GPUs than the box has is rightly skipped; any other skip means the child saw no device)
+            results[fn] = (all("needs" in o[1] and "GPUs" in o[1] for o in mine.values()), "skipped in the child process (no CUDA device there?)")
         else:
             results[fn] = (True, "")
     if late == LATE:
@@ -99,12 +100,15 @@ def test_wrapper_survives_failures_and_crashes(tmp_path):
                    "@pytest.mark.parametrize('k', [1, 2])\ndef test_a_passes(k):\n    assert k > 0\n"
                    "@pytest.mark.parametrize('k', [1, 2])\ndef test_b_fails_once(k):\n    assert k == 1, 'k was %d' % k\n"
                    "def test_c_crashes():\n    os.kill(os.getpid(), signal.SIGSEGV)\n"
-                   "def test_d_runs_in_a_second_child():\n    pass\n")
+                   "def test_d_runs_in_a_second_child():\n    pass\n"
+                   "def test_e_needs_gpus():\n    pytest.skip('needs 8 GPUs')\n"
+                   "def test_f_skipped_otherwise():\n    pytest.skip('no device')\n")
     (tmp_path / "conftest.py").write_text(open(os.path.join(ROOT, "tests", "late_gpu", "conftest.py")).read())
     r = late_results(str(sim), extra_args=())
     assert r["test_a_passes"][0] and r["test_d_runs_in_a_second_child"][0]
     assert not r["test_b_fails_once"][0] and "k was 2" in r["test_b_fails_once"][1]
     assert not r["test_c_crashes"][0] and "died or hung" in r["test_c_crashes"][1]
+    assert r["test_e_needs_gpus"][0] and not r["test_f_skipped_otherwise"][0]
 
 
 @pytest.mark.gpu
