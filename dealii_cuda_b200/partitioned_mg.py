@@ -11,7 +11,8 @@ communication is the interface exchange the operator already has:
                       result (a fine interface DoF interpolates from coarse DoFs of the same face only, so the local transpose sees its
                       whole row; the scaling counts it once);
   * prolongation    = local (replicas of interface DoFs see the same coarse values);
-  * coarse problem  = unpreconditioned CG on the coarsest level, still partitioned (min_level = 1: 8 cells per rank).
+  * coarse problem  = the global level-1 mesh replicated on every process (CollapsedCoarseSolver: one all-reduce of its right-hand
+                      side, the library's CG locally), or unpreconditioned CG over the partition (collapse_coarse = False).
 A field is a list of GpuVectors, one per box this process holds: ONE in a torchrun job (DistributedLevel: NCCL / NVLink exchange), ALL
 of them in LocalWorldLevel, which stages the exchange through the host and needs neither torch nor a second device -- that form runs
 the identical algorithm in tests and in the CPU emulation build."""
@@ -19,9 +20,9 @@ import ctypes as C
 
 import numpy as np
 
-from . import GpuVector, HyperCubeMesh, LaplaceOperatorGpu, _capi, check, lib
+from . import GpuVector, HyperCubeMesh, LaplaceOperatorGpu, _capi, check, lib, solver_cg
 from .multigrid import MGTransferMatrixFreeGpu
-from .partition import box_for_rank, build_exchange_plan, global_n_dofs
+from .partition import box_for_rank, build_exchange_plan, global_n_dofs, rank_coords
 
 
 class _Part:
@@ -96,10 +97,12 @@ class LocalWorldLevel(_LevelBase):
 
     def __init__(self, ctx, world, dim, degree, level, dtype=np.float64, strong=False, left=-1.0, right=1.0):
         self.ctx, self.world, self.level, self.dtype = ctx, world, level, dtype
+        self.dim, self.degree, self.strong, self.left, self.right = dim, degree, strong, left, right
         self.parts = []
         for rank in range(world):
             p = _Part()
-            box, _, _ = box_for_rank(rank, world, dim, level, left, right, strong)
+            box, p.me, _ = box_for_rank(rank, world, dim, level, left, right, strong)
+            p.box = box
             p.mesh = HyperCubeMesh(ctx, dim, degree, box=box)
             p.op = LaplaceOperatorGpu(ctx, dtype)
             p.op.reinit(p.mesh)
@@ -112,6 +115,9 @@ class LocalWorldLevel(_LevelBase):
 
     def _sum_over_processes(self, s):
         return s
+
+    def _sum_array_over_processes(self, a):
+        return a
 
     def exchange_add(self, field):
         if self.world == 1:
@@ -146,8 +152,10 @@ class DistributedLevel(_LevelBase):
         # (dop: an operator the caller already holds for this level, e.g. the finest one of a benchmark)
         self.dop = dop if dop is not None else DistributedLaplaceOperator(ctx, rank, world, dim, degree, level, dtype, left, right, strong=strong,
                                                                           overlap=overlap)
+        self.dim, self.degree, self.strong, self.left, self.right = dim, degree, strong, left, right
         p = _Part()
         p.mesh, p.op, p.n, p.plan = self.dop.mesh, self.dop.op, self.dop.n_local, self.dop.plan
+        p.box, p.me, _ = box_for_rank(rank, world, dim, level, left, right, strong)
         self.parts = [p]
         self.n_global = self.dop.n_global
         self._finish_setup()
@@ -160,6 +168,18 @@ class DistributedLevel(_LevelBase):
         t = torch.tensor([s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, group=self.dop.exchange.group)
         return float(t.item())
+
+    def _sum_array_over_processes(self, a):
+        if self.world == 1:
+            return a
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+        dist.all_reduce(t, group=self.dop.exchange.group)
+        return t.cpu().numpy()
+
+    def dot(self, a, b):
+        return self.dop.dot(a[0], b[0])          # one masked-dot kernel (mfg_vec_dot_masked) + all-reduce
 
     def exchange_add(self, field):
         self.dop.exchange.add_interface_contributions(field[0].getData())
@@ -298,11 +318,61 @@ def field_cg(level, x, b, abs_tol, max_iter, precond=None, history=None):
     return it, res
 
 
+class CollapsedCoarseSolver:
+    """The coarsest level on ONE mesh: the boxes' right-hand sides are summed into the vector of the global level-`min_level` mesh
+    (every DoF from the rank that owns it, one all-reduce of a few thousand numbers), every process solves that small system with the
+    library's CG (mfg_solver_cg, PreconditionIdentity, reduction 1e-10: bmop_mg.cu:75-82) -- identical arithmetic everywhere, so the
+    replicas agree -- and reads its box back.  Replaces a few hundred partitioned CG iterations, each of them latency-bound (an
+    exchange and two all-reduced dots for a handful of cells per rank), by one collective."""
+
+    def __init__(self, L):
+        self.L = L
+        dim, deg = L.dim, L.degree
+        _, g = rank_coords(0, L.world, dim)
+        lg = [L.level + (0 if L.strong else int(round(np.log2(g[d])))) for d in range(dim)] + [0] * (3 - dim)
+        box = dict(log2_cells=lg, origin=[L.left] * 3, h=(L.right - L.left) / (1 << L.level), dirichlet_faces=0x3f)
+        self.mesh = HyperCubeMesh(L.ctx, dim, deg, box=box)
+        assert self.mesh.n_dofs == L.n_global, (self.mesh.n_dofs, L.n_global)
+        self.op = LaplaceOperatorGpu(L.ctx, L.dtype)
+        self.op.reinit(self.mesh)
+        self.maps = []
+        for p in L.parts:
+            lgl = p.box["log2_cells"]
+            npts = [deg * (1 << lgl[d]) + 1 if d < dim else 1 for d in range(3)]
+            grid = np.stack(np.meshgrid(*[np.arange(n, dtype=np.int64) for n in npts], indexing="ij"), axis=-1).reshape(-1, 3)
+            off = np.array([p.me[d] * deg * (1 << lgl[d]) if d < dim else 0 for d in range(3)], dtype=np.int64)
+            loc = p.mesh.lattice_to_dof(grid.astype(np.uint32))
+            m = np.full(p.n, -1, dtype=np.int64)
+            m[loc] = self.mesh.lattice_to_dof((grid + off).astype(np.uint32))
+            assert (m >= 0).all()
+            self.maps.append(m)
+        self.bg, self.xg = GpuVector(L.ctx, self.mesh.n_dofs, L.dtype), GpuVector(L.ctx, self.mesh.n_dofs, L.dtype)
+        self.iterations = 0
+
+    def solve(self, x, b):
+        L = self.L
+        acc = np.zeros(self.mesh.n_dofs)
+        for p, m, v in zip(L.parts, self.maps, b):
+            own = p.plan.owned_mask.astype(bool)
+            acc[m[own]] += v.toVector().astype(np.float64)[own]
+        acc = L._sum_array_over_processes(acc)
+        a = np.ascontiguousarray(acc, dtype=L.dtype)
+        check(lib.mfg_vec_from_host(self.bg.h, a.ctypes.data_as(C.c_void_p), a.size))
+        self.xg.fill(0.0)
+        tol = (1e-10 if np.dtype(L.dtype) == np.float64 else 1e-4) * max(float(np.linalg.norm(acc)), 1e-300)
+        its, _ = solver_cg(self.op, self.xg, self.bg, tol, 10000, use_jacobi=False)[:2]
+        self.iterations += its
+        xs = self.xg.toVector()
+        for m, v in zip(self.maps, x):
+            part = np.ascontiguousarray(xs[m])
+            check(lib.mfg_vec_from_host(v.h, part.ctypes.data_as(C.c_void_p), part.size))
+
+
 class PartitionedMultigrid:
     """V-cycle (Multigrid::level_v_step, csrc/multigrid.cu mfg_mg::cycle) on partitioned levels min_level..max_level and the CG it
     preconditions.  make_level(l) returns the level object (LocalWorldLevel or DistributedLevel)."""
 
-    def __init__(self, make_level, min_level, max_level, smoother_degree=5, smoothing_range=15.0, eig_iterations=15):
+    def __init__(self, make_level, min_level, max_level, smoother_degree=5, smoothing_range=15.0, eig_iterations=15, collapse_coarse=True):
         assert 1 <= min_level <= max_level, "the coarsest partitioned level needs at least 2 cells per direction and box"
         self.min_level, self.max_level = min_level, max_level
         self.levels = {l: make_level(l) for l in range(min_level, max_level + 1)}
@@ -321,6 +391,8 @@ class PartitionedMultigrid:
         self.b = {l: L.new_field() for l, L in self.levels.items()}
         self.t = {l: L.new_field() for l, L in self.levels.items()}
         self.coarse_iterations = 0
+        # the coarse problem: on one replicated global mesh (default), or by CG over the partition
+        self.coarse = CollapsedCoarseSolver(self.levels[min_level]) if collapse_coarse else None
 
     @property
     def finest(self):
@@ -340,6 +412,11 @@ class PartitionedMultigrid:
 
     def _cycle(self, l):
         L, x, b, t = self.levels[l], self.x[l], self.b[l], self.t[l]
+        if l == self.min_level and self.coarse is not None:
+            before = self.coarse.iterations
+            self.coarse.solve(x, b)
+            self.coarse_iterations += self.coarse.iterations - before
+            return
         if l == self.min_level:
             for v in x:
                 v.fill(0.0)

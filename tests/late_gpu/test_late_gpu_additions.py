@@ -368,9 +368,9 @@ def test_adaptive_multigrid_through_the_cxx_facade():
 # multigrid over the box partition (dealii_cuda_b200/partitioned_mg.py): all boxes in this process (LocalWorldLevel: the exchange is
 # staged through the host), the same algorithm a torchrun job runs with one box per rank
 
-def _partitioned_mg(ctx, world, dim, p, r, strong=False):
+def _partitioned_mg(ctx, world, dim, p, r, strong=False, collapse=True):
     from dealii_cuda_b200.partitioned_mg import LocalWorldLevel, PartitionedMultigrid
-    return PartitionedMultigrid(lambda l: LocalWorldLevel(ctx, world, dim, p, l, np.float64, strong), 1, r)
+    return PartitionedMultigrid(lambda l: LocalWorldLevel(ctx, world, dim, p, l, np.float64, strong), 1, r, collapse_coarse=collapse)
 
 
 @pytest.mark.parametrize("dim,p,r", [(2, 2, 3), (3, 2, 2)])
@@ -393,14 +393,17 @@ def test_partitioned_multigrid_with_one_box_is_the_library_vcycle(ctx, dim, p, r
     assert np.linalg.norm(b1.toVector() - want) <= 1e-8 * np.linalg.norm(want)
 
 
-@pytest.mark.parametrize("world,dim,p,r,strong", [(2, 2, 2, 3, False), (4, 2, 3, 2, False), (2, 3, 2, 2, False), (8, 3, 2, 1, False), (4, 2, 2, 3, True)])
-def test_partitioned_multigrid_solves_the_global_problem(ctx, world, dim, p, r, strong):
+@pytest.mark.parametrize("world,dim,p,r,strong,collapse", [(2, 2, 2, 3, False, True), (2, 2, 2, 3, False, False), (4, 2, 3, 2, False, True),
+                                                           (2, 3, 2, 2, False, True), (8, 3, 2, 1, False, False), (8, 3, 2, 2, False, True),
+                                                           (4, 2, 2, 3, True, True), (4, 3, 4, 2, True, True)])
+def test_partitioned_multigrid_solves_the_global_problem(ctx, world, dim, p, r, strong, collapse):
     """several boxes: MG-preconditioned CG over the partition solves A u = b of the GLOBAL mesh (oracle operator on the global box) in a
-    handful of iterations, the V-cycle is symmetric in the global inner product, replicas of interface DoFs stay equal"""
+    handful of iterations, the V-cycle is symmetric in the global inner product, replicas of interface DoFs stay equal; the coarse
+    problem on one replicated global mesh (collapse) or by CG over the partition"""
     import dealii_cuda_b200 as mf
     from dealii_cuda_b200.partition import box_for_rank
     from test_partition import global_box, local_to_global_map
-    pm = _partitioned_mg(ctx, world, dim, p, r, strong)
+    pm = _partitioned_mg(ctx, world, dim, p, r, strong, collapse)
     L = pm.finest
     gbox, _ = global_box(world, dim, r, strong=strong)
     og = OracleMesh(dim, p, box=gbox)
