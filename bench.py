@@ -461,6 +461,35 @@ def main():
               "loop": "mfg_solver_cg: cell kernel (h = A d and the partial sums of d.h) + cg_residual + cg_advance (also the operator's zero pass)"}
         del ue, vb_, vx_
 
+    # the same kind of system by CG preconditioned with the geometric multigrid V-cycle (poisson_mg.cu:430-552: Chebyshev(5) smoothers
+    # with deal.II's eigenvalue estimate, levels 1..r, coarse CG), the library's loop mfg_mg_solve_cg; tools/solve_large.py is the same run
+    mg_solve = None
+    if not args.no_cg:
+        try:
+            from dealii_cuda_b200.multigrid import GeometricMultigrid
+            t0 = time.perf_counter()
+            gm = GeometricMultigrid(ctx, args.dim, args.degree, 1, args.refine, dtype)
+            ctx.synchronize()
+            mg_setup_s = time.perf_counter() - t0
+            gop = gm.ops[args.refine]
+            ue = mf.GpuVector.wrap(ctx, torch.rand((n,), dtype=tdtype, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
+            vb_, vx_ = mf.GpuVector(ctx, n, dtype), mf.GpuVector(ctx, n, dtype)
+            gop.vmult(vb_, ue)
+            gm.solve_cg(vx_, vb_, 0.0, 1)    # warm-up: one V-cycle
+            vx_.fill(0.0)
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            its2, res2 = gm.solve_cg(vx_, vb_, (1e-10 if args.dtype == "f64" else 1e-5) * vb_.l2_norm(), 100)
+            ctx.synchronize()
+            mg_s = time.perf_counter() - t0
+            vx_.add(-1.0, ue)
+            mg_solve = {"seconds": mg_s, "iterations": its2, "rel_error": vx_.l2_norm() / ue.l2_norm(), "n_dofs": n, "levels": args.refine,
+                        "setup_seconds": mg_setup_s, "tolerance": "1e-10*|b|" if args.dtype == "f64" else "1e-5*|b|",
+                        "preconditioner": "geometric multigrid V-cycle (mfg_mg_*): Chebyshev(5) smoothers, levels 1..%d, coarse CG" % args.refine}
+            del gm, gop, ue, vb_, vx_
+        except Exception as e:  # the apply / CG figures stand on their own
+            mg_solve = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
     peak, peak_src = measured_peaks()
     alg_bytes = b_alg(args.degree, args.dim, s) * n
     k_avg_ms = kernel_ms / max(1, kernel_launches) * op.cell_launches_per_vmult()
@@ -483,7 +512,7 @@ def main():
                        "l2": "inputs larger than L2 (index + coefficient + 2 vectors = %.0f MB)" %
                              ((mesh.n_cells * mesh.dofs_per_cell * (4 + s) + 2 * n * s) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * op.launches_per_vmult(), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "cg_solve": cg, "configs0_r5": configs0}
+            "cpu_baseline": cpu_baseline, "cg_solve": cg, "mg_solve": mg_solve, "configs0_r5": configs0}
     print(json.dumps(line))
     return 0
 
