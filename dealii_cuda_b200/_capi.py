@@ -144,6 +144,7 @@ def _load():
         "mfg_chebyshev_vmult": (C.c_int, [vp, vp, vp]),
         "mfg_chebyshev_step": (C.c_int, [vp, vp, vp]),
         "mfg_chebyshev_info": (C.c_int, [vp, dp, dp, dp, dp, C.POINTER(C.c_int)]),
+        "mfg_vec_chebyshev_update": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int]),
         "mfg_mg_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, pp]),
         "mfg_mg_destroy": (C.c_int, [vp]),
         "mfg_mg_vcycle": (C.c_int, [vp, vp, vp]),

@@ -396,6 +396,30 @@ int mfg_chebyshev_step(mfg_cheb *c, mfg_vec *dst, const mfg_vec *src)
     c->apply(dst, src, false);
   });
 }
+// the fused vector kernel of one Chebyshev product on its own (PreconditionChebyshev::vector_updates), for callers that own the
+// operator product -- the multigrid over the box partition, whose A x includes the interface exchange
+int mfg_vec_chebyshev_update(mfg_ctx *ctx, mfg_vec *x, mfg_vec *d, const mfg_vec *ax, const mfg_vec *b, const mfg_vec *dinv, double f1, double f2,
+                             int zero_start, int first)
+{
+  return guarded([&] {
+    MFG_REQUIRE(ctx && x && d && b && dinv && (ax || zero_start), "null argument");
+    const size_t n = x->n;
+    MFG_REQUIRE(d->n == n && b->n == n && dinv->n == n && (!ax || ax->n == n), "vector sizes differ");
+    MFG_REQUIRE(d->dt == x->dt && b->dt == x->dt && dinv->dt == x->dt && (!ax || ax->dt == x->dt), "vector types differ");
+    MFG_REQUIRE(x != d && x != b && d != b, "aliased argument");
+    if (!n) return;
+    const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16));
+    cudaStream_t   s = ctx->stream;
+    const void    *axp = ax ? ax->p : b->p;   // (never read with zero_start)
+    if (x->dt == MFG_F64)
+      cheb_update<double><<<nb, 256, 0, s>>>((double *)x->p, (double *)d->p, (const double *)axp, (const double *)b->p, (const double *)dinv->p, n, f1, f2,
+                                            zero_start != 0, first != 0);
+    else
+      cheb_update<float><<<nb, 256, 0, s>>>((float *)x->p, (float *)d->p, (const float *)axp, (const float *)b->p, (const float *)dinv->p, n, (float)f1,
+                                           (float)f2, zero_start != 0, first != 0);
+    MFG_CUDA_LAST();
+  });
+}
 int mfg_chebyshev_info(const mfg_cheb *c, double *lambda_max, double *lambda_min, double *theta, double *delta, int *eig_iterations)
 {
   return guarded([&] {

@@ -248,21 +248,10 @@ class PartitionedChebyshev:
         self.lambda_max, self.lambda_min = float(ev[-1]), float(ev[0])
 
     def _update(self, x, b, f1, f2, zero_start, first):
-        # t = A x on entry (ignored with zero_start):  r = Dinv (b - t);  d = f1 d + f2 r;  x += d   (cheb_update, csrc/multigrid.cu)
+        # t = A x on entry (ignored with zero_start):  r = Dinv (b - t);  d = f1 d + f2 r;  x += d   (ONE kernel per box: cheb_update of
+        # csrc/multigrid.cu through mfg_vec_chebyshev_update)
         for xi, bi, ti, di, dinv in zip(x, b, self.t, self.d, self.level.inv_diag):
-            if zero_start:
-                ti.assign(bi)
-            else:
-                ti.sadd(-1.0, 1.0, bi)
-            ti.scale(dinv)
-            if first:
-                di.equ(f2, ti)
-            else:
-                di.sadd(f1, f2, ti)
-            if zero_start:
-                xi.assign(di)
-            else:
-                xi.add(di)
+            check(lib.mfg_vec_chebyshev_update(self.level.ctx.h, xi.h, di.h, ti.h, bi.h, dinv.h, float(f1), float(f2), int(bool(zero_start)), int(bool(first))))
 
     def apply(self, x, b, zero_start):
         """PreconditionChebyshev::vmult (zero_start) / ::step"""

@@ -416,6 +416,12 @@ int mfg_chebyshev_destroy(mfg_cheb *c);
 int mfg_chebyshev_vmult(mfg_cheb *c, mfg_vec *dst, const mfg_vec *src);   /* dst = p(Dinv A) Dinv src from a zero guess */
 int mfg_chebyshev_step(mfg_cheb *c, mfg_vec *dst, const mfg_vec *src);    /* the same sweep starting from dst */
 int mfg_chebyshev_info(const mfg_cheb *c, double *lambda_max, double *lambda_min, double *theta, double *delta, int *eig_iterations);
+/* One Chebyshev product's vector update on its own (PreconditionChebyshev::vector_updates, precondition_chebyshev in deal.II):
+ *   zero_start: d = f2 Dinv b, x = d;   else: d = (first ? 0 : f1 d) + f2 Dinv (b - ax), x += d      with ax = A x from the caller
+ * (ax may be NULL with zero_start).  For callers whose operator product is not an mfg_laplace, e.g. the partitioned operator with
+ * its interface exchange (dealii_cuda_b200/partitioned_mg.py). */
+int mfg_vec_chebyshev_update(mfg_ctx *ctx, mfg_vec *x, mfg_vec *d, const mfg_vec *ax, const mfg_vec *b, const mfg_vec *dinv, double f1, double f2,
+                             int zero_start, int first);
 /* Geometric multigrid on hyper_cube(left,right) refine_global(min_level .. max_level): level LaplaceOperatorGpu (level_mg_handler,
  * laplace_operator_gpu.h:156-186; on a globally refined mesh a level IS a uniform mesh and its edge matrices are zero),
  * MGTransferMatrixFreeGpu, Chebyshev smoothers (poisson_mg.cu:461-470: degree 5, range 15, 15 eigenvalue iterations), coarse
