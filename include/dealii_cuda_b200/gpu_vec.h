@@ -96,16 +96,16 @@ private:
 
 // DiagonalMatrix<GpuVector<Number>> as the reference hands it to PreconditionChebyshev (laplace_operator_gpu.h:79, 423-429):
 // vmult = pointwise product with the stored vector
-template <typename Number> class DiagonalMatrix
+template <typename VectorType> class DiagonalMatrix   // (VectorType = GpuVector<Number>, as deal.II's DiagonalMatrix<VectorType>)
 {
 public:
-  explicit DiagonalMatrix(GpuVector<Number> &&diag) : diag_(std::move(diag)) {}
-  const GpuVector<Number> &get_vector() const { return diag_; }
-  void vmult(GpuVector<Number> &dst, const GpuVector<Number> &src) const { dst = src; dst.scale(diag_); }
+  explicit DiagonalMatrix(VectorType &&diag) : diag_(std::move(diag)) {}
+  const VectorType &get_vector() const { return diag_; }
+  void vmult(VectorType &dst, const VectorType &src) const { dst = src; dst.scale(diag_); }
   unsigned int m() const { return diag_.size(); }
 
 private:
-  GpuVector<Number> diag_;
+  VectorType diag_;
 };
 
 // GpuList<T>: immutable device index array.  Only what the facade needs: the index lists live inside the

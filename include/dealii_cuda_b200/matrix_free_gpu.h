@@ -17,6 +17,14 @@ public:
   {
     check(mfg_mesh_hyper_cube(default_context(), dim, (int)fe_degree, (int)n_refine, left, right, &m_));
   }
+  // a box of 2^k cells per direction with Dirichlet conditions on the faces named in the descriptor (partitions of the cube:
+  // BoxPartition::box() of distributed.h)
+  HyperCubeMesh(unsigned int fe_degree, const mfg_box_desc &box)
+  {
+    mfg_box_desc d = box;
+    d.dim = dim; d.degree = (int)fe_degree;
+    check(mfg_mesh_create_box(default_context(), &d, &m_));
+  }
   ~HyperCubeMesh() { if (m_) mfg_mesh_destroy(m_); }
   HyperCubeMesh(const HyperCubeMesh &) = delete;
   unsigned int n_dofs() const { return mfg_mesh_n_dofs(m_); }

@@ -457,3 +457,17 @@ def test_partitioned_multigrid_on_real_ranks(world, p, r, mode):
            "--master-port", str(port), os.path.join(root, "tests", "multirank_mg_worker.py"), str(p), str(r), mode]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root)
     assert out.returncode == 0 and out.stdout.count("MULTIRANK_MG_OK") == world, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("args", [("2", "3"), ("8", "2"), ("4", "3", "strong")])
+def test_partitioned_multigrid_through_the_cxx_facade(args):
+    """examples/partitioned_mg.cc: the same multigrid as C++ host code on the facade (include/dealii_cuda_b200/partitioned_mg.h:
+    LocalWorldLevel, PartitionedChebyshev, PartitionedMultigrid), 3D Q4, all boxes on this device"""
+    import re
+    import subprocess
+    exe = os.path.join(EXAMPLES_BUILD, "partitioned_mg")
+    assert os.path.exists(exe), "examples/_build/partitioned_mg is missing: run __graft_entry__.build()"
+    out = subprocess.run([exe] + list(args), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"(\d+) iterations.*error ([-0-9.e+]+)", out.stdout)
+    assert m and int(m.group(1)) <= 10 and float(m.group(2)) <= 1e-8, out.stdout

@@ -91,3 +91,12 @@ def test_poisson_driver_on_the_emulated_library(emu, dim, p, rmin, rmax, domain)
     assert len(errs) == rmax - rmin + 1
     for a, b in zip(errs[:-1], errs[1:]):
         assert 0.5 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), errs
+
+
+@pytest.mark.parametrize("args,dofs", [(("2", "4"), 2145), (("4", "4", "strong"), 1089)])
+def test_partitioned_multigrid_cxx_driver_on_the_emulated_library(emu, args, dofs):
+    """examples/partitioned_mg.cc (C++ facade partitioned_mg.h; 2D Q2 build): MG-CG over 2 boxes (weak) and 4 boxes (strong) converges in
+    the 5 iterations of the single-box hierarchy"""
+    out = _run(emu, "partitioned_mg_2d_q2", *args)
+    m = re.search(r"(\d+) dofs\t(\d+) iterations.*error ([-0-9.e+]+)", out)
+    assert m and int(m.group(1)) == dofs and int(m.group(2)) <= 6 and float(m.group(3)) <= 1e-10, out
