@@ -579,7 +579,7 @@ def bench_main(args, metric):
                       "in stream order), one host read of the convergence flag every 8 iterations"}
         extra["cg"] = cg
         # The same system by CG preconditioned with the multigrid V-cycle over the partition (partitioned_mg.py: every level partitioned
-        # like the finest, local transfers, Chebyshev(5) smoothers with exchanged diagonals, partitioned coarse CG).  First hardware run
+        # like the finest, local transfers, Chebyshev(5) smoothers with exchanged diagonals, replicated coarse solve).  First hardware run
         # of this leg is the driver's: any failure is reported in place of the figures, a hang is the watchdog's.
         section["name"] = "mg_solve"
         if not getattr(args, "no_mg", False):
@@ -604,8 +604,9 @@ def bench_main(args, metric):
                 extra["mg"] = {"seconds": mg_s, "iterations": its2, "rel_error": dop.dot(xf[0], xf[0]) ** 0.5 / dop.dot(ue, ue) ** 0.5,
                                "n_dofs": dop.n_global, "levels": args.refine, "coarse_cg_iterations": pm.coarse_iterations, "setup_seconds": mg_setup_s,
                                "tolerance": "1e-10*|b|" if args.dtype == "f64" else "1e-5*|b|",
-                               "preconditioner": "V-cycle over the box partition, levels 1..%d, Chebyshev(5), local transfers, partitioned coarse CG; "
-                                                 "host-orchestrated (one host read per dot product)" % args.refine}
+                               "preconditioner": "V-cycle over the box partition, levels 1..%d, Chebyshev(5) with the fused update kernel, local transfers, "
+                                                 "coarse level solved on one replicated global mesh; host-orchestrated (one host read per dot "
+                                                 "product)" % args.refine}
             except Exception as e:
                 extra["mg"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     watchdog.cancel()
