@@ -48,3 +48,14 @@ def ctx():
         import torch
         torch.cuda.init()
     return mf.Context(0, None)
+
+
+@pytest.fixture(scope="session")
+def emu(tmp_path_factory):
+    """libmfgpu_emu.so (the library's own sources compiled for the CPU, tests/emu/build_emu_lib.py), the examples built against it and
+    a copy of the Python binding next to it: {"so", "examples", "pkg"}"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu_lib
+    out = str(tmp_path_factory.mktemp("mfg_emu"))
+    so = build_emu_lib.build(out)
+    return {"so": so, "examples": build_emu_lib.build_examples(out, so), "pkg": build_emu_lib.build_package(out, so)}

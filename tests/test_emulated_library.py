@@ -20,14 +20,6 @@ LATE = os.path.join(ROOT, "tests", "late_gpu", "test_late_gpu_additions.py")
 sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    import build_emu_lib
-    out = str(tmp_path_factory.mktemp("mfg_emu"))
-    so = build_emu_lib.build(out)
-    return {"so": so, "examples": build_emu_lib.build_examples(out, so), "pkg": build_emu_lib.build_package(out, so)}
-
-
 def _env(emu):
     return dict(os.environ, MFG_EMULATION="1", MFG_RUN_LATE_GPU="1", MFG_EXAMPLES_BUILD=emu["examples"],
                 PYTHONPATH=os.pathsep.join([emu["pkg"], ROOT]))
