@@ -305,7 +305,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    metric = "3D Q%d %s Laplace apply throughput" % (args.degree, "FP64" if args.dtype == "f64" else "FP32")
+    metric = "%dD Q%d %s Laplace apply throughput" % (args.dim, args.degree, "FP64" if args.dtype == "f64" else "FP32")
     s = 8 if args.dtype == "f64" else 4
 
     if args.impl == "reference":

@@ -84,3 +84,18 @@ def test_multigrid_worker_on_the_emulation(emu):
     rc, out, err = run_ranks(emu, 2, os.path.join(ROOT, "tests", "multirank_mg_worker.py"), [1, 2, "weak"])
     assert rc == [0, 0], err[0][-3000:] + err[1][-3000:]
     assert sum(o.count("MULTIRANK_MG_OK") for o in out) == 2, out
+
+
+@pytest.mark.parametrize("mode", [["--adaptive", "--dim", 2, "--refine", 2, "--degree", 2], ["--spmv", "--refine", 2, "--degree", 2]])
+def test_bench_extra_modes_on_the_emulation(emu, mode):
+    """bench.py --adaptive (BASELINE configs[3]: pseudo-adaptive mesh with hanging nodes, apply + Jacobi-CG + local-smoothing MG-CG) and
+    --spmv (the assembled-matrix competitor row): never run on hardware, every statement runs here"""
+    rc, out, err = run_ranks(emu, 1, os.path.join(ROOT, "bench.py"), mode + ["--steps", 2, "--warmup", 3])
+    assert rc == [0], err[0][-3000:]
+    d = the_line(out[0])
+    assert d["value"] > 0 and d["roofline"]["frac"] > 0
+    if "--adaptive" in mode:
+        assert "hanging-node constraints" in d["config"]["workload"] and d["cg_solve"]["iterations"] > 0
+        assert "error" not in d["mg_solve"] and d["mg_solve"]["iterations"] <= 12 and d["mg_solve"]["rel_error"] < 1e-8
+    else:
+        assert d["matrix_free"]["value"] > 0 and d["matrix_bytes"] > 0
