@@ -193,6 +193,7 @@ def build_examples(out_dir, so):
             # (degree 2 builds: the emulation runs one OS thread per CUDA thread, the Q4 drivers take minutes at any useful size)
             (["-DADAPTIVE_GRID", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_adaptive_q2")]),
             (["-DBALL_GRID", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_ball_q2")]),
+            (["-DADAPTIVE_GRID", "-DDIMENSION=2", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_adaptive_2d_q2")]),
             (["-DDIMENSION=2", "-DDEGREE_FE=2", os.path.join(ex, "partitioned_mg.cc"), "-o", os.path.join(bld, "partitioned_mg_2d_q2")]),
             (["-DDEGREE_FE=2", os.path.join(ex, "partitioned_mg.cc"), "-o", os.path.join(bld, "partitioned_mg_q2")])]
 
