@@ -15,3 +15,7 @@ examples/_build/bmop_ball 4 2 > gpurun_out/bmop_ball.txt 2>&1
 examples/_build/bmop_adaptive 6 5 > gpurun_out/bmop_adaptive.txt 2>&1
 examples/_build/bmop_adaptive 6 6 mg >> gpurun_out/bmop_adaptive.txt 2>&1
 cat gpurun_out/bench_adaptive_q4.json gpurun_out/bench_spmv_q4_r4.json gpurun_out/bmop_adaptive.txt
+# multigrid over the box partition: all boxes on one GPU (C++ facade), then one box per rank in the N > 1 bench lines (mg_solve)
+examples/_build/partitioned_mg 8 4 > gpurun_out/partitioned_mg.txt 2>&1
+examples/_build/partitioned_mg 8 6 strong >> gpurun_out/partitioned_mg.txt 2>&1
+cat gpurun_out/partitioned_mg.txt
