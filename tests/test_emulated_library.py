@@ -39,8 +39,8 @@ def test_late_gpu_tests_on_the_emulated_library(emu):
     with all boxes in one process) pass against the emulation;
     the driver-based ones run below at smaller sizes"""
     args = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", ROOT, LATE, "-m", "gpu", "-rA",
-            "-k", "not poisson and not bmop and not cxx_facade and not (vcycle_and_cg and (3-2-1 or 2-3-1))"
-                  " and not (solves_the_global_problem and (4-2-3-2 or 8-3-2 or 2-3-2-2 or 4-3-4-2))"]   # (those take minutes on the emulation; they pass there)
+            "-k", "not poisson and not bmop and not cxx_facade"
+                  " and not (solves_the_global_problem and (4-2-3-2 or 8-3-2 or 4-3-4-2))"]   # (the slowest ones: 15 - 40 s each here; they pass)
     # (cwd is the package copy: `python -m` puts the cwd in front of PYTHONPATH, the repository's package must not win)
     r = subprocess.run(args, cwd=emu["pkg"], env=_env(emu), capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-6000:]
@@ -64,9 +64,9 @@ def test_bmop_drivers_on_the_emulated_library(emu):
     """bmop -DADAPTIVE_GRID / -DBALL_GRID through the C++ facade (degree-2 builds): DoF counts equal the host substrates' (bound from
     the real library, no device needed), the adaptive `mg` mode converges"""
     import dealii_cuda_b200 as mf
-    rows = [l.split() for l in _run(emu, "bmop_adaptive_q2", 4, 3).strip().splitlines()]
-    want = [mf.AdaptiveMesh(3, 2).pseudo_adaptive_refinement(r).distribute_dofs().n_dofs for r in (3, 4)]
-    assert [int(r[2]) for r in rows] == want and all(float(r[3]) > 0 for r in rows)
+    rows = [l.split() for l in _run(emu, "bmop_adaptive_2d_q2", 3, 3).strip().splitlines()]   # (2D build: the 3D rows take a minute here)
+    want = [mf.AdaptiveMesh(2, 2).pseudo_adaptive_refinement(3).distribute_dofs().n_dofs]
+    assert [int(r[2]) for r in rows] == want and want[0] > 500 and all(float(r[3]) > 0 for r in rows)
     rows = [l.split() for l in _run(emu, "bmop_ball_q2", 1, 0).strip().splitlines()]
     assert [int(r[2]) for r in rows] == [mf.BallMesh(3, 2, r).distribute_dofs().n_dofs for r in (0, 1)]
     out = _run(emu, "bmop_adaptive_2d_q2", 3, 3, "mg")   # (2D: 145 cells on 6 levels with hanging nodes in seconds; the 3D Q2 run at refinement 4 passes too, in a minute)
@@ -74,7 +74,7 @@ def test_bmop_drivers_on_the_emulated_library(emu):
     assert m and int(m.group(1)) <= 20 and float(m.group(2)) <= 1e-7, out
 
 
-@pytest.mark.parametrize("dim,p,rmin,rmax,domain", [(2, 2, 2, 3, "ball"), (2, 2, 3, 4, "nonuniform")])
+@pytest.mark.parametrize("dim,p,rmin,rmax,domain", [(2, 2, 2, 3, "ball"), (2, 2, 2, 3, "nonuniform")])
 def test_poisson_driver_on_the_emulated_library(emu, dim, p, rmin, rmax, domain):
     """examples/poisson.cu (precompiled operator + user-written right-hand-side / error functors of the generic path + CG) on the ball
     and on a locally refined mesh: the L2 error against the analytic solution falls like h^(p+1)"""
@@ -85,10 +85,10 @@ def test_poisson_driver_on_the_emulated_library(emu, dim, p, rmin, rmax, domain)
         assert 0.5 * 2 ** (p + 1) <= a / b <= 2.0 * 2 ** (p + 1), errs
 
 
-@pytest.mark.parametrize("args,dofs", [(("2", "4"), 2145), (("4", "4", "strong"), 1089)])
+@pytest.mark.parametrize("args,dofs", [(("2", "3"), 561)])
 def test_partitioned_multigrid_cxx_driver_on_the_emulated_library(emu, args, dofs):
-    """examples/partitioned_mg.cc (C++ facade partitioned_mg.h; 2D Q2 build): MG-CG over 2 boxes (weak) and 4 boxes (strong) converges in
-    the 5 iterations of the single-box hierarchy"""
+    """examples/partitioned_mg.cc (C++ facade partitioned_mg.h; 2D Q2 build): MG-CG over 2 boxes converges in the 5 iterations of the
+    single-box hierarchy (4 boxes, strong partition and r = 4 pass too, by hand: DESIGN 6.1)"""
     out = _run(emu, "partitioned_mg_2d_q2", *args)
     m = re.search(r"(\d+) dofs\t(\d+) iterations.*error ([-0-9.e+]+)", out)
     assert m and int(m.group(1)) == dofs and int(m.group(2)) <= 6 and float(m.group(3)) <= 1e-10, out
