@@ -3,8 +3,8 @@
 The .cu / .cuh files of dealii_cuda_b200/csrc are copied into a scratch directory with three textual changes -- kernel launches
 `k<<<grid, block, smem, stream>>>(args)` become `emu_launch4(grid, block, smem, stream, k, args)`, shared-memory declarations
 become static / a pointer into one buffer, inline PTX disappears -- and compiled by g++ against tests/emu/cuda_emu_runtime.h
-("device" memory = host memory, one OS thread per CUDA thread of a block; tests/emu/cub/cub.cuh stands in for the CUB scans of
-mesh.cu).  Not built: the slab3 / staged cell kernels (inline PTX: TMA, mbarrier); emu_stubs.cc reports them as unsupported, so
+("device" memory = host memory, the CUDA threads of a block are fibers switched at barriers; tests/emu/cub/cub.cuh stands in for the
+CUB scans of mesh.cu).  Not built: the slab3 / staged cell kernels (inline PTX: TMA, mbarrier); emu_stubs.cc reports them as unsupported, so
 every operator runs on the column kernel.  The result exports the same C ABI: the Python binding loads it when MFG_EMULATED_LIB names it, and GPU tests of
 code paths that need no fast kernel can run on the CPU (tests/test_emulated_library.py)."""
 import os
@@ -190,7 +190,7 @@ def build_examples(out_dir, so):
             ([os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop")]),
             (["-DADAPTIVE_GRID", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_adaptive")]),
             (["-DBALL_GRID", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_ball")]),
-            # (degree 2 builds: the emulation runs one OS thread per CUDA thread, the Q4 drivers take minutes at any useful size)
+            # (degree 2 builds: the Q4 drivers take minutes on the emulation at any useful size)
             (["-DADAPTIVE_GRID", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_adaptive_q2")]),
             (["-DBALL_GRID", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_ball_q2")]),
             (["-DADAPTIVE_GRID", "-DDIMENSION=2", "-DDEGREE_FE=2", os.path.join(ex, "bmop.cc"), "-o", os.path.join(bld, "bmop_adaptive_2d_q2")]),

@@ -1,6 +1,6 @@
 """The LIBRARY'S OWN SOURCES on the CPU: tests/emu/build_emu_lib.py compiles dealii_cuda_b200/csrc (everything except the slab3 /
-staged cell kernels, which are inline PTX) and the examples with g++ against a small CUDA stand-in (one OS thread per CUDA thread,
-blocks one after the other), giving libmfgpu_emu.so with the same C ABI.  A child pytest process then runs the GPU tests of
+staged cell kernels, which are inline PTX) and the examples with g++ against a small CUDA stand-in (the CUDA threads of a block as
+fibers with real barriers, blocks one after the other), giving libmfgpu_emu.so with the same C ABI.  A child pytest process then runs the GPU tests of
 tests/late_gpu/ -- code written after the round's GPU budget was spent, never run on hardware -- against it: host orchestration,
 launch arithmetic, every kernel's index logic, barriers and atomics of the column / general / CSR / transfer / solver / multigrid
 kernels and of the header-only generic path run for real, only the hardware is missing.  The drivers (bmop -DADAPTIVE_GRID,

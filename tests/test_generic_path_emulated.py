@@ -1,7 +1,7 @@
 """The DEVICE code of the header-only generic path (include/dealii_cuda_b200/fee_gpu.cuh: FEEvaluationGpu read_dof_values with the
 hanging-node interpolation, evaluate, quadrature-point operation, integrate, distribute_local_to_global with the transposed
 interpolation and atomic adds, apply_kernel_shmem) run on the CPU: tests/emu/cuda_emu.h supplies threadIdx / __syncthreads /
-atomicAdd / shared memory with one OS thread per CUDA thread, tests/emu/emu_generic.cc the functors of examples/generic_ops.cu and
+atomicAdd / shared memory (CUDA threads as fibers with real barriers), tests/emu/emu_generic.cc the functors of examples/generic_ops.cu and
 the two launches of cell_loop.  Compared with the numpy statements the GPU tests use -- so the kernel logic (not just its index
 arithmetic) has run before its first run on hardware."""
 import ctypes as C
