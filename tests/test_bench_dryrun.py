@@ -99,3 +99,11 @@ def test_bench_extra_modes_on_the_emulation(emu, mode):
         assert "error" not in d["mg_solve"] and d["mg_solve"]["iterations"] <= 12 and d["mg_solve"]["rel_error"] < 1e-8
     else:
         assert d["matrix_free"]["value"] > 0 and d["matrix_bytes"] > 0
+
+
+def test_multirank_apply_worker_on_the_emulation(emu):
+    """tests/multirank_worker.py (the torchrun worker of tests/test_gpu_multirank.py, hardware-verified at N = 2, 4, 8): the 2-rank apply,
+    global dot product and distributed CG against the GLOBAL oracle mesh, FP64 and FP32, strong partition -- here over gloo"""
+    rc, out, err = run_ranks(emu, 2, os.path.join(ROOT, "tests", "multirank_worker.py"), [2, 2, "strong"])
+    assert rc == [0, 0], err[0][-3000:] + err[1][-3000:]
+    assert sum(o.count("MULTIRANK_OK") for o in out) == 2, out
