@@ -74,4 +74,4 @@ template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultipro
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline unsigned __cvta_generic_to_shared(const void *) { return 0; }
-inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline void __syncwarp(unsigned = 0xffffffffu) { emu_arrive_and_wait(emu_blk.current->warp->sync); }   // (full mask: every lane of the warp calls)
