@@ -808,7 +808,10 @@ class LaplaceOperatorGpu:
         return lib.mfg_laplace_cell_launches_per_vmult(self.h)
 
     def active_variant(self):
-        return lib.mfg_laplace_active_variant(self.h)
+        v = lib.mfg_laplace_active_variant(self.h)
+        if v < 0:   # a requested variant this operator cannot run
+            raise MfgError(-4, lib.mfg_last_error().decode(errors="replace"))
+        return v
 
     def set_option(self, name, value):
         check(lib.mfg_laplace_set_option(self.h, name.encode(), int(value)))

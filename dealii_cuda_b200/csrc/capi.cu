@@ -417,7 +417,13 @@ int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launche
 {
   return guarded([&] { MFG_REQUIRE(op, "null operator"); laplace_kernel_time(op, total_ms, n_launches); });
 }
-int mfg_laplace_active_variant(const mfg_laplace *op) { return op ? laplace_active_variant(op) : 0; }
+int mfg_laplace_active_variant(const mfg_laplace *op)
+{
+  // (a requested variant the operator cannot run throws inside: no exception may cross the C boundary -- -1, mfg_last_error says why)
+  int       v = 0;
+  const int rc = guarded([&] { v = op ? laplace_active_variant(op) : 0; });
+  return rc == MFG_OK ? v : -1;
+}
 int mfg_laplace_stage_stats(const mfg_laplace *op, uint32_t out[8])
 {
   return guarded([&] { MFG_REQUIRE(op && out, "null argument"); for (int i = 0; i < 8; ++i) out[i] = op->st_stats[i]; });

@@ -337,7 +337,7 @@ int mfg_laplace_cell_launches_per_vmult(const mfg_laplace *op); /* cell-kernel l
  * bracketed launches. */
 int mfg_laplace_enable_kernel_timing(mfg_laplace *op, int on);
 int mfg_laplace_kernel_time_ms(mfg_laplace *op, double *total_ms, int *n_launches);
-int mfg_laplace_active_variant(const mfg_laplace *op);
+int mfg_laplace_active_variant(const mfg_laplace *op);   /* the kernel that will run (1 / 40 / 50); -1 if the requested variant cannot run on this operator (mfg_last_error) */
 /* staged cell kernel (variant 40): numbers of its plan after the first apply: out[0..7] = groups, staged groups, patterns,
  * and per staged group x 16: own DoFs, halo entries, plain-stored DoFs, red.add DoFs, shared-memory wavefronts of the
  * staged reads + writes */

@@ -4,8 +4,8 @@ The .cu / .cuh files of dealii_cuda_b200/csrc are copied into a scratch director
 `k<<<grid, block, smem, stream>>>(args)` become `emu_launch4(grid, block, smem, stream, k, args)`, shared-memory declarations
 become static / a pointer into one buffer, inline PTX disappears -- and compiled by g++ against tests/emu/cuda_emu_runtime.h
 ("device" memory = host memory, the CUDA threads of a block are fibers switched at barriers; tests/emu/cub/cub.cuh stands in for the
-CUB scans of mesh.cu).  Not built: the slab3 / staged cell kernels (inline PTX: TMA, mbarrier); emu_stubs.cc reports them as unsupported, so
-every operator runs on the column kernel.  The result exports the same C ABI: the Python binding loads it when MFG_EMULATED_LIB names it, and GPU tests of
+CUB scans of mesh.cu).  The slab3 kernel's PTX helpers (bulk-async copy + mbarrier, cp.async) get host bodies that copy at issue; the staged
+kernel (variant 40) is not built: emu_stubs.cc reports it as unsupported.  The result exports the same C ABI: the Python binding loads it when MFG_EMULATED_LIB names it, and GPU tests of
 code paths that need no fast kernel can run on the CPU (tests/test_emulated_library.py)."""
 import os
 import re
@@ -24,6 +24,8 @@ for dim in (2, 3):
     for f64 in (0, 1):
         UNITS.append(("kernels_v0_inst.cu", "_d%d_f%d" % (dim, f64), ["-DMFG_INST_DIM=%d" % dim, "-DMFG_INST_F64=%d" % f64]))
         UNITS.append(("kernels_general_inst.cu", "_d%d_f%d" % (dim, f64), ["-DMFG_INST_DIM=%d" % dim, "-DMFG_INST_F64=%d" % f64]))
+for f64 in (0, 1):
+    UNITS.append(("kernels_slab3_inst.cu", "_f%d" % f64, ["-DMFG_INST_F64=%d" % f64]))
 
 
 def _match_paren(s, i):
@@ -114,8 +116,21 @@ def remove_asm(s):
         pos = b      # keep the ';'
 
 
+# what the PTX of these helpers does, as host code, inserted at the top of their bodies (the asm itself is removed): the bulk-async
+# copy and cp.async complete at issue, so the waits (mbarrier, cp.async.wait_group) have nothing left to wait for
+PTX_HELPERS = {
+    "__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)\n{":
+        "\n  std::memcpy(smem_dst, gsrc, bytes);",
+    "template <int BYTES> __device__ __forceinline__ void slab3_cp_zfill(void *smem_dst, const void *gsrc, bool valid)\n{":
+        "\n  if (valid) std::memcpy(smem_dst, gsrc, BYTES); else std::memset(smem_dst, 0, BYTES);",
+}
+
+
 def transform(text):
     text = text.replace("#include <cuda_runtime.h>", '#include "cuda_emu_runtime.h"')
+    for head, body in PTX_HELPERS.items():
+        if head in text:
+            text = text.replace(head, head + body)
     text = remove_asm(text)
     text = rewrite_launches(text)
     # extern __shared__ [__align__(16)] T name[];  ->  T *name = reinterpret_cast<T *>(emu_dyn_smem);
@@ -135,9 +150,7 @@ def build(out_dir):
         if name.endswith((".cu", ".cuh", ".h")):
             text = open(os.path.join(CSRC, name)).read()
             # the slab3 / staged kernels themselves are not compiled (TMA, mbarrier, cp.async): only what their callers see
-            if name == "kernels_slab3.cuh":
-                text = '#pragma once\n#include "slab_common.cuh"\nnamespace mfg {\n' + text[text.index("template <typename Number>\nvoid launch_laplace_slab3("):]
-            elif name == "kernels_stage.cuh":
+            if name == "kernels_stage.cuh":
                 text = '#pragma once\n#include "slab_common.cuh"\n#include "stage_plan.h"\nnamespace mfg {\n' + text[text.index("struct StageGeom {"):]
             with open(os.path.join(mirror, name), "w") as f:
                 f.write(transform(text))

@@ -70,8 +70,34 @@ template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribu
 template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *b, F, int, size_t) { *b = 1; return cudaSuccess; }
 
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __forceinline__ inline
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline unsigned __cvta_generic_to_shared(const void *) { return 0; }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu_arrive_and_wait(emu_blk.current->warp->sync); }   // (full mask: every lane of the warp calls)
+
+// __shfl_sync with a full mask: every lane publishes its value, reads the source lane's (warp rendezvous on both sides)
+template <typename T> inline T __shfl_sync(unsigned, T v, int src_lane)
+{
+  emu_warp_ctx *w = emu_blk.current->warp;
+  const int     lane = (int)(threadIdx.x & 31u);
+  w->slot[lane] = (double)v;
+  emu_arrive_and_wait(w->sync);
+  const T r = (T)w->slot[src_lane & 31];
+  emu_arrive_and_wait(w->sync);
+  return r;
+}
+
+// cudaLaunchKernelEx with launch attributes (programmatic dependent launch): every emulated launch completes before it returns, so
+// the attributes have nothing to order
+struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
+enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 4 };
+struct cudaLaunchAttributeValue { int programmaticStreamSerializationAllowed; };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute *attrs; unsigned numAttrs; };
+template <typename Kernel, typename... Args> inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, Kernel kernel, Args... args)
+{
+  emu_launch4(cfg->gridDim.x, cfg->blockDim.x, cfg->dynamicSmemBytes, cfg->stream, [&](auto... a) { kernel(a...); }, args...);
+  return cudaGetLastError();
+}

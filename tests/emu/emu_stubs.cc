@@ -1,6 +1,5 @@
 // emu_stubs.cc -- TEST INFRASTRUCTURE: what libmfgpu_emu.so has in place of the units that are not built for the CPU emulation
-// (tests/emu/build_emu_lib.py): the slab3 / staged cell kernels (inline PTX).  They report "unsupported", so that every operator falls
-// to the column kernel.
+// (tests/emu/build_emu_lib.py): the staged cell kernel (variant 40; inline PTX).  It reports "unsupported".
 #include "kernels_slab3.cuh"
 #include "kernels_stage.cuh"
 #include "operators.cuh"
@@ -9,21 +8,9 @@ namespace mfg {
 
 static void unsupported(const char *what) { throw Error(MFG_ERR_UNSUPPORTED, std::string(what) + " is not part of the CPU emulation build"); }
 
-bool      slab2_supported(int, int, mfg_dtype) { return false; }
-Slab2Geom slab2_geom(int, mfg_dtype) { unsupported("the slab3 kernel"); return Slab2Geom(); }
 bool      stage_supported(int, int, mfg_dtype) { return false; }
 StageGeom stage_geom(int, mfg_dtype) { unsupported("the staged kernel"); return StageGeom(); }
 
-template <typename Number>
-void launch_laplace_slab3(int, const uint32_t *, const Number *, const Number *, Number *, uint32_t, const double *, const double *, int, cudaStream_t,
-                          const uint32_t *, const uint32_t *, bool, int, int, int, const uint32_t *, uint32_t, double *, uint32_t *)
-{
-  unsupported("the slab3 kernel");
-}
-template void launch_laplace_slab3<float>(int, const uint32_t *, const float *, const float *, float *, uint32_t, const double *, const double *, int, cudaStream_t,
-                                          const uint32_t *, const uint32_t *, bool, int, int, int, const uint32_t *, uint32_t, double *, uint32_t *);
-template void launch_laplace_slab3<double>(int, const uint32_t *, const double *, const double *, double *, uint32_t, const double *, const double *, int, cudaStream_t,
-                                           const uint32_t *, const uint32_t *, bool, int, int, int, const uint32_t *, uint32_t, double *, uint32_t *);
 template <typename Number>
 void launch_laplace_stage(int, const uint32_t *, const uint32_t *, const uint16_t *, int, const uint32_t *, const Number *, const Number *, Number *, uint32_t,
                           const double *, const double *, int, cudaStream_t, const uint32_t *, uint32_t, int, bool, bool, bool, int, bool)

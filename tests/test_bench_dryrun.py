@@ -65,6 +65,9 @@ def test_bench_two_rank_line_on_the_emulation(emu, scaling):
     assert d["e2e"]["value"] > 0 and d["e2e"]["steps"] >= 6
     assert d["cg_solve"]["iterations"] > 0 and d["cg_solve"]["rel_error"] < 1e-9
     assert "error" not in d["mg_solve"] and d["mg_solve"]["iterations"] <= 8 and d["mg_solve"]["rel_error"] < 1e-8, d["mg_solve"]
+    # the overlapped apply: slab3 kernel with the interface groups first, its self-check against the plain sequence
+    assert "variant 50" in d["roofline"]["kernel"] and d["overlap"].startswith("interface cell groups first")
+    assert d["selfcheck"]["overlapped_vs_sequential_max_rel_diff"] < 1e-12
 
 
 def test_bench_watchdog_prints_the_apply_line(emu):

@@ -1,10 +1,10 @@
-"""The LIBRARY'S OWN SOURCES on the CPU: tests/emu/build_emu_lib.py compiles dealii_cuda_b200/csrc (everything except the slab3 /
-staged cell kernels, which are inline PTX) and the examples with g++ against a small CUDA stand-in (the CUDA threads of a block as
-fibers with real barriers, blocks one after the other), giving libmfgpu_emu.so with the same C ABI.  A child pytest process then runs the GPU tests of
-tests/late_gpu/ -- code written after the round's GPU budget was spent, never run on hardware -- against it: host orchestration,
-launch arithmetic, every kernel's index logic, barriers and atomics of the column / general / CSR / transfer / solver / multigrid
-kernels and of the header-only generic path run for real, only the hardware is missing.  The drivers (bmop -DADAPTIVE_GRID,
--DBALL_GRID, poisson on the ball and on locally refined meshes) run at sizes the emulation finishes in seconds.
+"""The LIBRARY'S OWN SOURCES on the CPU: tests/emu/build_emu_lib.py compiles dealii_cuda_b200/csrc (everything except the staged cell
+kernel, variant 40) and the examples with g++ against a small CUDA stand-in (the CUDA threads of a block as fibers with real barriers,
+blocks one after the other; the PTX helpers of the slab3 kernel get host bodies), giving libmfgpu_emu.so with the same C ABI.  Child
+pytest processes then run GPU tests against it: the tests of tests/late_gpu/ -- code written after the round's GPU budget was spent,
+never run on hardware -- and the parity tests of the default cell kernel.  Host orchestration, launch arithmetic, every kernel's index
+logic, barriers, shuffles and atomics run for real, only the hardware is missing.  The drivers (bmop -DADAPTIVE_GRID, -DBALL_GRID,
+poisson on the ball and on locally refined meshes, partitioned_mg) run at sizes the emulation finishes in seconds.
 
 The product package has no emulation switch: the child sees a COPY of the Python binding next to libmfgpu_emu.so in front of the
 repository on PYTHONPATH.  Nothing here counts as a parity claim for the GPU (the -m gpu tests do); it is a pre-flight check."""
@@ -92,3 +92,20 @@ def test_partitioned_multigrid_cxx_driver_on_the_emulated_library(emu, args, dof
     out = _run(emu, "partitioned_mg_2d_q2", *args)
     m = re.search(r"(\d+) dofs\t(\d+) iterations.*error ([-0-9.e+]+)", out)
     assert m and int(m.group(1)) == dofs and int(m.group(2)) <= 6 and float(m.group(3)) <= 1e-10, out
+
+
+def test_default_cell_kernel_on_the_emulated_library(emu):
+    """the HOT PATH itself: the slab3 cell kernel (variants 50..54: warp per group of 32 cells, bulk-async coefficient loads behind an
+    mbarrier, register / cp.async gathers, early register face merges, shuffles, atomic scatter, work lists of the multi-GPU split, the
+    fused d.(A d) of conjugate gradients) runs on the emulation -- its PTX helpers get host bodies that copy at issue -- and the
+    hardware parity tests of tests/test_gpu_apply.py / test_gpu_solver.py pass on it against the oracle (the split apply of the multi-GPU path:
+    tests/test_bench_dryrun.py)"""
+    sel = "(variants_match_oracle and not -40-) or (fused_loop and 4-2) or (grouped_kernels_repeated_applies_and_box and not 40)"
+    args = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", ROOT, os.path.join(ROOT, "tests", "test_gpu_apply.py"),
+            os.path.join(ROOT, "tests", "test_gpu_solver.py"), "-m", "gpu", "-rA", "-k", sel]
+    r = subprocess.run(args, cwd=emu["pkg"], env=_env(emu), capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-6000:]
+    assert r.returncode == 0, tail
+    passed = re.findall(r"^PASSED (\S+)", r.stdout, flags=re.M)
+    assert len(passed) >= 100 and not re.search(r"^(FAILED|ERROR) ", r.stdout, flags=re.M), tail
+    assert all(any("-%d-" % v in p for p in passed) for v in (51, 52, 53, 54)) and any("fused_loop" in p for p in passed), passed[:5]
