@@ -4,8 +4,8 @@ The .cu / .cuh files of dealii_cuda_b200/csrc are copied into a scratch director
 `k<<<grid, block, smem, stream>>>(args)` become `emu_launch4(grid, block, smem, stream, k, args)`, shared-memory declarations
 become static / a pointer into one buffer, inline PTX disappears -- and compiled by g++ against tests/emu/cuda_emu_runtime.h
 ("device" memory = host memory, the CUDA threads of a block are fibers switched at barriers; tests/emu/cub/cub.cuh stands in for the
-CUB scans of mesh.cu).  The slab3 kernel's PTX helpers (bulk-async copy + mbarrier, cp.async) get host bodies that copy at issue; the staged
-kernel (variant 40) is not built: emu_stubs.cc reports it as unsupported.  The result exports the same C ABI: the Python binding loads it when MFG_EMULATED_LIB names it, and GPU tests of
+CUB scans of mesh.cu).  The PTX helpers of the slab3 and staged kernels (bulk-async copy + mbarrier, cp.async) get host bodies that copy at issue:
+every unit of the library is built, nothing is stubbed.  The result exports the same C ABI: the Python binding loads it when MFG_EMULATED_LIB names it, and GPU tests of
 code paths that need no fast kernel can run on the CPU (tests/test_emulated_library.py)."""
 import os
 import re
@@ -26,6 +26,7 @@ for dim in (2, 3):
         UNITS.append(("kernels_general_inst.cu", "_d%d_f%d" % (dim, f64), ["-DMFG_INST_DIM=%d" % dim, "-DMFG_INST_F64=%d" % f64]))
 for f64 in (0, 1):
     UNITS.append(("kernels_slab3_inst.cu", "_f%d" % f64, ["-DMFG_INST_F64=%d" % f64]))
+    UNITS.append(("kernels_stage_inst.cu", "_f%d" % f64, ["-DMFG_INST_F64=%d" % f64]))
 
 
 def _match_paren(s, i):
@@ -123,6 +124,8 @@ PTX_HELPERS = {
         "\n  std::memcpy(smem_dst, gsrc, bytes);",
     "template <int BYTES> __device__ __forceinline__ void slab3_cp_zfill(void *smem_dst, const void *gsrc, bool valid)\n{":
         "\n  if (valid) std::memcpy(smem_dst, gsrc, BYTES); else std::memset(smem_dst, 0, BYTES);",
+    "template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *smem_dst, const void *gsrc)\n{":
+        "\n  std::memcpy(smem_dst, gsrc, BYTES);",
 }
 
 
@@ -150,8 +153,6 @@ def build(out_dir):
         if name.endswith((".cu", ".cuh", ".h")):
             text = open(os.path.join(CSRC, name)).read()
             # the slab3 / staged kernels themselves are not compiled (TMA, mbarrier, cp.async): only what their callers see
-            if name == "kernels_stage.cuh":
-                text = '#pragma once\n#include "slab_common.cuh"\n#include "stage_plan.h"\nnamespace mfg {\n' + text[text.index("struct StageGeom {"):]
             with open(os.path.join(mirror, name), "w") as f:
                 f.write(transform(text))
     objs = []
@@ -168,7 +169,7 @@ def build(out_dir):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_unit, UNITS))
-    stub = os.path.join(out_dir, "emu_stubs.o")
+    stub = os.path.join(out_dir, "emu_stubs.o")   # (nothing is stubbed any more: the unit stays as the place for it)
     r = subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-w", "-DMFG_EMULATION", "-I", EMU, "-I", mirror, "-c",
                         os.path.join(EMU, "emu_stubs.cc"), "-o", stub], capture_output=True, text=True)
     if r.returncode != 0:

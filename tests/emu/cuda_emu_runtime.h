@@ -16,6 +16,8 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { int multiProcessorCount, major, minor, l2CacheSize; char name[64]; };
 struct float4 { float x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 enum { cudaErrorInvalidConfiguration = 9, cudaErrorIllegalAddress = 700 };

@@ -1,6 +1,5 @@
-"""The LIBRARY'S OWN SOURCES on the CPU: tests/emu/build_emu_lib.py compiles dealii_cuda_b200/csrc (everything except the staged cell
-kernel, variant 40) and the examples with g++ against a small CUDA stand-in (the CUDA threads of a block as fibers with real barriers,
-blocks one after the other; the PTX helpers of the slab3 kernel get host bodies), giving libmfgpu_emu.so with the same C ABI.  Child
+"""The LIBRARY'S OWN SOURCES on the CPU: tests/emu/build_emu_lib.py compiles dealii_cuda_b200/csrc (all of it) and the examples with g++ against a small CUDA stand-in (the CUDA threads of a block as fibers with real barriers,
+blocks one after the other; the PTX helpers of the slab3 / staged kernels get host bodies), giving libmfgpu_emu.so with the same C ABI.  Child
 pytest processes then run GPU tests against it: the tests of tests/late_gpu/ -- code written after the round's GPU budget was spent,
 never run on hardware -- and the parity tests of the default cell kernel.  Host orchestration, launch arithmetic, every kernel's index
 logic, barriers, shuffles and atomics run for real, only the hardware is missing.  The drivers (bmop -DADAPTIVE_GRID, -DBALL_GRID,
@@ -97,10 +96,11 @@ def test_partitioned_multigrid_cxx_driver_on_the_emulated_library(emu, args, dof
 def test_default_cell_kernel_on_the_emulated_library(emu):
     """the HOT PATH itself: the slab3 cell kernel (variants 50..54: warp per group of 32 cells, bulk-async coefficient loads behind an
     mbarrier, register / cp.async gathers, early register face merges, shuffles, atomic scatter, work lists of the multi-GPU split, the
-    fused d.(A d) of conjugate gradients) runs on the emulation -- its PTX helpers get host bodies that copy at issue -- and the
+    fused d.(A d) of conjugate gradients) and the staged kernel (variant 40: host-built plan, staged gather, plain stores for owned
+    DoFs) run on the emulation -- their PTX helpers get host bodies that copy at issue -- and the
     hardware parity tests of tests/test_gpu_apply.py / test_gpu_solver.py pass on it against the oracle (the split apply of the multi-GPU path:
     tests/test_bench_dryrun.py)"""
-    sel = "(variants_match_oracle and not -40-) or (fused_loop and 4-2) or (grouped_kernels_repeated_applies_and_box and not 40)"
+    sel = "variants_match_oracle or (fused_loop and 4-2) or grouped_kernels_repeated_applies_and_box or (staged_kernel_matches_oracle and 4-2)"
     args = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", ROOT, os.path.join(ROOT, "tests", "test_gpu_apply.py"),
             os.path.join(ROOT, "tests", "test_gpu_solver.py"), "-m", "gpu", "-rA", "-k", sel]
     r = subprocess.run(args, cwd=emu["pkg"], env=_env(emu), capture_output=True, text=True, timeout=900)
@@ -108,4 +108,4 @@ def test_default_cell_kernel_on_the_emulated_library(emu):
     assert r.returncode == 0, tail
     passed = re.findall(r"^PASSED (\S+)", r.stdout, flags=re.M)
     assert len(passed) >= 100 and not re.search(r"^(FAILED|ERROR) ", r.stdout, flags=re.M), tail
-    assert all(any("-%d-" % v in p for p in passed) for v in (51, 52, 53, 54)) and any("fused_loop" in p for p in passed), passed[:5]
+    assert all(any("-%d-" % v in p for p in passed) for v in (1, 40, 51, 52, 53, 54)) and any("fused_loop" in p for p in passed), passed[:5]
