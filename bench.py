@@ -439,27 +439,85 @@ def main():
            "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_blocking_s * 1e3,
            "host_buffers": "pinned, allocated on the GPU's NUMA node (node %d)" % numa_node if numa_node is not None else "pinned, no NUMA placement (topology not visible or a single node)"}
 
+    peak, peak_src = measured_peaks()
+    alg_bytes = b_alg(args.degree, args.dim, s) * n
+    k_avg_ms = kernel_ms / max(1, kernel_launches) * op.cell_launches_per_vmult()
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": PROFILED_TRAFFIC.get((args.dim, args.degree, args.dtype, args.refine, op.active_variant())),
+                "kernel": "laplace cell kernel (variant %d)" % op.active_variant(), "kernel_ms": k_avg_ms, "timed_launches": kernel_launches, "peak_source": peak_src,
+                "algorithmic_bytes_per_dof": b_alg(args.degree, args.dim, s),
+                "whole_vmult_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(args, args.cpu_steps, 2)
+
+    def make_line(cg, mg_solve):
+        line = {"metric": metric, "value": value, "unit": "DoFs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                "data": "synthetic",
+                "config": {"workload": "bmop: %dD unit-cube [-1,1]^%d variable-coefficient Laplace apply, FE_Q(%d), refine_global(%d): "
+                                       "%d cells, %d DoFs, %s scatter; bmop.cu loop" % (args.dim, args.dim, args.degree, args.refine,
+                                                                                        mesh.n_cells, n, "colored" if args.coloring else "atomic"),
+                           "l2": "inputs larger than L2 (index + coefficient + 2 vectors = %.0f MB)" %
+                                 ((mesh.n_cells * mesh.dofs_per_cell * (4 + s) + 2 * n * s) / 1e6)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * op.launches_per_vmult(), "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "cg_solve": cg, "mg_solve": mg_solve, "configs0_r5": configs0}
+        return line
+
+    # The solves come last and under a watchdog: the apply line is printed even if one of them hangs (their loops were refactored
+    # after the round's last hardware run); an exception is reported in place of the figures.
+    import threading
+    done = {"cg": None, "mg": None, "section": "cg_solve", "printed": False}
+    print_lock = threading.Lock()
+
+    def emit(note=None):
+        with print_lock:
+            if done["printed"]:
+                return
+            done["printed"] = True
+            line = make_line(done["cg"], done["mg"])
+            if note:
+                line["note"] = note
+            sys.stdout.write(json.dumps(line) + "\n")
+            sys.stdout.flush()
+
+    WATCHDOG_S = float(os.environ.get("MFG_BENCH_WATCHDOG_S", "300"))
+
+    def on_timeout():
+        emit("section '%s' did not finish within %g s: reported without it" % (done["section"], WATCHDOG_S))
+        os._exit(0)
+
+    watchdog = threading.Timer(WATCHDOG_S, on_timeout)
+    watchdog.daemon = True
+    watchdog.start()
+
     # CG solve time on the same operator (BASELINE metric "CG time"; poisson.cu:233-260 control flow, Jacobi
     # preconditioner, |r| <= 1e-12 |b|, right-hand side b = A u for a seeded random u)
     cg = None
     if not args.no_cg:
-        ue = mf.GpuVector.wrap(ctx, torch.rand((n,), dtype=tdtype, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
-        vb_, vx_ = mf.GpuVector(ctx, n, dtype), mf.GpuVector(ctx, n, dtype)
-        op.vmult(vb_, ue)
-        op.compute_diagonal()
-        mf.solver_cg(op, vx_, vb_, 0.0, 3)  # warm-up: loads the solver kernels (lazy module loading), like the warm-up applies
-        vx_.fill(0.0)
-        ctx.synchronize()
-        t0 = time.perf_counter()
-        its, res = mf.solver_cg(op, vx_, vb_, (1e-12 if args.dtype == "f64" else 1e-5) * vb_.l2_norm(), 10000)
-        ctx.synchronize()
-        cg_s = time.perf_counter() - t0
-        vx_.add(-1.0, ue)
-        cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "rel_error": vx_.l2_norm() / ue.l2_norm(),
-              "n_dofs": n, "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|",
-              "kernels_per_iteration": 3 if op.active_variant() == 50 else 5,
-              "loop": "mfg_solver_cg: cell kernel (h = A d and the partial sums of d.h) + cg_residual + cg_advance (also the operator's zero pass)"}
-        del ue, vb_, vx_
+        try:
+            ue = mf.GpuVector.wrap(ctx, torch.rand((n,), dtype=tdtype, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
+            vb_, vx_ = mf.GpuVector(ctx, n, dtype), mf.GpuVector(ctx, n, dtype)
+            op.vmult(vb_, ue)
+            op.compute_diagonal()
+            mf.solver_cg(op, vx_, vb_, 0.0, 3)  # warm-up: loads the solver kernels (lazy module loading), like the warm-up applies
+            vx_.fill(0.0)
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            its, res = mf.solver_cg(op, vx_, vb_, (1e-12 if args.dtype == "f64" else 1e-5) * vb_.l2_norm(), 10000)
+            ctx.synchronize()
+            cg_s = time.perf_counter() - t0
+            vx_.add(-1.0, ue)
+            cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "rel_error": vx_.l2_norm() / ue.l2_norm(),
+                  "n_dofs": n, "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|",
+                  "kernels_per_iteration": 3 if op.active_variant() == 50 else 5,
+                  "loop": "mfg_solver_cg: cell kernel (h = A d and the partial sums of d.h) + cg_residual + cg_advance (also the operator's zero pass)"}
+            del ue, vb_, vx_
+            done["cg"] = cg
+        except Exception as e:
+            done["cg"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    done["section"] = "mg_solve"
 
     # the same kind of system by CG preconditioned with the geometric multigrid V-cycle (poisson_mg.cu:430-552: Chebyshev(5) smoothers
     # with deal.II's eigenvalue estimate, levels 1..r, coarse CG), the library's loop mfg_mg_solve_cg; tools/solve_large.py is the same run
@@ -490,30 +548,9 @@ def main():
         except Exception as e:  # the apply / CG figures stand on their own
             mg_solve = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
-    peak, peak_src = measured_peaks()
-    alg_bytes = b_alg(args.degree, args.dim, s) * n
-    k_avg_ms = kernel_ms / max(1, kernel_launches) * op.cell_launches_per_vmult()
-    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": PROFILED_TRAFFIC.get((args.dim, args.degree, args.dtype, args.refine, op.active_variant())),
-                "kernel": "laplace cell kernel (variant %d)" % op.active_variant(), "kernel_ms": k_avg_ms, "timed_launches": kernel_launches, "peak_source": peak_src,
-                "algorithmic_bytes_per_dof": b_alg(args.degree, args.dim, s),
-                "whole_vmult_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
-    cpu_baseline = None
-    if not args.no_cpu_baseline:
-        cpu_baseline, _ = cpu_reference_run(args, args.cpu_steps, 2)
-
-    line = {"metric": metric, "value": value, "unit": "DoFs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-            "data": "synthetic",
-            "config": {"workload": "bmop: %dD unit-cube [-1,1]^%d variable-coefficient Laplace apply, FE_Q(%d), refine_global(%d): "
-                                   "%d cells, %d DoFs, %s scatter; bmop.cu loop" % (args.dim, args.dim, args.degree, args.refine,
-                                                                                    mesh.n_cells, n, "colored" if args.coloring else "atomic"),
-                       "l2": "inputs larger than L2 (index + coefficient + 2 vectors = %.0f MB)" %
-                             ((mesh.n_cells * mesh.dofs_per_cell * (4 + s) + 2 * n * s) / 1e6)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * op.launches_per_vmult(), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "cg_solve": cg, "mg_solve": mg_solve, "configs0_r5": configs0}
-    print(json.dumps(line))
+    done["mg"] = mg_solve
+    watchdog.cancel()
+    emit()
     return 0
 
 

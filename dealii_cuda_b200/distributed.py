@@ -490,140 +490,143 @@ def bench_main(args, metric):
     watchdog.daemon = True
     watchdog.start()
 
-    e2e_s = e2e_block_s = float("nan")
-    n_e2e = 0
-    if not getattr(args, "no_e2e", False):
-        # end to end: pinned host src -> H2D -> vmult (+exchange) -> D2H, two slots per rank pipelined on three streams (PCIe is
-        # full duplex: step k's D2H overlaps step k+1's H2D; the applies stay on the main stream).  Blocking figure next to it.
-        hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
-        hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
-        ds = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
-        dd = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
-        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-        ev_in = [torch.cuda.Event() for _ in range(2)]; ev_ap = [torch.cuda.Event() for _ in range(2)]; ev_out = [torch.cuda.Event() for _ in range(2)]
+    # (an exception in one of these sections -- as opposed to a hang, which is the watchdog's -- must not lose the apply line either)
+    try:
+        e2e_s = e2e_block_s = float("nan")
+        n_e2e = 0
+        if not getattr(args, "no_e2e", False):
+            # end to end: pinned host src -> H2D -> vmult (+exchange) -> D2H, two slots per rank pipelined on three streams (PCIe is
+            # full duplex: step k's D2H overlaps step k+1's H2D; the applies stay on the main stream).  Blocking figure next to it.
+            hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
+            hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
+            ds = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
+            dd = [torch.empty((n,), dtype=tdtype, device="cuda") for _ in range(2)]
+            s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            ev_in = [torch.cuda.Event() for _ in range(2)]; ev_ap = [torch.cuda.Event() for _ in range(2)]; ev_out = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_blocking():
-            ds[0].copy_(hs[0], non_blocking=True)
-            dop.vmult_ptr(dd[0].data_ptr(), ds[0].data_ptr())
-            hd[0].copy_(dd[0], non_blocking=True)
-            torch.cuda.synchronize()
+            def e2e_blocking():
+                ds[0].copy_(hs[0], non_blocking=True)
+                dop.vmult_ptr(dd[0].data_ptr(), ds[0].data_ptr())
+                hd[0].copy_(dd[0], non_blocking=True)
+                torch.cuda.synchronize()
 
-        def e2e_pipelined(steps):
-            for k in range(steps):
-                sl = k % 2
-                s_h2d.wait_event(ev_ap[sl])                      # the apply that read this slot's source two steps ago is done
-                with torch.cuda.stream(s_h2d):
-                    ds[sl].copy_(hs[sl], non_blocking=True)
-                    ev_in[sl].record(s_h2d)
-                main.wait_event(ev_in[sl])
-                main.wait_event(ev_out[sl])                      # this slot's previous result has left the device
-                dop.vmult_graphed(dd[sl].data_ptr(), ds[sl].data_ptr())
-                ev_ap[sl].record(main)
-                s_d2h.wait_event(ev_ap[sl])
-                with torch.cuda.stream(s_d2h):
-                    hd[sl].copy_(dd[sl], non_blocking=True)
-                    ev_out[sl].record(s_d2h)
-            torch.cuda.synchronize()
+            def e2e_pipelined(steps):
+                for k in range(steps):
+                    sl = k % 2
+                    s_h2d.wait_event(ev_ap[sl])                      # the apply that read this slot's source two steps ago is done
+                    with torch.cuda.stream(s_h2d):
+                        ds[sl].copy_(hs[sl], non_blocking=True)
+                        ev_in[sl].record(s_h2d)
+                    main.wait_event(ev_in[sl])
+                    main.wait_event(ev_out[sl])                      # this slot's previous result has left the device
+                    dop.vmult_graphed(dd[sl].data_ptr(), ds[sl].data_ptr())
+                    ev_ap[sl].record(main)
+                    s_d2h.wait_event(ev_ap[sl])
+                    with torch.cuda.stream(s_d2h):
+                        hd[sl].copy_(dd[sl], non_blocking=True)
+                        ev_out[sl].record(s_d2h)
+                torch.cuda.synchronize()
 
-        e2e_blocking()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
             e2e_blocking()
-        dist.barrier()
-        e2e_block_s = (time.perf_counter() - t0) / 3
-        e2e_pipelined(4)   # warm-up: captures the two graphs
-        n_e2e = max(args.e2e_steps, 6)
-        dist.barrier()
-        t0 = time.perf_counter()
-        e2e_pipelined(n_e2e)
-        dist.barrier()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        te = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_block_s = float(te[0]), float(te[1])
-        del hs, hd, ds, dd
-        extra["e2e"] = {"value": dop.n_global / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
-                        "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3,
-                        "host_buffers": "pinned, rank bound to the GPU's NUMA node (rank 0: node %d)" % numa_node if numa_node is not None
-                                        else "pinned, no NUMA binding (topology not visible or a single node)"}
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                e2e_blocking()
+            dist.barrier()
+            e2e_block_s = (time.perf_counter() - t0) / 3
+            e2e_pipelined(4)   # warm-up: captures the two graphs
+            n_e2e = max(args.e2e_steps, 6)
+            dist.barrier()
+            t0 = time.perf_counter()
+            e2e_pipelined(n_e2e)
+            dist.barrier()
+            e2e_s = (time.perf_counter() - t0) / n_e2e
+            te = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e_s, e2e_block_s = float(te[0]), float(te[1])
+            del hs, hd, ds, dd
+            extra["e2e"] = {"value": dop.n_global / e2e_s, "unit": "DoFs/s", "h2d_bytes_per_step": n * s * world, "d2h_bytes_per_step": n * s * world,
+                            "ms_per_step": e2e_s * 1e3, "steps": n_e2e, "pipelined_slots": 2, "blocking_single_call_ms": e2e_block_s * 1e3,
+                            "host_buffers": "pinned, rank bound to the GPU's NUMA node (rank 0: node %d)" % numa_node if numa_node is not None
+                                            else "pinned, no NUMA binding (topology not visible or a single node)"}
 
 
-    # CG solve over all GPUs (BASELINE metric "CG time"): b = A u for a vector u whose interface replicas agree
-    cg = None
-    section["name"] = "cg_solve"
-    if not args.no_cg:
-        from . import GpuVector as GV
-        ta.fill_(1.0)
-        dop.vmult_ptr(tb.data_ptr(), ta.data_ptr())      # tb = A 1: bit-identical on the replicas of interface DoFs
-        amax = tb.abs().max()
-        dist.all_reduce(amax, op=dist.ReduceOp.MAX)
-        uvec_t = tb / amax.clamp_min(1e-300) + 1.0       # u = 1 + A1 / max|A1|
-        ue = GV.wrap(ctx, uvec_t)
-        vb, vx = GV(ctx, n, dtype), GV(ctx, n, dtype)
-        dop.vmult(vb, ue)
-        vx.fill(0.0)
-        bnorm = dop.dot(vb, vb) ** 0.5
-        solver_cg_distributed(dop, vx, vb, 0.0, 3)
-        vx.fill(0.0)
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        its, res = solver_cg_distributed(dop, vx, vb, (1e-12 if args.dtype == "f64" else 1e-5) * bnorm, 20000)
-        torch.cuda.synchronize(); dist.barrier()
-        cg_s = time.perf_counter() - t0
-        vx.add(-1.0, ue)
-        err = dop.dot(vx, vx) ** 0.5 / dop.dot(ue, ue) ** 0.5
-        cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "rel_error": err, "n_dofs": dop.n_global,
-              "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|",
-              "loop": "distributed.solver_cg_distributed: graph-replayed apply + mfg_cgd_* kernels, scalars all-reduced on the device (NCCL, "
-                      "in stream order), one host read of the convergence flag every 8 iterations"}
-        extra["cg"] = cg
-        # The same system by CG preconditioned with the multigrid V-cycle over the partition (partitioned_mg.py: every level partitioned
-        # like the finest, local transfers, Chebyshev(5) smoothers with exchanged diagonals, replicated coarse solve).  First hardware run
-        # of this leg is the driver's: any failure is reported in place of the figures, a hang is the watchdog's.
-        section["name"] = "mg_solve"
-        if not getattr(args, "no_mg", False):
-            try:
-                from .partitioned_mg import DistributedLevel, PartitionedMultigrid
-                t0 = time.perf_counter()
-                pm = PartitionedMultigrid(lambda l: DistributedLevel(ctx, rank, world, args.dim, args.degree, l, dtype, strong,
-                                                                     dop=dop if l == args.refine else None), 1, args.refine)
-                torch.cuda.synchronize(); dist.barrier()
-                mg_setup_s = time.perf_counter() - t0
-                xf = [GV(ctx, n, dtype)]
-                xf[0].fill(0.0)
-                pm.solve_cg(xf, [vb], 0.0, 1)                  # warm-up: one iteration = one V-cycle
-                xf[0].fill(0.0)
-                pm.coarse_iterations = 0
-                torch.cuda.synchronize(); dist.barrier()
-                t0 = time.perf_counter()
-                its2, res2 = pm.solve_cg(xf, [vb], (1e-10 if args.dtype == "f64" else 1e-5) * bnorm, 100)
-                torch.cuda.synchronize(); dist.barrier()
-                mg_s = time.perf_counter() - t0
-                xf[0].add(-1.0, ue)
-                extra["mg"] = {"seconds": mg_s, "iterations": its2, "rel_error": dop.dot(xf[0], xf[0]) ** 0.5 / dop.dot(ue, ue) ** 0.5,
-                               "n_dofs": dop.n_global, "levels": args.refine, "coarse_cg_iterations": pm.coarse_iterations, "setup_seconds": mg_setup_s,
-                               "tolerance": "1e-10*|b|" if args.dtype == "f64" else "1e-5*|b|",
-                               "preconditioner": "V-cycle over the box partition, levels 1..%d, Chebyshev(5) with the fused update kernel, local transfers, "
-                                                 "coarse level solved on one replicated global mesh; host-orchestrated (one host read per dot "
-                                                 "product)" % args.refine}
-            except Exception as e:
-                extra["mg"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        # CG solve over all GPUs (BASELINE metric "CG time"): b = A u for a vector u whose interface replicas agree
+        cg = None
+        section["name"] = "cg_solve"
+        if not args.no_cg:
+            from . import GpuVector as GV
+            ta.fill_(1.0)
+            dop.vmult_ptr(tb.data_ptr(), ta.data_ptr())      # tb = A 1: bit-identical on the replicas of interface DoFs
+            amax = tb.abs().max()
+            dist.all_reduce(amax, op=dist.ReduceOp.MAX)
+            uvec_t = tb / amax.clamp_min(1e-300) + 1.0       # u = 1 + A1 / max|A1|
+            ue = GV.wrap(ctx, uvec_t)
+            vb, vx = GV(ctx, n, dtype), GV(ctx, n, dtype)
+            dop.vmult(vb, ue)
+            vx.fill(0.0)
+            bnorm = dop.dot(vb, vb) ** 0.5
+            solver_cg_distributed(dop, vx, vb, 0.0, 3)
+            vx.fill(0.0)
+            torch.cuda.synchronize(); dist.barrier()
+            t0 = time.perf_counter()
+            its, res = solver_cg_distributed(dop, vx, vb, (1e-12 if args.dtype == "f64" else 1e-5) * bnorm, 20000)
+            torch.cuda.synchronize(); dist.barrier()
+            cg_s = time.perf_counter() - t0
+            vx.add(-1.0, ue)
+            err = dop.dot(vx, vx) ** 0.5 / dop.dot(ue, ue) ** 0.5
+            cg = {"seconds": cg_s, "iterations": its, "ms_per_iteration": 1e3 * cg_s / max(1, its), "rel_error": err, "n_dofs": dop.n_global,
+                  "preconditioner": "jacobi (Chebyshev degree 0)", "tolerance": "1e-12*|b|" if args.dtype == "f64" else "1e-5*|b|",
+                  "loop": "distributed.solver_cg_distributed: graph-replayed apply + mfg_cgd_* kernels, scalars all-reduced on the device (NCCL, "
+                          "in stream order), one host read of the convergence flag every 8 iterations"}
+            extra["cg"] = cg
+            # The same system by CG preconditioned with the multigrid V-cycle over the partition (partitioned_mg.py: every level partitioned
+            # like the finest, local transfers, Chebyshev(5) smoothers with exchanged diagonals, replicated coarse solve).  First hardware run
+            # of this leg is the driver's: any failure is reported in place of the figures, a hang is the watchdog's.
+            section["name"] = "mg_solve"
+            if not getattr(args, "no_mg", False):
+                try:
+                    from .partitioned_mg import DistributedLevel, PartitionedMultigrid
+                    t0 = time.perf_counter()
+                    pm = PartitionedMultigrid(lambda l: DistributedLevel(ctx, rank, world, args.dim, args.degree, l, dtype, strong,
+                                                                         dop=dop if l == args.refine else None), 1, args.refine)
+                    torch.cuda.synchronize(); dist.barrier()
+                    mg_setup_s = time.perf_counter() - t0
+                    xf = [GV(ctx, n, dtype)]
+                    xf[0].fill(0.0)
+                    pm.solve_cg(xf, [vb], 0.0, 1)                  # warm-up: one iteration = one V-cycle
+                    xf[0].fill(0.0)
+                    pm.coarse_iterations = 0
+                    torch.cuda.synchronize(); dist.barrier()
+                    t0 = time.perf_counter()
+                    its2, res2 = pm.solve_cg(xf, [vb], (1e-10 if args.dtype == "f64" else 1e-5) * bnorm, 100)
+                    torch.cuda.synchronize(); dist.barrier()
+                    mg_s = time.perf_counter() - t0
+                    xf[0].add(-1.0, ue)
+                    extra["mg"] = {"seconds": mg_s, "iterations": its2, "rel_error": dop.dot(xf[0], xf[0]) ** 0.5 / dop.dot(ue, ue) ** 0.5,
+                                   "n_dofs": dop.n_global, "levels": args.refine, "coarse_cg_iterations": pm.coarse_iterations, "setup_seconds": mg_setup_s,
+                                   "tolerance": "1e-10*|b|" if args.dtype == "f64" else "1e-5*|b|",
+                                   "preconditioner": "V-cycle over the box partition, levels 1..%d, Chebyshev(5) with the fused update kernel, local transfers, "
+                                                     "coarse level solved on one replicated global mesh; host-orchestrated (one host read per dot "
+                                                     "product)" % args.refine}
+                except Exception as e:
+                    extra["mg"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    except Exception as e:
+        extra["section_error"] = "section '%s': %s: %s" % (section["name"], type(e).__name__, str(e)[:300])
     watchdog.cancel()
     if rank == 0:
-        line = make_line(extra["e2e"], extra["cg"], None)
+        line = make_line(extra["e2e"], extra["cg"], extra.get("section_error"))
         line["mg_solve"] = extra["mg"]
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     # Teardown: ncclCommDestroy hung on this stack (torch 2.11 / NCCL 2.28) after captured graphs that hold NCCL kernels had
     # run; the graphs are released first and the teardown gets 20 s on a watchdog thread before the ranks leave without it.
-    graphs.clear()
-    getattr(dop, "_graphs", {}).clear()
-    torch.cuda.synchronize()
-    __import__("sys").stdout.flush()
-    __import__("sys").stderr.flush()
-    import threading
     threading.Timer(20.0, lambda: os._exit(0)).start()
     try:
+        graphs.clear()
+        getattr(dop, "_graphs", {}).clear()
+        torch.cuda.synchronize()       # (raises after a sticky device error of a failed section: the line is out, the rank still leaves with 0)
+        __import__("sys").stdout.flush()
+        __import__("sys").stderr.flush()
         dist.barrier()
         dist.destroy_process_group()
     finally:

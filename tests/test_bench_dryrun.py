@@ -82,6 +82,21 @@ def test_bench_watchdog_prints_the_apply_line(emu):
     assert d["value"] > 0 and d["roofline"]["frac"] > 0 and "did not finish within 1 s" in d["note"]
 
 
+def test_bench_single_gpu_watchdog_prints_the_apply_line(emu):
+    """N = 1: the CG / multigrid solves behind the timed region run under a watchdog too; the apply line (with roofline, e2e and the CPU
+    baseline, all measured before them) is printed once when they do not finish in time"""
+    os.environ["MFG_BENCH_WATCHDOG_S"] = "0.001"
+    try:
+        rc, out, err = run_ranks(emu, 1, os.path.join(ROOT, "bench.py"), ["--gpus", 1, "--steps", 3, "--warmup", 3, "--refine", 2, "--degree", 2,
+                                                                        "--e2e-steps", 2, "--cpu-steps", 2])
+    finally:
+        del os.environ["MFG_BENCH_WATCHDOG_S"]
+    assert rc == [0], err[0][-3000:]
+    d = the_line(out[0])
+    assert d["value"] > 0 and d["roofline"]["frac"] > 0 and d["e2e"]["value"] > 0 and d["cpu_baseline"]["value"] > 0
+    assert "did not finish within 0.001 s" in d["note"]
+
+
 def test_multigrid_worker_on_the_emulation(emu):
     """tests/multirank_mg_worker.py (the torchrun worker of the late GPU test): multigrid over the partition with one box per rank"""
     rc, out, err = run_ranks(emu, 2, os.path.join(ROOT, "tests", "multirank_mg_worker.py"), [1, 2, "weak"])
