@@ -413,10 +413,13 @@ def main():
     from dealii_cuda_b200.distributed import bind_to_gpu_numa_node
     saved_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa_node = bind_to_gpu_numa_node(local_rank)
+    saved_threads = torch.get_num_threads()
+    torch.set_num_threads(1)       # (no worker threads are born with the narrowed mask: the CPU baseline below must see every core)
     try:
         hs = [torch.full((n,), 0.1, dtype=tdtype).pin_memory() for _ in range(2)]
         hd = [torch.empty((n,), dtype=tdtype).pin_memory() for _ in range(2)]
     finally:
+        torch.set_num_threads(saved_threads)
         if numa_node is not None and saved_affinity:
             os.sched_setaffinity(0, saved_affinity)
     op.vmult_host(hd[0].numpy(), hs[0].numpy())
